@@ -1,0 +1,161 @@
+/*
+ * include/zfb.h -- C ABI of the B200-native zfp fixed-rate codec + fused CBench error metrics.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  Each entry point names
+ * the reference interface it replaces (paths relative to the lanl/VizAly-Foresight tree).  The CBench
+ * plugin shim that binds these (vizaly-foresight_b200/cbench/zfpB200Compressor.hpp and
+ * gpuMetrics.hpp) is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - dtype: ZFB_FLOAT (1) / ZFB_DOUBLE (2)        (zfp_type_float / zfp_type_double,
+ *                                                    zfpCompressorGpu.hpp:56-66)
+ *   - dims 1..3 and nx,ny,nz with x the FASTEST axis (zfp_field_3d(input, type, n[2], n[1], n[0]),
+ *     zfpCompressorGpu.hpp:110-118).  Unused extents are 1.
+ *   - maxbits: bits per 4^dims block, from zfb_maxbits() (zfp_stream_set_rate, :129)
+ *   - every function returns 0 on success or a negative ZFB_E* code; nothing throws across the ABI.
+ *   - "dev" entry points take DEVICE pointers and enqueue on the context's stream (or the stream given
+ *     to zfb_set_stream) without synchronising; "host" entry points take HOST pointers, do the
+ *     host<->device copies themselves and return when the result is in host memory.
+ *   - There is no CPU fallback: without a usable CUDA device every compute call returns ZFB_ENODEV.
+ */
+#ifndef ZFB_H
+#define ZFB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ZFB_FLOAT 1
+#define ZFB_DOUBLE 2
+
+#define ZFB_OK 0
+#define ZFB_EINVAL (-1)   /* bad argument (dims, dtype, maxbits below 1+EBITS, null pointer)          */
+#define ZFB_ENODEV (-2)   /* no CUDA device / CUDA extension unusable: there is no CPU fallback        */
+#define ZFB_ECUDA (-3)    /* a CUDA call failed; zfb_last_error() has the text                          */
+#define ZFB_ENOMEM (-4)
+#define ZFB_ESTATE (-5)   /* call order violated (e.g. fused metrics requested with no resident field)  */
+
+#define ZFB_NBINS 1024    /* histogram bins (absoluteError.hpp:111, relativeError.hpp:124, minmaxMetric.hpp:98) */
+
+typedef struct zfb_ctx zfb_ctx;
+
+/* Everything the five CBench metrics need, for one rank's sub-field.  The SUM / MAX / MIN members are
+ * exactly the quantities the reference MPI_Allreduces (absoluteError.hpp:80-92, relativeError.hpp:93-105,
+ * meansquareError.hpp:70-71, psnrError.hpp:75-83, minmaxMetric.hpp:77-81), laid out so that a multi-GPU
+ * combine is three small all-reduces: SUM over sum[0..2] and n, MAX over max[0..3] (min is stored
+ * negated so that MAX works for it too). */
+typedef struct zfb_partials {
+  double sum_sq;    /* sum (o-a)^2          -> mse, psnr                                   */
+  double sum_abs;   /* sum |o-a|            -> absolute_error log lines                     */
+  double sum_rel;   /* sum relError(o,a,1)  -> relative_error log lines                     */
+  double max_abs;   /* max |o-a|            -> absolute_error value                         */
+  double max_rel;   /* max relError         -> relative_error value                         */
+  double max_orig;  /* max o                -> psnr, minmax value                           */
+  double neg_min_orig; /* -(min o)          -> minmax log                                   */
+  uint64_t n;       /* number of values                                                     */
+} zfb_partials;
+
+/* ---- parameters (pure host arithmetic, usable without a GPU) ------------------------------------ */
+
+/* zfp_stream_set_rate(zfp, rate, type, dims, wra): bits per block.
+ * Replaces the call at zfpCompressorGpu.hpp:129,232 (CBench passes wra = 8, i.e. non-zero). */
+unsigned zfb_maxbits(int dtype, int dims, double rate, int wra);
+
+/* Bytes zfp_compress() returns (= CompressorInterface::cbytes, zfpCompressorGpu.hpp:145,156-157). */
+size_t zfb_stream_bytes(int dims, size_t nx, size_t ny, size_t nz, unsigned maxbits);
+
+/* Bytes zfp_stream_maximum_size() returns (buffer CBench mallocs, zfpCompressorGpu.hpp:134-135). */
+size_t zfb_stream_capacity(int dims, size_t nx, size_t ny, size_t nz, unsigned maxbits);
+
+/* CBench's recursive-bisection domain split (dataLoaderInterface.hpp:123-215): extents n[3] (slowest
+ * first) over nranks ranks; writes this rank's count[3] and offset[3]. */
+int zfb_partition(int rank, int nranks, const size_t n[3], size_t count[3], size_t offset[3]);
+
+/* ---- context ------------------------------------------------------------------------------------- */
+
+/* Binds a context to CUDA device `device` (CompressorInterface::init, zfpCompressorGpu.hpp:50-53, plus
+ * zfp_stream_set_execution(zfp, zfp_exec_cuda), :143).  Returns ZFB_ENODEV when no device is usable. */
+int zfb_create(zfb_ctx** ctx, int device);
+int zfb_destroy(zfb_ctx* ctx);                       /* CompressorInterface::close, :269-272 */
+/* Use an existing CUDA stream (a cudaStream_t passed as void*) for all "dev" calls; NULL = own stream. */
+int zfb_set_stream(zfb_ctx* ctx, void* cuda_stream);
+int zfb_synchronize(zfb_ctx* ctx);
+const char* zfb_last_error(const zfb_ctx* ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t zfb_launch_count(const zfb_ctx* ctx);
+
+/* ---- device-pointer hot path ----------------------------------------------------------------------- */
+
+/* zfp_compress (zfpCompressorGpu.hpp:145): d_in = field, d_stream receives zfb_stream_bytes() bytes. */
+int zfb_encode_dev(zfb_ctx* ctx, int dtype, int dims, size_t nx, size_t ny, size_t nz, unsigned maxbits,
+                   const void* d_in, void* d_stream);
+
+/* zfp_decompress (zfpCompressorGpu.hpp:249) fused with the five metric passes of main.cpp:306-352:
+ * d_out receives the decompressed field; when d_orig != NULL the metric partials of (d_orig, d_out)
+ * are accumulated in the same pass and left in the context (zfb_partials_dev / zfb_partials_get). */
+int zfb_decode_dev(zfb_ctx* ctx, int dtype, int dims, size_t nx, size_t ny, size_t nz, unsigned maxbits,
+                   const void* d_stream, void* d_out, const void* d_orig);
+
+/* Stand-alone streaming metric pass over two device arrays (any compressor's output):
+ * absoluteError/relativeError/meansquareError/psnrError/minmaxMetric::execute first loops. */
+int zfb_metrics_dev(zfb_ctx* ctx, int dtype, const void* d_orig, const void* d_approx, size_t n);
+
+/* Device address of the context's zfb_partials (valid after the stream reaches the producing call);
+ * multi-GPU callers all-reduce it in place (NCCL) before reading. */
+void* zfb_partials_dev(zfb_ctx* ctx);
+/* Synchronise and copy the partials to the host. */
+int zfb_partials_get(zfb_ctx* ctx, zfb_partials* out);
+/* Overwrite the device partials (used after a host-side / MPI combine so histograms see global values). */
+int zfb_partials_set(zfb_ctx* ctx, const zfb_partials* in);
+
+/* Second-pass histograms (absoluteError.hpp:104-139, relativeError.hpp:117-153, minmaxMetric.hpp:92-133).
+ * which: 0 = abs error over [0, hi], 1 = rel error over [0, hi], 2 = approx values over [lo, hi].
+ * d_counts: ZFB_NBINS uint64 device counters, zero-initialised by the call.  Values outside the range
+ * are clamped to the end bins (the reference indexes out of bounds there) and counted in *d_oob
+ * (nullable device uint64). */
+int zfb_histogram_dev(zfb_ctx* ctx, int dtype, int which, double lo, double hi, const void* d_orig,
+                      const void* d_approx, size_t n, uint64_t* d_counts, uint64_t* d_oob);
+
+/* ---- host-pointer entry points (what the CBench plugin binds) -------------------------------------- */
+
+/* ZFPCompressorGpu::compress body (zfpCompressorGpu.hpp:104-157): h_in host field -> h_stream (caller
+ * allocated, >= zfb_stream_bytes()).  The uploaded field stays resident on the device, keyed by h_in,
+ * so that the following zfb_decompress_host can fuse the metrics without a second upload. */
+int zfb_compress_host(zfb_ctx* ctx, int dtype, int dims, size_t nx, size_t ny, size_t nz, unsigned maxbits,
+                      const void* h_in, void* h_stream, size_t* cbytes);
+
+/* ZFPCompressorGpu::decompress body (zfpCompressorGpu.hpp:205-262): h_stream -> h_out (caller allocated,
+ * nx*ny*nz*sizeof(T)).  If h_orig != NULL the metrics of (h_orig, h_out) are fused into the pass; the
+ * resident copy from zfb_compress_host is used when h_orig is the pointer it was given. */
+int zfb_decompress_host(zfb_ctx* ctx, int dtype, int dims, size_t nx, size_t ny, size_t nz, unsigned maxbits,
+                        const void* h_stream, void* h_out, const void* h_orig);
+
+/* MetricInterface::execute(original, approx, n) for host arrays (main.cpp:336): reuses the fused
+ * partials when (h_orig, h_approx) are the buffers of the last zfb_decompress_host, else uploads both. */
+int zfb_metrics_host(zfb_ctx* ctx, int dtype, const void* h_orig, const void* h_approx, size_t n,
+                     zfb_partials* out);
+
+/* Histogram of host arrays; counts[ZFB_NBINS] host uint64.  Uses resident device copies when the
+ * pointers match the last compress/decompress pair. */
+int zfb_histogram_host(zfb_ctx* ctx, int dtype, int which, double lo, double hi, const void* h_orig,
+                       const void* h_approx, size_t n, uint64_t* counts, uint64_t* oob);
+
+/* Drop the resident device copies (called from CompressorInterface::close / between scalars). */
+int zfb_release_resident(zfb_ctx* ctx);
+
+/* ---- scalar metric values from (combined) partials: pure host arithmetic --------------------------- */
+double zfb_value_absolute_error(const zfb_partials* p); /* absoluteError.hpp:78-82   */
+double zfb_value_relative_error(const zfb_partials* p); /* relativeError.hpp:91-95   */
+double zfb_value_mse(const zfb_partials* p);            /* meansquareError.hpp:64-72 */
+double zfb_value_psnr(const zfb_partials* p);           /* psnrError.hpp:85-88       */
+double zfb_value_minmax(const zfb_partials* p);         /* minmaxMetric.hpp:89-90    */
+/* Combine `count` ranks' partials the way the reference's Allreduces do (SUM / MAX / MIN). */
+void zfb_partials_combine(zfb_partials* acc, const zfb_partials* in, int count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ZFB_H */

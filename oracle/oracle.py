@@ -24,7 +24,7 @@ _ref = None
 def build(force=False):
     """make -C oracle (also builds _ref/ when /root/reference is present)."""
     so = os.path.join(HERE, "liboracle.so")
-    srcs = [os.path.join(HERE, f) for f in ("zfp_ref.c", "metrics_ref.c", "Makefile")]
+    srcs = [os.path.join(HERE, f) for f in ("zfp_ref.c", "metrics_ref.c", "cbench_step_ref.c", "Makefile")]
     stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
     if force or stale:
         subprocess.run(["make", "-C", HERE, "liboracle.so"], check=True, capture_output=True)
@@ -60,6 +60,8 @@ def lib():
         L.zfo_decode_ints_u32.argtypes = [vp, u, u, u, vp]
         L.zfo_roundtrip_slabs.restype = C.c_double
         L.zfo_roundtrip_slabs.argtypes = [i, i, sz, sz, sz, u, vp, vp, vp, i, i, dp, dp]
+        L.zfo_cbench_step.restype = C.c_double
+        L.zfo_cbench_step.argtypes = [i, sz, sz, sz, u, vp, vp, vp, i, i, dp, dp]
         L.zfo_abs_error.restype = None
         L.zfo_abs_error.argtypes = [vp, vp, sz, dp, vp]
         L.zfo_rel_error.restype = None
@@ -207,6 +209,23 @@ def ref_metric(name, orig, approx, hist=False):
     v = R.cbref_metric(name.encode(), o.ctypes.data, a.ctypes.data, o.size, int(hist), log, 4096, extra,
                        1 << 16, C.byref(loc))
     return {"value": v, "local": loc.value, "log": log.value.decode(), "extra": extra.value.decode()}
+
+
+def cbench_step(field_slabs, mb, nthreads=0):
+    """CBench scalar iteration on CPU: field_slabs[r] is rank r's float32 sub-field (all the same shape).
+    Returns dict(wall, t_compress, t_decompress, t_metrics, values)."""
+    a = np.ascontiguousarray(field_slabs, dtype=np.float32)
+    nranks = a.shape[0]
+    d, nx, ny, nz = dims_of(a.shape[1:])
+    sbytes = int(lib().zfo_stream_bytes(d, nx, ny, nz, mb))
+    stream = np.zeros(nranks * sbytes + 16, dtype=np.uint8)
+    out = np.empty_like(a)
+    times = (C.c_double * 3)()
+    vals = (C.c_double * 5)()
+    w = lib().zfo_cbench_step(d, nx, ny, nz, mb, a.ctypes.data, stream.ctypes.data, out.ctypes.data, nranks,
+                              int(nthreads), times, vals)
+    return {"wall": w, "t_compress": times[0], "t_decompress": times[1], "t_metrics": times[2],
+            "values": list(vals), "out": out, "stream": stream[: nranks * sbytes]}
 
 
 def parse_hist_script(text):

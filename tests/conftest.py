@@ -30,6 +30,24 @@ def smooth_field(shape, seed=0, dtype=np.float32, amp=1.0):
 
 
 @pytest.fixture(scope="session")
+def pkg():
+    import __graft_entry__ as g
+
+    return g.load_package()
+
+
+@pytest.fixture(scope="session")
+def codec(pkg):
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    c = pkg.Codec(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="session")
 def oracle():
     import oracle as O
 

@@ -1,0 +1,94 @@
+// tests/host_emul.cpp -- TEST INFRASTRUCTURE.  Compiles the device block codec
+// (vizaly-foresight_b200/csrc/zfb_codec.cuh, which is __host__ __device__) for the CPU so that the
+// exact kernel arithmetic can be bit-compared with the oracle in this GPU-less container.
+// Never linked into the product library.
+#include <cstring>
+#include <cstdint>
+#include <cstddef>
+#include "../vizaly-foresight_b200/csrc/zfb_codec.cuh"
+
+using namespace zfb;
+
+template <typename Scalar, int DIMS>
+static void run(bool enc, size_t nx, size_t ny, size_t nz, unsigned maxbits, Scalar* data, uint64_t* stream,
+                size_t stream_words)
+{
+  constexpr int BS = 1 << (2 * DIMS);
+  if (DIMS < 2) ny = 1;
+  if (DIMS < 3) nz = 1;
+  const size_t bx = (nx + 3) / 4, by = (ny + 3) / 4, bz = (nz + 3) / 4;
+  const bool aligned = (maxbits % 64) == 0;
+  if (enc) std::memset(stream, 0, stream_words * 8);
+  for (size_t b = 0; b < bx * by * bz; b++) {
+    const size_t ix = b % bx, iy = (b / bx) % by, iz = b / (bx * by);
+    const size_t x0 = 4 * ix, y0 = 4 * iy, z0 = 4 * iz;
+    const unsigned mx = (unsigned)(nx - x0 < 4 ? nx - x0 : 4);
+    const unsigned my = DIMS >= 2 ? (unsigned)(ny - y0 < 4 ? ny - y0 : 4) : 1;
+    const unsigned mz = DIMS >= 3 ? (unsigned)(nz - z0 < 4 ? nz - z0 : 4) : 1;
+    Scalar f[BS];
+    const size_t startbit = b * (size_t)maxbits;
+    if (enc) {
+      for (int i = 0; i < BS; i++) f[i] = 0;
+      for (unsigned k = 0; k < mz; k++)
+        for (unsigned j = 0; j < my; j++)
+          for (unsigned i = 0; i < mx; i++) f[16 * k + 4 * j + i] = data[(x0 + i) + nx * ((y0 + j) + ny * (z0 + k))];
+      if (mx < 4 || my < (DIMS >= 2 ? 4u : 1u) || mz < (DIMS >= 3 ? 4u : 1u)) pad_block<Scalar, DIMS>(f, mx, my, mz);
+      if (aligned) {
+        aligned_sink sink(stream + startbit / 64, maxbits / 64);
+        encode_block<Scalar, DIMS>(f, maxbits, sink);
+      } else {
+        or_sink sink(stream, startbit, maxbits);
+        encode_block<Scalar, DIMS>(f, maxbits, sink);
+      }
+    } else {
+      slot_reader r(stream + (startbit >> 6), (unsigned)(stream_words - (startbit >> 6)), (unsigned)(startbit & 63));
+      decode_block<Scalar, DIMS>(f, maxbits, r);
+      for (unsigned k = 0; k < mz; k++)
+        for (unsigned j = 0; j < my; j++)
+          for (unsigned i = 0; i < mx; i++) data[(x0 + i) + nx * ((y0 + j) + ny * (z0 + k))] = f[16 * k + 4 * j + i];
+    }
+  }
+}
+
+template <typename Scalar>
+static int dispatch(bool enc, int dims, size_t nx, size_t ny, size_t nz, unsigned maxbits, void* data, void* stream,
+                    size_t stream_words)
+{
+  Scalar* d = (Scalar*)data;
+  uint64_t* s = (uint64_t*)stream;
+  if (dims == 1) run<Scalar, 1>(enc, nx, ny, nz, maxbits, d, s, stream_words);
+  else if (dims == 2) run<Scalar, 2>(enc, nx, ny, nz, maxbits, d, s, stream_words);
+  else if (dims == 3) run<Scalar, 3>(enc, nx, ny, nz, maxbits, d, s, stream_words);
+  else return -1;
+  return 0;
+}
+
+extern "C" {
+// type: 1 float, 2 double (same codes as the oracle and include/zfb.h)
+int emul_compress(int type, int dims, size_t nx, size_t ny, size_t nz, unsigned maxbits, const void* in, void* stream,
+                  size_t stream_words)
+{
+  return type == 1 ? dispatch<float>(true, dims, nx, ny, nz, maxbits, (void*)in, stream, stream_words)
+                   : dispatch<double>(true, dims, nx, ny, nz, maxbits, (void*)in, stream, stream_words);
+}
+int emul_decompress(int type, int dims, size_t nx, size_t ny, size_t nz, unsigned maxbits, const void* stream,
+                    void* out, size_t stream_words)
+{
+  return type == 1 ? dispatch<float>(false, dims, nx, ny, nz, maxbits, out, (void*)stream, stream_words)
+                   : dispatch<double>(false, dims, nx, ny, nz, maxbits, out, (void*)stream, stream_words);
+}
+void emul_transpose32(uint32_t* a)
+{
+  uint32_t t[32];
+  for (int i = 0; i < 32; i++) t[i] = a[i];
+  transpose32(t);
+  for (int i = 0; i < 32; i++) a[i] = t[i];
+}
+void emul_transpose64(uint64_t* a)
+{
+  uint64_t t[64];
+  for (int i = 0; i < 64; i++) t[i] = a[i];
+  transpose64(t);
+  for (int i = 0; i < 64; i++) a[i] = t[i];
+}
+}

@@ -1,0 +1,292 @@
+"""GPU parity tests proper (run with -m gpu on the B200 box).  Everything goes through the C ABI
+(include/zfb.h) via the ctypes wrapper; the oracle is only the checker.
+
+Bars: compressed streams and decompressed values BIT-EXACT with the oracle; metrics within 1e-6 relative
+(reduction order differs), max/min quantities exact; histogram counts exact.
+"""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import smooth_field
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+REL = 1e-6  # tolerance north_star states for the metrics
+
+
+def _torch():
+    import torch
+
+    return torch
+
+
+def gpu_roundtrip(codec, f, mb, with_metrics=True):
+    torch = _torch()
+    d_f = torch.from_numpy(f).cuda()
+    stream = codec.encode(d_f, mb)
+    tdt = torch.float32 if f.dtype == np.float32 else torch.float64
+    out = codec.decode(stream, f.shape, tdt, mb, orig=d_f if with_metrics else None)
+    part = codec.partials() if with_metrics else None
+    return stream.cpu().numpy(), out.cpu().numpy(), part
+
+
+def assert_bits_equal(a, b, what):
+    assert a.shape == b.shape, what
+    assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), what
+
+
+def check_metrics(pkg, oracle, part, f, g_ref, what):
+    m_ref = oracle.metrics(f, g_ref)
+    v = pkg.metric_values(part)
+    assert v["n"] == f.size
+    for k in ("absolute_error", "minmax", "min", "max"):      # max/min of identical floats: exact
+        assert v[k] == m_ref[k], (what, k, v[k], m_ref[k])
+    for k in ("relative_error", "mse", "psnr"):
+        assert abs(v[k] - m_ref[k]) <= REL * abs(m_ref[k]) + 1e-300, (what, k, v[k], m_ref[k])
+    assert abs(v["sum_abs"] - m_ref["abs_sum"]) <= REL * abs(m_ref["abs_sum"]) + 1e-300, what
+    assert abs(v["sum_rel"] - m_ref["rel_sum"]) <= REL * abs(m_ref["rel_sum"]) + 1e-300, what
+
+
+SMALL = [
+    (np.float32, (10,)), (np.float32, (4099,)), (np.float32, (5, 7)), (np.float32, (64, 64)), (np.float32, (5, 6, 7)),
+    (np.float32, (33, 33, 33)), (np.float32, (16, 32, 64)), (np.float32, (1, 1, 1)), (np.float32, (4, 4, 4)),
+    (np.float64, (1001,)), (np.float64, (17, 19)), (np.float64, (5, 6, 7)), (np.float64, (16, 16, 32)),
+]
+
+
+@pytest.mark.parametrize("dtype,shape", SMALL)
+def test_small_fields_bit_exact(codec, pkg, oracle, dtype, shape):
+    kinds = {
+        "smooth": smooth_field(shape, seed=11, dtype=dtype, amp=100.0),
+        "noise": (900 * np.random.default_rng(5).standard_normal(shape)).astype(dtype),
+        "lognormal": np.exp(2.0 * smooth_field(shape, seed=12, dtype=np.float64)).astype(dtype),
+    }
+    rates = (1, 3, 4, 8, 16, 32) if dtype == np.float32 else (1, 5, 8, 16, 32, 64)
+    for label, f in kinds.items():
+        for rate in rates:
+            for wra in (1, 0):
+                mb = oracle.maxbits(dtype, len(shape), rate, wra)
+                assert mb == pkg.maxbits(dtype, len(shape), rate, wra)
+                s_ref = oracle.compress(f, mb)
+                g_ref = oracle.decompress(s_ref, shape, dtype, mb)
+                s, g, part = gpu_roundtrip(codec, f, mb, with_metrics=(dtype == np.float32))
+                assert np.array_equal(s, s_ref), (label, rate, wra)
+                assert_bits_equal(g, g_ref, (label, rate, wra))
+                if dtype == np.float32:
+                    check_metrics(pkg, oracle, part, f, g_ref, (label, rate, wra))
+
+
+TILE_SHAPES = [(8, 8, 256), (8, 8, 1028), (36, 40, 72), (64, 64, 64), (4, 4, 4), (12, 8, 516), (32, 256, 512)]
+
+
+@pytest.mark.parametrize("shape", TILE_SHAPES)
+@pytest.mark.parametrize("rate", [4, 8, 16, 3, 32])
+def test_tile_kernels_bit_exact(codec, pkg, oracle, shape, rate):
+    """3D float fields with dims % 4 == 0 take the TMA tile kernels (boxes straddling row ends included)."""
+    f = np.exp(1.2 * smooth_field(shape, seed=rate, dtype=np.float64)).astype(np.float32)
+    mb = pkg.maxbits(np.float32, 3, rate)
+    s_ref = oracle.compress(f, mb)
+    g_ref = oracle.decompress(s_ref, shape, np.float32, mb)
+    s, g, part = gpu_roundtrip(codec, f, mb)
+    assert np.array_equal(s, s_ref)
+    assert_bits_equal(g, g_ref, "decoded")
+    check_metrics(pkg, oracle, part, f, g_ref, (shape, rate))
+    # decode without metrics takes the other kernel instantiation
+    s2, g2, _ = gpu_roundtrip(codec, f, mb, with_metrics=False)
+    assert_bits_equal(g2, g_ref, "decoded (no metrics)")
+
+
+def test_extreme_values(codec, pkg, oracle):
+    rng = np.random.default_rng(3)
+    cases = {
+        "zeros": np.zeros((8, 8, 8), np.float32),
+        "tiny": (rng.standard_normal((8, 8, 8)) * 1e-35).astype(np.float32),
+        "denorm": (rng.standard_normal((8, 8, 8)) * 1e-42).astype(np.float32),
+        "huge": (rng.standard_normal((8, 8, 8)) * 1e37).astype(np.float32),
+        "mixed": (rng.standard_normal((8, 8, 8)) * 10.0 ** rng.integers(-30, 30, (8, 8, 8))).astype(np.float32),
+        "neg": -np.abs(rng.standard_normal((8, 8, 8))).astype(np.float32),
+        "ragged": (rng.standard_normal((7, 9, 11)) * 5).astype(np.float32),
+    }
+    for label, f in cases.items():
+        for mb in (64, 256, 512, 1024, 2048, 100, 9, 37):
+            s_ref = oracle.compress(f, mb)
+            g_ref = oracle.decompress(s_ref, f.shape, np.float32, mb)
+            s, g, _ = gpu_roundtrip(codec, f, mb, with_metrics=False)
+            assert np.array_equal(s, s_ref), (label, mb)
+            assert_bits_equal(g, g_ref, (label, mb))
+
+
+def test_known_answer_hashes_on_gpu(codec, oracle):
+    import make_golden
+
+    kat = json.load(open(os.path.join(GOLD, "codec_kat.json")))
+    for case in kat["cases"]:
+        f = make_golden.case_input(case)
+        assert hashlib.sha256(f.tobytes()).hexdigest() == case["input_sha256"], case["name"]
+        s, g, _ = gpu_roundtrip(codec, f, case["maxbits"], with_metrics=False)
+        assert len(s) == case["stream_bytes"]
+        assert hashlib.sha256(s.tobytes()).hexdigest() == case["stream_sha256"], case["name"]
+        assert hashlib.sha256(g.tobytes()).hexdigest() == case["decoded_sha256"], case["name"]
+
+
+def test_reference_toy_data(codec, pkg, oracle):
+    """Real inputs lifted from the reference's toy files (testing/data), all metrics included."""
+    nyx = np.fromfile(os.path.join(GOLD, "nyx_z255_32_baryon_density.f32"), dtype=np.float32).reshape(32, 32, 32)
+    hacc = np.fromfile(os.path.join(GOLD, "hacc_m000_x_4096.f32"), dtype=np.float32)
+    for f, rates in ((nyx, (4, 8, 14, 16)), (hacc, (8, 16, 24))):
+        for rate in rates:
+            mb = pkg.maxbits(np.float32, f.ndim, int(rate))   # "bits" is int-truncated, zfpCompressorGpu.hpp:83,99
+            s_ref = oracle.compress(f, mb)
+            g_ref = oracle.decompress(s_ref, f.shape, np.float32, mb)
+            s, g, part = gpu_roundtrip(codec, f, mb)
+            assert np.array_equal(s, s_ref)
+            assert_bits_equal(g, g_ref, rate)
+            check_metrics(pkg, oracle, part, f, g_ref, rate)
+
+
+def test_metrics_match_reference_vectors(codec, pkg, oracle):
+    """Stand-alone metric kernel against values produced by the reference's own classes (metrics_kat.json)."""
+    torch = _torch()
+    kat = json.load(open(os.path.join(GOLD, "metrics_kat.json")))
+    for case in kat["cases"]:
+        rng = np.random.default_rng(case["seed"])
+        n, kind = case["n"], case["kind"]
+        if kind == "noise":
+            o = rng.standard_normal(n).astype(np.float32) * 3
+            a = (o + 0.01 * rng.standard_normal(n)).astype(np.float32)
+        elif kind == "big":
+            o = (rng.standard_normal(n) * 1e4).astype(np.float32)
+            a = (o * (1 + 1e-3 * rng.standard_normal(n))).astype(np.float32)
+        else:
+            side = int(round(n ** (1 / 3)))
+            o = smooth_field((side, side, side), seed=case["seed"], amp=50.0)
+            mb = 512 if kind == "codec8" else 256
+            a = oracle.decompress(oracle.compress(o, mb), o.shape, np.float32, mb)
+        part = codec.metrics(torch.from_numpy(o.ravel()).cuda(), torch.from_numpy(a.ravel()).cuda())
+        v = pkg.metric_values(part)
+        assert v["absolute_error"] == case["absolute_error"]
+        assert v["minmax"] == case["minmax"]
+        for k in ("relative_error", "mse", "psnr"):
+            assert abs(v[k] - case[k]) <= REL * abs(case[k]), (kind, k, v[k], case[k])
+
+
+def test_histograms_match_oracle(codec, pkg, oracle):
+    torch = _torch()
+    f = smooth_field((32, 32, 64), seed=4, amp=30.0)
+    mb = 256
+    g = oracle.decompress(oracle.compress(f, mb), f.shape, np.float32, mb)
+    m = oracle.metrics(f, g, hist=True)
+    d_f, d_g = torch.from_numpy(f).cuda(), torch.from_numpy(g).cuda()
+    n = f.size
+    cnt, oob = codec.histogram(0, 0.0, m["absolute_error"], d_f, d_g)
+    assert int(oob.item()) == 0 and int(cnt.sum().item()) == n
+    assert np.array_equal((cnt.cpu().numpy().astype(np.float32) / np.float32(n)), m["abs_hist"])
+    cnt, oob = codec.histogram(1, 0.0, m["relative_error"], d_f, d_g)
+    assert int(cnt.sum().item()) == n
+    assert np.array_equal((cnt.cpu().numpy().astype(np.float32) / np.float32(n)), m["rel_hist"])
+    cnt, oob = codec.histogram(2, m["min"], m["max"], None, d_g)
+    assert int(cnt.sum().item()) == n
+    assert np.array_equal(cnt.cpu().numpy().astype(np.float32), m["minmax_hist"])
+    assert int(oob.item()) == m["minmax_oob"]
+
+
+def test_generic_and_tile_paths_agree(pkg, oracle):
+    """ZFB_FORCE_GENERIC=1 routes a tile-eligible field through the generic kernels: same bits."""
+    torch = _torch()
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    f = smooth_field((16, 64, 512), seed=8, amp=10.0)
+    mb = 512
+    os.environ["ZFB_FORCE_GENERIC"] = "1"
+    try:
+        c2 = pkg.Codec(0)
+    finally:
+        del os.environ["ZFB_FORCE_GENERIC"]
+    s_ref = oracle.compress(f, mb)
+    s, g, part = gpu_roundtrip(c2, f, mb)
+    assert np.array_equal(s, s_ref)
+    check_metrics(pkg, oracle, part, f, oracle.decompress(s_ref, f.shape, np.float32, mb), "generic")
+    c2.close()
+
+
+def test_host_entry_points_and_fused_metrics(codec, pkg, oracle):
+    """zfb_compress_host / zfb_decompress_host / zfb_metrics_host, multi-slab pipeline included."""
+    shape = (96, 512, 512)   # 96 MiB -> two slabs in the host pipeline
+    f = smooth_field(shape, seed=2, amp=1000.0)
+    mb = 512
+    s = codec.compress_host(f, mb)
+    g = codec.decompress_host(s, shape, np.float32, mb, orig=f)
+    part = codec.metrics_host(f, g)       # the fused partials, no re-upload
+    s_ref = oracle.compress(f, mb)
+    g_ref = oracle.decompress(s_ref, shape, np.float32, mb)
+    assert np.array_equal(s, s_ref)
+    assert_bits_equal(g, g_ref, "host decode")
+    check_metrics(pkg, oracle, part, f, g_ref, "fused host")
+    # stand-alone: different buffers -> uploads both and runs the metric kernel
+    g2 = g.copy()
+    part2 = codec.metrics_host(f, g2)
+    check_metrics(pkg, oracle, part2, f, g_ref, "standalone host")
+    cnt, oob = codec.histogram_host(0, 0.0, part.max_abs, f, g2)
+    assert int(cnt.sum()) == f.size
+    codec.release()
+    # 1D, ragged length, unaligned slots
+    h = (256 * np.random.default_rng(1).random(100003)).astype(np.float32)
+    for mb1 in (64, 32, 45):
+        s1 = codec.compress_host(h, mb1)
+        g1 = codec.decompress_host(s1, h.shape, np.float32, mb1, orig=h)
+        assert np.array_equal(s1, oracle.compress(h, mb1)), mb1
+        assert_bits_equal(g1, oracle.decompress(s1, h.shape, np.float32, mb1), mb1)
+    codec.release()
+
+
+def test_slab_streams_concatenate(codec, pkg):
+    """slabs along the slowest axis (thickness % 4 == 0) concatenate to the whole-field stream."""
+    torch = _torch()
+    f = torch.from_numpy(smooth_field((64, 64, 128), seed=6)).cuda()
+    mb = 512
+    whole = codec.encode(f, mb).clone()
+    parts = [codec.encode(f[z:z + 16].contiguous(), mb).clone() for z in range(0, 64, 16)]
+    assert torch.equal(whole, torch.cat(parts))
+
+
+def test_nyx_512_full_size_against_oracle(codec, pkg, oracle):
+    """BASELINE config 3 at full size: 512^3 float32, rate 8; oracle runs slab-parallel on the host cores."""
+    import ctypes as C
+    torch = _torch()
+    shape = (512, 512, 512)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    base = torch.from_numpy(smooth_field((64, 64, 64), seed=1, amp=1.0)).cuda()
+    f = torch.nn.functional.interpolate(base[None, None], size=shape, mode="trilinear", align_corners=False)[0, 0]
+    f = torch.exp(1.5 * f + 0.05 * torch.randn(shape, device="cuda", generator=g)).contiguous()
+    mb = pkg.maxbits(np.float32, 3, 8)
+    stream = codec.encode(f, mb)
+    out = codec.decode(stream, shape, torch.float32, mb, orig=f)
+    part = codec.partials()
+    h = f.cpu().numpy()
+    nslab = 32
+    st = np.zeros(stream.numel(), dtype=np.uint8)
+    dec = np.empty_like(h)
+    oracle.lib().zfo_roundtrip_slabs(1, 3, 512, 512, 512 // nslab, mb, h.ctypes.data, st.ctypes.data, dec.ctypes.data,
+                                     nslab, 0, None, None)
+    assert np.array_equal(stream.cpu().numpy(), st)
+    assert_bits_equal(out.cpu().numpy(), dec, "512^3 decode")
+    v = pkg.metric_values(part)
+    d = (h.astype(np.float32) - dec).astype(np.float64)
+    assert abs(v["mse"] - float(np.mean(d * d))) <= REL * float(np.mean(d * d))
+    assert v["absolute_error"] == float(np.abs(h - dec).max())
+    assert v["max"] == float(h.max()) and v["min"] == float(h.min())
+
+
+def test_bad_arguments_return_einval(codec, pkg):
+    import ctypes as C
+    torch = _torch()
+    t = torch.zeros(64, device="cuda")
+    L = pkg.lib()
+    assert L.zfb_encode_dev(codec._h, 1, 4, 4, 4, 4, 512, t.data_ptr(), t.data_ptr()) == -1   # dims 4
+    assert L.zfb_encode_dev(codec._h, 3, 1, 64, 1, 1, 64, t.data_ptr(), t.data_ptr()) == -1   # dtype
+    assert L.zfb_encode_dev(codec._h, 1, 1, 64, 1, 1, 8, t.data_ptr(), t.data_ptr()) == -1    # maxbits < 1+EBITS
+    assert L.zfb_encode_dev(codec._h, 1, 1, 64, 1, 1, 64, None, t.data_ptr()) == -1

@@ -1,0 +1,115 @@
+"""The device block codec (zfb_codec.cuh) compiled for the CPU (tests/host_emul.cpp) must produce the
+oracle's streams and decoded values bit for bit.  This pins the kernel arithmetic without a GPU."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, smooth_field
+
+_lib = None
+
+
+def emul():
+    global _lib
+    if _lib is None:
+        so = os.path.join(ROOT, "build", "libhost_emul.so")
+        src = os.path.join(ROOT, "tests", "host_emul.cpp")
+        hdr = os.path.join(ROOT, "vizaly-foresight_b200", "csrc", "zfb_codec.cuh")
+        os.makedirs(os.path.dirname(so), exist_ok=True)
+        if (not os.path.exists(so)) or max(os.path.getmtime(src), os.path.getmtime(hdr)) > os.path.getmtime(so):
+            cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+            subprocess.run([cxx, "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-o", so, src],
+                           check=True)
+        L = C.CDLL(so)
+        for f in (L.emul_compress, L.emul_decompress):
+            f.restype = C.c_int
+            f.argtypes = [C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_uint, C.c_void_p, C.c_void_p,
+                          C.c_size_t]
+        _lib = L
+    return _lib
+
+
+def emul_roundtrip(O, f, mb):
+    d, nx, ny, nz = O.dims_of(f.shape)
+    t = 1 if f.dtype == np.float32 else 2
+    nbytes = O.stream_bytes(f.shape, mb)
+    s = np.zeros(nbytes // 8 + 1, dtype=np.uint64)
+    assert emul().emul_compress(t, d, nx, ny, nz, mb, f.ctypes.data, s.ctypes.data, nbytes // 8) == 0
+    g = np.empty_like(f)
+    assert emul().emul_decompress(t, d, nx, ny, nz, mb, s.ctypes.data, g.ctypes.data, nbytes // 8) == 0
+    return s.view(np.uint8)[:nbytes], g
+
+
+def test_transposes_are_lsb_transposes():
+    L = emul()
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 2 ** 32, size=32, dtype=np.uint64).astype(np.uint32)
+    b = a.copy()
+    L.emul_transpose32(b.ctypes.data_as(C.c_void_p))
+    for k in range(32):
+        for i in range(32):
+            assert (int(b[k]) >> i) & 1 == (int(a[i]) >> k) & 1
+    a = rng.integers(0, 2 ** 63, size=64, dtype=np.uint64) * 2 + rng.integers(0, 2, size=64, dtype=np.uint64)
+    b = a.copy()
+    L.emul_transpose64(b.ctypes.data_as(C.c_void_p))
+    for k in range(64):
+        for i in range(64):
+            assert (int(b[k]) >> i) & 1 == (int(a[i]) >> k) & 1
+
+
+CASES = [
+    (np.float32, (10,)), (np.float32, (4099,)), (np.float32, (5, 7)), (np.float32, (64, 64)),
+    (np.float32, (5, 6, 7)), (np.float32, (33, 33, 33)), (np.float32, (16, 32, 64)),
+    (np.float64, (1001,)), (np.float64, (17, 19)), (np.float64, (5, 6, 7)), (np.float64, (16, 16, 32)),
+]
+
+
+@pytest.mark.parametrize("dtype,shape", CASES)
+def test_device_codec_equals_oracle(oracle, dtype, shape):
+    O = oracle
+    kinds = {
+        "smooth": smooth_field(shape, seed=11, dtype=dtype, amp=100.0),
+        "noise": (900 * np.random.default_rng(5).standard_normal(shape)).astype(dtype),
+        "lognormal": np.exp(2.0 * smooth_field(shape, seed=12, dtype=np.float64)).astype(dtype),
+        "sparse": (smooth_field(shape, seed=13, dtype=dtype) * (np.random.default_rng(6).random(shape) > 0.9)).astype(dtype),
+    }
+    rates = (1, 3, 4, 8, 16, 32) if dtype == np.float32 else (1, 5, 8, 16, 32, 64)
+    for label, f in kinds.items():
+        for rate in rates:
+            for wra in (1, 0):
+                mb = O.maxbits(dtype, len(shape), rate, wra)
+                s_ref = O.compress(f, mb)
+                g_ref = O.decompress(s_ref, shape, dtype, mb)
+                s, g = emul_roundtrip(O, f, mb)
+                assert np.array_equal(s, s_ref), (label, rate, wra, mb)
+                assert np.array_equal(g.view(np.uint8), g_ref.view(np.uint8)), (label, rate, wra, mb)
+
+
+def test_device_codec_extremes(oracle):
+    O = oracle
+    rng = np.random.default_rng(3)
+    cases = {
+        "zeros": np.zeros((8, 8, 8), np.float32),
+        "tiny": (rng.standard_normal((8, 8, 8)) * 1e-35).astype(np.float32),  # scale overflow edge (A.5)
+        "denorm": (rng.standard_normal((8, 8, 8)) * 1e-42).astype(np.float32),
+        "huge": (rng.standard_normal((8, 8, 8)) * 1e37).astype(np.float32),
+        "mixed": (rng.standard_normal((8, 8, 8)) * 10.0 ** rng.integers(-30, 30, (8, 8, 8))).astype(np.float32),
+        "one_nonzero": np.pad(np.ones((1, 1, 1), np.float32), ((3, 4), (2, 5), (0, 7))),
+        "neg": -np.abs(rng.standard_normal((8, 8, 8))).astype(np.float32),
+    }
+    for label, f in cases.items():
+        for mb in (64, 256, 512, 1024, 2048, 100, 9, 37):
+            s_ref = O.compress(f, mb)
+            g_ref = O.decompress(s_ref, f.shape, np.float32, mb)
+            s, g = emul_roundtrip(O, f, mb)
+            assert np.array_equal(s, s_ref), (label, mb)
+            assert np.array_equal(g.view(np.uint8), g_ref.view(np.uint8)), (label, mb)
+    fd = (rng.standard_normal((4, 8, 8)) * 1e-300).astype(np.float64)
+    for mb in (64, 512, 4096, 12, 77):
+        s_ref = O.compress(fd, mb)
+        s, g = emul_roundtrip(O, fd, mb)
+        assert np.array_equal(s, s_ref), mb
+        assert np.array_equal(g.view(np.uint8), O.decompress(s_ref, fd.shape, np.float64, mb).view(np.uint8)), mb

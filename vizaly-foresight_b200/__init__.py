@@ -1,0 +1,332 @@
+"""vizaly-foresight_b200 -- B200-native fixed-rate zfp codec + fused CBench error metrics.
+
+Python here is plumbing only: it loads the C-ABI shared library (include/zfb.h, built from
+csrc/*.cu for sm_100a) with ctypes and passes raw device / host pointers to it.  torch is used for
+device memory and streams, numpy for host arrays.  There is NO CPU fallback: if the CUDA library is
+missing or no B200-class device is present, construction fails loudly.
+
+The directory name has a hyphen, so import it through ``__graft_entry__.load_package()`` (tests/conftest.py
+does this) under the module name ``vizaly_foresight_b200``.
+"""
+import ctypes as C
+import os
+import re
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+LIB_PATH = os.path.join(HERE, "libzfb.so")
+HEADER = os.path.join(ROOT, "include", "zfb.h")
+FLOAT, DOUBLE = 1, 2
+NBINS = 1024
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
+              "-shared"]
+
+
+class ZfbError(RuntimeError):
+    pass
+
+
+class Partials(C.Structure):
+    _fields_ = [("sum_sq", C.c_double), ("sum_abs", C.c_double), ("sum_rel", C.c_double), ("max_abs", C.c_double),
+                ("max_rel", C.c_double), ("max_orig", C.c_double), ("neg_min_orig", C.c_double), ("n", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def build_library(force=False, verbose=False):
+    """nvcc -> vizaly-foresight_b200/libzfb.so (in-tree, so it travels to the GPU box)."""
+    srcs = [os.path.join(HERE, "csrc", f) for f in ("zfb_api.cu", "zfb_kernels.cuh", "zfb_codec.cuh")] + [HEADER]
+    stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    if not (force or stale):
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    if not os.path.exists(nvcc):
+        nvcc = "nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, srcs[0]]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise ZfbError("nvcc failed:\n" + r.stderr[-4000:])
+    return r.stderr if verbose else LIB_PATH
+
+
+def declared_symbols():
+    """Every function include/zfb.h declares."""
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(zfb_[a-z0-9_]+)\s*\(", text)))
+
+
+_lib = None
+
+
+def lib():
+    """Load libzfb.so.  Never falls back to anything else: a missing library is an error."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ZfbError("CUDA extension %s is missing: run __graft_entry__.build() (no CPU fallback exists)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    sz, u, i, vp, d = C.c_size_t, C.c_uint, C.c_int, C.c_void_p, C.c_double
+    PP = C.POINTER(Partials)
+    sig = {
+        "zfb_maxbits": (u, [i, i, d, i]),
+        "zfb_stream_bytes": (sz, [i, sz, sz, sz, u]),
+        "zfb_stream_capacity": (sz, [i, sz, sz, sz, u]),
+        "zfb_partition": (i, [i, i, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)]),
+        "zfb_create": (i, [C.POINTER(vp), i]),
+        "zfb_destroy": (i, [vp]),
+        "zfb_set_stream": (i, [vp, vp]),
+        "zfb_synchronize": (i, [vp]),
+        "zfb_last_error": (C.c_char_p, [vp]),
+        "zfb_launch_count": (C.c_uint64, [vp]),
+        "zfb_encode_dev": (i, [vp, i, i, sz, sz, sz, u, vp, vp]),
+        "zfb_decode_dev": (i, [vp, i, i, sz, sz, sz, u, vp, vp, vp]),
+        "zfb_metrics_dev": (i, [vp, i, vp, vp, sz]),
+        "zfb_partials_dev": (vp, [vp]),
+        "zfb_partials_get": (i, [vp, PP]),
+        "zfb_partials_set": (i, [vp, PP]),
+        "zfb_histogram_dev": (i, [vp, i, i, d, d, vp, vp, sz, vp, vp]),
+        "zfb_compress_host": (i, [vp, i, i, sz, sz, sz, u, vp, vp, C.POINTER(sz)]),
+        "zfb_decompress_host": (i, [vp, i, i, sz, sz, sz, u, vp, vp, vp]),
+        "zfb_metrics_host": (i, [vp, i, vp, vp, sz, PP]),
+        "zfb_histogram_host": (i, [vp, i, i, d, d, vp, vp, sz, vp, C.POINTER(C.c_uint64)]),
+        "zfb_release_resident": (i, [vp]),
+        "zfb_value_absolute_error": (d, [PP]),
+        "zfb_value_relative_error": (d, [PP]),
+        "zfb_value_mse": (d, [PP]),
+        "zfb_value_psnr": (d, [PP]),
+        "zfb_value_minmax": (d, [PP]),
+        "zfb_partials_combine": (None, [PP, PP, i]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = args
+    _lib = L
+    return L
+
+
+def dims_of(shape):
+    """CBench order (n[0] slowest ... n[d-1] fastest) -> (dims, nx, ny, nz); zfpCompressorGpu.hpp:110-118."""
+    shape = tuple(int(s) for s in shape)
+    if len(shape) == 1:
+        return 1, shape[0], 1, 1
+    if len(shape) == 2:
+        return 2, shape[1], shape[0], 1
+    if len(shape) == 3:
+        return 3, shape[2], shape[1], shape[0]
+    raise ValueError("1 to 3 dimensions")
+
+
+def _dtype_code(dt):
+    import numpy as np
+
+    if isinstance(dt, type) and issubclass(dt, np.generic):
+        dt = np.dtype(dt)
+    else:
+        dt = np.dtype(str(dt).replace("torch.", ""))
+    if dt == np.float32:
+        return FLOAT
+    if dt == np.float64:
+        return DOUBLE
+    raise TypeError("float32 / float64 only: %s" % dt)
+
+
+def maxbits(dtype, dims, rate, wra=1):
+    return int(lib().zfb_maxbits(_dtype_code(dtype), dims, float(rate), int(wra)))
+
+
+def stream_bytes(shape, mb):
+    d, nx, ny, nz = dims_of(shape)
+    return int(lib().zfb_stream_bytes(d, nx, ny, nz, mb))
+
+
+def stream_capacity(shape, mb):
+    d, nx, ny, nz = dims_of(shape)
+    return int(lib().zfb_stream_capacity(d, nx, ny, nz, mb))
+
+
+def partition(rank, nranks, shape3):
+    """CBench's getPartition (dataLoaderInterface.hpp:123-215): -> (count[3], offset[3]), slowest axis first."""
+    n = (C.c_size_t * 3)(*shape3)
+    cnt, off = (C.c_size_t * 3)(), (C.c_size_t * 3)()
+    rc = lib().zfb_partition(rank, nranks, n, cnt, off)
+    if rc:
+        raise ZfbError("zfb_partition: %d" % rc)
+    return tuple(cnt), tuple(off)
+
+
+def metric_values(p):
+    """The five CSV values (getGlobalValue of each metric, main.cpp:340) from (combined) partials."""
+    L = lib()
+    r = C.byref(p)
+    return {"absolute_error": L.zfb_value_absolute_error(r), "relative_error": L.zfb_value_relative_error(r),
+            "mse": L.zfb_value_mse(r), "psnr": L.zfb_value_psnr(r), "minmax": L.zfb_value_minmax(r),
+            "min": -p.neg_min_orig, "max": p.max_orig, "sum_abs": p.sum_abs, "sum_rel": p.sum_rel,
+            "sum_sq": p.sum_sq, "n": p.n}
+
+
+def combine_partials(parts):
+    """Allreduce semantics of the reference metrics (SUM / MAX / MIN) over a list of Partials."""
+    acc = Partials(0.0, 0.0, 0.0, 0.0, 0.0, -1.7976931348623157e308, -1.7976931348623157e308, 0)
+    arr = (Partials * len(parts))(*parts)
+    lib().zfb_partials_combine(C.byref(acc), arr, len(parts))
+    return acc
+
+
+class Codec:
+    """One context = one GPU (zfb_create).  Device methods take torch CUDA tensors, host methods numpy arrays."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        rc = lib().zfb_create(C.byref(self._h), int(device))
+        if rc:
+            self._h = None
+            raise ZfbError("zfb_create(device=%d) failed with %d: no usable sm_100 device (there is no CPU fallback)"
+                           % (device, rc))
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().zfb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc:
+            raise ZfbError("%s failed (%d): %s" % (what, rc, lib().zfb_last_error(self._h).decode()))
+
+    def use_stream(self, cuda_stream_ptr):
+        self._check(lib().zfb_set_stream(self._h, C.c_void_p(cuda_stream_ptr)), "zfb_set_stream")
+
+    def use_torch_stream(self):
+        import torch
+
+        self.use_stream(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def synchronize(self):
+        self._check(lib().zfb_synchronize(self._h), "zfb_synchronize")
+
+    @property
+    def launches(self):
+        return int(lib().zfb_launch_count(self._h))
+
+    # ---- device path -------------------------------------------------------------------------
+    def encode(self, field, mb, out=None):
+        import torch
+
+        d, nx, ny, nz = dims_of(field.shape)
+        nbytes = int(lib().zfb_stream_bytes(d, nx, ny, nz, mb))
+        if out is None:
+            out = torch.empty(nbytes + 16, dtype=torch.uint8, device=field.device)
+        assert field.is_contiguous() and out.numel() >= nbytes
+        self._check(lib().zfb_encode_dev(self._h, _dtype_code(field.dtype), d, nx, ny, nz, mb, field.data_ptr(),
+                                         out.data_ptr()), "zfb_encode_dev")
+        return out[:nbytes]
+
+    def decode(self, stream, shape, dtype, mb, orig=None, out=None):
+        import torch
+
+        d, nx, ny, nz = dims_of(shape)
+        if out is None:
+            out = torch.empty(tuple(shape), dtype=dtype, device=stream.device)
+        self._check(lib().zfb_decode_dev(self._h, _dtype_code(dtype), d, nx, ny, nz, mb, stream.data_ptr(),
+                                         out.data_ptr(), orig.data_ptr() if orig is not None else None),
+                    "zfb_decode_dev")
+        return out
+
+    def metrics(self, orig, approx):
+        self._check(lib().zfb_metrics_dev(self._h, _dtype_code(orig.dtype), orig.data_ptr(), approx.data_ptr(),
+                                          orig.numel()), "zfb_metrics_dev")
+        return self.partials()
+
+    def partials(self):
+        p = Partials()
+        self._check(lib().zfb_partials_get(self._h, C.byref(p)), "zfb_partials_get")
+        return p
+
+    def set_partials(self, p):
+        self._check(lib().zfb_partials_set(self._h, C.byref(p)), "zfb_partials_set")
+
+    def partials_tensor(self):
+        """The context's device-resident zfb_partials viewed as 8 x int64 (raw bits; reinterpret with .view)."""
+        import torch
+
+        ptr = lib().zfb_partials_dev(self._h)
+        n = C.sizeof(Partials) // 8
+        iface = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3}
+        holder = type("_P", (), {"__cuda_array_interface__": iface})()
+        return torch.as_tensor(holder, device="cuda:%d" % self.device)
+
+    def histogram(self, which, lo, hi, orig, approx):
+        import torch
+
+        counts = torch.zeros(NBINS + 1, dtype=torch.int64, device=approx.device)
+        self._check(lib().zfb_histogram_dev(self._h, _dtype_code(approx.dtype), which, float(lo), float(hi),
+                                            orig.data_ptr() if orig is not None else None, approx.data_ptr(),
+                                            approx.numel(), counts.data_ptr(), counts.data_ptr() + 8 * NBINS),
+                    "zfb_histogram_dev")
+        return counts[:NBINS], counts[NBINS:]
+
+    # ---- host path (what the CBench plugin calls) -------------------------------------------
+    def compress_host(self, a, mb, out=None):
+        import numpy as np
+
+        d, nx, ny, nz = dims_of(a.shape)
+        nbytes = int(lib().zfb_stream_bytes(d, nx, ny, nz, mb))
+        if out is None:
+            out = np.empty(nbytes, dtype=np.uint8)
+        cb = C.c_size_t()
+        self._check(lib().zfb_compress_host(self._h, _dtype_code(a.dtype), d, nx, ny, nz, mb, a.ctypes.data,
+                                            out.ctypes.data, C.byref(cb)), "zfb_compress_host")
+        return out[: cb.value]
+
+    def decompress_host(self, stream, shape, dtype, mb, orig=None, out=None):
+        import numpy as np
+
+        d, nx, ny, nz = dims_of(shape)
+        if out is None:
+            out = np.empty(tuple(shape), dtype=dtype)
+        self._check(lib().zfb_decompress_host(self._h, _dtype_code(dtype), d, nx, ny, nz, mb, stream.ctypes.data,
+                                              out.ctypes.data, orig.ctypes.data if orig is not None else None),
+                    "zfb_decompress_host")
+        return out
+
+    def compress_host_ptr(self, dtype_code, shape, mb, in_ptr, out_ptr):
+        d, nx, ny, nz = dims_of(shape)
+        cb = C.c_size_t()
+        self._check(lib().zfb_compress_host(self._h, dtype_code, d, nx, ny, nz, mb, in_ptr, out_ptr, C.byref(cb)),
+                    "zfb_compress_host")
+        return cb.value
+
+    def decompress_host_ptr(self, dtype_code, shape, mb, stream_ptr, out_ptr, orig_ptr=None):
+        d, nx, ny, nz = dims_of(shape)
+        self._check(lib().zfb_decompress_host(self._h, dtype_code, d, nx, ny, nz, mb, stream_ptr, out_ptr, orig_ptr),
+                    "zfb_decompress_host")
+
+    def metrics_host(self, orig, approx):
+        p = Partials()
+        self._check(lib().zfb_metrics_host(self._h, _dtype_code(orig.dtype), orig.ctypes.data, approx.ctypes.data,
+                                           orig.size, C.byref(p)), "zfb_metrics_host")
+        return p
+
+    def histogram_host(self, which, lo, hi, orig, approx):
+        import numpy as np
+
+        counts = np.zeros(NBINS, dtype=np.uint64)
+        oob = C.c_uint64()
+        self._check(lib().zfb_histogram_host(self._h, _dtype_code(approx.dtype), which, float(lo), float(hi),
+                                             orig.ctypes.data if orig is not None else None, approx.ctypes.data,
+                                             approx.size, counts.ctypes.data, C.byref(oob)), "zfb_histogram_host")
+        return counts, oob.value
+
+    def release(self):
+        self._check(lib().zfb_release_resident(self._h), "zfb_release_resident")

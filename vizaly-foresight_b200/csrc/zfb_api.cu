@@ -1,0 +1,763 @@
+// zfb_api.cu -- the C ABI of include/zfb.h: context, kernel dispatch, TMA descriptors, host-pointer
+// wrappers.  No CPU fallback anywhere: every compute entry point needs a live CUDA context.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <deque>
+
+#include "../../include/zfb.h"
+#include "zfb_kernels.cuh"
+
+using namespace zfb;
+
+static_assert(sizeof(zfb_partials) == sizeof(partials_dev), "zfb_partials layout");
+
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct devbuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+struct zfb_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  encode_tiled_fn encode_tiled = nullptr;
+  double* part = nullptr;       // per-CTA partial rows
+  int part_rows = 0;
+  partials_dev* result = nullptr;
+  uint64_t launches = 0;
+  std::string err;
+  bool force_generic = false;
+  // host-pointer path: resident device copies
+  devbuf d_orig, d_stream, d_out, d_hist;
+  const void* h_orig_key = nullptr;   // host pointer the resident original came from
+  size_t orig_bytes = 0;
+  const void* h_out_key = nullptr;    // host pointer the last decompressed field went to
+  size_t out_bytes = 0;
+  bool fused_valid = false;           // result holds metrics of (h_orig_key, h_out_key)
+  int occ_enc[80] = {0}, occ_dec[80] = {0}, occ_decm[80] = {0};  // resident CTAs per SM, by slot words
+};
+
+#define CU_TRY(ctx, call)                                                                   \
+  do {                                                                                      \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess) {                                                                \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                      \
+      return ZFB_ECUDA;                                                                     \
+    }                                                                                       \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// pure host arithmetic
+// ------------------------------------------------------------------------------------------------
+extern "C" unsigned zfb_maxbits(int dtype, int dims, double rate, int wra)
+{
+  if (dims < 1 || dims > 3 || (dtype != ZFB_FLOAT && dtype != ZFB_DOUBLE)) return 0;
+  const unsigned n = 1u << (2 * dims);
+  unsigned bits = (unsigned)std::floor(n * rate + 0.5);
+  const unsigned lo = dtype == ZFB_FLOAT ? 9u : 12u;   // 1 + EBITS
+  if (bits < lo) bits = lo;
+  if (wra) bits = (bits + 63u) & ~63u;                 // stream_word_bits = 64
+  return bits;
+}
+
+static size_t count_blocks(int dims, size_t nx, size_t ny, size_t nz)
+{
+  size_t b = (nx + 3) / 4;
+  if (dims >= 2) b *= (ny + 3) / 4;
+  if (dims >= 3) b *= (nz + 3) / 4;
+  return b;
+}
+
+extern "C" size_t zfb_stream_bytes(int dims, size_t nx, size_t ny, size_t nz, unsigned maxbits)
+{
+  const size_t bits = count_blocks(dims, nx, ny, nz) * (size_t)maxbits;
+  return ((bits + 63) / 64) * 8;
+}
+
+extern "C" size_t zfb_stream_capacity(int dims, size_t nx, size_t ny, size_t nz, unsigned maxbits)
+{
+  const size_t bits = 148 + count_blocks(dims, nx, ny, nz) * (size_t)maxbits;  // ZFP_HEADER_MAX_BITS
+  return ((bits + 63) & ~(size_t)63) / 8;
+}
+
+extern "C" int zfb_partition(int rank, int nranks, const size_t n[3], size_t count[3], size_t offset[3])
+{
+  if (!n || !count || !offset || nranks < 1 || rank < 0 || rank >= nranks) return ZFB_EINVAL;
+  struct box { size_t lo[3], hi[3]; };
+  std::deque<box> q;
+  q.push_back(box{{0, 0, 0}, {n[0], n[1], n[2]}});
+  int axis = 0;
+  int stuck = 0;
+  while ((int)q.size() < nranks && stuck < 3) {
+    const size_t cur = q.size();
+    bool split_any = false;
+    for (size_t i = 0; i < cur; i++) {
+      box parent = q.front();
+      q.pop_front();
+      if (parent.hi[axis] - parent.lo[axis] <= 1) { q.push_back(parent); continue; }
+      box a = parent, b = parent;
+      a.hi[axis] = (parent.lo[axis] + parent.hi[axis]) / 2;
+      b.lo[axis] = a.hi[axis];
+      q.push_back(a);
+      q.push_back(b);
+      split_any = true;
+      if ((int)q.size() >= nranks) break;
+    }
+    stuck = split_any ? 0 : stuck + 1;
+    axis = (axis + 1) % 3;
+  }
+  if (rank >= (int)q.size()) return ZFB_EINVAL;
+  const box& me = q[rank];
+  for (int d = 0; d < 3; d++) { count[d] = me.hi[d] - me.lo[d]; offset[d] = me.lo[d]; }
+  return ZFB_OK;
+}
+
+extern "C" double zfb_value_absolute_error(const zfb_partials* p) { return p->max_abs; }
+extern "C" double zfb_value_relative_error(const zfb_partials* p) { return p->max_rel; }
+extern "C" double zfb_value_mse(const zfb_partials* p) { return p->sum_sq / (double)p->n; }
+extern "C" double zfb_value_psnr(const zfb_partials* p)
+{
+  const double mse = p->sum_sq / (double)p->n;
+  return 10 * std::log10(std::pow(p->max_orig, 2.0) / mse);
+}
+extern "C" double zfb_value_minmax(const zfb_partials* p) { return p->max_orig; }
+
+extern "C" void zfb_partials_combine(zfb_partials* acc, const zfb_partials* in, int count)
+{
+  for (int i = 0; i < count; i++) {
+    const zfb_partials& s = in[i];
+    acc->sum_sq += s.sum_sq; acc->sum_abs += s.sum_abs; acc->sum_rel += s.sum_rel;
+    acc->max_abs = std::fmax(acc->max_abs, s.max_abs); acc->max_rel = std::fmax(acc->max_rel, s.max_rel);
+    acc->max_orig = std::fmax(acc->max_orig, s.max_orig);
+    acc->neg_min_orig = std::fmax(acc->neg_min_orig, s.neg_min_orig);
+    acc->n += s.n;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+static const size_t ENC_TILE_SMEM_BASE = BOXES_PER_TILE * BOX_FLOATS * sizeof(float);
+
+static size_t enc_tile_smem(unsigned W) { return ENC_TILE_SMEM_BASE + (size_t)TILE_THREADS * W * 8 + 2 * 8; }
+static size_t dec_tile_smem(unsigned W, bool metrics)
+{
+  return (metrics ? ENC_TILE_SMEM_BASE : 0) + 2 * (size_t)TILE_THREADS * W * 8 + 4 * 8;
+}
+
+extern "C" int zfb_create(zfb_ctx** out, int device)
+{
+  if (!out) return ZFB_EINVAL;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    return ZFB_ENODEV;  // no CPU fallback
+  }
+  zfb_ctx* c = new (std::nothrow) zfb_ctx();
+  if (!c) return ZFB_ENOMEM;
+  c->device = device;
+  if (cudaSetDevice(device) != cudaSuccess) { delete c; return ZFB_ENODEV; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete c; return ZFB_ENODEV; }
+  if (prop.major < 10) {  // kernels are built for sm_100a only
+    delete c;
+    return ZFB_ENODEV;
+  }
+  c->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return ZFB_ECUDA; }
+  c->stream = c->own_stream;
+  c->part_rows = c->sm_count * 32;
+  if (cudaMalloc(&c->part, (size_t)c->part_rows * PART_STRIDE * sizeof(double)) != cudaSuccess ||
+      cudaMalloc(&c->result, sizeof(partials_dev)) != cudaSuccess) {
+    delete c;
+    return ZFB_ENOMEM;
+  }
+  cudaMemset(c->result, 0, sizeof(partials_dev));
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+      qres == cudaDriverEntryPointSuccess)
+    c->encode_tiled = (encode_tiled_fn)fn;
+  const char* fg = std::getenv("ZFB_FORCE_GENERIC");
+  c->force_generic = fg && fg[0] == '1';
+  // opt in to large dynamic shared memory for the tile kernels
+  const int max_smem = (int)prop.sharedMemPerBlockOptin;
+  cudaFuncSetAttribute(enc3_f32_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  cudaFuncSetAttribute(dec3_f32_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  cudaFuncSetAttribute(dec3_f32_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
+  cudaGetLastError();
+  *out = c;
+  return ZFB_OK;
+}
+
+static void free_buf(devbuf& b)
+{
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.cap = 0;
+}
+
+extern "C" int zfb_release_resident(zfb_ctx* c)
+{
+  if (!c) return ZFB_EINVAL;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  free_buf(c->d_orig); free_buf(c->d_stream); free_buf(c->d_out); free_buf(c->d_hist);
+  c->h_orig_key = c->h_out_key = nullptr;
+  c->orig_bytes = c->out_bytes = 0;
+  c->fused_valid = false;
+  return ZFB_OK;
+}
+
+extern "C" int zfb_destroy(zfb_ctx* c)
+{
+  if (!c) return ZFB_EINVAL;
+  zfb_release_resident(c);
+  if (c->part) cudaFree(c->part);
+  if (c->result) cudaFree(c->result);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+  return ZFB_OK;
+}
+
+extern "C" int zfb_set_stream(zfb_ctx* c, void* s)
+{
+  if (!c) return ZFB_EINVAL;
+  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  return ZFB_OK;
+}
+
+extern "C" int zfb_synchronize(zfb_ctx* c)
+{
+  if (!c) return ZFB_EINVAL;
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return ZFB_OK;
+}
+
+extern "C" const char* zfb_last_error(const zfb_ctx* c) { return c ? c->err.c_str() : "null context"; }
+extern "C" uint64_t zfb_launch_count(const zfb_ctx* c) { return c ? c->launches : 0; }
+extern "C" void* zfb_partials_dev(zfb_ctx* c) { return c ? (void*)c->result : nullptr; }
+
+extern "C" int zfb_partials_get(zfb_ctx* c, zfb_partials* out)
+{
+  if (!c || !out) return ZFB_EINVAL;
+  CU_TRY(c, cudaMemcpyAsync(out, c->result, sizeof(partials_dev), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return ZFB_OK;
+}
+
+extern "C" int zfb_partials_set(zfb_ctx* c, const zfb_partials* in)
+{
+  if (!c || !in) return ZFB_EINVAL;
+  CU_TRY(c, cudaMemcpyAsync(c->result, in, sizeof(partials_dev), cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return ZFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// dispatch helpers
+// ------------------------------------------------------------------------------------------------
+static int check_args(zfb_ctx* c, int dtype, int dims, size_t nx, size_t ny, size_t nz, unsigned maxbits)
+{
+  if (!c) return ZFB_EINVAL;
+  if (dims < 1 || dims > 3 || !nx || (dims >= 2 && !ny) || (dims >= 3 && !nz)) { c->err = "bad dims"; return ZFB_EINVAL; }
+  if (dtype != ZFB_FLOAT && dtype != ZFB_DOUBLE) { c->err = "bad dtype"; return ZFB_EINVAL; }
+  if (maxbits < (dtype == ZFB_FLOAT ? 9u : 12u) || maxbits > 4160u) { c->err = "bad maxbits"; return ZFB_EINVAL; }
+  return ZFB_OK;
+}
+
+static geom make_geom(int dims, size_t nx, size_t ny, size_t nz, unsigned maxbits)
+{
+  geom g;
+  g.nx = nx; g.ny = dims >= 2 ? ny : 1; g.nz = dims >= 3 ? nz : 1;
+  g.bx = (g.nx + 3) / 4; g.by = (g.ny + 3) / 4; g.bz = (g.nz + 3) / 4;
+  g.nblocks = g.bx * g.by * g.bz;
+  g.stream_words = (g.nblocks * (size_t)maxbits + 63) / 64;
+  return g;
+}
+
+static bool tile_path_ok(const zfb_ctx* c, int dtype, int dims, const geom& g, unsigned maxbits, bool metrics)
+{
+  if (c->force_generic || !c->encode_tiled) return false;
+  if (dtype != ZFB_FLOAT || dims != 3) return false;
+  if ((g.nx | g.ny | g.nz) & 3) return false;
+  if (maxbits & 63u) return false;
+  const unsigned W = maxbits >> 6;
+  if (!(W % 2 == 0 || g.bx % 2 == 0)) return false;  // bulk copies need 16-byte granularity
+  if (g.nx >= (1ull << 31) || g.ny >= (1ull << 31) || g.nz >= (1ull << 31)) return false;
+  const size_t bpr = (g.bx + BOX_BLOCKS - 1) / BOX_BLOCKS;
+  if (bpr * g.by * g.bz >= (1ull << 31)) return false;
+  const size_t smem = metrics ? dec_tile_smem(W, true) : enc_tile_smem(W);
+  if (smem > 100 * 1024 || enc_tile_smem(W) > 100 * 1024) return false;
+  return true;
+}
+
+static tile_geom make_tile_geom(const geom& g, unsigned maxbits)
+{
+  tile_geom t;
+  t.nbx = (unsigned)g.bx; t.nby = (unsigned)g.by; t.nbz = (unsigned)g.bz;
+  t.bpr = (t.nbx + BOX_BLOCKS - 1) / BOX_BLOCKS;
+  t.nboxes = t.bpr * t.nby * t.nbz;
+  t.ntiles = (t.nboxes + BOXES_PER_TILE - 1) / BOXES_PER_TILE;
+  t.nx = (unsigned)g.nx; t.ny = (unsigned)g.ny; t.nz = (unsigned)g.nz;
+  t.W = maxbits >> 6;
+  return t;
+}
+
+static int make_tmap_3d_f32(zfb_ctx* c, CUtensorMap* tm, const void* base, const geom& g)
+{
+  cuuint64_t gdim[3] = {(cuuint64_t)g.nx, (cuuint64_t)g.ny, (cuuint64_t)g.nz};
+  cuuint64_t gstr[2] = {(cuuint64_t)g.nx * 4, (cuuint64_t)g.nx * g.ny * 4};
+  cuuint32_t box[3] = {256, 4, 4};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = c->encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    c->err = "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r);
+    return ZFB_ECUDA;
+  }
+  return ZFB_OK;
+}
+
+static int generic_grid(const zfb_ctx* c, size_t nblocks)
+{
+  size_t want = (nblocks + 127) / 128;
+  size_t cap = (size_t)c->sm_count * 16;
+  if (cap > (size_t)c->part_rows) cap = c->part_rows;
+  return (int)(want < cap ? (want ? want : 1) : cap);
+}
+
+static int finalize(zfb_ctx* c, int rows, size_t n)
+{
+  finalize_partials_kernel<<<1, 256, 0, c->stream>>>(c->part, rows, c->result, (unsigned long long)n);
+  c->launches++;
+  CU_TRY(c, cudaGetLastError());
+  return ZFB_OK;
+}
+
+template <typename Scalar>
+static int launch_enc_generic(zfb_ctx* c, int dims, const geom& g, unsigned maxbits, const void* d_in, void* d_stream,
+                              int edge_only)
+{
+  const int grid = generic_grid(c, g.nblocks);
+  const Scalar* in = (const Scalar*)d_in;
+  uint64_t* st = (uint64_t*)d_stream;
+  if (dims == 1) enc_generic_kernel<Scalar, 1><<<grid, 128, 0, c->stream>>>(in, st, g, maxbits, edge_only);
+  else if (dims == 2) enc_generic_kernel<Scalar, 2><<<grid, 128, 0, c->stream>>>(in, st, g, maxbits, edge_only);
+  else enc_generic_kernel<Scalar, 3><<<grid, 128, 0, c->stream>>>(in, st, g, maxbits, edge_only);
+  c->launches++;
+  CU_TRY(c, cudaGetLastError());
+  return ZFB_OK;
+}
+
+template <typename Scalar, bool METRICS>
+static int launch_dec_generic(zfb_ctx* c, int dims, const geom& g, unsigned maxbits, const void* d_stream, void* d_out,
+                              const void* d_orig, int edge_only, int* rows)
+{
+  const int grid = generic_grid(c, g.nblocks);
+  const uint64_t* st = (const uint64_t*)d_stream;
+  Scalar* out = (Scalar*)d_out;
+  const Scalar* orig = (const Scalar*)d_orig;
+  if (dims == 1) dec_generic_kernel<Scalar, 1, METRICS><<<grid, 128, 0, c->stream>>>(st, out, orig, g, maxbits, edge_only, c->part);
+  else if (dims == 2) dec_generic_kernel<Scalar, 2, METRICS><<<grid, 128, 0, c->stream>>>(st, out, orig, g, maxbits, edge_only, c->part);
+  else dec_generic_kernel<Scalar, 3, METRICS><<<grid, 128, 0, c->stream>>>(st, out, orig, g, maxbits, edge_only, c->part);
+  c->launches++;
+  *rows = grid;
+  CU_TRY(c, cudaGetLastError());
+  return ZFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device-pointer hot path
+// ------------------------------------------------------------------------------------------------
+extern "C" int zfb_encode_dev(zfb_ctx* c, int dtype, int dims, size_t nx, size_t ny, size_t nz, unsigned maxbits,
+                              const void* d_in, void* d_stream)
+{
+  int rc = check_args(c, dtype, dims, nx, ny, nz, maxbits);
+  if (rc) return rc;
+  if (!d_in || !d_stream) { c->err = "null pointer"; return ZFB_EINVAL; }
+  CU_TRY(c, cudaSetDevice(c->device));
+  const geom g = make_geom(dims, nx, ny, nz, maxbits);
+  if (tile_path_ok(c, dtype, dims, g, maxbits, false) && ((uintptr_t)d_in & 15) == 0 && ((uintptr_t)d_stream & 15) == 0) {
+    CUtensorMap tm;
+    rc = make_tmap_3d_f32(c, &tm, d_in, g);
+    if (rc) return rc;
+    const tile_geom tg = make_tile_geom(g, maxbits);
+    const size_t smem = enc_tile_smem(tg.W);
+    int nb = c->occ_enc[tg.W];
+    if (!nb) {
+      CU_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, enc3_f32_tile_kernel, TILE_THREADS, smem));
+      if (nb < 1) nb = 1;
+      c->occ_enc[tg.W] = nb;
+    }
+    unsigned grid = (unsigned)c->sm_count * (unsigned)nb;
+    if (grid > tg.ntiles) grid = tg.ntiles;
+    enc3_f32_tile_kernel<<<grid, TILE_THREADS, smem, c->stream>>>(tm, (uint64_t*)d_stream, tg, maxbits);
+    c->launches++;
+    CU_TRY(c, cudaGetLastError());
+    return ZFB_OK;
+  }
+  if (maxbits & 63u) {  // unaligned slots are OR-ed into a zeroed stream
+    CU_TRY(c, cudaMemsetAsync(d_stream, 0, g.stream_words * 8, c->stream));
+  }
+  if (dtype == ZFB_FLOAT) return launch_enc_generic<float>(c, dims, g, maxbits, d_in, d_stream, 0);
+  return launch_enc_generic<double>(c, dims, g, maxbits, d_in, d_stream, 0);
+}
+
+extern "C" int zfb_decode_dev(zfb_ctx* c, int dtype, int dims, size_t nx, size_t ny, size_t nz, unsigned maxbits,
+                              const void* d_stream, void* d_out, const void* d_orig)
+{
+  int rc = check_args(c, dtype, dims, nx, ny, nz, maxbits);
+  if (rc) return rc;
+  if (!d_out || !d_stream) { c->err = "null pointer"; return ZFB_EINVAL; }
+  CU_TRY(c, cudaSetDevice(c->device));
+  const geom g = make_geom(dims, nx, ny, nz, maxbits);
+  const size_t n = g.nx * g.ny * g.nz;
+  const bool metrics = d_orig != nullptr;
+  int rows = 0;
+  if (tile_path_ok(c, dtype, dims, g, maxbits, metrics) && ((uintptr_t)d_out & 15) == 0 &&
+      ((uintptr_t)d_stream & 15) == 0 && (!metrics || ((uintptr_t)d_orig & 15) == 0)) {
+    CUtensorMap tm;
+    memset(&tm, 0, sizeof tm);
+    if (metrics) {
+      rc = make_tmap_3d_f32(c, &tm, d_orig, g);
+      if (rc) return rc;
+    }
+    const tile_geom tg = make_tile_geom(g, maxbits);
+    const size_t smem = dec_tile_smem(tg.W, metrics);
+    int nb = metrics ? c->occ_decm[tg.W] : c->occ_dec[tg.W];
+    if (!nb) {
+      if (metrics) CU_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, dec3_f32_tile_kernel<true>, TILE_THREADS, smem));
+      else CU_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, dec3_f32_tile_kernel<false>, TILE_THREADS, smem));
+      if (nb < 1) nb = 1;
+      (metrics ? c->occ_decm[tg.W] : c->occ_dec[tg.W]) = nb;
+    }
+    unsigned grid = (unsigned)c->sm_count * (unsigned)nb;
+    if (grid > tg.ntiles) grid = tg.ntiles;
+    if ((int)grid > c->part_rows) grid = c->part_rows;
+    if (metrics)
+      dec3_f32_tile_kernel<true><<<grid, TILE_THREADS, smem, c->stream>>>(tm, (const uint64_t*)d_stream, (float*)d_out, tg, maxbits, c->part);
+    else
+      dec3_f32_tile_kernel<false><<<grid, TILE_THREADS, smem, c->stream>>>(tm, (const uint64_t*)d_stream, (float*)d_out, tg, maxbits, c->part);
+    c->launches++;
+    CU_TRY(c, cudaGetLastError());
+    rows = (int)grid;
+  } else {
+    if (dtype == ZFB_FLOAT) {
+      rc = metrics ? launch_dec_generic<float, true>(c, dims, g, maxbits, d_stream, d_out, d_orig, 0, &rows)
+                   : launch_dec_generic<float, false>(c, dims, g, maxbits, d_stream, d_out, d_orig, 0, &rows);
+    } else {
+      rc = metrics ? launch_dec_generic<double, true>(c, dims, g, maxbits, d_stream, d_out, d_orig, 0, &rows)
+                   : launch_dec_generic<double, false>(c, dims, g, maxbits, d_stream, d_out, d_orig, 0, &rows);
+    }
+    if (rc) return rc;
+  }
+  if (metrics) return finalize(c, rows, n);
+  return ZFB_OK;
+}
+
+extern "C" int zfb_metrics_dev(zfb_ctx* c, int dtype, const void* d_orig, const void* d_approx, size_t n)
+{
+  if (!c || !d_orig || !d_approx || !n || (dtype != ZFB_FLOAT && dtype != ZFB_DOUBLE)) return ZFB_EINVAL;
+  CU_TRY(c, cudaSetDevice(c->device));
+  size_t want = (n / 4 + 255) / 256;
+  int grid = (int)(want < (size_t)c->sm_count * 8 ? (want ? want : 1) : (size_t)c->sm_count * 8);
+  if (grid > c->part_rows) grid = c->part_rows;
+  if (dtype == ZFB_FLOAT) {
+    if (((uintptr_t)d_orig | (uintptr_t)d_approx) & 15) { c->err = "metrics: pointers must be 16-byte aligned"; return ZFB_EINVAL; }
+    metrics_kernel<float><<<grid, 256, 0, c->stream>>>((const float*)d_orig, (const float*)d_approx, n, c->part);
+  } else {
+    metrics_kernel<double><<<grid, 256, 0, c->stream>>>((const double*)d_orig, (const double*)d_approx, n, c->part);
+  }
+  c->launches++;
+  CU_TRY(c, cudaGetLastError());
+  return finalize(c, grid, n);
+}
+
+extern "C" int zfb_histogram_dev(zfb_ctx* c, int dtype, int which, double lo, double hi, const void* d_orig,
+                                 const void* d_approx, size_t n, uint64_t* d_counts, uint64_t* d_oob)
+{
+  if (!c || !d_approx || !d_counts || which < 0 || which > 2 || (which != 2 && !d_orig)) return ZFB_EINVAL;
+  if (dtype != ZFB_FLOAT && dtype != ZFB_DOUBLE) return ZFB_EINVAL;
+  CU_TRY(c, cudaSetDevice(c->device));
+  CU_TRY(c, cudaMemsetAsync(d_counts, 0, ZFB_NBINS * sizeof(uint64_t), c->stream));
+  if (d_oob) CU_TRY(c, cudaMemsetAsync(d_oob, 0, sizeof(uint64_t), c->stream));
+  size_t want = (n + 255) / 256;
+  int grid = (int)(want < (size_t)c->sm_count * 8 ? (want ? want : 1) : (size_t)c->sm_count * 8);
+  if (dtype == ZFB_FLOAT)
+    hist_kernel<float><<<grid, 256, 0, c->stream>>>(which, lo, hi, (const float*)d_orig, (const float*)d_approx, n,
+                                                    (unsigned long long*)d_counts, (unsigned long long*)d_oob);
+  else
+    hist_kernel<double><<<grid, 256, 0, c->stream>>>(which, lo, hi, (const double*)d_orig, (const double*)d_approx, n,
+                                                     (unsigned long long*)d_counts, (unsigned long long*)d_oob);
+  c->launches++;
+  CU_TRY(c, cudaGetLastError());
+  return ZFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-pointer entry points
+// ------------------------------------------------------------------------------------------------
+static int ensure(zfb_ctx* c, devbuf& b, size_t bytes)
+{
+  if (b.cap >= bytes) return ZFB_OK;
+  if (b.p) { cudaStreamSynchronize(c->stream); cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+  if (cudaMalloc(&b.p, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    c->err = "cudaMalloc failed";
+    return ZFB_ENOMEM;
+  }
+  b.cap = bytes;
+  return ZFB_OK;
+}
+
+// Chunked, double-buffered pipeline along the slowest axis.  In fixed-rate mode with whole-word slots a
+// slab whose thickness is a multiple of 4 compresses to a contiguous piece of the whole-field stream
+// (SURVEY 8e), so the upload of slab i+1, the kernel on slab i and the download of slab i-1 overlap.
+struct slab_plan {
+  size_t nslabs, thick, slowest;      // slabs, thickness (in rows of the slowest axis), extent
+  size_t row_elems;                   // elements per unit of the slowest axis
+  size_t blocks_per_4rows;            // blocks per 4 rows of the slowest axis (dims > 1) or per 4 elements
+};
+
+static slab_plan plan_slabs(int dims, size_t nx, size_t ny, size_t nz, unsigned maxbits, size_t esz)
+{
+  slab_plan p;
+  p.slowest = dims == 1 ? nx : dims == 2 ? ny : nz;
+  p.row_elems = dims == 1 ? 1 : dims == 2 ? nx : nx * ny;
+  p.blocks_per_4rows = dims == 1 ? 1 : dims == 2 ? (nx + 3) / 4 : ((nx + 3) / 4) * ((ny + 3) / 4);
+  const size_t target = (size_t)64 << 20;  // ~64 MiB of field per slab
+  size_t thick = target / (p.row_elems * esz);
+  // a slab must be a whole number of block rows (4) and its piece of the stream a whole number of
+  // 16-byte units, so that every slab keeps the fast path's alignment: q*blocks*maxbits % 128 == 0
+  size_t q = 1;
+  while (((q * p.blocks_per_4rows * (size_t)maxbits) & 127u) != 0) q++;
+  const size_t quantum = 4 * q;
+  thick = thick / quantum * quantum;
+  if (thick < quantum) thick = quantum;
+  if (thick >= p.slowest) { p.thick = p.slowest; p.nslabs = 1; }
+  else { p.thick = thick; p.nslabs = (p.slowest + thick - 1) / thick; }
+  return p;
+}
+
+static void slab_dims(int dims, size_t nx, size_t ny, size_t nz, size_t rows, size_t& sx, size_t& sy, size_t& sz)
+{
+  sx = nx; sy = ny; sz = nz;
+  if (dims == 1) sx = rows;
+  else if (dims == 2) sy = rows;
+  else sz = rows;
+}
+
+extern "C" int zfb_compress_host(zfb_ctx* c, int dtype, int dims, size_t nx, size_t ny, size_t nz, unsigned maxbits,
+                                 const void* h_in, void* h_stream, size_t* cbytes)
+{
+  int rc = check_args(c, dtype, dims, nx, ny, nz, maxbits);
+  if (rc) return rc;
+  if (!h_in || !h_stream) { c->err = "null pointer"; return ZFB_EINVAL; }
+  CU_TRY(c, cudaSetDevice(c->device));
+  const size_t esz = dtype == ZFB_FLOAT ? 4 : 8;
+  const geom g = make_geom(dims, nx, ny, nz, maxbits);
+  const size_t n = g.nx * g.ny * g.nz;
+  const size_t sbytes = g.stream_words * 8;
+  if ((rc = ensure(c, c->d_orig, n * esz))) return rc;
+  if ((rc = ensure(c, c->d_stream, sbytes + 16))) return rc;
+  c->fused_valid = false;
+  c->h_orig_key = nullptr;
+
+  const slab_plan sp = plan_slabs(dims, nx, ny, nz, maxbits, esz);
+  cudaStream_t up, down;
+  cudaEvent_t ev_up[2], ev_k[2];
+  CU_TRY(c, cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking));
+  CU_TRY(c, cudaStreamCreateWithFlags(&down, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; i++) { cudaEventCreateWithFlags(&ev_up[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming); }
+  int status = ZFB_OK;
+  size_t row0 = 0, word0 = 0;
+  for (size_t s = 0; s < sp.nslabs && status == ZFB_OK; s++) {
+    const size_t rows = (row0 + sp.thick <= sp.slowest) ? sp.thick : sp.slowest - row0;
+    size_t sx, sy, sz;
+    slab_dims(dims, nx, ny, nz, rows, sx, sy, sz);
+    const geom sg = make_geom(dims, sx, sy, sz, maxbits);
+    const size_t off_e = row0 * sp.row_elems;
+    const char* hsrc = (const char*)h_in + off_e * esz;
+    char* dsrc = (char*)c->d_orig.p + off_e * esz;
+    char* dst = (char*)c->d_stream.p + word0 * 8;
+    const int b = (int)(s & 1);
+    if (cudaMemcpyAsync(dsrc, hsrc, rows * sp.row_elems * esz, cudaMemcpyHostToDevice, up) != cudaSuccess) { status = ZFB_ECUDA; break; }
+    cudaEventRecord(ev_up[b], up);
+    cudaStreamWaitEvent(c->stream, ev_up[b], 0);
+    status = zfb_encode_dev(c, dtype, dims, sx, sy, sz, maxbits, dsrc, dst);
+    if (status) break;
+    cudaEventRecord(ev_k[b], c->stream);
+    cudaStreamWaitEvent(down, ev_k[b], 0);
+    if (cudaMemcpyAsync((char*)h_stream + word0 * 8, dst, sg.stream_words * 8, cudaMemcpyDeviceToHost, down) != cudaSuccess) { status = ZFB_ECUDA; break; }
+    row0 += rows;
+    word0 += sg.stream_words;
+  }
+  cudaError_t e1 = cudaStreamSynchronize(up), e2 = cudaStreamSynchronize(c->stream), e3 = cudaStreamSynchronize(down);
+  for (int i = 0; i < 2; i++) { cudaEventDestroy(ev_up[i]); cudaEventDestroy(ev_k[i]); }
+  cudaStreamDestroy(up);
+  cudaStreamDestroy(down);
+  if (status == ZFB_OK && (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)) {
+    c->err = std::string("compress_host: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3);
+    status = ZFB_ECUDA;
+  }
+  if (status) return status;
+  if (word0 != g.stream_words) { c->err = "internal: slab streams do not tile the stream"; return ZFB_ESTATE; }
+  if (cbytes) *cbytes = sbytes;
+  c->h_orig_key = h_in;
+  c->orig_bytes = n * esz;
+  return ZFB_OK;
+}
+
+extern "C" int zfb_decompress_host(zfb_ctx* c, int dtype, int dims, size_t nx, size_t ny, size_t nz, unsigned maxbits,
+                                   const void* h_stream, void* h_out, const void* h_orig)
+{
+  int rc = check_args(c, dtype, dims, nx, ny, nz, maxbits);
+  if (rc) return rc;
+  if (!h_out || !h_stream) { c->err = "null pointer"; return ZFB_EINVAL; }
+  CU_TRY(c, cudaSetDevice(c->device));
+  const size_t esz = dtype == ZFB_FLOAT ? 4 : 8;
+  const geom g = make_geom(dims, nx, ny, nz, maxbits);
+  const size_t n = g.nx * g.ny * g.nz;
+  const size_t sbytes = g.stream_words * 8;
+  if ((rc = ensure(c, c->d_stream, sbytes + 16))) return rc;
+  if ((rc = ensure(c, c->d_out, n * esz))) return rc;
+  const bool metrics = h_orig != nullptr;
+  bool orig_resident = metrics && h_orig == c->h_orig_key && c->orig_bytes == n * esz && c->d_orig.p;
+  if (metrics && !orig_resident) {
+    if ((rc = ensure(c, c->d_orig, n * esz))) return rc;
+  }
+  c->fused_valid = false;
+
+  // The fused partials are per-launch, so slabs are combined on the host in slab order.
+  const slab_plan sp = plan_slabs(dims, nx, ny, nz, maxbits, esz);
+  cudaStream_t up, down;
+  cudaEvent_t ev_up[2], ev_k[2];
+  CU_TRY(c, cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking));
+  CU_TRY(c, cudaStreamCreateWithFlags(&down, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; i++) { cudaEventCreateWithFlags(&ev_up[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming); }
+  std::vector<zfb_partials> slab_parts(metrics ? sp.nslabs : 0);
+  partials_dev* d_slab_parts = nullptr;
+  if (metrics && cudaMalloc(&d_slab_parts, sp.nslabs * sizeof(partials_dev)) != cudaSuccess) { cudaGetLastError(); return ZFB_ENOMEM; }
+  int status = ZFB_OK;
+  size_t row0 = 0, word0 = 0;
+  for (size_t s = 0; s < sp.nslabs && status == ZFB_OK; s++) {
+    const size_t rows = (row0 + sp.thick <= sp.slowest) ? sp.thick : sp.slowest - row0;
+    size_t sx, sy, sz;
+    slab_dims(dims, nx, ny, nz, rows, sx, sy, sz);
+    const geom sg = make_geom(dims, sx, sy, sz, maxbits);
+    const size_t off_e = row0 * sp.row_elems;
+    const size_t slab_bytes = rows * sp.row_elems * esz;
+    char* dstream = (char*)c->d_stream.p + word0 * 8;
+    char* dout = (char*)c->d_out.p + off_e * esz;
+    char* dorig = metrics ? (char*)c->d_orig.p + off_e * esz : nullptr;
+    const int b = (int)(s & 1);
+    if (cudaMemcpyAsync(dstream, (const char*)h_stream + word0 * 8, sg.stream_words * 8, cudaMemcpyHostToDevice, up) != cudaSuccess) { status = ZFB_ECUDA; break; }
+    if (metrics && !orig_resident &&
+        cudaMemcpyAsync(dorig, (const char*)h_orig + off_e * esz, slab_bytes, cudaMemcpyHostToDevice, up) != cudaSuccess) { status = ZFB_ECUDA; break; }
+    cudaEventRecord(ev_up[b], up);
+    cudaStreamWaitEvent(c->stream, ev_up[b], 0);
+    status = zfb_decode_dev(c, dtype, dims, sx, sy, sz, maxbits, dstream, dout, dorig);
+    if (status) break;
+    if (metrics) cudaMemcpyAsync(d_slab_parts + s, c->result, sizeof(partials_dev), cudaMemcpyDeviceToDevice, c->stream);
+    cudaEventRecord(ev_k[b], c->stream);
+    cudaStreamWaitEvent(down, ev_k[b], 0);
+    if (cudaMemcpyAsync((char*)h_out + off_e * esz, dout, slab_bytes, cudaMemcpyDeviceToHost, down) != cudaSuccess) { status = ZFB_ECUDA; break; }
+    row0 += rows;
+    word0 += sg.stream_words;
+  }
+  cudaError_t e1 = cudaStreamSynchronize(up), e2 = cudaStreamSynchronize(c->stream), e3 = cudaStreamSynchronize(down);
+  if (status == ZFB_OK && metrics) {
+    if (cudaMemcpy(slab_parts.data(), d_slab_parts, sp.nslabs * sizeof(partials_dev), cudaMemcpyDeviceToHost) != cudaSuccess) status = ZFB_ECUDA;
+  }
+  if (d_slab_parts) cudaFree(d_slab_parts);
+  for (int i = 0; i < 2; i++) { cudaEventDestroy(ev_up[i]); cudaEventDestroy(ev_k[i]); }
+  cudaStreamDestroy(up);
+  cudaStreamDestroy(down);
+  if (status == ZFB_OK && (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)) {
+    c->err = std::string("decompress_host: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3);
+    status = ZFB_ECUDA;
+  }
+  if (status) return status;
+  if (metrics) {
+    zfb_partials total;
+    memset(&total, 0, sizeof total);
+    total.max_orig = -1.7976931348623157e308;
+    total.neg_min_orig = -1.7976931348623157e308;
+    zfb_partials_combine(&total, slab_parts.data(), (int)sp.nslabs);
+    if ((rc = zfb_partials_set(c, &total))) return rc;
+    c->h_orig_key = h_orig;
+    c->orig_bytes = n * esz;
+    c->fused_valid = true;
+  }
+  c->h_out_key = h_out;
+  c->out_bytes = n * esz;
+  return ZFB_OK;
+}
+
+extern "C" int zfb_metrics_host(zfb_ctx* c, int dtype, const void* h_orig, const void* h_approx, size_t n,
+                                zfb_partials* out)
+{
+  if (!c || !h_orig || !h_approx || !n || !out) return ZFB_EINVAL;
+  CU_TRY(c, cudaSetDevice(c->device));
+  const size_t esz = dtype == ZFB_FLOAT ? 4 : 8;
+  if (c->fused_valid && h_orig == c->h_orig_key && h_approx == c->h_out_key && n * esz == c->out_bytes)
+    return zfb_partials_get(c, out);
+  int rc;
+  const bool orig_res = h_orig == c->h_orig_key && c->orig_bytes == n * esz && c->d_orig.p;
+  const bool out_res = h_approx == c->h_out_key && c->out_bytes == n * esz && c->d_out.p;
+  if (!orig_res) {
+    if ((rc = ensure(c, c->d_orig, n * esz))) return rc;
+    CU_TRY(c, cudaMemcpyAsync(c->d_orig.p, h_orig, n * esz, cudaMemcpyHostToDevice, c->stream));
+    c->h_orig_key = h_orig; c->orig_bytes = n * esz;
+  }
+  if (!out_res) {
+    if ((rc = ensure(c, c->d_out, n * esz))) return rc;
+    CU_TRY(c, cudaMemcpyAsync(c->d_out.p, h_approx, n * esz, cudaMemcpyHostToDevice, c->stream));
+    c->h_out_key = h_approx; c->out_bytes = n * esz;
+  }
+  if ((rc = zfb_metrics_dev(c, dtype, c->d_orig.p, c->d_out.p, n))) return rc;
+  c->fused_valid = true;
+  return zfb_partials_get(c, out);
+}
+
+extern "C" int zfb_histogram_host(zfb_ctx* c, int dtype, int which, double lo, double hi, const void* h_orig,
+                                  const void* h_approx, size_t n, uint64_t* counts, uint64_t* oob)
+{
+  if (!c || !h_approx || !counts || !n) return ZFB_EINVAL;
+  CU_TRY(c, cudaSetDevice(c->device));
+  const size_t esz = dtype == ZFB_FLOAT ? 4 : 8;
+  int rc;
+  const bool orig_res = h_orig && h_orig == c->h_orig_key && c->orig_bytes == n * esz && c->d_orig.p;
+  const bool out_res = h_approx == c->h_out_key && c->out_bytes == n * esz && c->d_out.p;
+  if (h_orig && !orig_res) {
+    if ((rc = ensure(c, c->d_orig, n * esz))) return rc;
+    CU_TRY(c, cudaMemcpyAsync(c->d_orig.p, h_orig, n * esz, cudaMemcpyHostToDevice, c->stream));
+    c->h_orig_key = h_orig; c->orig_bytes = n * esz; c->fused_valid = false;
+  }
+  if (!out_res) {
+    if ((rc = ensure(c, c->d_out, n * esz))) return rc;
+    CU_TRY(c, cudaMemcpyAsync(c->d_out.p, h_approx, n * esz, cudaMemcpyHostToDevice, c->stream));
+    c->h_out_key = h_approx; c->out_bytes = n * esz; c->fused_valid = false;
+  }
+  if ((rc = ensure(c, c->d_hist, (ZFB_NBINS + 1) * sizeof(uint64_t)))) return rc;
+  uint64_t* dh = (uint64_t*)c->d_hist.p;
+  if ((rc = zfb_histogram_dev(c, dtype, which, lo, hi, h_orig ? c->d_orig.p : nullptr, c->d_out.p, n, dh, dh + ZFB_NBINS))) return rc;
+  std::vector<uint64_t> tmp(ZFB_NBINS + 1);
+  CU_TRY(c, cudaMemcpyAsync(tmp.data(), dh, (ZFB_NBINS + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  memcpy(counts, tmp.data(), ZFB_NBINS * sizeof(uint64_t));
+  if (oob) *oob = tmp[ZFB_NBINS];
+  return ZFB_OK;
+}

@@ -1,0 +1,636 @@
+// zfb_kernels.cuh -- sm_100a kernels for the CBench hot path:
+//   compress   = ZFPCompressorGpu::compress   -> zfp_compress    (zfpCompressorGpu.hpp:145)
+//   decompress = ZFPCompressorGpu::decompress -> zfp_decompress  (zfpCompressorGpu.hpp:249)
+//   metrics    = the five MetricInterface::execute passes of main.cpp:306-352
+//                (absoluteError.hpp:65-143, relativeError.hpp:66-155, meansquareError.hpp:55-78,
+//                 psnrError.hpp:56-96, minmaxMetric.hpp:60-135), fused into the decode pass.
+//
+// Work decomposition (B200-first, not cuZFP's): one 4^d block per thread with all 4^d values in
+// registers (zfb_codec.cuh).  What differs between kernels is only how bytes move:
+//   * enc3/dec3 "tile" kernels (3D, dims % 4 == 0): persistent CTAs; a CTA owns two boxes of
+//     256x4x4 values (= 64 x-consecutive blocks each); boxes arrive in shared memory through TMA
+//     (cp.async.bulk.tensor.3d + mbarrier) one tile ahead of the math, so each thread's 16 row loads
+//     are conflict-free 128-bit LDS; compressed slots of a tile are contiguous in the stream and move
+//     with one bulk copy (cp.async.bulk) in each direction; decoded rows leave as coalesced 128-bit
+//     stores (a warp writes 512 contiguous bytes per row).
+//   * generic kernels (1D, 2D, partial blocks, unaligned slots, double): same codec, direct global
+//     access; 1D full blocks use one 128-bit load per block.
+// Metric partials: per-thread -> warp shuffle -> CTA -> one row of `part` per CTA -> fixed-order
+// final reduction (deterministic for a given grid).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include "zfb_codec.cuh"
+
+namespace zfb {
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers (sm_100a): mbarrier, TMA tensor / bulk copies, proxy fences
+// ---------------------------------------------------------------------------------------------
+namespace ptx {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init()
+{
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// 3D tiled TMA load: box at element coordinates (x, y, z) -> shared memory, completion on mbarrier
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tmap, int x, int y, int z, uint64_t* bar)
+{
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
+      : "memory");
+}
+// 1D bulk copy global -> shared (bytes % 16 == 0, both addresses 16-byte aligned)
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// 1D bulk copy shared -> global
+__device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, uint32_t bytes)
+{
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// make generic-proxy writes to shared memory visible to the async proxy (TMA / bulk store)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* t)
+{
+  asm volatile("prefetch.tensormap [%0];" ::"l"(t) : "memory");
+}
+}  // namespace ptx
+
+// ---------------------------------------------------------------------------------------------
+// geometry shared by host and device
+// ---------------------------------------------------------------------------------------------
+struct geom {
+  size_t nx, ny, nz;     // extents, x fastest; unused = 1
+  size_t bx, by, bz;     // blocks per axis
+  size_t nblocks;
+  size_t stream_words;   // 64-bit words in the stream
+};
+
+constexpr int PART_STRIDE = 8;  // doubles per CTA row in the partials scratch
+
+// ---------------------------------------------------------------------------------------------
+// metric accumulation (one thread)
+// ---------------------------------------------------------------------------------------------
+struct macc {
+  double s_sq, s_abs, s_rel;
+  double m_abs, m_rel, m_o, m_no;  // maxima; m_no = max(-o)
+  __device__ __forceinline__ void init()
+  {
+    s_sq = s_abs = s_rel = 0.0;
+    m_abs = 0.0;  // the reference's error vectors start with n zeros (absoluteError.hpp:66)
+    m_rel = 0.0;
+    m_o = -1.7976931348623157e308;
+    m_no = -1.7976931348623157e308;
+  }
+};
+
+// float: accumulates one row of 4 values into float partial sums (flushed to double by the caller)
+struct frow {
+  float ssq, sab, srl, mab, mrl, mo, mno;
+  __device__ __forceinline__ void init()
+  {
+    ssq = sab = srl = 0.f;
+    mab = mrl = 0.f;
+    mo = -3.402823466e38f;
+    mno = -3.402823466e38f;
+  }
+  __device__ __forceinline__ void add(float o, float a)
+  {
+    const float d = o - a;            // float subtraction, as in the reference (static_cast<float*>)
+    const float ad = fabsf(d);
+    const float ao = fabsf(o);
+    // relError(o, a, 1): |o| < 1 -> absolute error, else |d|/|o| (relativeError.hpp:66-75)
+    float q;
+    if (ao > 8.0e37f) q = ad / ao;    // __fdividef returns 0 for huge divisors
+    else q = __fdividef(ad, ao);
+    const float rl = ao < 1.0f ? ad : q;
+    ssq = fmaf(d, d, ssq);
+    sab += ad;
+    srl += rl;
+    mab = fmaxf(mab, ad);
+    mrl = fmaxf(mrl, rl);
+    mo = fmaxf(mo, o);
+    mno = fmaxf(mno, -o);
+  }
+  __device__ __forceinline__ void flush(macc& m)
+  {
+    m.s_sq += (double)ssq; m.s_abs += (double)sab; m.s_rel += (double)srl;
+    m.m_abs = fmax(m.m_abs, (double)mab); m.m_rel = fmax(m.m_rel, (double)mrl);
+    m.m_o = fmax(m.m_o, (double)mo); m.m_no = fmax(m.m_no, (double)mno);
+    init();
+  }
+};
+
+__device__ __forceinline__ void macc_add(macc& m, double o, double a)
+{
+  // double fields: same formulas carried out in double (the reference reinterprets doubles as floats,
+  // which is meaningless)
+  const double d = o - a, ad = fabs(d), ao = fabs(o);
+  const double rl = ao < 1.0 ? ad : ad / ao;
+  m.s_sq += d * d; m.s_abs += ad; m.s_rel += rl;
+  m.m_abs = fmax(m.m_abs, ad); m.m_rel = fmax(m.m_rel, rl);
+  m.m_o = fmax(m.m_o, o); m.m_no = fmax(m.m_no, -o);
+}
+
+__device__ __forceinline__ double shfl_xor_d(double v, int lane)
+{
+  return __shfl_xor_sync(0xffffffffu, v, lane);
+}
+
+// CTA-wide reduction of the per-thread accumulators; thread 0 writes one row of `part`.
+// red: shared scratch of 7 * (blockDim.x / 32) doubles.
+__device__ __forceinline__ void macc_block_store(macc m, double* red, double* part_row)
+{
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    m.s_sq += shfl_xor_d(m.s_sq, o);
+    m.s_abs += shfl_xor_d(m.s_abs, o);
+    m.s_rel += shfl_xor_d(m.s_rel, o);
+    m.m_abs = fmax(m.m_abs, shfl_xor_d(m.m_abs, o));
+    m.m_rel = fmax(m.m_rel, shfl_xor_d(m.m_rel, o));
+    m.m_o = fmax(m.m_o, shfl_xor_d(m.m_o, o));
+    m.m_no = fmax(m.m_no, shfl_xor_d(m.m_no, o));
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+  if (lane == 0) {
+    double* r = red + 7 * warp;
+    r[0] = m.s_sq; r[1] = m.s_abs; r[2] = m.s_rel; r[3] = m.m_abs; r[4] = m.m_rel; r[5] = m.m_o; r[6] = m.m_no;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a0 = 0, a1 = 0, a2 = 0, a3 = 0, a4 = 0, a5 = -1.7976931348623157e308, a6 = -1.7976931348623157e308;
+    for (int w = 0; w < nw; w++) {  // fixed order
+      const double* r = red + 7 * w;
+      a0 += r[0]; a1 += r[1]; a2 += r[2];
+      a3 = fmax(a3, r[3]); a4 = fmax(a4, r[4]); a5 = fmax(a5, r[5]); a6 = fmax(a6, r[6]);
+    }
+    part_row[0] = a0; part_row[1] = a1; part_row[2] = a2; part_row[3] = a3; part_row[4] = a4; part_row[5] = a5;
+    part_row[6] = a6; part_row[7] = 0.0;
+  }
+}
+
+struct partials_dev {  // mirrors zfb_partials (include/zfb.h)
+  double sum_sq, sum_abs, sum_rel, max_abs, max_rel, max_orig, neg_min_orig;
+  unsigned long long n;
+};
+
+// fixed-order reduction of the per-CTA rows into the context's partials
+__global__ void __launch_bounds__(256) finalize_partials_kernel(const double* __restrict__ part, int nrows,
+                                                                partials_dev* __restrict__ out, unsigned long long n)
+{
+  __shared__ double red[7 * 8];
+  macc m;
+  m.init();
+  for (int r = threadIdx.x; r < nrows; r += blockDim.x) {
+    const double* p = part + (size_t)r * PART_STRIDE;
+    m.s_sq += p[0]; m.s_abs += p[1]; m.s_rel += p[2];
+    m.m_abs = fmax(m.m_abs, p[3]); m.m_rel = fmax(m.m_rel, p[4]); m.m_o = fmax(m.m_o, p[5]); m.m_no = fmax(m.m_no, p[6]);
+  }
+  __shared__ double row[PART_STRIDE];
+  macc_block_store(m, red, row);
+  if (threadIdx.x == 0) {
+    out->sum_sq = row[0]; out->sum_abs = row[1]; out->sum_rel = row[2]; out->max_abs = row[3]; out->max_rel = row[4];
+    out->max_orig = row[5]; out->neg_min_orig = row[6]; out->n = n;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// generic kernels: any dims / dtype / maxbits, partial blocks, optional "edge only" mode
+// ---------------------------------------------------------------------------------------------
+template <typename Scalar> struct vec4;
+template <> struct vec4<float> { typedef float4 type; };
+template <> struct vec4<double> { typedef double4 type; };
+
+template <typename Scalar, int DIMS>
+__global__ void __launch_bounds__(128) enc_generic_kernel(const Scalar* __restrict__ in, uint64_t* __restrict__ stream,
+                                                          geom g, unsigned maxbits, int edge_only)
+{
+  constexpr int BS = 1 << (2 * DIMS);
+  const bool aligned = (maxbits & 63u) == 0;
+  for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < g.nblocks; b += (size_t)gridDim.x * blockDim.x) {
+    const size_t ix = b % g.bx, iy = (b / g.bx) % g.by, iz = b / (g.bx * g.by);
+    const size_t x0 = 4 * ix, y0 = 4 * iy, z0 = 4 * iz;
+    const unsigned mx = (unsigned)(g.nx - x0 < 4 ? g.nx - x0 : 4);
+    const unsigned my = DIMS >= 2 ? (unsigned)(g.ny - y0 < 4 ? g.ny - y0 : 4) : 1u;
+    const unsigned mz = DIMS >= 3 ? (unsigned)(g.nz - z0 < 4 ? g.nz - z0 : 4) : 1u;
+    const bool full = mx == 4 && (DIMS < 2 || my == 4) && (DIMS < 3 || mz == 4);
+    if (edge_only && full) continue;
+    Scalar f[BS];
+    if (DIMS == 1 && full) {
+      if constexpr (sizeof(Scalar) == 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(in + x0));
+        f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+      } else {
+        const double2 v0 = __ldg(reinterpret_cast<const double2*>(in + x0));
+        const double2 v1 = __ldg(reinterpret_cast<const double2*>(in + x0 + 2));
+        f[0] = v0.x; f[1] = v0.y; f[2] = v1.x; f[3] = v1.y;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < (DIMS >= 3 ? 4 : 1); k++)
+#pragma unroll
+        for (int j = 0; j < (DIMS >= 2 ? 4 : 1); j++)
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const bool ok = (unsigned)i < mx && (unsigned)j < my && (unsigned)k < mz;
+            f[(16 * k + 4 * j + i) & (BS - 1)] = ok ? __ldg(in + (x0 + i) + g.nx * ((y0 + j) + g.ny * (z0 + k))) : (Scalar)0;
+          }
+      if (!full) pad_block<Scalar, DIMS>(f, mx, my, mz);
+    }
+    if (aligned) {
+      aligned_sink sink(stream + b * (size_t)(maxbits >> 6), maxbits >> 6);
+      encode_block<Scalar, DIMS>(f, maxbits, sink);
+    } else {
+      or_sink sink(stream, b * (size_t)maxbits, maxbits);
+      encode_block<Scalar, DIMS>(f, maxbits, sink);
+    }
+  }
+}
+
+template <typename Scalar, int DIMS, bool METRICS>
+__global__ void __launch_bounds__(128) dec_generic_kernel(const uint64_t* __restrict__ stream, Scalar* __restrict__ out,
+                                                          const Scalar* __restrict__ orig, geom g, unsigned maxbits,
+                                                          int edge_only, double* __restrict__ part)
+{
+  constexpr int BS = 1 << (2 * DIMS);
+  __shared__ double red[7 * 4];
+  macc m;
+  m.init();
+  for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < g.nblocks; b += (size_t)gridDim.x * blockDim.x) {
+    const size_t ix = b % g.bx, iy = (b / g.bx) % g.by, iz = b / (g.bx * g.by);
+    const size_t x0 = 4 * ix, y0 = 4 * iy, z0 = 4 * iz;
+    const unsigned mx = (unsigned)(g.nx - x0 < 4 ? g.nx - x0 : 4);
+    const unsigned my = DIMS >= 2 ? (unsigned)(g.ny - y0 < 4 ? g.ny - y0 : 4) : 1u;
+    const unsigned mz = DIMS >= 3 ? (unsigned)(g.nz - z0 < 4 ? g.nz - z0 : 4) : 1u;
+    const bool full = mx == 4 && (DIMS < 2 || my == 4) && (DIMS < 3 || mz == 4);
+    if (edge_only && full) continue;
+    const size_t startbit = b * (size_t)maxbits;
+    const size_t w0 = startbit >> 6;
+    const size_t left = g.stream_words - w0;
+    slot_reader r(stream + w0, left > 0xffffffffull ? 0xffffffffu : (unsigned)left, (unsigned)(startbit & 63));
+    Scalar f[BS];
+    decode_block<Scalar, DIMS>(f, maxbits, r);
+    if (DIMS == 1 && full && sizeof(Scalar) == 4) {
+      if constexpr (sizeof(Scalar) == 4) {
+        float4 v;
+        v.x = f[0]; v.y = f[1]; v.z = f[2]; v.w = f[3];
+        if (METRICS) {
+          const float4 o = __ldg(reinterpret_cast<const float4*>(orig + x0));
+          frow fr;
+          fr.init();
+          fr.add(o.x, v.x); fr.add(o.y, v.y); fr.add(o.z, v.z); fr.add(o.w, v.w);
+          fr.flush(m);
+        }
+        *reinterpret_cast<float4*>(out + x0) = v;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < (DIMS >= 3 ? 4 : 1); k++)
+#pragma unroll
+        for (int j = 0; j < (DIMS >= 2 ? 4 : 1); j++)
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const bool ok = (unsigned)i < mx && (unsigned)j < my && (unsigned)k < mz;
+            if (ok) {
+              const size_t idx = (x0 + i) + g.nx * ((y0 + j) + g.ny * (z0 + k));
+              const Scalar a = f[(16 * k + 4 * j + i) & (BS - 1)];
+              out[idx] = a;
+              if (METRICS) {
+                if constexpr (sizeof(Scalar) == 4) {
+                  frow fr;
+                  fr.init();
+                  fr.add(__ldg(orig + idx), a);
+                  fr.flush(m);
+                } else {
+                  macc_add(m, (double)__ldg(orig + idx), (double)a);
+                }
+              }
+            }
+          }
+    }
+  }
+  if (METRICS) macc_block_store(m, red, part + (size_t)blockIdx.x * PART_STRIDE);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3D float tile kernels (dims % 4 == 0; slots whole words; see file header)
+// ---------------------------------------------------------------------------------------------
+constexpr int TILE_THREADS = 128;              // 4 warps, one 4x4x4 block per thread
+constexpr int BOX_BLOCKS = 64;                 // blocks per TMA box (256 x-values)
+constexpr int BOX_FLOATS = 256 * 4 * 4;        // 16 KiB
+constexpr int BOXES_PER_TILE = TILE_THREADS / BOX_BLOCKS;
+
+struct tile_geom {
+  unsigned nbx, nby, nbz;    // blocks per axis
+  unsigned bpr;              // boxes per block-row = ceil(nbx / 64)
+  unsigned nboxes;           // bpr * nby * nbz
+  unsigned ntiles;           // ceil(nboxes / 2)
+  unsigned nx, ny, nz;
+  unsigned W;                // 64-bit words per slot
+};
+
+struct box_info {
+  unsigned x0, y0, z0;   // element coordinates of the box origin
+  size_t blk0;           // first block index (stream order)
+  unsigned nvalid;       // blocks of the box that exist (<= 64); 0 if the box does not exist
+};
+
+__device__ __forceinline__ box_info box_of(const tile_geom& tg, unsigned q)
+{
+  box_info b;
+  if (q >= tg.nboxes) { b.x0 = b.y0 = b.z0 = 0; b.blk0 = 0; b.nvalid = 0; return b; }
+  const unsigned row = q / tg.bpr, xb = q - row * tg.bpr;
+  const unsigned iy = row % tg.nby, iz = row / tg.nby;
+  b.x0 = xb * 256u; b.y0 = iy * 4u; b.z0 = iz * 4u;
+  b.blk0 = (size_t)row * tg.nbx + (size_t)xb * BOX_BLOCKS;
+  const unsigned rem = tg.nbx - xb * BOX_BLOCKS;
+  b.nvalid = rem < (unsigned)BOX_BLOCKS ? rem : (unsigned)BOX_BLOCKS;
+  return b;
+}
+
+// dynamic shared memory layout (encode): [tile: 2 boxes x 16 KiB][out: 128*W words][2 mbarriers]
+__global__ void __launch_bounds__(TILE_THREADS, 4)
+enc3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t* __restrict__ stream, tile_geom tg,
+                     unsigned maxbits)
+{
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  float* tile = reinterpret_cast<float*>(smem_raw);
+  uint64_t* outw = reinterpret_cast<uint64_t*>(smem_raw + BOXES_PER_TILE * BOX_FLOATS * sizeof(float));
+  uint64_t* bars = outw + (size_t)TILE_THREADS * tg.W;
+
+  const unsigned tid = threadIdx.x;
+  const unsigned box = tid >> 6, lb = tid & 63;
+
+  if (tid == 0) {
+    ptx::prefetch_tmap(&tmap);
+    ptx::mbar_init(&bars[0], 1);
+    ptx::mbar_init(&bars[1], 1);
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+
+  auto issue_loads = [&](unsigned t) {
+#pragma unroll
+    for (int q = 0; q < BOXES_PER_TILE; q++) {
+      const box_info bi = box_of(tg, 2 * t + q);
+      if (bi.nvalid) {
+        ptx::mbar_expect_tx(&bars[q], BOX_FLOATS * sizeof(float));
+        ptx::tma_load_3d(tile + q * BOX_FLOATS, &tmap, (int)bi.x0, (int)bi.y0, (int)bi.z0, &bars[q]);
+      }
+    }
+  };
+
+  unsigned t = blockIdx.x;
+  if (tid == 0 && t < tg.ntiles) issue_loads(t);
+
+  for (unsigned it = 0; t < tg.ntiles; t += gridDim.x, it++) {
+    const box_info b0 = box_of(tg, 2 * t), b1 = box_of(tg, 2 * t + 1);
+    const box_info mine = box ? b1 : b0;
+    const bool active = lb < mine.nvalid;
+    float f[64];
+    if (mine.nvalid) {
+      ptx::mbar_wait(&bars[box], it & 1);
+      if (active) {
+        const float4* src = reinterpret_cast<const float4*>(tile + box * BOX_FLOATS) + lb;
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+          const float4 v = src[r * 64];  // row r of the box is 256 floats = 64 float4
+          f[4 * r] = v.x; f[4 * r + 1] = v.y; f[4 * r + 2] = v.z; f[4 * r + 3] = v.w;
+        }
+      }
+    }
+    if (tid == 0) ptx::bulk_wait_read0();  // previous tile's slot store has finished reading `outw`
+    __syncthreads();                      // tile buffer consumed; outw free
+    if (tid == 0 && t + gridDim.x < tg.ntiles) issue_loads(t + gridDim.x);
+
+    const unsigned p = (box ? b0.nvalid : 0u) + lb;  // slot position inside the tile's contiguous span
+    if (active) {
+      aligned_sink sink(outw + (size_t)p * tg.W, tg.W);
+      encode_block<float, 3>(f, maxbits, sink);
+    }
+    ptx::fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      const unsigned nslots = b0.nvalid + b1.nvalid;
+      ptx::bulk_store(stream + b0.blk0 * tg.W, outw, nslots * tg.W * 8u);
+      ptx::bulk_commit();
+    }
+  }
+  if (tid == 0) ptx::bulk_wait0();
+}
+
+// dynamic shared memory layout (decode): [orig tile: 2 x 16 KiB (METRICS only)][slots: 2 x 128*W words][4 mbarriers]
+template <bool METRICS>
+__global__ void __launch_bounds__(TILE_THREADS, 4)
+dec3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64_t* __restrict__ stream,
+                     float* __restrict__ out, tile_geom tg, unsigned maxbits, double* __restrict__ part)
+{
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  float* tile = reinterpret_cast<float*>(smem_raw);
+  uint64_t* slots = reinterpret_cast<uint64_t*>(smem_raw + (METRICS ? BOXES_PER_TILE * BOX_FLOATS * sizeof(float) : 0));
+  const unsigned slot_words = TILE_THREADS * tg.W;
+  uint64_t* bars = slots + 2 * (size_t)slot_words;  // [0,1] slots full (double buffer), [2,3] orig boxes full
+  __shared__ double red[7 * 4];
+
+  const unsigned tid = threadIdx.x;
+  const unsigned box = tid >> 6, lb = tid & 63;
+
+  if (tid == 0) {
+    if (METRICS) ptx::prefetch_tmap(&tmap_orig);
+    for (int i = 0; i < 4; i++) ptx::mbar_init(&bars[i], 1);
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+
+  auto issue_slots = [&](unsigned t, unsigned buf) {
+    const box_info b0 = box_of(tg, 2 * t), b1 = box_of(tg, 2 * t + 1);
+    const unsigned bytes = (b0.nvalid + b1.nvalid) * tg.W * 8u;
+    ptx::mbar_expect_tx(&bars[buf], bytes);
+    ptx::bulk_load(slots + (size_t)buf * slot_words, stream + b0.blk0 * tg.W, bytes, &bars[buf]);
+  };
+  auto issue_orig = [&](unsigned t) {
+#pragma unroll
+    for (int q = 0; q < BOXES_PER_TILE; q++) {
+      const box_info bi = box_of(tg, 2 * t + q);
+      if (bi.nvalid) {
+        ptx::mbar_expect_tx(&bars[2 + q], BOX_FLOATS * sizeof(float));
+        ptx::tma_load_3d(tile + q * BOX_FLOATS, &tmap_orig, (int)bi.x0, (int)bi.y0, (int)bi.z0, &bars[2 + q]);
+      }
+    }
+  };
+
+  unsigned t = blockIdx.x;
+  if (tid == 0) {
+    if (t < tg.ntiles) { issue_slots(t, 0); if (METRICS) issue_orig(t); }
+    if (t + gridDim.x < tg.ntiles) issue_slots(t + gridDim.x, 1);
+  }
+
+  macc m;
+  m.init();
+  for (unsigned it = 0; t < tg.ntiles; t += gridDim.x, it++) {
+    const unsigned buf = it & 1;
+    const box_info b0 = box_of(tg, 2 * t), b1 = box_of(tg, 2 * t + 1);
+    const box_info mine = box ? b1 : b0;
+    const bool active = lb < mine.nvalid;
+    const unsigned nslots = b0.nvalid + b1.nvalid;
+    ptx::mbar_wait(&bars[buf], (it >> 1) & 1);
+    if (active) {
+      const unsigned p = (box ? b0.nvalid : 0u) + lb;
+      slot_reader r(slots + (size_t)buf * slot_words + (size_t)p * tg.W, (nslots - p) * tg.W, 0);
+      float f[64];
+      decode_block<float, 3>(f, maxbits, r);
+      float* dst = out + ((size_t)mine.z0 * tg.ny + mine.y0) * tg.nx + mine.x0 + 4 * lb;
+      if (METRICS) {
+        ptx::mbar_wait(&bars[2 + box], it & 1);
+        const float4* src = reinterpret_cast<const float4*>(tile + box * BOX_FLOATS) + lb;
+        frow fr;
+        fr.init();
+#pragma unroll
+        for (int r16 = 0; r16 < 16; r16++) {
+          const float4 o = src[r16 * 64];
+          fr.add(o.x, f[4 * r16]); fr.add(o.y, f[4 * r16 + 1]); fr.add(o.z, f[4 * r16 + 2]); fr.add(o.w, f[4 * r16 + 3]);
+          if ((r16 & 3) == 3) fr.flush(m);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          float4 v;
+          v.x = f[16 * k + 4 * j]; v.y = f[16 * k + 4 * j + 1]; v.z = f[16 * k + 4 * j + 2]; v.w = f[16 * k + 4 * j + 3];
+          __stcs(reinterpret_cast<float4*>(dst + ((size_t)k * tg.ny + j) * tg.nx), v);
+        }
+    } else if (METRICS && mine.nvalid) {
+      ptx::mbar_wait(&bars[2 + box], it & 1);  // keep every thread's view of the barrier phase in step
+    }
+    __syncthreads();  // slots[buf] and the orig tile are consumed
+    if (tid == 0) {
+      const unsigned t2 = t + 2 * gridDim.x, t1 = t + gridDim.x;
+      if (t2 < tg.ntiles) issue_slots(t2, buf);
+      if (METRICS && t1 < tg.ntiles) issue_orig(t1);
+    }
+  }
+  if (METRICS) macc_block_store(m, red, part + (size_t)blockIdx.x * PART_STRIDE);
+}
+
+// ---------------------------------------------------------------------------------------------
+// stand-alone streaming metrics and histograms
+// ---------------------------------------------------------------------------------------------
+template <typename Scalar>
+__global__ void __launch_bounds__(256) metrics_kernel(const Scalar* __restrict__ orig, const Scalar* __restrict__ approx,
+                                                      size_t n, double* __restrict__ part)
+{
+  __shared__ double red[7 * 8];
+  macc m;
+  m.init();
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if constexpr (sizeof(Scalar) == 4) {
+    const size_t n4 = n / 4;
+    const float4* o4 = reinterpret_cast<const float4*>(orig);
+    const float4* a4 = reinterpret_cast<const float4*>(approx);
+    frow fr;
+    fr.init();
+    int cnt = 0;
+    for (; i < n4; i += stride) {
+      const float4 o = __ldcs(o4 + i), a = __ldcs(a4 + i);
+      fr.add(o.x, a.x); fr.add(o.y, a.y); fr.add(o.z, a.z); fr.add(o.w, a.w);
+      if (++cnt == 4) { fr.flush(m); cnt = 0; }
+    }
+    const size_t tail = n4 * 4 + ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
+    if (tail < n) fr.add(orig[tail], approx[tail]);
+    fr.flush(m);
+  } else {
+    for (; i < n; i += stride) macc_add(m, (double)orig[i], (double)approx[i]);
+  }
+  macc_block_store(m, red, part + (size_t)blockIdx.x * PART_STRIDE);
+}
+
+// which: 0 abs error, 1 rel error, 2 approx value.  Binning follows the reference expression by
+// expression (double arithmetic, int truncation, `if (pos >= numBins) pos = pos - 1`), with out-of-range
+// positions clamped and counted instead of indexing out of bounds.
+template <typename Scalar>
+__global__ void __launch_bounds__(256) hist_kernel(int which, double lo, double hi, const Scalar* __restrict__ orig,
+                                                   const Scalar* __restrict__ approx, size_t n,
+                                                   unsigned long long* __restrict__ counts,
+                                                   unsigned long long* __restrict__ oob)
+{
+  __shared__ unsigned int h[1024];
+  __shared__ unsigned int bad;
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) h[i] = 0;
+  if (threadIdx.x == 0) bad = 0;
+  __syncthreads();
+  const double range = hi - lo;
+  const double bin = range / 1024.0;
+  // a CTA handles at most 2^31 values between flushes, so 32-bit shared counters cannot overflow
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    double q;
+    if (which == 2) {
+      const double v = (double)approx[i];
+      q = (range * ((v - lo) / range)) / bin;  // minmaxMetric.hpp:112
+    } else {
+      double err;
+      if constexpr (sizeof(Scalar) == 4) {
+        const float o = orig[i], a = approx[i];
+        const float ad = fabsf(o - a);
+        if (which == 0) err = (double)ad;                                                    // absoluteError.hpp:119
+        else err = (double)(fabsf(o) < 1.0f ? ad : (float)((double)ad / (double)fabsf(o)));  // relativeError.hpp:131
+      } else {
+        const double o = (double)orig[i], a = (double)approx[i];
+        const double ad = fabs(o - a);
+        err = (which == 0 || fabs(o) < 1.0) ? ad : ad / fabs(o);
+      }
+      q = err / bin;
+    }
+    int pos;
+    if (!(q >= 0.0)) { pos = 0; atomicAdd(&bad, 1u); }
+    else if (q >= 1025.0) { pos = 1023; atomicAdd(&bad, 1u); }
+    else {
+      pos = (int)q;
+      if (pos >= 1024) pos = pos - 1;
+      if (pos >= 1024) { pos = 1023; atomicAdd(&bad, 1u); }
+    }
+    atomicAdd(&h[pos], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x)
+    if (h[i]) atomicAdd(&counts[i], (unsigned long long)h[i]);
+  if (threadIdx.x == 0 && bad && oob) atomicAdd(oob, (unsigned long long)bad);
+}
+
+}  // namespace zfb
