@@ -80,8 +80,10 @@ int zfb_partition(int rank, int nranks, const size_t n[3], size_t count[3], size
  * zfp_stream_set_execution(zfp, zfp_exec_cuda), :143).  Returns ZFB_ENODEV when no device is usable. */
 int zfb_create(zfb_ctx** ctx, int device);
 int zfb_destroy(zfb_ctx* ctx);                       /* CompressorInterface::close, :269-272 */
-/* Use an existing CUDA stream (a cudaStream_t passed as void*) for all "dev" calls; NULL = own stream. */
+/* Enqueue all "dev" calls on an existing CUDA stream (a cudaStream_t passed as void*; NULL is the legacy
+ * default stream, as in the CUDA runtime).  zfb_reset_stream goes back to the context's own stream. */
 int zfb_set_stream(zfb_ctx* ctx, void* cuda_stream);
+int zfb_reset_stream(zfb_ctx* ctx);
 int zfb_synchronize(zfb_ctx* ctx);
 const char* zfb_last_error(const zfb_ctx* ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */

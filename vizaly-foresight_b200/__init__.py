@@ -79,6 +79,7 @@ def lib():
         "zfb_create": (i, [C.POINTER(vp), i]),
         "zfb_destroy": (i, [vp]),
         "zfb_set_stream": (i, [vp, vp]),
+        "zfb_reset_stream": (i, [vp]),
         "zfb_synchronize": (i, [vp]),
         "zfb_last_error": (C.c_char_p, [vp]),
         "zfb_launch_count": (C.c_uint64, [vp]),
@@ -208,9 +209,13 @@ class Codec:
         self._check(lib().zfb_set_stream(self._h, C.c_void_p(cuda_stream_ptr)), "zfb_set_stream")
 
     def use_torch_stream(self):
+        """Order the codec's kernels with torch ops: enqueue on torch's current stream of this device."""
         import torch
 
         self.use_stream(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def use_own_stream(self):
+        self._check(lib().zfb_reset_stream(self._h), "zfb_reset_stream")
 
     def synchronize(self):
         self._check(lib().zfb_synchronize(self._h), "zfb_synchronize")
@@ -223,6 +228,7 @@ class Codec:
     def encode(self, field, mb, out=None):
         import torch
 
+        self.use_torch_stream()
         d, nx, ny, nz = dims_of(field.shape)
         nbytes = int(lib().zfb_stream_bytes(d, nx, ny, nz, mb))
         if out is None:
@@ -235,6 +241,7 @@ class Codec:
     def decode(self, stream, shape, dtype, mb, orig=None, out=None):
         import torch
 
+        self.use_torch_stream()
         d, nx, ny, nz = dims_of(shape)
         if out is None:
             out = torch.empty(tuple(shape), dtype=dtype, device=stream.device)
@@ -244,6 +251,7 @@ class Codec:
         return out
 
     def metrics(self, orig, approx):
+        self.use_torch_stream()
         self._check(lib().zfb_metrics_dev(self._h, _dtype_code(orig.dtype), orig.data_ptr(), approx.data_ptr(),
                                           orig.numel()), "zfb_metrics_dev")
         return self.partials()
@@ -269,6 +277,7 @@ class Codec:
     def histogram(self, which, lo, hi, orig, approx):
         import torch
 
+        self.use_torch_stream()
         counts = torch.zeros(NBINS + 1, dtype=torch.int64, device=approx.device)
         self._check(lib().zfb_histogram_dev(self._h, _dtype_code(approx.dtype), which, float(lo), float(hi),
                                             orig.data_ptr() if orig is not None else None, approx.data_ptr(),

@@ -191,11 +191,14 @@ extern "C" int zfb_create(zfb_ctx** out, int device)
   const char* fg = std::getenv("ZFB_FORCE_GENERIC");
   c->force_generic = fg && fg[0] == '1';
   // opt in to large dynamic shared memory for the tile kernels
-  const int max_smem = (int)prop.sharedMemPerBlockOptin;
-  cudaFuncSetAttribute(enc3_f32_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-  cudaFuncSetAttribute(dec3_f32_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-  cudaFuncSetAttribute(dec3_f32_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem);
-  cudaGetLastError();
+  // (the limit applies to static + dynamic, and the decode kernels keep a small static reduction buffer)
+  const int max_smem = 100 * 1024 + 1024;
+  if (cudaFuncSetAttribute(enc3_f32_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) != cudaSuccess ||
+      cudaFuncSetAttribute(dec3_f32_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) != cudaSuccess ||
+      cudaFuncSetAttribute(dec3_f32_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) != cudaSuccess) {
+    cudaGetLastError();
+    c->encode_tiled = nullptr;  // tile kernels unusable: everything goes through the generic kernels
+  }
   *out = c;
   return ZFB_OK;
 }
@@ -233,7 +236,14 @@ extern "C" int zfb_destroy(zfb_ctx* c)
 extern "C" int zfb_set_stream(zfb_ctx* c, void* s)
 {
   if (!c) return ZFB_EINVAL;
-  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  c->stream = (cudaStream_t)s;
+  return ZFB_OK;
+}
+
+extern "C" int zfb_reset_stream(zfb_ctx* c)
+{
+  if (!c) return ZFB_EINVAL;
+  c->stream = c->own_stream;
   return ZFB_OK;
 }
 
