@@ -6,8 +6,26 @@
 #include <cstdint>
 #include <cstddef>
 #include "../vizaly-foresight_b200/csrc/zfb_codec.cuh"
+#include "../vizaly-foresight_b200/csrc/zfb_codec_f3.cuh"
+#include <type_traits>
 
 using namespace zfb;
+
+static int g_use_f3 = 1;  // float/3D goes through the fast coder (zfb_codec_f3.cuh) unless switched off
+static uint16_t g_enc[256];
+static uint32_t g_dec[512];
+static f3::tables host_tables()
+{
+  static bool built = false;
+  if (!built) {
+    for (unsigned i = 0; i < 256; i++) g_enc[i] = f3::enc_entry(i);
+    for (unsigned i = 0; i < 512; i++) g_dec[i] = f3::dec_entry(i >> 8, i & 255);
+    built = true;
+  }
+  f3::tables t;
+  t.enc = g_enc; t.dec = g_dec;
+  return t;
+}
 
 template <typename Scalar, int DIMS>
 static void run(bool enc, size_t nx, size_t ny, size_t nz, unsigned maxbits, Scalar* data, uint64_t* stream,
@@ -33,6 +51,23 @@ static void run(bool enc, size_t nx, size_t ny, size_t nz, unsigned maxbits, Sca
         for (unsigned j = 0; j < my; j++)
           for (unsigned i = 0; i < mx; i++) f[16 * k + 4 * j + i] = data[(x0 + i) + nx * ((y0 + j) + ny * (z0 + k))];
       if (mx < 4 || my < (DIMS >= 2 ? 4u : 1u) || mz < (DIMS >= 3 ? 4u : 1u)) pad_block<Scalar, DIMS>(f, mx, my, mz);
+      if constexpr (std::is_same<Scalar, float>::value && DIMS == 3) {
+        if (g_use_f3) {
+          const f3::tables tb = host_tables();
+          uint32_t* s32 = reinterpret_cast<uint32_t*>(stream);
+          f3::u32x4 rows[16];
+          f3::plane_rows ps;
+          ps.p = rows; ps.stride = 1;
+          if (aligned) {
+            f3::sink32 sink(s32 + startbit / 32, maxbits / 32);
+            f3::encode_block(f, maxbits, sink, tb, ps);
+          } else {
+            f3::or_sink32 sink(s32, startbit, maxbits);
+            f3::encode_block(f, maxbits, sink, tb, ps);
+          }
+          continue;
+        }
+      }
       if (aligned) {
         aligned_sink sink(stream + startbit / 64, maxbits / 64);
         encode_block<Scalar, DIMS>(f, maxbits, sink);
@@ -41,8 +76,23 @@ static void run(bool enc, size_t nx, size_t ny, size_t nz, unsigned maxbits, Sca
         encode_block<Scalar, DIMS>(f, maxbits, sink);
       }
     } else {
-      slot_reader r(stream + (startbit >> 6), (unsigned)(stream_words - (startbit >> 6)), (unsigned)(startbit & 63));
-      decode_block<Scalar, DIMS>(f, maxbits, r);
+      bool done = false;
+      if constexpr (std::is_same<Scalar, float>::value && DIMS == 3) {
+        if (g_use_f3) {
+          const f3::tables tb = host_tables();
+          const uint32_t* s32 = reinterpret_cast<const uint32_t*>(stream);
+          f3::reader32 r(s32 + (startbit >> 5), (unsigned)(2 * stream_words - (startbit >> 5)), (unsigned)(startbit & 31));
+          f3::u32x4 rows[16];
+          f3::plane_rows ps;
+          ps.p = rows; ps.stride = 1;
+          f3::decode_block(f, maxbits, r, tb, ps);
+          done = true;
+        }
+      }
+      if (!done) {
+        slot_reader r(stream + (startbit >> 6), (unsigned)(stream_words - (startbit >> 6)), (unsigned)(startbit & 63));
+        decode_block<Scalar, DIMS>(f, maxbits, r);
+      }
       for (unsigned k = 0; k < mz; k++)
         for (unsigned j = 0; j < my; j++)
           for (unsigned i = 0; i < mx; i++) data[(x0 + i) + nx * ((y0 + j) + ny * (z0 + k))] = f[16 * k + 4 * j + i];
@@ -64,6 +114,7 @@ static int dispatch(bool enc, int dims, size_t nx, size_t ny, size_t nz, unsigne
 }
 
 extern "C" {
+void emul_use_f3(int on) { g_use_f3 = on; }
 // type: 1 float, 2 double (same codes as the oracle and include/zfb.h)
 int emul_compress(int type, int dims, size_t nx, size_t ny, size_t nz, unsigned maxbits, const void* in, void* stream,
                   size_t stream_words)

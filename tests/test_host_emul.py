@@ -113,3 +113,26 @@ def test_device_codec_extremes(oracle):
         s, g = emul_roundtrip(O, fd, mb)
         assert np.array_equal(s, s_ref), mb
         assert np.array_equal(g.view(np.uint8), O.decompress(s_ref, fd.shape, np.float64, mb).view(np.uint8)), mb
+
+
+def test_fast_coder_budget_boundaries(oracle):
+    """float/3D fast coder (zfb_codec_f3.cuh): every budget from 9 to 2200 bits on fields that drive the
+    coder through its table steps, its exact single-bit steps (budget end, last coefficients) and the
+    lazily finished lower planes."""
+    O = oracle
+    rng = np.random.default_rng(42)
+    base = smooth_field((4, 8, 8), seed=3, amp=7.0)
+    fields = [
+        base,
+        (rng.standard_normal((4, 8, 8)) * 900).astype(np.float32),
+        (base * (rng.random((4, 8, 8)) > 0.8)).astype(np.float32),
+        np.where(rng.random((4, 8, 8)) > 0.97, 1.0e3, 1.0e-3).astype(np.float32),
+        np.full((4, 8, 8), -3.25, np.float32),
+        np.cumsum(np.ones((4, 8, 8), np.float32)).reshape(4, 8, 8),
+    ]
+    for f in fields:
+        for mb in list(range(9, 140)) + list(range(140, 2200, 37)) + [256, 512, 1024, 2048]:
+            s_ref = O.compress(f, mb)
+            s, g = emul_roundtrip(O, f, mb)
+            assert np.array_equal(s, s_ref), mb
+            assert np.array_equal(g.view(np.uint8), O.decompress(s_ref, f.shape, np.float32, mb).view(np.uint8)), mb

@@ -1,0 +1,504 @@
+// zfb_codec_f3.cuh -- the hot instantiation of the block codec: float32, 3D (64 coefficients, 32 planes).
+//
+// Same bit stream as encode_block<float,3> / decode_block<float,3> in zfb_codec.cuh (and therefore as
+// zfp 0.5.5 fixed-rate; reference call sites zfpCompressorGpu.hpp:145,249),
+// but organised for SIMT execution with one block per lane:
+//
+//   * no per-bit and no per-coefficient loops in the embedded coder.  zfp's group-test / unary code for
+//     the not-yet-significant part of a bit plane is the substitution  0 -> "0", 1 -> "1 t"  (t = "more
+//     ones follow") behind a leading test bit; the encoder expands a byte at a time through a 256-entry
+//     table, the decoder parses a byte at a time through a 2x256-entry finite-state table.  Work per
+//     plane is ceil(region/8) table steps instead of one divergent iteration per coefficient.
+//   * all bit I/O in 32-bit words with funnel shifts (no emulated 64-bit shifts); the decoder keeps a
+//     64-bit register window over the slot.
+//   * bit planes come from a 32x32 SWAR transpose whose 16- and 8-bit stages are byte permutes (PRMT);
+//     the halves holding planes 31..16 and 15..0 are finished lazily, so blocks whose budget ends in the
+//     upper planes (the common case at <= 8 bits/value) never pay for the lower ones.
+//
+// Host-device like zfb_codec.cuh so tests/host_emul.cpp can bit-compare it with the oracle on the CPU.
+#pragma once
+#include "zfb_codec.cuh"
+
+#if defined(__CUDACC__)
+#define ZFB_NOUNROLL _Pragma("unroll 1")
+#else
+#define ZFB_NOUNROLL
+#endif
+
+namespace zfb {
+namespace f3 {
+
+// Plane scratch of one block: 16 rows of four words; row r = { plane 2r of coefficients 0..31, plane 2r of
+// coefficients 32..63, plane 2r+1 (0..31), plane 2r+1 (32..63) }.  In the kernels the rows live in the
+// thread's own 16-byte columns of the shared-memory tile (row r of lane l at 16 B * (r * stride + l)), so
+// every access is a conflict-free 128-bit LDS/STS.  Parking the planes in memory is what lets the coder
+// run as a real loop over planes: fully unrolled it is > 200 KB of SASS and the kernel stalls on
+// instruction fetch (profiles/r01_notes.md).
+struct alignas(16) u32x4 {
+  uint32_t x, y, z, w;
+};
+struct plane_rows {
+  u32x4* p;
+  unsigned stride;
+  ZFB_HD u32x4 ld(int r) const { return p[(unsigned)r * stride]; }
+  ZFB_HD void st(int r, const u32x4& v) const { p[(unsigned)r * stride] = v; }
+};
+
+// ---------------------------------------------------------------------------------------------
+// small 32-bit helpers
+// ---------------------------------------------------------------------------------------------
+ZFB_HD uint32_t mask32(unsigned m)  // m in [0, 32]
+{
+  return m >= 32 ? 0xffffffffu : ((1u << m) - 1u);
+}
+ZFB_HD uint32_t fsr(uint32_t lo, uint32_t hi, unsigned s)  // low word of (hi:lo) >> s, s in [0, 32]
+{
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_rc(lo, hi, s);
+#else
+  return s == 0 ? lo : s >= 32 ? hi : (lo >> s) | (hi << (32 - s));
+#endif
+}
+ZFB_HD uint32_t carry_out(uint32_t v, unsigned s)  // bits of v that fall off the top of a word when shifted left by s < 32
+{
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_l(v, 0u, s);
+#else
+  return s ? v >> (32 - s) : 0u;
+#endif
+}
+ZFB_HD int popc32(uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+  return __popc(v);
+#else
+  return __builtin_popcount(v);
+#endif
+}
+ZFB_HD int msb32(uint32_t v)  // v != 0
+{
+#if defined(__CUDA_ARCH__)
+  return 31 - __clz((int)v);
+#else
+  return 31 - __builtin_clz(v);
+#endif
+}
+ZFB_HD uint32_t bperm(uint32_t a, uint32_t b, uint32_t sel)
+{
+#if defined(__CUDA_ARCH__)
+  return __byte_perm(a, b, sel);
+#else
+  const uint64_t t = ((uint64_t)b << 32) | a;
+  uint32_t r = 0;
+  for (int i = 0; i < 4; i++) r |= (uint32_t)((t >> (8 * ((sel >> (4 * i)) & 7))) & 0xff) << (8 * i);
+  return r;
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// coder tables (built once per CTA into shared memory; 512 B + 2 KiB)
+// ---------------------------------------------------------------------------------------------
+// ENC[b]: byte b (LSB = first coefficient) expanded by 0 -> "0", 1 -> "11"; 8 + popc(b) bits.
+ZFB_HD uint16_t enc_entry(unsigned b)
+{
+  unsigned e = 0, pos = 0;
+  for (int i = 0; i < 8; i++) {
+    if ((b >> i) & 1u) { e |= 3u << pos; pos += 2; }
+    else pos += 1;
+  }
+  return (uint16_t)e;
+}
+
+// DEC[state][v]: run zfp's group-test parser over the 8 stream bits v (LSB first) from `state`
+//   state 0 (A) = expecting a test bit, state 1 (B) = inside a zero run (next bit is a coefficient bit).
+// Entry: bits 0-7 ones deposited (relative to the current coefficient index), 8-11 coefficients advanced,
+//        12-15 stream bits consumed, 16-17 next state (0 A, 1 B, 2 END = a zero test bit was consumed).
+ZFB_HD uint32_t dec_entry(unsigned state, unsigned v)
+{
+  unsigned pattern = 0, npos = 0, nbits = 0;
+  while (nbits < 8 && state != 2) {
+    const unsigned bit = (v >> nbits) & 1u;
+    nbits++;
+    if (state == 0) state = bit ? 1u : 2u;
+    else {
+      if (bit) { pattern |= 1u << npos; state = 0; }
+      npos++;
+    }
+  }
+  return pattern | (npos << 8) | (nbits << 12) | (state << 16);
+}
+
+struct tables {
+  const uint16_t* enc;  // 256 entries
+  const uint32_t* dec;  // 512 entries
+};
+
+// ---------------------------------------------------------------------------------------------
+// bit planes of 64 x uint32 coefficients, finished lazily in two halves
+// ---------------------------------------------------------------------------------------------
+// a[] / b[] hold coefficients 0..31 / 32..63.  After split16(): words 16..31 of each array carry the
+// upper 16 bits of all 32 coefficients, words 0..15 the lower 16 bits.  finish(16) / finish(0) complete
+// the transpose of that half; afterwards word k of a/b is plane k of coefficients 0..31 / 32..63.
+struct planes64 {
+  uint32_t a[32], b[32];
+
+  ZFB_HD static void stage16(uint32_t (&w)[32])
+  {
+    ZFB_UNROLL for (int k = 0; k < 16; k++) {
+      const uint32_t lo = bperm(w[k], w[k + 16], 0x5410), hi = bperm(w[k], w[k + 16], 0x7632);
+      w[k] = lo; w[k + 16] = hi;
+    }
+  }
+  // stages 8, 4, 2, 1 on words [base, base+16)
+  ZFB_HD static void stages_low(uint32_t (&w)[32], int base)
+  {
+    ZFB_UNROLL for (int k = 0; k < 8; k++) {
+      const uint32_t p = w[base + k], q = w[base + k + 8];
+      w[base + k] = bperm(p, q, 0x6240); w[base + k + 8] = bperm(p, q, 0x7351);
+    }
+    ZFB_UNROLL for (int g = 0; g < 16; g += 8)
+      ZFB_UNROLL for (int k = 0; k < 4; k++) {
+        const uint32_t p = w[base + g + k], q = w[base + g + k + 4];
+        w[base + g + k] = (p & 0x0f0f0f0fu) | ((q << 4) & 0xf0f0f0f0u);
+        w[base + g + k + 4] = ((p >> 4) & 0x0f0f0f0fu) | (q & 0xf0f0f0f0u);
+      }
+    ZFB_UNROLL for (int g = 0; g < 16; g += 4)
+      ZFB_UNROLL for (int k = 0; k < 2; k++) {
+        const uint32_t p = w[base + g + k], q = w[base + g + k + 2];
+        w[base + g + k] = (p & 0x33333333u) | ((q << 2) & 0xccccccccu);
+        w[base + g + k + 2] = ((p >> 2) & 0x33333333u) | (q & 0xccccccccu);
+      }
+    ZFB_UNROLL for (int g = 0; g < 16; g += 2) {
+      const uint32_t p = w[base + g], q = w[base + g + 1];
+      w[base + g] = (p & 0x55555555u) | ((q << 1) & 0xaaaaaaaau);
+      w[base + g + 1] = ((p >> 1) & 0x55555555u) | (q & 0xaaaaaaaau);
+    }
+  }
+  ZFB_HD void split16() { stage16(a); stage16(b); }
+  ZFB_HD void finish(int base) { stages_low(a, base); stages_low(b, base); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// 32-bit word sinks / writer
+// ---------------------------------------------------------------------------------------------
+struct sink32 {  // slot on a word boundary, whole number of 32-bit words (maxbits % 64 == 0)
+  uint32_t* dst;
+  unsigned widx, nwords;
+  ZFB_HD sink32(uint32_t* d, unsigned n) : dst(d), widx(0), nwords(n) {}
+  ZFB_HD void word(uint32_t w)
+  {
+    if (widx < nwords) dst[widx] = w;
+    widx++;
+  }
+  ZFB_HD void finish()
+  {
+    for (; widx < nwords; widx++) dst[widx] = 0;
+  }
+};
+
+struct or_sink32 {  // arbitrary bit offset in a pre-zeroed stream (maxbits % 64 != 0)
+  uint32_t* base;
+  size_t startbit;
+  unsigned maxbits, j;
+  ZFB_HD or_sink32(uint32_t* b, size_t sb, unsigned mb) : base(b), startbit(sb), maxbits(mb), j(0) {}
+  ZFB_HD static void or32(uint32_t* p, uint32_t v)
+  {
+#if defined(__CUDA_ARCH__)
+    atomicOr(p, v);
+#else
+    *p |= v;
+#endif
+  }
+  ZFB_HD void word(uint32_t w)
+  {
+    const unsigned off = 32u * j++;
+    if (off >= maxbits) return;
+    const unsigned valid = maxbits - off;
+    if (valid < 32) w &= mask32(valid);
+    if (!w) return;
+    const size_t pos = startbit + off;
+    const unsigned s = (unsigned)(pos & 31);
+    or32(base + (pos >> 5), w << s);
+    const uint32_t c = carry_out(w, s);
+    if (c) or32(base + (pos >> 5) + 1, c);
+  }
+  ZFB_HD void finish() {}
+};
+
+template <class Sink> struct writer32 {
+  Sink& sink;
+  uint32_t acc;
+  unsigned cnt;    // bits held in acc, < 32
+  unsigned total;  // bits emitted
+  ZFB_HD explicit writer32(Sink& s) : sink(s), acc(0), cnt(0), total(0) {}
+  ZFB_HD void put(uint32_t v, unsigned len)  // len in [0, 32]; bits of v above len are zero
+  {
+    acc |= v << cnt;
+    const uint32_t c = carry_out(v, cnt);
+    cnt += len;
+    total += len;
+    if (cnt >= 32) { sink.word(acc); acc = c; cnt -= 32; }
+  }
+  ZFB_HD void flush()
+  {
+    if (cnt) sink.word(acc);
+    acc = 0; cnt = 0;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// encode
+// ---------------------------------------------------------------------------------------------
+template <class Sink>
+ZFB_HD void encode_block(const float (&f)[64], unsigned maxbits, Sink& sink, const tables& tb, const plane_rows& ps)
+{
+  typedef traits<float> T;
+  float mx = 0.f;
+  ZFB_UNROLL for (int i = 0; i < 64; i++) {
+#if defined(__CUDA_ARCH__)
+    mx = fmaxf(mx, fabsf(f[i]));  // NaN operands are ignored, exactly like `if (max < f) max = f`
+#else
+    const float a = f[i] < 0 ? -f[i] : f[i];
+    mx = (mx < a) ? a : mx;
+#endif
+  }
+  if (!(mx > 0.f)) { sink.finish(); return; }
+  const int E = T::expfield(mx);
+  const int emax = E - 126;
+
+  planes64 P;
+  {
+    int32_t ib[64];
+    const int se = 30 - emax;
+    const float s = T::pow2(se);
+    ZFB_UNROLL for (int i = 0; i < 64; i++) ib[i] = T::trunc_cast(s * f[i]);
+    if (se > 127) { ZFB_UNROLL for (int i = 0; i < 64; i++) ib[i] = T::int_min(); }  // see zfb_codec.cuh
+    fwd_xform<int32_t, 3>(ib);
+    ZFB_UNROLL for (int i = 0; i < 32; i++) {
+      P.a[i] = ((uint32_t)ib[order<3>::at(i)] + T::NBMASK) ^ T::NBMASK;
+      P.b[i] = ((uint32_t)ib[order<3>::at(i + 32)] + T::NBMASK) ^ T::NBMASK;
+    }
+  }
+  P.split16();
+  P.finish(16);
+  // rows 8..15: planes 16..31, finished.  rows 0..7: the lower halves, still un-transposed; they are
+  // finished only if the budget reaches plane 15.
+  ZFB_UNROLL for (int r = 0; r < 16; r++) {
+    u32x4 v;
+    v.x = P.a[2 * r]; v.y = P.b[2 * r]; v.z = P.a[2 * r + 1]; v.w = P.b[2 * r + 1];
+    ps.st(r, v);
+  }
+
+  writer32<Sink> bw(sink);
+  bw.put(2u * (uint32_t)(E + 1) + 1u, 9);
+
+  unsigned n = 0;
+  u32x4 cur;
+  cur.x = cur.y = cur.z = cur.w = 0u;
+  ZFB_NOUNROLL for (int k = 31; k >= 0; k--) {
+    if (bw.total >= maxbits) break;
+    if (k == 15) {
+      planes64 Q;
+      ZFB_UNROLL for (int r = 0; r < 8; r++) {
+        const u32x4 v = ps.ld(r);
+        Q.a[2 * r] = v.x; Q.b[2 * r] = v.y; Q.a[2 * r + 1] = v.z; Q.b[2 * r + 1] = v.w;
+      }
+      Q.finish(0);
+      ZFB_UNROLL for (int r = 0; r < 8; r++) {
+        u32x4 v;
+        v.x = Q.a[2 * r]; v.y = Q.b[2 * r]; v.z = Q.a[2 * r + 1]; v.w = Q.b[2 * r + 1];
+        ps.st(r, v);
+      }
+    }
+    if (k & 1) cur = ps.ld(k >> 1);
+    const uint32_t xl = (k & 1) ? cur.z : cur.x, xh = (k & 1) ? cur.w : cur.y;
+    uint32_t yl, yh;
+    if (n == 0) { yl = xl; yh = xh; }
+    else if (n < 32) {
+      bw.put(xl & mask32(n), n);
+      yl = fsr(xl, xh, n); yh = xh >> n;
+    } else {
+      bw.put(xl, 32);
+      bw.put(xh & mask32(n - 32), n - 32);
+      yl = n < 64 ? xh >> (n - 32) : 0u; yh = 0u;
+    }
+    if (n < 64) {
+      if ((yl | yh) == 0u) bw.put(0u, 1);
+      else {
+        const unsigned plast = yh ? 32u + (unsigned)msb32(yh) : (unsigned)msb32(yl);
+        const unsigned nfull = plast >> 3;                 // bytes before the one holding the last one-bit
+        bw.put(1u, 1);                                     // first group test
+        for (unsigned j = 0; j < nfull; j++) {
+          const uint32_t b = yl & 0xffu;
+          bw.put(tb.enc[b], 8u + (unsigned)popc32(b));
+          yl = fsr(yl, yh, 8); yh >>= 8;
+        }
+        {
+          const uint32_t b = yl & 0xffu;
+          uint32_t e = tb.enc[b];
+          unsigned len = (plast & 7u) + 1u + (unsigned)popc32(b);
+          if (n + plast == 63u) len -= 2;                  // the last coefficient's one is implicit, no test follows
+          else e &= ~(1u << (len - 1));                    // final group test: no more ones in this plane
+          bw.put(e & mask32(len), len);
+        }
+        n += plast + 1u;
+      }
+    }
+  }
+  bw.flush();
+  sink.finish();
+}
+
+// ---------------------------------------------------------------------------------------------
+// decode
+// ---------------------------------------------------------------------------------------------
+// Register window over a slot: (hi:lo) holds the next `avail` >= 32 stream bits (fewer only at the end).
+struct reader32 {
+  const uint32_t* w;
+  unsigned nwords, widx;
+  uint32_t lo, hi;
+  unsigned avail;
+  // p = first word of the slot region, n = words that may be read from p, startbit < 32
+  ZFB_HD reader32(const uint32_t* p, unsigned n, unsigned startbit) : w(p), nwords(n), widx(2), avail(64)
+  {
+    lo = n > 0 ? p[0] : 0u;
+    hi = n > 1 ? p[1] : 0u;
+    if (startbit) consume(startbit);
+  }
+  ZFB_HD void consume(unsigned k)  // k in [0, 32]
+  {
+    lo = fsr(lo, hi, k);
+    hi = k < 32 ? hi >> k : 0u;
+    avail -= k;
+    if (avail < 32) {  // hi == 0 here
+      const uint32_t nw = widx < nwords ? w[widx] : 0u;
+      widx++;
+      lo |= nw << avail;
+      hi = carry_out(nw, avail);
+      avail += 32;
+    }
+  }
+  ZFB_HD uint32_t take(unsigned k)  // k in [0, 32]
+  {
+    const uint32_t v = lo & mask32(k);
+    consume(k);
+    return v;
+  }
+};
+
+// Phase 1: parse the slot into bit planes (left in P).  Returns false for an all-zero block.
+template <class Reader>
+ZFB_HD bool decode_planes(planes64& P, int& emax, bool& low_used_out, unsigned maxbits, Reader& r, const tables& tb,
+                          const plane_rows& ps)
+{
+  const uint32_t head = r.lo;
+  emax = 0;
+  low_used_out = false;
+  if (!(head & 1u)) return false;
+  emax = (int)((head >> 1) & 0xffu) - 127;
+  r.consume(9);
+
+  {
+    u32x4 z;
+    z.x = z.y = z.z = z.w = 0u;
+    ZFB_UNROLL for (int q = 0; q < 16; q++) ps.st(q, z);
+  }
+  unsigned remaining = maxbits - 9u;
+  unsigned n = 0;
+  bool low_used = false;
+  u32x4 cur;
+  cur.x = cur.y = cur.z = cur.w = 0u;
+  int k = 31;
+  ZFB_NOUNROLL for (; k >= 0; k--) {
+    if (!remaining) break;
+    if (k == 15) low_used = true;
+    const unsigned m = n < remaining ? n : remaining;
+    remaining -= m;
+    uint32_t xl = 0u, xh = 0u;
+    if (m > 32) { xl = r.take(32); xh = r.take(m - 32); }
+    else if (m) xl = r.take(m);
+    unsigned state = 0;
+    while (n < 64u && remaining) {
+      const uint32_t e = tb.dec[(state << 8) | (r.lo & 0xffu)];
+      const unsigned npos = (e >> 8) & 15u, nbits = (e >> 12) & 15u;
+      if (n + npos <= 63u && nbits <= remaining) {
+        // table step: deposit up to 8 coefficient bits at once
+        const uint32_t pat = e & 0xffu;
+        if (n < 32) { xl |= pat << n; xh |= carry_out(pat, n); }
+        else xh |= pat << (n - 32);
+        n += npos;
+        remaining -= nbits;
+        r.consume(nbits);
+        state = (e >> 16) & 3u;
+        if (state == 2u) break;
+      } else {
+        // exact single-bit step near the end of the budget or of the block (zfp's loop conditions)
+        if (state == 0u) {
+          remaining--;
+          if (!r.take(1)) break;
+          state = 1u;
+        } else {
+          bool one = true;
+          if (n < 63u && remaining) { remaining--; one = r.take(1) != 0u; }
+          if (one) {
+            if (n < 32) xl |= 1u << n; else xh |= 1u << (n - 32);
+            state = 0u;
+          }
+          n++;
+        }
+      }
+    }
+    if (state == 1u) {
+      // the budget ran out inside a zero run: zfp's decoder still deposits a one at the current index
+      if (n < 32) xl |= 1u << n; else xh |= 1u << (n - 32);
+      n++;
+    }
+    if (k & 1) { cur.z = xl; cur.w = xh; }
+    else { cur.x = xl; cur.y = xh; ps.st(k >> 1, cur); }
+  }
+  if (k >= 0 && !(k & 1)) {  // stopped with the odd plane of a row pending (k is the first plane NOT decoded)
+    cur.x = 0u; cur.y = 0u;
+    ps.st(k >> 1, cur);
+  }
+
+  ZFB_UNROLL for (int q = 0; q < 16; q++) {
+    const u32x4 v = ps.ld(q);
+    P.a[2 * q] = v.x; P.b[2 * q] = v.y; P.a[2 * q + 1] = v.z; P.b[2 * q + 1] = v.w;
+  }
+  low_used_out = low_used;
+  return true;
+}
+
+// Phase 2: planes -> coefficients -> inverse transform -> floats.
+ZFB_HD void decode_finish(float (&f)[64], planes64& P, int emax, bool nonzero, bool low_used)
+{
+  typedef traits<float> T;
+  if (!nonzero) {
+    ZFB_UNROLL for (int i = 0; i < 64; i++) f[i] = 0.f;
+    return;
+  }
+  P.finish(16);
+  if (low_used) P.finish(0);
+  P.split16();
+  int32_t ib[64];
+  ZFB_UNROLL for (int i = 0; i < 32; i++) {
+    ib[order<3>::at(i)] = (int32_t)((P.a[i] ^ T::NBMASK) - T::NBMASK);
+    ib[order<3>::at(i + 32)] = (int32_t)((P.b[i] ^ T::NBMASK) - T::NBMASK);
+  }
+  inv_xform<int32_t, 3>(ib);
+  const float s = T::pow2(emax - 30);
+  ZFB_UNROLL for (int i = 0; i < 64; i++) f[i] = s * T::to_scalar(ib[i]);
+}
+
+template <class Reader>
+ZFB_HD void decode_block(float (&f)[64], unsigned maxbits, Reader& r, const tables& tb, const plane_rows& ps)
+{
+  planes64 P;
+  int emax;
+  bool low_used;
+  const bool nonzero = decode_planes(P, emax, low_used, maxbits, r, tb, ps);
+  decode_finish(f, P, emax, nonzero, low_used);
+}
+
+}  // namespace f3
+}  // namespace zfb

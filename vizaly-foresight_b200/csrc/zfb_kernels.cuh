@@ -21,6 +21,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include "zfb_codec.cuh"
+#include "zfb_codec_f3.cuh"
 
 namespace zfb {
 
@@ -103,6 +104,31 @@ struct geom {
 
 constexpr int PART_STRIDE = 8;  // doubles per CTA row in the partials scratch
 
+// float/3D coder tables in shared memory (zfb_codec_f3.cuh); every thread of the CTA must call this
+struct coder_smem {
+  uint32_t dec[512];
+  uint16_t enc[256];
+};
+__device__ __forceinline__ f3::tables build_coder_tables(coder_smem& cs)
+{
+  for (unsigned i = threadIdx.x; i < 512; i += blockDim.x) cs.dec[i] = f3::dec_entry(i >> 8, i & 255u);
+  for (unsigned i = threadIdx.x; i < 256; i += blockDim.x) cs.enc[i] = f3::enc_entry(i);
+  __syncthreads();
+  f3::tables t;
+  t.enc = cs.enc; t.dec = cs.dec;
+  return t;
+}
+
+// plane scratch of the float/3D coder for kernels without a shared-memory tile (generic path):
+// 16 rows x blockDim (128) x 16 B; only the float/3D instantiations carry it
+template <bool FAST> struct fast_scratch {
+  __device__ __forceinline__ f3::plane_rows rows() { f3::plane_rows r; r.p = nullptr; r.stride = 0; return r; }
+};
+template <> struct fast_scratch<true> {
+  f3::u32x4 buf[16 * 128];
+  __device__ __forceinline__ f3::plane_rows rows() { f3::plane_rows r; r.p = buf + threadIdx.x; r.stride = 128; return r; }
+};
+
 // ---------------------------------------------------------------------------------------------
 // metric accumulation (one thread)
 // ---------------------------------------------------------------------------------------------
@@ -135,9 +161,9 @@ struct frow {
     const float ad = fabsf(d);
     const float ao = fabsf(o);
     // relError(o, a, 1): |o| < 1 -> absolute error, else |d|/|o| (relativeError.hpp:66-75)
-    float q;
-    if (ao > 8.0e37f) q = ad / ao;    // __fdividef returns 0 for huge divisors
-    else q = __fdividef(ad, ao);
+    // __fdividef (MUFU.RCP + FMUL, <= 2 ulp) misbehaves for divisors above 2^126, so both operands are
+    // scaled by 1/4 first (exact); the metric tolerance is 1e-6 relative
+    const float q = __fdividef(ad * 0.25f, ao * 0.25f);
     const float rl = ao < 1.0f ? ad : q;
     ssq = fmaf(d, d, ssq);
     sab += ad;
@@ -241,6 +267,12 @@ __global__ void __launch_bounds__(128) enc_generic_kernel(const Scalar* __restri
                                                           geom g, unsigned maxbits, int edge_only)
 {
   constexpr int BS = 1 << (2 * DIMS);
+  constexpr bool FAST = sizeof(Scalar) == 4 && DIMS == 3;
+  __shared__ coder_smem cs;
+  __shared__ fast_scratch<FAST> fsc;
+  f3::tables tb;
+  if (FAST) tb = build_coder_tables(cs);
+  const f3::plane_rows ps = fsc.rows();
   const bool aligned = (maxbits & 63u) == 0;
   for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < g.nblocks; b += (size_t)gridDim.x * blockDim.x) {
     const size_t ix = b % g.bx, iy = (b / g.bx) % g.by, iz = b / (g.bx * g.by);
@@ -272,12 +304,23 @@ __global__ void __launch_bounds__(128) enc_generic_kernel(const Scalar* __restri
           }
       if (!full) pad_block<Scalar, DIMS>(f, mx, my, mz);
     }
-    if (aligned) {
-      aligned_sink sink(stream + b * (size_t)(maxbits >> 6), maxbits >> 6);
-      encode_block<Scalar, DIMS>(f, maxbits, sink);
+    if constexpr (FAST) {
+      uint32_t* s32 = reinterpret_cast<uint32_t*>(stream);
+      if (aligned) {
+        f3::sink32 sink(s32 + b * (size_t)(maxbits >> 5), maxbits >> 5);
+        f3::encode_block(f, maxbits, sink, tb, ps);
+      } else {
+        f3::or_sink32 sink(s32, b * (size_t)maxbits, maxbits);
+        f3::encode_block(f, maxbits, sink, tb, ps);
+      }
     } else {
-      or_sink sink(stream, b * (size_t)maxbits, maxbits);
-      encode_block<Scalar, DIMS>(f, maxbits, sink);
+      if (aligned) {
+        aligned_sink sink(stream + b * (size_t)(maxbits >> 6), maxbits >> 6);
+        encode_block<Scalar, DIMS>(f, maxbits, sink);
+      } else {
+        or_sink sink(stream, b * (size_t)maxbits, maxbits);
+        encode_block<Scalar, DIMS>(f, maxbits, sink);
+      }
     }
   }
 }
@@ -288,7 +331,13 @@ __global__ void __launch_bounds__(128) dec_generic_kernel(const uint64_t* __rest
                                                           int edge_only, double* __restrict__ part)
 {
   constexpr int BS = 1 << (2 * DIMS);
+  constexpr bool FAST = sizeof(Scalar) == 4 && DIMS == 3;
   __shared__ double red[7 * 4];
+  __shared__ coder_smem cs;
+  __shared__ fast_scratch<FAST> fsc;
+  f3::tables tb;
+  if (FAST) tb = build_coder_tables(cs);
+  const f3::plane_rows ps = fsc.rows();
   macc m;
   m.init();
   for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < g.nblocks; b += (size_t)gridDim.x * blockDim.x) {
@@ -302,9 +351,17 @@ __global__ void __launch_bounds__(128) dec_generic_kernel(const uint64_t* __rest
     const size_t startbit = b * (size_t)maxbits;
     const size_t w0 = startbit >> 6;
     const size_t left = g.stream_words - w0;
-    slot_reader r(stream + w0, left > 0xffffffffull ? 0xffffffffu : (unsigned)left, (unsigned)(startbit & 63));
     Scalar f[BS];
-    decode_block<Scalar, DIMS>(f, maxbits, r);
+    if constexpr (FAST) {
+      const size_t v0 = startbit >> 5;
+      const size_t left32 = 2 * g.stream_words - v0;
+      f3::reader32 r(reinterpret_cast<const uint32_t*>(stream) + v0, left32 > 0xffffffffull ? 0xffffffffu : (unsigned)left32,
+                     (unsigned)(startbit & 31));
+      f3::decode_block(f, maxbits, r, tb, ps);
+    } else {
+      slot_reader r(stream + w0, left > 0xffffffffull ? 0xffffffffu : (unsigned)left, (unsigned)(startbit & 63));
+      decode_block<Scalar, DIMS>(f, maxbits, r);
+    }
     if (DIMS == 1 && full && sizeof(Scalar) == 4) {
       if constexpr (sizeof(Scalar) == 4) {
         float4 v;
@@ -383,7 +440,10 @@ __device__ __forceinline__ box_info box_of(const tile_geom& tg, unsigned q)
   return b;
 }
 
-// dynamic shared memory layout (encode): [tile: 2 boxes x 16 KiB][out: 128*W words][2 mbarriers]
+// dynamic shared memory layout (encode): [tile: 2 boxes x 16 KiB][out: 2 x 128*W words][2 mbarriers]
+// Per tile: wait for the TMA boxes -> 16 LDS.128 per thread -> transform in registers -> bit planes parked
+// in the thread's own 16-byte columns of the tile (in place) -> plane loop emits the slot into out[it&1]
+// -> one __syncthreads -> thread 0 issues the next tile's TMA loads and this tile's bulk store.
 __global__ void __launch_bounds__(TILE_THREADS, 4)
 enc3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t* __restrict__ stream, tile_geom tg,
                      unsigned maxbits)
@@ -391,7 +451,9 @@ enc3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t* __restr
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   float* tile = reinterpret_cast<float*>(smem_raw);
   uint64_t* outw = reinterpret_cast<uint64_t*>(smem_raw + BOXES_PER_TILE * BOX_FLOATS * sizeof(float));
-  uint64_t* bars = outw + (size_t)TILE_THREADS * tg.W;
+  const unsigned out_words = TILE_THREADS * tg.W;
+  uint64_t* bars = outw + 2 * (size_t)out_words;
+  __shared__ coder_smem cs;
 
   const unsigned tid = threadIdx.x;
   const unsigned box = tid >> 6, lb = tid & 63;
@@ -402,7 +464,7 @@ enc3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t* __restr
     ptx::mbar_init(&bars[1], 1);
     ptx::fence_barrier_init();
   }
-  __syncthreads();
+  const f3::tables tb = build_coder_tables(cs);  // includes the __syncthreads that publishes the barriers
 
   auto issue_loads = [&](unsigned t) {
 #pragma unroll
@@ -418,43 +480,49 @@ enc3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t* __restr
   unsigned t = blockIdx.x;
   if (tid == 0 && t < tg.ntiles) issue_loads(t);
 
+  f3::plane_rows ps;
+  ps.p = reinterpret_cast<f3::u32x4*>(tile + box * BOX_FLOATS) + lb;
+  ps.stride = 64;
+
   for (unsigned it = 0; t < tg.ntiles; t += gridDim.x, it++) {
     const box_info b0 = box_of(tg, 2 * t), b1 = box_of(tg, 2 * t + 1);
     const box_info mine = box ? b1 : b0;
     const bool active = lb < mine.nvalid;
-    float f[64];
+    uint64_t* obuf = outw + (size_t)(it & 1) * out_words;
     if (mine.nvalid) {
       ptx::mbar_wait(&bars[box], it & 1);
       if (active) {
+        float f[64];
         const float4* src = reinterpret_cast<const float4*>(tile + box * BOX_FLOATS) + lb;
 #pragma unroll
         for (int r = 0; r < 16; r++) {
           const float4 v = src[r * 64];  // row r of the box is 256 floats = 64 float4
           f[4 * r] = v.x; f[4 * r + 1] = v.y; f[4 * r + 2] = v.z; f[4 * r + 3] = v.w;
         }
+        const unsigned p = (box ? b0.nvalid : 0u) + lb;  // slot position inside the tile's contiguous span
+        f3::sink32 sink(reinterpret_cast<uint32_t*>(obuf + (size_t)p * tg.W), 2 * tg.W);
+        f3::encode_block(f, maxbits, sink, tb, ps);
       }
     }
-    if (tid == 0) ptx::bulk_wait_read0();  // previous tile's slot store has finished reading `outw`
-    __syncthreads();                      // tile buffer consumed; outw free
-    if (tid == 0 && t + gridDim.x < tg.ntiles) issue_loads(t + gridDim.x);
-
-    const unsigned p = (box ? b0.nvalid : 0u) + lb;  // slot position inside the tile's contiguous span
-    if (active) {
-      aligned_sink sink(outw + (size_t)p * tg.W, tg.W);
-      encode_block<float, 3>(f, maxbits, sink);
-    }
-    ptx::fence_proxy_async();
-    __syncthreads();
+    ptx::fence_proxy_async();              // slot words and the in-place plane rows -> async proxy
+    if (tid == 0) ptx::bulk_wait_read0();  // the store issued one tile ago has finished reading out[(it-1)&1]
+    __syncthreads();                       // tile buffer and out[it&1] complete; out[(it+1)&1] free
     if (tid == 0) {
+      if (t + gridDim.x < tg.ntiles) issue_loads(t + gridDim.x);
       const unsigned nslots = b0.nvalid + b1.nvalid;
-      ptx::bulk_store(stream + b0.blk0 * tg.W, outw, nslots * tg.W * 8u);
+      ptx::bulk_store(stream + b0.blk0 * tg.W, obuf, nslots * tg.W * 8u);
       ptx::bulk_commit();
     }
   }
   if (tid == 0) ptx::bulk_wait0();
 }
 
-// dynamic shared memory layout (decode): [orig tile: 2 x 16 KiB (METRICS only)][slots: 2 x 128*W words][4 mbarriers]
+// dynamic shared memory layout (decode): [tile: 2 x 16 KiB plane scratch, then the original boxes]
+//                                        [slots: 2 x 128*W words][4 mbarriers]
+// Per tile: wait for the slot span (bulk copy, two tiles ahead) -> plane loop parses the slot into the
+// thread's plane rows -> rows back into registers -> __syncthreads -> thread 0 starts the TMA load of the
+// ORIGINAL boxes into the same buffer while all threads run the inverse transform -> metrics against the
+// original rows (LDS.128) -> 16 coalesced 128-bit stores of the decoded rows -> __syncthreads.
 template <bool METRICS>
 __global__ void __launch_bounds__(TILE_THREADS, 4)
 dec3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64_t* __restrict__ stream,
@@ -462,10 +530,11 @@ dec3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64
 {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   float* tile = reinterpret_cast<float*>(smem_raw);
-  uint64_t* slots = reinterpret_cast<uint64_t*>(smem_raw + (METRICS ? BOXES_PER_TILE * BOX_FLOATS * sizeof(float) : 0));
+  uint64_t* slots = reinterpret_cast<uint64_t*>(smem_raw + BOXES_PER_TILE * BOX_FLOATS * sizeof(float));
   const unsigned slot_words = TILE_THREADS * tg.W;
   uint64_t* bars = slots + 2 * (size_t)slot_words;  // [0,1] slots full (double buffer), [2,3] orig boxes full
   __shared__ double red[7 * 4];
+  __shared__ coder_smem cs;
 
   const unsigned tid = threadIdx.x;
   const unsigned box = tid >> 6, lb = tid & 63;
@@ -475,7 +544,7 @@ dec3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64
     for (int i = 0; i < 4; i++) ptx::mbar_init(&bars[i], 1);
     ptx::fence_barrier_init();
   }
-  __syncthreads();
+  const f3::tables tb = build_coder_tables(cs);  // includes the __syncthreads that publishes the barriers
 
   auto issue_slots = [&](unsigned t, unsigned buf) {
     const box_info b0 = box_of(tg, 2 * t), b1 = box_of(tg, 2 * t + 1);
@@ -496,9 +565,13 @@ dec3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64
 
   unsigned t = blockIdx.x;
   if (tid == 0) {
-    if (t < tg.ntiles) { issue_slots(t, 0); if (METRICS) issue_orig(t); }
+    if (t < tg.ntiles) issue_slots(t, 0);
     if (t + gridDim.x < tg.ntiles) issue_slots(t + gridDim.x, 1);
   }
+
+  f3::plane_rows ps;
+  ps.p = reinterpret_cast<f3::u32x4*>(tile + box * BOX_FLOATS) + lb;
+  ps.stride = 64;
 
   macc m;
   m.init();
@@ -509,11 +582,23 @@ dec3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64
     const bool active = lb < mine.nvalid;
     const unsigned nslots = b0.nvalid + b1.nvalid;
     ptx::mbar_wait(&bars[buf], (it >> 1) & 1);
+    f3::planes64 P;
+    int emax = 0;
+    bool nonzero = false, low_used = false;
     if (active) {
       const unsigned p = (box ? b0.nvalid : 0u) + lb;
-      slot_reader r(slots + (size_t)buf * slot_words + (size_t)p * tg.W, (nslots - p) * tg.W, 0);
+      f3::reader32 r(reinterpret_cast<const uint32_t*>(slots + (size_t)buf * slot_words + (size_t)p * tg.W),
+                     2 * (nslots - p) * tg.W, 0);
+      nonzero = f3::decode_planes(P, emax, low_used, maxbits, r, tb, ps);
+    }
+    if (METRICS) {
+      ptx::fence_proxy_async();  // plane-row writes (generic proxy) before the TMA load overwrites the buffer
+      __syncthreads();           // every thread has its planes back in registers
+      if (tid == 0) issue_orig(t);
+    }
+    if (active) {
       float f[64];
-      decode_block<float, 3>(f, maxbits, r);
+      f3::decode_finish(f, P, emax, nonzero, low_used);
       float* dst = out + ((size_t)mine.z0 * tg.ny + mine.y0) * tg.nx + mine.x0 + 4 * lb;
       if (METRICS) {
         ptx::mbar_wait(&bars[2 + box], it & 1);
@@ -538,11 +623,10 @@ dec3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64
     } else if (METRICS && mine.nvalid) {
       ptx::mbar_wait(&bars[2 + box], it & 1);  // keep every thread's view of the barrier phase in step
     }
-    __syncthreads();  // slots[buf] and the orig tile are consumed
+    __syncthreads();  // slots[buf] and the tile buffer are consumed
     if (tid == 0) {
-      const unsigned t2 = t + 2 * gridDim.x, t1 = t + gridDim.x;
+      const unsigned t2 = t + 2 * gridDim.x;
       if (t2 < tg.ntiles) issue_slots(t2, buf);
-      if (METRICS && t1 < tg.ntiles) issue_orig(t1);
     }
   }
   if (METRICS) macc_block_store(m, red, part + (size_t)blockIdx.x * PART_STRIDE);
