@@ -49,7 +49,11 @@ struct plane_rows {
 // ---------------------------------------------------------------------------------------------
 ZFB_HD uint32_t mask32(unsigned m)  // m in [0, 32]
 {
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_rc(0xffffffffu, 0u, 32u - m);  // (0:ffffffff) >> (32 - m), shift clamped to 32
+#else
   return m >= 32 ? 0xffffffffu : ((1u << m) - 1u);
+#endif
 }
 ZFB_HD uint32_t fsr(uint32_t lo, uint32_t hi, unsigned s)  // low word of (hi:lo) >> s, s in [0, 32]
 {
@@ -65,6 +69,14 @@ ZFB_HD uint32_t carry_out(uint32_t v, unsigned s)  // bits of v that fall off th
   return __funnelshift_l(v, 0u, s);
 #else
   return s ? v >> (32 - s) : 0u;
+#endif
+}
+ZFB_HD uint32_t shl_pair(uint32_t lo, uint32_t hi, unsigned s)  // high word of (hi:lo) << s, s in [0, 32)
+{
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_l(lo, hi, s);
+#else
+  return s ? (hi << s) | (lo >> (32 - s)) : hi;
 #endif
 }
 ZFB_HD int popc32(uint32_t v)
@@ -190,6 +202,12 @@ struct sink32 {  // slot on a word boundary, whole number of 32-bit words (maxbi
     if (widx < nwords) dst[widx] = w;
     widx++;
   }
+  ZFB_HD void word2(uint32_t w0, uint32_t w1)
+  {
+    if (widx + 2 <= nwords) { dst[widx] = w0; dst[widx + 1] = w1; }
+    else if (widx < nwords) dst[widx] = w0;
+    widx += 2;
+  }
   ZFB_HD void finish()
   {
     for (; widx < nwords; widx++) dst[widx] = 0;
@@ -222,6 +240,7 @@ struct or_sink32 {  // arbitrary bit offset in a pre-zeroed stream (maxbits % 64
     const uint32_t c = carry_out(w, s);
     if (c) or32(base + (pos >> 5) + 1, c);
   }
+  ZFB_HD void word2(uint32_t w0, uint32_t w1) { word(w0); word(w1); }
   ZFB_HD void finish() {}
 };
 
@@ -238,6 +257,14 @@ template <class Sink> struct writer32 {
     cnt += len;
     total += len;
     if (cnt >= 32) { sink.word(acc); acc = c; cnt -= 32; }
+  }
+  ZFB_HD void put64(uint32_t xl, uint32_t xh)  // a whole plane of 64 significant coefficients
+  {
+    const uint32_t w0 = acc | (xl << cnt);
+    const uint32_t w1 = shl_pair(xl, xh, cnt);
+    acc = carry_out(xh, cnt);
+    sink.word2(w0, w1);
+    total += 64;
   }
   ZFB_HD void flush()
   {
@@ -312,6 +339,7 @@ ZFB_HD void encode_block(const float (&f)[64], unsigned maxbits, Sink& sink, con
     }
     if (k & 1) cur = ps.ld(k >> 1);
     const uint32_t xl = (k & 1) ? cur.z : cur.x, xh = (k & 1) ? cur.w : cur.y;
+    if (n == 64u) { bw.put64(xl, xh); continue; }  // every coefficient significant: the plane goes out verbatim
     uint32_t yl, yh;
     if (n == 0) { yl = xl; yh = xh; }
     else if (n < 32) {
@@ -320,29 +348,28 @@ ZFB_HD void encode_block(const float (&f)[64], unsigned maxbits, Sink& sink, con
     } else {
       bw.put(xl, 32);
       bw.put(xh & mask32(n - 32), n - 32);
-      yl = n < 64 ? xh >> (n - 32) : 0u; yh = 0u;
+      yl = xh >> (n - 32); yh = 0u;
     }
-    if (n < 64) {
-      if ((yl | yh) == 0u) bw.put(0u, 1);
-      else {
-        const unsigned plast = yh ? 32u + (unsigned)msb32(yh) : (unsigned)msb32(yl);
-        const unsigned nfull = plast >> 3;                 // bytes before the one holding the last one-bit
-        bw.put(1u, 1);                                     // first group test
-        for (unsigned j = 0; j < nfull; j++) {
-          const uint32_t b = yl & 0xffu;
-          bw.put(tb.enc[b], 8u + (unsigned)popc32(b));
-          yl = fsr(yl, yh, 8); yh >>= 8;
-        }
-        {
-          const uint32_t b = yl & 0xffu;
-          uint32_t e = tb.enc[b];
-          unsigned len = (plast & 7u) + 1u + (unsigned)popc32(b);
-          if (n + plast == 63u) len -= 2;                  // the last coefficient's one is implicit, no test follows
-          else e &= ~(1u << (len - 1));                    // final group test: no more ones in this plane
-          bw.put(e & mask32(len), len);
-        }
-        n += plast + 1u;
+    if ((yl | yh) == 0u) bw.put(0u, 1);
+    else {
+      const unsigned plast = yh ? 32u + (unsigned)msb32(yh) : (unsigned)msb32(yl);
+      const unsigned nfull = plast >> 3;                 // bytes before the one holding the last one-bit
+      uint32_t lead = 1u;                                // the first group test rides on the first byte's code
+      for (unsigned j = 0; j < nfull; j++) {
+        const uint32_t b = yl & 0xffu;
+        bw.put((tb.enc[b] << lead) | lead, 8u + (unsigned)popc32(b) + lead);
+        lead = 0u;
+        yl = fsr(yl, yh, 8); yh >>= 8;
       }
+      {
+        const uint32_t b = yl & 0xffu;
+        uint32_t e = tb.enc[b];
+        unsigned len = (plast & 7u) + 1u + (unsigned)popc32(b);
+        if (n + plast == 63u) len -= 2;                  // the last coefficient's one is implicit, no test follows
+        else e &= ~(1u << (len - 1));                    // final group test: no more ones in this plane
+        bw.put(((e & mask32(len)) << lead) | lead, len + lead);
+      }
+      n += plast + 1u;
     }
   }
   bw.flush();
@@ -358,8 +385,9 @@ struct reader32 {
   unsigned nwords, widx;
   uint32_t lo, hi;
   unsigned avail;
+  unsigned bit0;  // bit offset of the slot inside word 0
   // p = first word of the slot region, n = words that may be read from p, startbit < 32
-  ZFB_HD reader32(const uint32_t* p, unsigned n, unsigned startbit) : w(p), nwords(n), widx(2), avail(64)
+  ZFB_HD reader32(const uint32_t* p, unsigned n, unsigned startbit) : w(p), nwords(n), widx(2), avail(64), bit0(startbit)
   {
     lo = n > 0 ? p[0] : 0u;
     hi = n > 1 ? p[1] : 0u;
@@ -383,6 +411,15 @@ struct reader32 {
     const uint32_t v = lo & mask32(k);
     consume(k);
     return v;
+  }
+  ZFB_HD uint32_t word_at(unsigned i) const { return i < nwords ? w[i] : 0u; }
+  // 64 stream bits starting `pos` bits into the slot, straight from memory (independent of the window)
+  ZFB_HD void read64_at(unsigned pos, uint32_t& xl, uint32_t& xh) const
+  {
+    const unsigned p = pos + bit0, i = p >> 5, sh = p & 31u;
+    const uint32_t w0 = word_at(i), w1 = word_at(i + 1), w2 = word_at(i + 2);
+    xl = fsr(w0, w1, sh);
+    xh = fsr(w1, w2, sh);
   }
 };
 
@@ -412,46 +449,77 @@ ZFB_HD bool decode_planes(planes64& P, int& emax, bool& low_used_out, unsigned m
   ZFB_NOUNROLL for (; k >= 0; k--) {
     if (!remaining) break;
     if (k == 15) low_used = true;
-    const unsigned m = n < remaining ? n : remaining;
-    remaining -= m;
     uint32_t xl = 0u, xh = 0u;
-    if (m > 32) { xl = r.take(32); xh = r.take(m - 32); }
-    else if (m) xl = r.take(m);
-    unsigned state = 0;
-    while (n < 64u && remaining) {
-      const uint32_t e = tb.dec[(state << 8) | (r.lo & 0xffu)];
-      const unsigned npos = (e >> 8) & 15u, nbits = (e >> 12) & 15u;
-      if (n + npos <= 63u && nbits <= remaining) {
-        // table step: deposit up to 8 coefficient bits at once
+    if (n == 64u) {
+      // every coefficient significant: the plane is the next min(64, remaining) stream bits
+      const unsigned m = remaining < 64u ? remaining : 64u;
+      r.read64_at(maxbits - remaining, xl, xh);
+      if (m < 64u) {
+        if (m < 32u) { xl &= mask32(m); xh = 0u; }
+        else xh &= mask32(m - 32u);
+      }
+      remaining -= m;
+    } else {
+      const unsigned m = n < remaining ? n : remaining;
+      remaining -= m;
+      if (m > 32) { xl = r.take(32); xh = r.take(m - 32); }
+      else if (m) xl = r.take(m);
+      unsigned state = 0;
+      while (n < 64u && remaining) {
+        uint32_t wb = r.lo;
+        const bool forced = remaining < 8u;
+        // at the end of the budget a terminator is forced behind the last valid bit: in state B it becomes
+        // the one zfp's decoder deposits when the budget ends inside a zero run, in state A it deposits nothing
+        if (forced) wb = (wb & mask32(remaining)) | (1u << remaining);
+        const uint32_t e = tb.dec[(state << 8) | (wb & 0xffu)];
+        const unsigned npos = (e >> 8) & 15u, nbits = (e >> 12) & 15u;
         const uint32_t pat = e & 0xffu;
-        if (n < 32) { xl |= pat << n; xh |= carry_out(pat, n); }
-        else xh |= pat << (n - 32);
-        n += npos;
-        remaining -= nbits;
-        r.consume(nbits);
-        state = (e >> 16) & 3u;
-        if (state == 2u) break;
-      } else {
-        // exact single-bit step near the end of the budget or of the block (zfp's loop conditions)
-        if (state == 0u) {
-          remaining--;
-          if (!r.take(1)) break;
-          state = 1u;
+        if (n + npos <= 63u) {
+          // table step: deposit up to 8 coefficient bits at once
+          if (n < 32) { xl |= pat << n; xh |= carry_out(pat, n); }
+          else xh |= pat << (n - 32);
+          n += npos;
+          if (nbits > remaining) { remaining = 0u; state = 0u; break; }  // ran into the forced terminator
+          remaining -= nbits;
+          r.consume(nbits);
+          state = (e >> 16) & 3u;
+          if (state == 2u) break;
+        } else if (!forced) {
+          // the step would read a bit for coefficient 63, whose one is implicit: keep the L = 63 - n positions
+          // before it; they used L coefficient bits, one test bit per deposited one, and the opening test bit
+          const unsigned L = 63u - n;
+          const uint32_t pt = pat & mask32(L);
+          const unsigned nb = L + (unsigned)popc32(pt) + (state == 0u ? 1u : 0u);
+          if (n < 32) { xl |= pt << n; xh |= carry_out(pt, n); }
+          else xh |= pt << (n - 32);
+          xh |= 0x80000000u;
+          n = 64u;
+          remaining -= nb;
+          r.consume(nb);
+          state = 0u;
+          break;
         } else {
-          bool one = true;
-          if (n < 63u && remaining) { remaining--; one = r.take(1) != 0u; }
-          if (one) {
-            if (n < 32) xl |= 1u << n; else xh |= 1u << (n - 32);
-            state = 0u;
+          // budget end and block end together (rare): exact single-bit steps with zfp's loop conditions
+          if (state == 0u) {
+            remaining--;
+            if (!r.take(1)) break;
+            state = 1u;
+          } else {
+            bool one = true;
+            if (n < 63u && remaining) { remaining--; one = r.take(1) != 0u; }
+            if (one) {
+              if (n < 32) xl |= 1u << n; else xh |= 1u << (n - 32);
+              state = 0u;
+            }
+            n++;
           }
-          n++;
         }
       }
-    }
-    if (state == 1u) {
-      // the budget ran out inside a zero run: zfp's decoder still deposits a one at the current index
-      if (n < 32) xl |= 1u << n; else xh |= 1u << (n - 32);
-      n++;
+      if (state == 1u) {
+        // the budget ran out inside a zero run: zfp's decoder still deposits a one at the current index
+        if (n < 32) xl |= 1u << n; else xh |= 1u << (n - 32);
+        n++;
+      }
     }
     if (k & 1) { cur.z = xl; cur.w = xh; }
     else { cur.x = xl; cur.y = xh; ps.st(k >> 1, cur); }

@@ -161,9 +161,11 @@ struct frow {
     const float ad = fabsf(d);
     const float ao = fabsf(o);
     // relError(o, a, 1): |o| < 1 -> absolute error, else |d|/|o| (relativeError.hpp:66-75)
-    // __fdividef (MUFU.RCP + FMUL, <= 2 ulp) misbehaves for divisors above 2^126, so both operands are
-    // scaled by 1/4 first (exact); the metric tolerance is 1e-6 relative
-    const float q = __fdividef(ad * 0.25f, ao * 0.25f);
+    // div.approx.ftz (MUFU.RCP + FMUL, <= 2 ulp, no denormal fix-up code) returns 0 for divisors above
+    // 2^126, so both operands are scaled by 1/4 first (exact); q is only used when |o| >= 1, and the
+    // metric tolerance is 1e-6 relative
+    float q;
+    asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(q) : "f"(ad * 0.25f), "f"(ao * 0.25f));
     const float rl = ao < 1.0f ? ad : q;
     ssq = fmaf(d, d, ssq);
     sab += ad;
