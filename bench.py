@@ -239,21 +239,15 @@ def main():
     codec = pkg.Codec(local)
     codec.use_torch_stream()
     want_metrics = dtype == "float32" or True
-    red_sum = torch.zeros(4, dtype=torch.float64, device=dev)
-    red_max = torch.zeros(4, dtype=torch.float64, device=dev)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("zfb_dist", os.path.join(ROOT, "vizaly-foresight_b200", "dist.py"))
+    zdist = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(zdist)
+    scratch = (torch.zeros(4, dtype=torch.float64, device=dev), torch.zeros(4, dtype=torch.float64, device=dev))
 
     def allreduce_partials():
-        # the only exchange step: three tiny NCCL all-reduces over NVLink (SUM f64[3]+n, MAX f64[4])
-        p = codec.partials_tensor()
-        pf = p.view(torch.float64)
-        red_sum[:3] = pf[:3]
-        red_sum[3] = p[7].to(torch.float64)
-        red_max[:] = pf[3:7]
-        dist.all_reduce(red_sum, op=dist.ReduceOp.SUM)
-        dist.all_reduce(red_max, op=dist.ReduceOp.MAX)
-        pf[:3] = red_sum[:3]
-        pf[3:7] = red_max
-        p[7] = red_sum[3].to(torch.int64)
+        # the only exchange step: two tiny NCCL all-reduces over NVLink (SUM f64[3]+n, MAX f64[4])
+        zdist.allreduce_partials(codec.partials_tensor(), dist, scratch)
 
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
 
