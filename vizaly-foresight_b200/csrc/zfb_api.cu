@@ -149,7 +149,7 @@ extern "C" void zfb_partials_combine(zfb_partials* acc, const zfb_partials* in, 
 static const size_t ENC_TILE_SMEM_BASE = BOXES_PER_TILE * BOX_FLOATS * sizeof(float);
 
 // [tile / plane scratch 32 KiB][2 x slot staging][mbarriers]  (layouts documented at the kernels)
-static size_t enc_tile_smem(unsigned W) { return ENC_TILE_SMEM_BASE + 2 * (size_t)TILE_THREADS * W * 8 + 2 * 8; }
+static size_t enc_tile_smem(unsigned W) { return ENC_TILE_SMEM_BASE + (size_t)TILE_THREADS * W * 8 + 2 * 8; }
 static size_t dec_tile_smem(unsigned W, bool /*metrics*/)
 {
   return ENC_TILE_SMEM_BASE + 2 * (size_t)TILE_THREADS * W * 8 + 4 * 8;

@@ -406,6 +406,19 @@ struct reader32 {
       avail += 32;
     }
   }
+  ZFB_HD void consume_small(unsigned k)  // k in [0, 31]
+  {
+    lo = fsr(lo, hi, k);
+    hi >>= k;
+    avail -= k;
+    if (avail < 32) {
+      const uint32_t nw = widx < nwords ? w[widx] : 0u;
+      widx++;
+      lo |= nw << avail;
+      hi = carry_out(nw, avail);
+      avail += 32;
+    }
+  }
   ZFB_HD uint32_t take(unsigned k)  // k in [0, 32]
   {
     const uint32_t v = lo & mask32(k);
@@ -465,7 +478,21 @@ ZFB_HD bool decode_planes(planes64& P, int& emax, bool& low_used_out, unsigned m
       if (m > 32) { xl = r.take(32); xh = r.take(m - 32); }
       else if (m) xl = r.take(m);
       unsigned state = 0;
-      while (n < 64u && remaining) {
+      // fast steps: far from the end of the budget (>= 16 bits) and of the block (n <= 48) a table step
+      // (<= 8 stream bits, <= 8 coefficients) cannot run into either limit, so only "end of plane" is tested
+      while (remaining >= 16u && n <= 48u) {
+        const uint32_t e = tb.dec[(state << 8) | (r.lo & 0xffu)];
+        const unsigned npos = (e >> 8) & 15u, nbits = (e >> 12) & 15u;
+        const uint32_t pat = e & 0xffu;
+        if (n < 32) { xl |= pat << n; xh |= carry_out(pat, n); }
+        else xh |= pat << (n - 32);
+        n += npos;
+        remaining -= nbits;
+        r.consume_small(nbits);
+        state = (e >> 16) & 3u;
+        if (state == 2u) break;
+      }
+      while (state != 2u && n < 64u && remaining) {
         uint32_t wb = r.lo;
         const bool forced = remaining < 8u;
         // at the end of the budget a terminator is forced behind the last valid bit: in state B it becomes

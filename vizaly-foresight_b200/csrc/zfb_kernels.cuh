@@ -442,11 +442,13 @@ __device__ __forceinline__ box_info box_of(const tile_geom& tg, unsigned q)
   return b;
 }
 
-// dynamic shared memory layout (encode): [tile: 2 boxes x 16 KiB][out: 2 x 128*W words][2 mbarriers]
+// dynamic shared memory layout (encode): [tile: 2 boxes x 16 KiB][out: 128*W words][2 mbarriers]
 // Per tile: wait for the TMA boxes -> 16 LDS.128 per thread -> transform in registers -> bit planes parked
-// in the thread's own 16-byte columns of the tile (in place) -> plane loop emits the slot into out[it&1]
-// -> one __syncthreads -> thread 0 issues the next tile's TMA loads and this tile's bulk store.
-__global__ void __launch_bounds__(TILE_THREADS, 4)
+// in the thread's own 16-byte columns of the tile (in place) -> plane loop emits the slot into `out`
+// -> one __syncthreads -> thread 0 issues this tile's bulk store, waits until the store has read `out`,
+// and only then issues the next tile's TMA loads: every thread waits for those loads before it touches
+// `out` again, so one staging buffer is enough (43 KiB per CTA -> 5 CTAs per SM at 95 registers).
+__global__ void __launch_bounds__(TILE_THREADS, 5)
 enc3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t* __restrict__ stream, tile_geom tg,
                      unsigned maxbits)
 {
@@ -454,7 +456,7 @@ enc3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t* __restr
   float* tile = reinterpret_cast<float*>(smem_raw);
   uint64_t* outw = reinterpret_cast<uint64_t*>(smem_raw + BOXES_PER_TILE * BOX_FLOATS * sizeof(float));
   const unsigned out_words = TILE_THREADS * tg.W;
-  uint64_t* bars = outw + 2 * (size_t)out_words;
+  uint64_t* bars = outw + (size_t)out_words;
   __shared__ coder_smem cs;
 
   const unsigned tid = threadIdx.x;
@@ -490,7 +492,7 @@ enc3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t* __restr
     const box_info b0 = box_of(tg, 2 * t), b1 = box_of(tg, 2 * t + 1);
     const box_info mine = box ? b1 : b0;
     const bool active = lb < mine.nvalid;
-    uint64_t* obuf = outw + (size_t)(it & 1) * out_words;
+    uint64_t* obuf = outw;
     if (mine.nvalid) {
       ptx::mbar_wait(&bars[box], it & 1);
       if (active) {
@@ -507,13 +509,13 @@ enc3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t* __restr
       }
     }
     ptx::fence_proxy_async();              // slot words and the in-place plane rows -> async proxy
-    if (tid == 0) ptx::bulk_wait_read0();  // the store issued one tile ago has finished reading out[(it-1)&1]
-    __syncthreads();                       // tile buffer and out[it&1] complete; out[(it+1)&1] free
+    __syncthreads();                       // tile buffer consumed, `out` complete
     if (tid == 0) {
-      if (t + gridDim.x < tg.ntiles) issue_loads(t + gridDim.x);
       const unsigned nslots = b0.nvalid + b1.nvalid;
       ptx::bulk_store(stream + b0.blk0 * tg.W, obuf, nslots * tg.W * 8u);
       ptx::bulk_commit();
+      ptx::bulk_wait_read0();              // `out` may be rewritten once the next tile's loads have landed
+      if (t + gridDim.x < tg.ntiles) issue_loads(t + gridDim.x);
     }
   }
   if (tid == 0) ptx::bulk_wait0();
