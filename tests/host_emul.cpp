@@ -7,6 +7,7 @@
 #include <cstddef>
 #include "../vizaly-foresight_b200/csrc/zfb_codec.cuh"
 #include "../vizaly-foresight_b200/csrc/zfb_codec_f3.cuh"
+#include "../vizaly-foresight_b200/csrc/zfb_codec_f1.cuh"
 #include <type_traits>
 
 using namespace zfb;
@@ -24,6 +25,22 @@ static f3::tables host_tables()
   }
   f3::tables t;
   t.enc = g_enc; t.dec = g_dec;
+  return t;
+}
+
+static uint16_t g1_enc[64], g1_dec[512];
+static uint32_t g1_spread[256];
+static f1::tables host_tables1()
+{
+  static bool built = false;
+  if (!built) {
+    for (unsigned i = 0; i < 64; i++) g1_enc[i] = f1::enc_entry(i);
+    for (unsigned i = 0; i < 512; i++) g1_dec[i] = f1::dec_entry(i);
+    for (unsigned i = 0; i < 256; i++) g1_spread[i] = f1::spread_entry(i);
+    built = true;
+  }
+  f1::tables t;
+  t.enc = g1_enc; t.dec = g1_dec; t.spread = g1_spread;
   return t;
 }
 
@@ -51,6 +68,16 @@ static void run(bool enc, size_t nx, size_t ny, size_t nz, unsigned maxbits, Sca
         for (unsigned j = 0; j < my; j++)
           for (unsigned i = 0; i < mx; i++) f[16 * k + 4 * j + i] = data[(x0 + i) + nx * ((y0 + j) + ny * (z0 + k))];
       if (mx < 4 || my < (DIMS >= 2 ? 4u : 1u) || mz < (DIMS >= 3 ? 4u : 1u)) pad_block<Scalar, DIMS>(f, mx, my, mz);
+      if constexpr (std::is_same<Scalar, float>::value && DIMS == 1) {
+        if (g_use_f3 && mx == 4 && (maxbits % 32) == 0 && maxbits <= 128) {
+          const f1::tables tb = host_tables1();
+          uint32_t o[4];
+          f1::encode_block<4>(f, maxbits, o, tb);
+          uint32_t* s32 = reinterpret_cast<uint32_t*>(stream) + startbit / 32;
+          for (unsigned i = 0; i < maxbits / 32; i++) s32[i] = o[i];
+          continue;
+        }
+      }
       if constexpr (std::is_same<Scalar, float>::value && DIMS == 3) {
         if (g_use_f3) {
           const f3::tables tb = host_tables();
@@ -77,6 +104,16 @@ static void run(bool enc, size_t nx, size_t ny, size_t nz, unsigned maxbits, Sca
       }
     } else {
       bool done = false;
+      if constexpr (std::is_same<Scalar, float>::value && DIMS == 1) {
+        if (g_use_f3 && mx == 4 && (maxbits % 32) == 0 && maxbits <= 128) {
+          const f1::tables tb = host_tables1();
+          uint32_t in4[4] = {0, 0, 0, 0};
+          const uint32_t* s32 = reinterpret_cast<const uint32_t*>(stream) + startbit / 32;
+          for (unsigned i = 0; i < maxbits / 32; i++) in4[i] = s32[i];
+          f1::decode_block<4>(f, maxbits, in4, tb);
+          done = true;
+        }
+      }
       if constexpr (std::is_same<Scalar, float>::value && DIMS == 3) {
         if (g_use_f3) {
           const f3::tables tb = host_tables();

@@ -136,3 +136,30 @@ def test_fast_coder_budget_boundaries(oracle):
             s, g = emul_roundtrip(O, f, mb)
             assert np.array_equal(s, s_ref), mb
             assert np.array_equal(g.view(np.uint8), O.decompress(s_ref, f.shape, np.float32, mb).view(np.uint8)), mb
+
+
+def test_fast_1d_coder(oracle):
+    """float/1D fast coder (zfb_codec_f1.cuh): budgets 32/64/96/128, HACC-like and adversarial arrays."""
+    O = oracle
+    rng = np.random.default_rng(9)
+    n = 4096
+    arrays = {
+        "uniform256": (256 * rng.random(n)).astype(np.float32),
+        "normal900": (900 * rng.standard_normal(n)).astype(np.float32),
+        "smooth": smooth_field((n,), seed=2, amp=50.0),
+        "ramp": np.arange(n, dtype=np.float32) * 0.37,
+        "const": np.full(n, 7.5, np.float32),
+        "zeros": np.zeros(n, np.float32),
+        "sparse": (rng.standard_normal(n) * (rng.random(n) > 0.9)).astype(np.float32),
+        "tiny": (rng.standard_normal(n) * 1e-36).astype(np.float32),
+        "mixed": (rng.standard_normal(n) * 10.0 ** rng.integers(-20, 20, n)).astype(np.float32),
+        "one_of_four": np.tile(np.array([3.0, 0, 0, 0], np.float32), n // 4),
+        "last_of_four": np.tile(np.array([0, 0, 0, -5.0], np.float32), n // 4),
+        "golden_hacc": np.fromfile(os.path.join(ROOT, "tests", "golden", "hacc_m000_x_4096.f32"), dtype=np.float32),
+    }
+    for label, f in arrays.items():
+        for mb in (32, 64, 96, 128):
+            s_ref = O.compress(f, mb)
+            s, g = emul_roundtrip(O, f, mb)
+            assert np.array_equal(s, s_ref), (label, mb)
+            assert np.array_equal(g.view(np.uint8), O.decompress(s_ref, f.shape, np.float32, mb).view(np.uint8)), (label, mb)

@@ -152,7 +152,7 @@ static const size_t ENC_TILE_SMEM_BASE = BOXES_PER_TILE * BOX_FLOATS * sizeof(fl
 static size_t enc_tile_smem(unsigned W) { return ENC_TILE_SMEM_BASE + (size_t)TILE_THREADS * W * 8 + 2 * 8; }
 static size_t dec_tile_smem(unsigned W, bool /*metrics*/)
 {
-  return ENC_TILE_SMEM_BASE + 2 * (size_t)TILE_THREADS * W * 8 + 4 * 8;
+  return ENC_TILE_SMEM_BASE + (size_t)TILE_THREADS * W * 8 + 4 * 8;
 }
 
 extern "C" int zfb_create(zfb_ctx** out, int device)
@@ -313,6 +313,13 @@ static bool tile_path_ok(const zfb_ctx* c, int dtype, int dims, const geom& g, u
   return true;
 }
 
+// 1D float fast path: slots that are whole 32-bit words, at most 128 bits
+static bool line_path_ok(const zfb_ctx* c, int dtype, int dims, const geom& g, unsigned maxbits)
+{
+  if (c->force_generic) return false;
+  return dtype == ZFB_FLOAT && dims == 1 && (maxbits & 31u) == 0 && maxbits <= 128u && g.nx >= 4;
+}
+
 static tile_geom make_tile_geom(const geom& g, unsigned maxbits)
 {
   tile_geom t;
@@ -359,14 +366,14 @@ static int finalize(zfb_ctx* c, int rows, size_t n)
 
 template <typename Scalar>
 static int launch_enc_generic(zfb_ctx* c, int dims, const geom& g, unsigned maxbits, const void* d_in, void* d_stream,
-                              int edge_only)
+                              int edge_only, size_t b_begin = 0)
 {
-  const int grid = generic_grid(c, g.nblocks);
+  const int grid = generic_grid(c, g.nblocks - b_begin);
   const Scalar* in = (const Scalar*)d_in;
   uint64_t* st = (uint64_t*)d_stream;
-  if (dims == 1) enc_generic_kernel<Scalar, 1><<<grid, 128, 0, c->stream>>>(in, st, g, maxbits, edge_only);
-  else if (dims == 2) enc_generic_kernel<Scalar, 2><<<grid, 128, 0, c->stream>>>(in, st, g, maxbits, edge_only);
-  else enc_generic_kernel<Scalar, 3><<<grid, 128, 0, c->stream>>>(in, st, g, maxbits, edge_only);
+  if (dims == 1) enc_generic_kernel<Scalar, 1><<<grid, 128, 0, c->stream>>>(in, st, g, maxbits, edge_only, b_begin);
+  else if (dims == 2) enc_generic_kernel<Scalar, 2><<<grid, 128, 0, c->stream>>>(in, st, g, maxbits, edge_only, b_begin);
+  else enc_generic_kernel<Scalar, 3><<<grid, 128, 0, c->stream>>>(in, st, g, maxbits, edge_only, b_begin);
   c->launches++;
   CU_TRY(c, cudaGetLastError());
   return ZFB_OK;
@@ -374,15 +381,17 @@ static int launch_enc_generic(zfb_ctx* c, int dims, const geom& g, unsigned maxb
 
 template <typename Scalar, bool METRICS>
 static int launch_dec_generic(zfb_ctx* c, int dims, const geom& g, unsigned maxbits, const void* d_stream, void* d_out,
-                              const void* d_orig, int edge_only, int* rows)
+                              const void* d_orig, int edge_only, int* rows, size_t b_begin = 0, int row0 = 0)
 {
-  const int grid = generic_grid(c, g.nblocks);
+  int grid = generic_grid(c, g.nblocks - b_begin);
+  if (grid > c->part_rows - row0) grid = c->part_rows - row0;
   const uint64_t* st = (const uint64_t*)d_stream;
   Scalar* out = (Scalar*)d_out;
   const Scalar* orig = (const Scalar*)d_orig;
-  if (dims == 1) dec_generic_kernel<Scalar, 1, METRICS><<<grid, 128, 0, c->stream>>>(st, out, orig, g, maxbits, edge_only, c->part);
-  else if (dims == 2) dec_generic_kernel<Scalar, 2, METRICS><<<grid, 128, 0, c->stream>>>(st, out, orig, g, maxbits, edge_only, c->part);
-  else dec_generic_kernel<Scalar, 3, METRICS><<<grid, 128, 0, c->stream>>>(st, out, orig, g, maxbits, edge_only, c->part);
+  double* part = c->part + (size_t)row0 * PART_STRIDE;
+  if (dims == 1) dec_generic_kernel<Scalar, 1, METRICS><<<grid, 128, 0, c->stream>>>(st, out, orig, g, maxbits, edge_only, part, b_begin);
+  else if (dims == 2) dec_generic_kernel<Scalar, 2, METRICS><<<grid, 128, 0, c->stream>>>(st, out, orig, g, maxbits, edge_only, part, b_begin);
+  else dec_generic_kernel<Scalar, 3, METRICS><<<grid, 128, 0, c->stream>>>(st, out, orig, g, maxbits, edge_only, part, b_begin);
   c->launches++;
   *rows = grid;
   CU_TRY(c, cudaGetLastError());
@@ -417,6 +426,24 @@ extern "C" int zfb_encode_dev(zfb_ctx* c, int dtype, int dims, size_t nx, size_t
     enc3_f32_tile_kernel<<<grid, TILE_THREADS, smem, c->stream>>>(tm, (uint64_t*)d_stream, tg, maxbits);
     c->launches++;
     CU_TRY(c, cudaGetLastError());
+    return ZFB_OK;
+  }
+  if (line_path_ok(c, dtype, dims, g, maxbits) && ((uintptr_t)d_in & 15) == 0 && ((uintptr_t)d_stream & 15) == 0) {
+    // a trailing partial block is OR-ed into the stream by the generic kernel; when slots are not whole
+    // 64-bit words it may share the last word with the last full block, so that word is cleared FIRST
+    if ((g.nx & 3) && (maxbits & 63u)) CU_TRY(c, cudaMemsetAsync((char*)d_stream + (g.stream_words - 1) * 8, 0, 8, c->stream));
+    const size_t nfull = g.nx / 4;
+    const unsigned nw = maxbits >> 5;
+    size_t want = (nfull + 255) / 256;
+    const int grid = (int)(want < (size_t)c->sm_count * 8 ? (want ? want : 1) : (size_t)c->sm_count * 8);
+    const float* in = (const float*)d_in;
+    uint32_t* st = (uint32_t*)d_stream;
+    if (nw == 1) enc1_f32_kernel<1><<<grid, 256, 0, c->stream>>>(in, st, nfull, maxbits);
+    else if (nw == 2) enc1_f32_kernel<2><<<grid, 256, 0, c->stream>>>(in, st, nfull, maxbits);
+    else enc1_f32_kernel<4><<<grid, 256, 0, c->stream>>>(in, st, nfull, maxbits);
+    c->launches++;
+    CU_TRY(c, cudaGetLastError());
+    if (g.nx & 3) return launch_enc_generic<float>(c, dims, g, maxbits, d_in, d_stream, 1, g.nblocks - 1);
     return ZFB_OK;
   }
   if (maxbits & 63u) {  // unaligned slots are OR-ed into a zeroed stream
@@ -464,6 +491,35 @@ extern "C" int zfb_decode_dev(zfb_ctx* c, int dtype, int dims, size_t nx, size_t
     c->launches++;
     CU_TRY(c, cudaGetLastError());
     rows = (int)grid;
+  } else if (line_path_ok(c, dtype, dims, g, maxbits) && ((uintptr_t)d_out & 15) == 0 && ((uintptr_t)d_stream & 15) == 0 &&
+             (!metrics || ((uintptr_t)d_orig & 15) == 0)) {
+    const size_t nfull = g.nx / 4;
+    const unsigned nw = maxbits >> 5;
+    size_t want = (nfull + 255) / 256;
+    int grid = (int)(want < (size_t)c->sm_count * 8 ? (want ? want : 1) : (size_t)c->sm_count * 8);
+    if (grid > c->part_rows - 1) grid = c->part_rows - 1;
+    const uint32_t* st = (const uint32_t*)d_stream;
+    float* o = (float*)d_out;
+    const float* og = (const float*)d_orig;
+#define ZFB_DEC1(W)                                                                                              \
+    do {                                                                                                         \
+      if (metrics) dec1_f32_kernel<W, true><<<grid, 256, 0, c->stream>>>(st, o, og, nfull, maxbits, c->part);    \
+      else dec1_f32_kernel<W, false><<<grid, 256, 0, c->stream>>>(st, o, og, nfull, maxbits, c->part);           \
+    } while (0)
+    if (nw == 1) ZFB_DEC1(1);
+    else if (nw == 2) ZFB_DEC1(2);
+    else ZFB_DEC1(4);
+#undef ZFB_DEC1
+    c->launches++;
+    CU_TRY(c, cudaGetLastError());
+    rows = grid;
+    if (g.nx & 3) {
+      int erows = 0;
+      rc = metrics ? launch_dec_generic<float, true>(c, dims, g, maxbits, d_stream, d_out, d_orig, 1, &erows, g.nblocks - 1, rows)
+                   : launch_dec_generic<float, false>(c, dims, g, maxbits, d_stream, d_out, d_orig, 1, &erows, g.nblocks - 1, rows);
+      if (rc) return rc;
+      rows += erows;
+    }
   } else {
     if (dtype == ZFB_FLOAT) {
       rc = metrics ? launch_dec_generic<float, true>(c, dims, g, maxbits, d_stream, d_out, d_orig, 0, &rows)

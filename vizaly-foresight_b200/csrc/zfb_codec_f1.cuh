@@ -1,0 +1,291 @@
+// zfb_codec_f1.cuh -- float32, 1D blocks (4 coefficients): the HACC particle-array instantiation.
+//
+// Same bit stream as encode_block<float,1> / decode_block<float,1> (zfp 0.5.5 fixed-rate, SURVEY
+// Appendix A; reference call sites zfpCompressorGpu.hpp:145,249 with zfp_field_1d), organised so that a
+// block costs ~200 instructions instead of a 32-iteration plane loop:
+//
+//   * planes above the highest set bit of any coefficient are single zero test bits: skipped with one clz
+//   * "head" planes (while fewer than 4 coefficients are significant): one table step per plane, keyed by
+//     (n, 4-bit plane) for the encoder and (n, next 7 stream bits) for the decoder
+//   * once all 4 coefficients are significant every further plane is 4 verbatim bits, so the rest of the
+//     slot is the 4-way bit interleave of the coefficients' remaining bits, MSB first: done without a loop
+//     over planes through byte spread / gather steps.
+//
+// Works for any maxbits that is a multiple of 32 (CBench's wra rounding gives 64); other budgets take the
+// generic path.  Host-device so tests/host_emul.cpp can bit-compare it with the oracle on the CPU.
+#pragma once
+#include "zfb_codec.cuh"
+#include "zfb_codec_f3.cuh"
+
+namespace zfb {
+namespace f1 {
+
+using f3::carry_out;
+using f3::fsr;
+using f3::mask32;
+using f3::popc32;
+
+ZFB_HD uint32_t brev32(uint32_t v)
+{
+#if defined(__CUDA_ARCH__)
+  return __brev(v);
+#else
+  v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+  v = ((v >> 2) & 0x33333333u) | ((v & 0x33333333u) << 2);
+  v = ((v >> 4) & 0x0f0f0f0fu) | ((v & 0x0f0f0f0fu) << 4);
+  v = ((v >> 8) & 0x00ff00ffu) | ((v & 0x00ff00ffu) << 8);
+  return (v >> 16) | (v << 16);
+#endif
+}
+ZFB_HD int clz32(uint32_t v)  // v != 0
+{
+#if defined(__CUDA_ARCH__)
+  return __clz((int)v);
+#else
+  return __builtin_clz(v);
+#endif
+}
+ZFB_HD int ctz32(uint32_t v)  // v != 0
+{
+#if defined(__CUDA_ARCH__)
+  return __ffs((int)v) - 1;
+#else
+  return __builtin_ctz(v);
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// tables
+// ---------------------------------------------------------------------------------------------
+// zfp's coder for one plane of a 4-coefficient block: n coefficients already significant, plane value x
+// (bit i = coefficient i).  Returns the emitted bits (LSB first), their count, and the new n.
+ZFB_HD void plane_code(unsigned n, unsigned x, unsigned& code, unsigned& len, unsigned& newn)
+{
+  code = x & ((1u << n) - 1u);
+  len = n;
+  x >>= n;
+  while (n < 4u) {
+    const unsigned t = x != 0u;
+    code |= t << len; len++;
+    if (!t) break;
+    while (n < 3u) {
+      const unsigned b = x & 1u;
+      code |= b << len; len++;
+      if (b) break;
+      x >>= 1; n++;
+    }
+    x >>= 1; n++;
+  }
+  newn = n;
+}
+
+// ENC[n*16 + x] = code | len << 8 | newn << 12      (n = 0..3)
+ZFB_HD uint16_t enc_entry(unsigned idx)
+{
+  unsigned code, len, newn;
+  plane_code(idx >> 4, idx & 15u, code, len, newn);
+  return (uint16_t)(code | (len << 8) | (newn << 12));
+}
+
+// DEC[n*128 + next 7 stream bits] = x | len << 4 | newn << 8   (n = 0..3): the unique plane whose code is a
+// prefix of the 7 bits (codes are at most 7 bits long and prefix free for a given n)
+ZFB_HD uint16_t dec_entry(unsigned idx)
+{
+  const unsigned n = idx >> 7, bits = idx & 127u;
+  for (unsigned x = 0; x < 16u; x++) {
+    unsigned code, len, newn;
+    plane_code(n, x, code, len, newn);
+    if ((bits & ((1u << len) - 1u)) == code) return (uint16_t)(x | (len << 4) | (newn << 8));
+  }
+  return 0;
+}
+
+// SPREAD[b]: bit j of byte b -> bit 4j
+ZFB_HD uint32_t spread_entry(unsigned b)
+{
+  uint32_t r = 0;
+  for (int j = 0; j < 8; j++) r |= ((b >> j) & 1u) << (4 * j);
+  return r;
+}
+
+struct tables {
+  const uint16_t* enc;     // 64
+  const uint16_t* dec;     // 512
+  const uint32_t* spread;  // 256
+};
+
+ZFB_HD uint32_t gather4(uint32_t w)  // bits 0,4,8,...,28 of w -> bits 0..7
+{
+  w &= 0x11111111u;
+  w = (w | (w >> 3)) & 0x03030303u;
+  w = (w | (w >> 6)) & 0x000f000fu;
+  w = (w | (w >> 12)) & 0xffu;
+  return w;
+}
+
+// ---------------------------------------------------------------------------------------------
+// encode: writes maxbits/32 words to out[]
+// ---------------------------------------------------------------------------------------------
+template <int MAXW>
+ZFB_HD void encode_block(const float (&f)[4], unsigned maxbits, uint32_t (&out)[MAXW], const tables& tb)
+{
+  typedef traits<float> T;
+  const unsigned nw = maxbits >> 5;
+  ZFB_UNROLL for (int i = 0; i < MAXW; i++) out[i] = 0u;
+  float mx = 0.f;
+  ZFB_UNROLL for (int i = 0; i < 4; i++) {
+    const float a = f[i] < 0 ? -f[i] : f[i];
+    mx = (mx < a) ? a : mx;
+  }
+  if (!(mx > 0.f)) return;
+  const int E = T::expfield(mx);
+  const int emax = E - 126;
+  int32_t ib[4];
+  {
+    const int se = 30 - emax;
+    const float s = T::pow2(se);
+    ZFB_UNROLL for (int i = 0; i < 4; i++) ib[i] = T::trunc_cast(s * f[i]);
+    if (se > 127) { ZFB_UNROLL for (int i = 0; i < 4; i++) ib[i] = T::int_min(); }
+  }
+  fwd_lift(ib[0], ib[1], ib[2], ib[3]);
+  uint32_t u[4];
+  ZFB_UNROLL for (int i = 0; i < 4; i++) u[i] = ((uint32_t)ib[i] + T::NBMASK) ^ T::NBMASK;
+
+  // bit position bookkeeping: bits are OR-ed into out[] at `pos`; everything past maxbits is dropped
+  unsigned pos = 0;
+  auto put = [&](uint32_t v, unsigned len) {  // len <= 32, v < 2^len
+    const unsigned w = pos >> 5, s = pos & 31u;
+    ZFB_UNROLL for (int i = 0; i < MAXW; i++) {
+      if ((unsigned)i == w) out[i] |= v << s;
+      if ((unsigned)i == w + 1) out[i] |= carry_out(v, s);
+    }
+    pos += len;
+  };
+  put(2u * (uint32_t)(E + 1) + 1u, 9);
+  const uint32_t any = u[0] | u[1] | u[2] | u[3];
+  if (!any) return;  // cannot happen for finite input (the block maximum maps to >= 2^29); kept for safety
+  int k = 31 - clz32(any);
+  pos += (unsigned)(31 - k);  // planes above k: one zero group-test bit each
+  unsigned n = 0;
+  while (n < 4u && k >= 0 && pos < maxbits) {
+    const unsigned x = ((u[0] >> k) & 1u) | (((u[1] >> k) & 1u) << 1) | (((u[2] >> k) & 1u) << 2) | (((u[3] >> k) & 1u) << 3);
+    const unsigned e = tb.enc[n * 16u + x];
+    put(e & 0xffu, (e >> 8) & 15u);
+    n = e >> 12;
+    k--;
+  }
+  if (n == 4u && k >= 0 && pos < maxbits) {
+    // planes k, k-1, ... : 4 verbatim bits each = interleave of the coefficients' bits below plane k+1
+    uint32_t v[4];
+    ZFB_UNROLL for (int i = 0; i < 4; i++) v[i] = brev32(u[i] << (31 - k));  // bit j = bit (k - j) of u[i]
+    const unsigned planes = (unsigned)k + 1u;
+    // 32 stream bits (8 planes) per step; the writer drops what falls beyond maxbits
+    for (unsigned c = 0; c * 8u < planes && pos < maxbits; c++) {
+      const unsigned sh = 8u * c;
+      uint32_t w = tb.spread[(v[0] >> sh) & 0xffu] | (tb.spread[(v[1] >> sh) & 0xffu] << 1) |
+                   (tb.spread[(v[2] >> sh) & 0xffu] << 2) | (tb.spread[(v[3] >> sh) & 0xffu] << 3);
+      const unsigned left = planes - 8u * c;  // planes available in this chunk
+      unsigned len = left >= 8u ? 32u : 4u * left;
+      put(w & mask32(len), len);
+    }
+  }
+  // clear anything written past the budget (pos may have overshot inside the last word only if maxbits % 32 != 0,
+  // which this path does not accept; words beyond nw are simply not stored by the caller)
+  (void)nw;
+}
+
+// ---------------------------------------------------------------------------------------------
+// decode: reads maxbits/32 words from in[]
+// ---------------------------------------------------------------------------------------------
+template <int MAXW>
+ZFB_HD void decode_block(float (&f)[4], unsigned maxbits, const uint32_t (&in)[MAXW], const tables& tb)
+{
+  typedef traits<float> T;
+  if (!(in[0] & 1u)) {
+    ZFB_UNROLL for (int i = 0; i < 4; i++) f[i] = 0.f;
+    return;
+  }
+  const int emax = (int)((in[0] >> 1) & 0xffu) - 127;
+  unsigned pos = 9;
+  auto peek = [&](unsigned p) -> uint32_t {  // 32 stream bits starting at p (zeros beyond the slot words)
+    const unsigned w = p >> 5, s = p & 31u;
+    uint32_t lo = 0u, hi = 0u;
+    ZFB_UNROLL for (int i = 0; i < MAXW; i++) {
+      if ((unsigned)i == w) lo = in[i];
+      if ((unsigned)i == w + 1) hi = in[i];
+    }
+    return fsr(lo, hi, s);
+  };
+  uint32_t u[4] = {0u, 0u, 0u, 0u};
+  unsigned remaining = maxbits - 9u;
+  // leading all-zero planes: zero group tests while n == 0
+  int k = 31;
+  {
+    uint32_t w = peek(pos);
+    if (remaining < 32u) w &= mask32(remaining);
+    const unsigned z = w ? (unsigned)ctz32(w) : 32u;   // zero test bits before the first one
+    const unsigned skip = z < remaining ? z : remaining;
+    // at most 32 planes exist; a slot that is all zero after the header decodes to zero coefficients
+    const unsigned sk = skip > 32u ? 32u : skip;
+    pos += sk; remaining -= sk; k -= (int)sk;
+  }
+  unsigned n = 0;
+  while (n < 4u && k >= 0 && remaining) {
+    const uint32_t w = peek(pos);
+    const unsigned e = tb.dec[n * 128u + (w & 127u)];
+    const unsigned len = (e >> 4) & 15u;
+    if (len <= remaining) {
+      const unsigned x = e & 15u;
+      ZFB_UNROLL for (int i = 0; i < 4; i++) u[i] |= ((x >> i) & 1u) << k;
+      n = e >> 8;
+      pos += len; remaining -= len;
+    } else {
+      // the budget ends inside this plane's code: exact bit-serial steps (zfp's loop conditions)
+      unsigned bits = remaining, x = 0, m = n < bits ? n : bits, p = pos;
+      bits -= m;
+      x = w & ((1u << m) - 1u);
+      uint32_t ww = w >> m;
+      p += m;
+      unsigned nn = n;
+      while (nn < 4u && bits) {
+        bits--;
+        const unsigned t = ww & 1u; ww >>= 1;
+        if (!t) break;
+        while (nn < 3u && bits) {
+          bits--;
+          const unsigned b = ww & 1u; ww >>= 1;
+          if (b) break;
+          nn++;
+        }
+        x |= 1u << nn;
+        nn++;
+      }
+      ZFB_UNROLL for (int i = 0; i < 4; i++) u[i] |= ((x >> i) & 1u) << k;
+      remaining = 0;
+      n = nn;
+    }
+    k--;
+  }
+  if (n == 4u && k >= 0 && remaining) {
+    const unsigned planes = (unsigned)k + 1u;
+    uint32_t v[4] = {0u, 0u, 0u, 0u};
+    for (unsigned c = 0; c * 8u < planes && remaining; c++) {
+      uint32_t w = peek(pos);
+      const unsigned left = planes - 8u * c;
+      unsigned len = left >= 8u ? 32u : 4u * left;
+      if (len > remaining) len = remaining;
+      w &= mask32(len);
+      ZFB_UNROLL for (int i = 0; i < 4; i++) v[i] |= gather4(w >> i) << (8u * c);
+      pos += len; remaining -= len;
+    }
+    ZFB_UNROLL for (int i = 0; i < 4; i++) u[i] |= brev32(v[i]) >> (31 - k);
+  }
+  int32_t ib[4];
+  ZFB_UNROLL for (int i = 0; i < 4; i++) ib[i] = (int32_t)((u[i] ^ T::NBMASK) - T::NBMASK);
+  inv_lift(ib[0], ib[1], ib[2], ib[3]);
+  const float s = T::pow2(emax - 30);
+  ZFB_UNROLL for (int i = 0; i < 4; i++) f[i] = s * T::to_scalar(ib[i]);
+}
+
+}  // namespace f1
+}  // namespace zfb

@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 #include "zfb_codec.cuh"
 #include "zfb_codec_f3.cuh"
+#include "zfb_codec_f1.cuh"
 
 namespace zfb {
 
@@ -266,7 +267,7 @@ template <> struct vec4<double> { typedef double4 type; };
 
 template <typename Scalar, int DIMS>
 __global__ void __launch_bounds__(128) enc_generic_kernel(const Scalar* __restrict__ in, uint64_t* __restrict__ stream,
-                                                          geom g, unsigned maxbits, int edge_only)
+                                                          geom g, unsigned maxbits, int edge_only, size_t b_begin)
 {
   constexpr int BS = 1 << (2 * DIMS);
   constexpr bool FAST = sizeof(Scalar) == 4 && DIMS == 3;
@@ -276,7 +277,7 @@ __global__ void __launch_bounds__(128) enc_generic_kernel(const Scalar* __restri
   if (FAST) tb = build_coder_tables(cs);
   const f3::plane_rows ps = fsc.rows();
   const bool aligned = (maxbits & 63u) == 0;
-  for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < g.nblocks; b += (size_t)gridDim.x * blockDim.x) {
+  for (size_t b = b_begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < g.nblocks; b += (size_t)gridDim.x * blockDim.x) {
     const size_t ix = b % g.bx, iy = (b / g.bx) % g.by, iz = b / (g.bx * g.by);
     const size_t x0 = 4 * ix, y0 = 4 * iy, z0 = 4 * iz;
     const unsigned mx = (unsigned)(g.nx - x0 < 4 ? g.nx - x0 : 4);
@@ -330,7 +331,7 @@ __global__ void __launch_bounds__(128) enc_generic_kernel(const Scalar* __restri
 template <typename Scalar, int DIMS, bool METRICS>
 __global__ void __launch_bounds__(128) dec_generic_kernel(const uint64_t* __restrict__ stream, Scalar* __restrict__ out,
                                                           const Scalar* __restrict__ orig, geom g, unsigned maxbits,
-                                                          int edge_only, double* __restrict__ part)
+                                                          int edge_only, double* __restrict__ part, size_t b_begin)
 {
   constexpr int BS = 1 << (2 * DIMS);
   constexpr bool FAST = sizeof(Scalar) == 4 && DIMS == 3;
@@ -342,7 +343,7 @@ __global__ void __launch_bounds__(128) dec_generic_kernel(const uint64_t* __rest
   const f3::plane_rows ps = fsc.rows();
   macc m;
   m.init();
-  for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < g.nblocks; b += (size_t)gridDim.x * blockDim.x) {
+  for (size_t b = b_begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < g.nblocks; b += (size_t)gridDim.x * blockDim.x) {
     const size_t ix = b % g.bx, iy = (b / g.bx) % g.by, iz = b / (g.bx * g.by);
     const size_t x0 = 4 * ix, y0 = 4 * iy, z0 = 4 * iz;
     const unsigned mx = (unsigned)(g.nx - x0 < 4 ? g.nx - x0 : 4);
@@ -522,13 +523,17 @@ enc3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t* __restr
 }
 
 // dynamic shared memory layout (decode): [tile: 2 x 16 KiB plane scratch, then the original boxes]
-//                                        [slots: 2 x 128*W words][4 mbarriers]
-// Per tile: wait for the slot span (bulk copy, two tiles ahead) -> plane loop parses the slot into the
-// thread's plane rows -> rows back into registers -> __syncthreads -> thread 0 starts the TMA load of the
-// ORIGINAL boxes into the same buffer while all threads run the inverse transform -> metrics against the
-// original rows (LDS.128) -> 16 coalesced 128-bit stores of the decoded rows -> __syncthreads.
+//                                        [slots: 128*W words][3 mbarriers]
+// Per tile: wait for the slot span (bulk copy) -> plane loop parses the slot into the thread's plane rows
+// -> rows back into registers -> __syncthreads -> thread 0 starts the bulk copy of the NEXT tile's slots
+// and the TMA load of this tile's ORIGINAL boxes into the plane-scratch buffer while all threads run the
+// inverse transform -> metrics against the original rows (LDS.128) -> 16 coalesced 128-bit stores of the
+// decoded rows -> __syncthreads.
+#ifndef ZFB_DEC_CTAS
+#define ZFB_DEC_CTAS 5
+#endif
 template <bool METRICS>
-__global__ void __launch_bounds__(TILE_THREADS, 4)
+__global__ void __launch_bounds__(TILE_THREADS, ZFB_DEC_CTAS)
 dec3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64_t* __restrict__ stream,
                      float* __restrict__ out, tile_geom tg, unsigned maxbits, double* __restrict__ part)
 {
@@ -536,7 +541,7 @@ dec3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64
   float* tile = reinterpret_cast<float*>(smem_raw);
   uint64_t* slots = reinterpret_cast<uint64_t*>(smem_raw + BOXES_PER_TILE * BOX_FLOATS * sizeof(float));
   const unsigned slot_words = TILE_THREADS * tg.W;
-  uint64_t* bars = slots + 2 * (size_t)slot_words;  // [0,1] slots full (double buffer), [2,3] orig boxes full
+  uint64_t* bars = slots + (size_t)slot_words;  // [0] slots full, [1,2] orig boxes full
   __shared__ double red[7 * 4];
   __shared__ coder_smem cs;
 
@@ -545,33 +550,30 @@ dec3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64
 
   if (tid == 0) {
     if (METRICS) ptx::prefetch_tmap(&tmap_orig);
-    for (int i = 0; i < 4; i++) ptx::mbar_init(&bars[i], 1);
+    for (int i = 0; i < 3; i++) ptx::mbar_init(&bars[i], 1);
     ptx::fence_barrier_init();
   }
   const f3::tables tb = build_coder_tables(cs);  // includes the __syncthreads that publishes the barriers
 
-  auto issue_slots = [&](unsigned t, unsigned buf) {
+  auto issue_slots = [&](unsigned t) {
     const box_info b0 = box_of(tg, 2 * t), b1 = box_of(tg, 2 * t + 1);
     const unsigned bytes = (b0.nvalid + b1.nvalid) * tg.W * 8u;
-    ptx::mbar_expect_tx(&bars[buf], bytes);
-    ptx::bulk_load(slots + (size_t)buf * slot_words, stream + b0.blk0 * tg.W, bytes, &bars[buf]);
+    ptx::mbar_expect_tx(&bars[0], bytes);
+    ptx::bulk_load(slots, stream + b0.blk0 * tg.W, bytes, &bars[0]);
   };
   auto issue_orig = [&](unsigned t) {
 #pragma unroll
     for (int q = 0; q < BOXES_PER_TILE; q++) {
       const box_info bi = box_of(tg, 2 * t + q);
       if (bi.nvalid) {
-        ptx::mbar_expect_tx(&bars[2 + q], BOX_FLOATS * sizeof(float));
-        ptx::tma_load_3d(tile + q * BOX_FLOATS, &tmap_orig, (int)bi.x0, (int)bi.y0, (int)bi.z0, &bars[2 + q]);
+        ptx::mbar_expect_tx(&bars[1 + q], BOX_FLOATS * sizeof(float));
+        ptx::tma_load_3d(tile + q * BOX_FLOATS, &tmap_orig, (int)bi.x0, (int)bi.y0, (int)bi.z0, &bars[1 + q]);
       }
     }
   };
 
   unsigned t = blockIdx.x;
-  if (tid == 0) {
-    if (t < tg.ntiles) issue_slots(t, 0);
-    if (t + gridDim.x < tg.ntiles) issue_slots(t + gridDim.x, 1);
-  }
+  if (tid == 0 && t < tg.ntiles) issue_slots(t);
 
   f3::plane_rows ps;
   ps.p = reinterpret_cast<f3::u32x4*>(tile + box * BOX_FLOATS) + lb;
@@ -580,32 +582,31 @@ dec3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64
   macc m;
   m.init();
   for (unsigned it = 0; t < tg.ntiles; t += gridDim.x, it++) {
-    const unsigned buf = it & 1;
     const box_info b0 = box_of(tg, 2 * t), b1 = box_of(tg, 2 * t + 1);
     const box_info mine = box ? b1 : b0;
     const bool active = lb < mine.nvalid;
     const unsigned nslots = b0.nvalid + b1.nvalid;
-    ptx::mbar_wait(&bars[buf], (it >> 1) & 1);
+    ptx::mbar_wait(&bars[0], it & 1);
     f3::planes64 P;
     int emax = 0;
     bool nonzero = false, low_used = false;
     if (active) {
       const unsigned p = (box ? b0.nvalid : 0u) + lb;
-      f3::reader32 r(reinterpret_cast<const uint32_t*>(slots + (size_t)buf * slot_words + (size_t)p * tg.W),
-                     2 * (nslots - p) * tg.W, 0);
+      f3::reader32 r(reinterpret_cast<const uint32_t*>(slots + (size_t)p * tg.W), 2 * (nslots - p) * tg.W, 0);
       nonzero = f3::decode_planes(P, emax, low_used, maxbits, r, tb, ps);
     }
-    if (METRICS) {
-      ptx::fence_proxy_async();  // plane-row writes (generic proxy) before the TMA load overwrites the buffer
-      __syncthreads();           // every thread has its planes back in registers
-      if (tid == 0) issue_orig(t);
+    ptx::fence_proxy_async();  // plane-row writes (generic proxy) before the TMA load overwrites the buffer
+    __syncthreads();           // slots parsed; every thread has its planes back in registers
+    if (tid == 0) {
+      if (t + gridDim.x < tg.ntiles) issue_slots(t + gridDim.x);
+      if (METRICS) issue_orig(t);
     }
     if (active) {
       float f[64];
       f3::decode_finish(f, P, emax, nonzero, low_used);
       float* dst = out + ((size_t)mine.z0 * tg.ny + mine.y0) * tg.nx + mine.x0 + 4 * lb;
       if (METRICS) {
-        ptx::mbar_wait(&bars[2 + box], it & 1);
+        ptx::mbar_wait(&bars[1 + box], it & 1);
         const float4* src = reinterpret_cast<const float4*>(tile + box * BOX_FLOATS) + lb;
         frow fr;
         fr.init();
@@ -616,24 +617,102 @@ dec3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64
           if ((r16 & 3) == 3) fr.flush(m);
         }
       }
+      const size_t rs = tg.nx, ps2 = (size_t)tg.ny * tg.nx;
 #pragma unroll
-      for (int k = 0; k < 4; k++)
+      for (int k = 0; k < 4; k++) {
+        float* rowp = dst + (size_t)k * ps2;
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           float4 v;
           v.x = f[16 * k + 4 * j]; v.y = f[16 * k + 4 * j + 1]; v.z = f[16 * k + 4 * j + 2]; v.w = f[16 * k + 4 * j + 3];
-          __stcs(reinterpret_cast<float4*>(dst + ((size_t)k * tg.ny + j) * tg.nx), v);
+          __stcs(reinterpret_cast<float4*>(rowp + (size_t)j * rs), v);
         }
+      }
     } else if (METRICS && mine.nvalid) {
-      ptx::mbar_wait(&bars[2 + box], it & 1);  // keep every thread's view of the barrier phase in step
+      ptx::mbar_wait(&bars[1 + box], it & 1);  // keep every thread's view of the barrier phase in step
     }
-    __syncthreads();  // slots[buf] and the tile buffer are consumed
-    if (tid == 0) {
-      const unsigned t2 = t + 2 * gridDim.x;
-      if (t2 < tg.ntiles) issue_slots(t2, buf);
-    }
+    if (METRICS) __syncthreads();  // the original rows are consumed before the next tile's planes land there
   }
   if (METRICS) macc_block_store(m, red, part + (size_t)blockIdx.x * PART_STRIDE);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 1D float kernels (HACC particle arrays): one 4-value block per thread, one 128-bit load / store per
+// block, slot words written with one 4/8/16-byte store per thread (coalesced across the warp).
+// Only FULL blocks (b < nfull); a trailing partial block goes through the generic kernel.
+// ---------------------------------------------------------------------------------------------
+struct coder1_smem {
+  uint32_t spread[256];
+  uint16_t dec[512];
+  uint16_t enc[64];
+};
+__device__ __forceinline__ f1::tables build_coder1_tables(coder1_smem& cs)
+{
+  for (unsigned i = threadIdx.x; i < 256; i += blockDim.x) cs.spread[i] = f1::spread_entry(i);
+  for (unsigned i = threadIdx.x; i < 512; i += blockDim.x) cs.dec[i] = f1::dec_entry(i);
+  for (unsigned i = threadIdx.x; i < 64; i += blockDim.x) cs.enc[i] = f1::enc_entry(i);
+  __syncthreads();
+  f1::tables t;
+  t.enc = cs.enc; t.dec = cs.dec; t.spread = cs.spread;
+  return t;
+}
+
+template <int MAXW>
+__global__ void __launch_bounds__(256) enc1_f32_kernel(const float* __restrict__ in, uint32_t* __restrict__ stream,
+                                                       size_t nfull, unsigned maxbits)
+{
+  __shared__ coder1_smem cs;
+  const f1::tables tb = build_coder1_tables(cs);
+  const unsigned nw = maxbits >> 5;
+  for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < nfull; b += (size_t)gridDim.x * blockDim.x) {
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(in) + b);
+    const float f[4] = {v.x, v.y, v.z, v.w};
+    uint32_t o[MAXW];
+    f1::encode_block<MAXW>(f, maxbits, o, tb);
+    if constexpr (MAXW == 1) stream[b] = o[0];
+    else if constexpr (MAXW == 2) reinterpret_cast<uint2*>(stream)[b] = make_uint2(o[0], o[1]);
+    else {
+      if (nw == 4) reinterpret_cast<uint4*>(stream)[b] = make_uint4(o[0], o[1], o[2], o[3]);
+      else { stream[3 * b] = o[0]; stream[3 * b + 1] = o[1]; stream[3 * b + 2] = o[2]; }
+    }
+  }
+}
+
+template <int MAXW, bool METRICS>
+__global__ void __launch_bounds__(256) dec1_f32_kernel(const uint32_t* __restrict__ stream, float* __restrict__ out,
+                                                       const float* __restrict__ orig, size_t nfull, unsigned maxbits,
+                                                       double* __restrict__ part)
+{
+  __shared__ coder1_smem cs;
+  __shared__ double red[7 * 8];
+  const f1::tables tb = build_coder1_tables(cs);
+  const unsigned nw = maxbits >> 5;
+  macc m;
+  m.init();
+  frow fr;
+  fr.init();
+  int pending = 0;
+  for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < nfull; b += (size_t)gridDim.x * blockDim.x) {
+    uint32_t w[MAXW];
+    if constexpr (MAXW == 1) w[0] = __ldcs(stream + b);
+    else if constexpr (MAXW == 2) { const uint2 t = __ldcs(reinterpret_cast<const uint2*>(stream) + b); w[0] = t.x; w[1] = t.y; }
+    else {
+      if (nw == 4) { const uint4 t = __ldcs(reinterpret_cast<const uint4*>(stream) + b); w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w; }
+      else { w[0] = stream[3 * b]; w[1] = stream[3 * b + 1]; w[2] = stream[3 * b + 2]; w[3] = 0u; }
+    }
+    float f[4];
+    f1::decode_block<MAXW>(f, maxbits, w, tb);
+    if (METRICS) {
+      const float4 o = __ldcs(reinterpret_cast<const float4*>(orig) + b);
+      fr.add(o.x, f[0]); fr.add(o.y, f[1]); fr.add(o.z, f[2]); fr.add(o.w, f[3]);
+      if (++pending == 4) { fr.flush(m); pending = 0; }
+    }
+    __stcs(reinterpret_cast<float4*>(out) + b, make_float4(f[0], f[1], f[2], f[3]));
+  }
+  if (METRICS) {
+    fr.flush(m);
+    macc_block_store(m, red, part + (size_t)blockIdx.x * PART_STRIDE);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
