@@ -17,9 +17,11 @@
 #if defined(__CUDACC__)
 #define ZFB_HD __host__ __device__ __forceinline__
 #define ZFB_UNROLL _Pragma("unroll")
+#define ZFB_ROLLED _Pragma("unroll 1")
 #else
 #define ZFB_HD inline
 #define ZFB_UNROLL
+#define ZFB_ROLLED
 #endif
 
 namespace zfb {
@@ -542,7 +544,9 @@ ZFB_HD void encode_block(const Scalar (&f)[1 << (2 * DIMS)], unsigned maxbits, S
   bw.put(2 * (uint64_t)(E + 1) + 1, 1 + T::EBITS);
 
   unsigned n = 0;
-  ZFB_UNROLL for (int k = T::PBITS - 1; k >= 0; k--) {
+  // The plane loop stays rolled: fully unrolled it is hundreds of KB of SASS per kernel and the kernels stall
+  // on instruction fetch.  P is then indexed dynamically (thread-local memory, L1 resident).
+  ZFB_ROLLED for (int k = T::PBITS - 1; k >= 0; k--) {
     if (bw.total >= maxbits || k < kmin) break;
     uint64_t x = P.get(k);
     // first n coefficients are already significant: their bits go out verbatim
@@ -590,7 +594,7 @@ ZFB_HD void decode_block(Scalar (&f)[1 << (2 * DIMS)], unsigned maxbits, Reader&
   P.clear();
   unsigned remaining = maxbits - (1 + T::EBITS);
   unsigned n = 0;
-  ZFB_UNROLL for (int k = T::PBITS - 1; k >= 0; k--) {
+  ZFB_UNROLL for (int k = T::PBITS - 1; k >= 0; k--) {  // unrolled: P stays in registers (a rolled loop puts it in local memory and is slower here)
     if (!remaining || k < kmin) break;
     const unsigned m = n < remaining ? n : remaining;
     remaining -= m;
