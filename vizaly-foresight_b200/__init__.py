@@ -37,7 +37,8 @@ class Partials(C.Structure):
 
 def build_library(force=False, verbose=False):
     """nvcc -> vizaly-foresight_b200/libzfb.so (in-tree, so it travels to the GPU box)."""
-    srcs = [os.path.join(HERE, "csrc", f) for f in ("zfb_api.cu", "zfb_kernels.cuh", "zfb_codec.cuh")] + [HEADER]
+    csrc = os.path.join(HERE, "csrc")
+    srcs = [os.path.join(csrc, "zfb_api.cu")] + sorted(os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")) + [HEADER]
     stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
     if not (force or stale):
         return LIB_PATH

@@ -95,6 +95,16 @@ ZFB_HD int msb32(uint32_t v)  // v != 0
   return 31 - __builtin_clz(v);
 #endif
 }
+ZFB_HD uint32_t bitsel(uint32_t a, uint32_t b, uint32_t m)  // (a & ~m) | (b & m) as one LOP3
+{
+#if defined(__CUDA_ARCH__)
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xD8;" : "=r"(d) : "r"(a), "r"(b), "r"(m));
+  return d;
+#else
+  return (a & ~m) | (b & m);
+#endif
+}
 ZFB_HD uint32_t bperm(uint32_t a, uint32_t b, uint32_t sel)
 {
 #if defined(__CUDA_ARCH__)
@@ -171,19 +181,19 @@ struct planes64 {
     ZFB_UNROLL for (int g = 0; g < 16; g += 8)
       ZFB_UNROLL for (int k = 0; k < 4; k++) {
         const uint32_t p = w[base + g + k], q = w[base + g + k + 4];
-        w[base + g + k] = (p & 0x0f0f0f0fu) | ((q << 4) & 0xf0f0f0f0u);
-        w[base + g + k + 4] = ((p >> 4) & 0x0f0f0f0fu) | (q & 0xf0f0f0f0u);
+        w[base + g + k] = bitsel(p, q << 4, 0xf0f0f0f0u);
+        w[base + g + k + 4] = bitsel(q, p >> 4, 0x0f0f0f0fu);
       }
     ZFB_UNROLL for (int g = 0; g < 16; g += 4)
       ZFB_UNROLL for (int k = 0; k < 2; k++) {
         const uint32_t p = w[base + g + k], q = w[base + g + k + 2];
-        w[base + g + k] = (p & 0x33333333u) | ((q << 2) & 0xccccccccu);
-        w[base + g + k + 2] = ((p >> 2) & 0x33333333u) | (q & 0xccccccccu);
+        w[base + g + k] = bitsel(p, q << 2, 0xccccccccu);
+        w[base + g + k + 2] = bitsel(q, p >> 2, 0x33333333u);
       }
     ZFB_UNROLL for (int g = 0; g < 16; g += 2) {
       const uint32_t p = w[base + g], q = w[base + g + 1];
-      w[base + g] = (p & 0x55555555u) | ((q << 1) & 0xaaaaaaaau);
-      w[base + g + 1] = ((p >> 1) & 0x55555555u) | (q & 0xaaaaaaaau);
+      w[base + g] = bitsel(p, q << 1, 0xaaaaaaaau);
+      w[base + g + 1] = bitsel(q, p >> 1, 0x55555555u);
     }
   }
   ZFB_HD void split16() { stage16(a); stage16(b); }
