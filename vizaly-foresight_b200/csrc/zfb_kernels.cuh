@@ -176,6 +176,26 @@ struct frow {
     mo = fmaxf(mo, o);
     mno = fmaxf(mno, -o);
   }
+  // one row of four values; nested fmaxf lets the compiler use the 3-input FMNMX3
+  __device__ __forceinline__ void add4(const float4& o, float a0, float a1, float a2, float a3)
+  {
+    const float d0 = o.x - a0, d1 = o.y - a1, d2 = o.z - a2, d3 = o.w - a3;
+    const float e0 = fabsf(d0), e1 = fabsf(d1), e2 = fabsf(d2), e3 = fabsf(d3);
+    const float b0 = fabsf(o.x), b1 = fabsf(o.y), b2 = fabsf(o.z), b3 = fabsf(o.w);
+    float q0, q1, q2, q3;
+    asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(q0) : "f"(e0 * 0.25f), "f"(b0 * 0.25f));
+    asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(q1) : "f"(e1 * 0.25f), "f"(b1 * 0.25f));
+    asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(q2) : "f"(e2 * 0.25f), "f"(b2 * 0.25f));
+    asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(q3) : "f"(e3 * 0.25f), "f"(b3 * 0.25f));
+    const float r0 = b0 < 1.0f ? e0 : q0, r1 = b1 < 1.0f ? e1 : q1, r2 = b2 < 1.0f ? e2 : q2, r3 = b3 < 1.0f ? e3 : q3;
+    ssq = fmaf(d0, d0, ssq); ssq = fmaf(d1, d1, ssq); ssq = fmaf(d2, d2, ssq); ssq = fmaf(d3, d3, ssq);
+    sab += (e0 + e1) + (e2 + e3);
+    srl += (r0 + r1) + (r2 + r3);
+    mab = fmaxf(fmaxf(mab, e0), e1); mab = fmaxf(fmaxf(mab, e2), e3);
+    mrl = fmaxf(fmaxf(mrl, r0), r1); mrl = fmaxf(fmaxf(mrl, r2), r3);
+    mo = fmaxf(fmaxf(mo, o.x), o.y); mo = fmaxf(fmaxf(mo, o.z), o.w);
+    mno = fmaxf(fmaxf(mno, -o.x), -o.y); mno = fmaxf(fmaxf(mno, -o.z), -o.w);
+  }
   __device__ __forceinline__ void flush(macc& m)
   {
     m.s_sq += (double)ssq; m.s_abs += (double)sab; m.s_rel += (double)srl;
@@ -463,34 +483,37 @@ enc3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t* __restr
   const unsigned tid = threadIdx.x;
   const unsigned box = tid >> 6, lb = tid & 63;
 
+  // box descriptors of the current / next tile, computed once by thread 0 (integer divisions) and read by all
+  __shared__ box_info sb[2][BOXES_PER_TILE];
+  unsigned t = blockIdx.x;
   if (tid == 0) {
     ptx::prefetch_tmap(&tmap);
     ptx::mbar_init(&bars[0], 1);
     ptx::mbar_init(&bars[1], 1);
     ptx::fence_barrier_init();
+    sb[0][0] = box_of(tg, 2 * t);
+    sb[0][1] = box_of(tg, 2 * t + 1);
   }
-  const f3::tables tb = build_coder_tables(cs);  // includes the __syncthreads that publishes the barriers
+  const f3::tables tb = build_coder_tables(cs);  // includes the __syncthreads that publishes barriers and sb[0]
 
-  auto issue_loads = [&](unsigned t) {
+  auto issue_loads = [&](const box_info* bi) {
 #pragma unroll
     for (int q = 0; q < BOXES_PER_TILE; q++) {
-      const box_info bi = box_of(tg, 2 * t + q);
-      if (bi.nvalid) {
+      if (bi[q].nvalid) {
         ptx::mbar_expect_tx(&bars[q], BOX_FLOATS * sizeof(float));
-        ptx::tma_load_3d(tile + q * BOX_FLOATS, &tmap, (int)bi.x0, (int)bi.y0, (int)bi.z0, &bars[q]);
+        ptx::tma_load_3d(tile + q * BOX_FLOATS, &tmap, (int)bi[q].x0, (int)bi[q].y0, (int)bi[q].z0, &bars[q]);
       }
     }
   };
 
-  unsigned t = blockIdx.x;
-  if (tid == 0 && t < tg.ntiles) issue_loads(t);
+  if (tid == 0 && t < tg.ntiles) issue_loads(sb[0]);
 
   f3::plane_rows ps;
   ps.p = reinterpret_cast<f3::u32x4*>(tile + box * BOX_FLOATS) + lb;
   ps.stride = 64;
 
   for (unsigned it = 0; t < tg.ntiles; t += gridDim.x, it++) {
-    const box_info b0 = box_of(tg, 2 * t), b1 = box_of(tg, 2 * t + 1);
+    const box_info b0 = sb[it & 1][0], b1 = sb[it & 1][1];
     const box_info mine = box ? b1 : b0;
     const bool active = lb < mine.nvalid;
     uint64_t* obuf = outw;
@@ -510,13 +533,17 @@ enc3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t* __restr
       }
     }
     ptx::fence_proxy_async();              // slot words and the in-place plane rows -> async proxy
-    __syncthreads();                       // tile buffer consumed, `out` complete
+    if (tid == 0) {
+      sb[(it + 1) & 1][0] = box_of(tg, 2 * (t + gridDim.x));
+      sb[(it + 1) & 1][1] = box_of(tg, 2 * (t + gridDim.x) + 1);
+    }
+    __syncthreads();                       // tile buffer consumed, `out` complete, next descriptors published
     if (tid == 0) {
       const unsigned nslots = b0.nvalid + b1.nvalid;
       ptx::bulk_store(stream + b0.blk0 * tg.W, obuf, nslots * tg.W * 8u);
       ptx::bulk_commit();
       ptx::bulk_wait_read0();              // `out` may be rewritten once the next tile's loads have landed
-      if (t + gridDim.x < tg.ntiles) issue_loads(t + gridDim.x);
+      if (t + gridDim.x < tg.ntiles) issue_loads(sb[(it + 1) & 1]);
     }
   }
   if (tid == 0) ptx::bulk_wait0();
@@ -548,32 +575,33 @@ dec3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64
   const unsigned tid = threadIdx.x;
   const unsigned box = tid >> 6, lb = tid & 63;
 
+  __shared__ box_info sb[2][BOXES_PER_TILE];  // box descriptors of the current / next tile (thread 0 computes)
+  unsigned t = blockIdx.x;
   if (tid == 0) {
     if (METRICS) ptx::prefetch_tmap(&tmap_orig);
     for (int i = 0; i < 3; i++) ptx::mbar_init(&bars[i], 1);
     ptx::fence_barrier_init();
+    sb[0][0] = box_of(tg, 2 * t);
+    sb[0][1] = box_of(tg, 2 * t + 1);
   }
-  const f3::tables tb = build_coder_tables(cs);  // includes the __syncthreads that publishes the barriers
+  const f3::tables tb = build_coder_tables(cs);  // includes the __syncthreads that publishes barriers and sb[0]
 
-  auto issue_slots = [&](unsigned t) {
-    const box_info b0 = box_of(tg, 2 * t), b1 = box_of(tg, 2 * t + 1);
-    const unsigned bytes = (b0.nvalid + b1.nvalid) * tg.W * 8u;
+  auto issue_slots = [&](const box_info* bi) {
+    const unsigned bytes = (bi[0].nvalid + bi[1].nvalid) * tg.W * 8u;
     ptx::mbar_expect_tx(&bars[0], bytes);
-    ptx::bulk_load(slots, stream + b0.blk0 * tg.W, bytes, &bars[0]);
+    ptx::bulk_load(slots, stream + bi[0].blk0 * tg.W, bytes, &bars[0]);
   };
-  auto issue_orig = [&](unsigned t) {
+  auto issue_orig = [&](const box_info* bi) {
 #pragma unroll
     for (int q = 0; q < BOXES_PER_TILE; q++) {
-      const box_info bi = box_of(tg, 2 * t + q);
-      if (bi.nvalid) {
+      if (bi[q].nvalid) {
         ptx::mbar_expect_tx(&bars[1 + q], BOX_FLOATS * sizeof(float));
-        ptx::tma_load_3d(tile + q * BOX_FLOATS, &tmap_orig, (int)bi.x0, (int)bi.y0, (int)bi.z0, &bars[1 + q]);
+        ptx::tma_load_3d(tile + q * BOX_FLOATS, &tmap_orig, (int)bi[q].x0, (int)bi[q].y0, (int)bi[q].z0, &bars[1 + q]);
       }
     }
   };
 
-  unsigned t = blockIdx.x;
-  if (tid == 0 && t < tg.ntiles) issue_slots(t);
+  if (tid == 0 && t < tg.ntiles) issue_slots(sb[0]);
 
   f3::plane_rows ps;
   ps.p = reinterpret_cast<f3::u32x4*>(tile + box * BOX_FLOATS) + lb;
@@ -582,7 +610,7 @@ dec3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64
   macc m;
   m.init();
   for (unsigned it = 0; t < tg.ntiles; t += gridDim.x, it++) {
-    const box_info b0 = box_of(tg, 2 * t), b1 = box_of(tg, 2 * t + 1);
+    const box_info b0 = sb[it & 1][0], b1 = sb[it & 1][1];
     const box_info mine = box ? b1 : b0;
     const bool active = lb < mine.nvalid;
     const unsigned nslots = b0.nvalid + b1.nvalid;
@@ -596,10 +624,14 @@ dec3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64
       nonzero = f3::decode_planes(P, emax, low_used, maxbits, r, tb, ps);
     }
     ptx::fence_proxy_async();  // plane-row writes (generic proxy) before the TMA load overwrites the buffer
-    __syncthreads();           // slots parsed; every thread has its planes back in registers
     if (tid == 0) {
-      if (t + gridDim.x < tg.ntiles) issue_slots(t + gridDim.x);
-      if (METRICS) issue_orig(t);
+      sb[(it + 1) & 1][0] = box_of(tg, 2 * (t + gridDim.x));
+      sb[(it + 1) & 1][1] = box_of(tg, 2 * (t + gridDim.x) + 1);
+    }
+    __syncthreads();           // slots parsed; planes back in registers; next descriptors published
+    if (tid == 0) {
+      if (t + gridDim.x < tg.ntiles) issue_slots(sb[(it + 1) & 1]);
+      if (METRICS) issue_orig(sb[it & 1]);
     }
     if (active) {
       float f[64];
@@ -613,7 +645,7 @@ dec3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64
 #pragma unroll
         for (int r16 = 0; r16 < 16; r16++) {
           const float4 o = src[r16 * 64];
-          fr.add(o.x, f[4 * r16]); fr.add(o.y, f[4 * r16 + 1]); fr.add(o.z, f[4 * r16 + 2]); fr.add(o.w, f[4 * r16 + 3]);
+          fr.add4(o, f[4 * r16], f[4 * r16 + 1], f[4 * r16 + 2], f[4 * r16 + 3]);
           if ((r16 & 3) == 3) fr.flush(m);
         }
       }
@@ -704,7 +736,7 @@ __global__ void __launch_bounds__(256) dec1_f32_kernel(const uint32_t* __restric
     f1::decode_block<MAXW>(f, maxbits, w, tb);
     if (METRICS) {
       const float4 o = __ldcs(reinterpret_cast<const float4*>(orig) + b);
-      fr.add(o.x, f[0]); fr.add(o.y, f[1]); fr.add(o.z, f[2]); fr.add(o.w, f[3]);
+      fr.add4(o, f[0], f[1], f[2], f[3]);
       if (++pending == 4) { fr.flush(m); pending = 0; }
     }
     __stcs(reinterpret_cast<float4*>(out) + b, make_float4(f[0], f[1], f[2], f[3]));
@@ -736,7 +768,7 @@ __global__ void __launch_bounds__(256) metrics_kernel(const Scalar* __restrict__
     int cnt = 0;
     for (; i < n4; i += stride) {
       const float4 o = __ldcs(o4 + i), a = __ldcs(a4 + i);
-      fr.add(o.x, a.x); fr.add(o.y, a.y); fr.add(o.z, a.z); fr.add(o.w, a.w);
+      fr.add4(o, a.x, a.y, a.z, a.w);
       if (++cnt == 4) { fr.flush(m); cnt = 0; }
     }
     const size_t tail = n4 * 4 + ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
