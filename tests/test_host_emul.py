@@ -156,6 +156,14 @@ def test_fast_1d_coder(oracle):
         "one_of_four": np.tile(np.array([3.0, 0, 0, 0], np.float32), n // 4),
         "last_of_four": np.tile(np.array([0, 0, 0, -5.0], np.float32), n // 4),
         "golden_hacc": np.fromfile(os.path.join(ROOT, "tests", "golden", "hacc_m000_x_4096.f32"), dtype=np.float32),
+        # long runs of planes with 1 or 2 significant coefficients (run-based head coder)
+        "dc_plus_tiny": (1000.0 + 1e-4 * rng.standard_normal(n)).astype(np.float32),
+        "dc_plus_small": (1000.0 + 1e-1 * rng.standard_normal(n)).astype(np.float32),
+        "steps": np.repeat((rng.standard_normal(n // 4) * 50).astype(np.float32), 4),
+        "slopes": (np.arange(n) * np.repeat(10.0 ** rng.integers(-6, 3, n // 4), 4)).astype(np.float32),
+        "last_differs": (np.repeat((rng.random(n // 4) * 9).astype(np.float32), 4)
+                         + np.tile(np.array([0, 0, 0, 1e-3], np.float32), n // 4)),
+        "pairwise": np.repeat((rng.standard_normal(n // 2) * 3).astype(np.float32), 2),
     }
     for label, f in arrays.items():
         for mb in (32, 64, 96, 128):

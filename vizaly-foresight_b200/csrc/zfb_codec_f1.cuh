@@ -123,6 +123,50 @@ ZFB_HD uint32_t gather4(uint32_t w)  // bits 0,4,8,...,28 of w -> bits 0..7
   return w;
 }
 
+ZFB_HD uint32_t spread2(uint32_t x)  // bit j (j < 16) -> bit 2j
+{
+  x = (x | (x << 8)) & 0x00ff00ffu;
+  x = (x | (x << 4)) & 0x0f0f0f0fu;
+  x = (x | (x << 2)) & 0x33333333u;
+  x = (x | (x << 1)) & 0x55555555u;
+  return x;
+}
+ZFB_HD uint32_t gather2(uint32_t x)  // bit 2j -> bit j
+{
+  x &= 0x55555555u;
+  x = (x | (x >> 1)) & 0x33333333u;
+  x = (x | (x >> 2)) & 0x0f0f0f0fu;
+  x = (x | (x >> 4)) & 0x00ff00ffu;
+  x = (x | (x >> 8)) & 0x0000ffffu;
+  return x;
+}
+ZFB_HD uint32_t spread3(uint32_t x)  // bit j (j < 10) -> bit 3j
+{
+  x &= 0x3ffu;
+  x = (x | (x << 16)) & 0x030000ffu;
+  x = (x | (x << 8)) & 0x0300f00fu;
+  x = (x | (x << 4)) & 0x030c30c3u;
+  x = (x | (x << 2)) & 0x09249249u;
+  return x;
+}
+ZFB_HD uint32_t gather3(uint32_t x)  // bit 3j (j < 10) -> bit j
+{
+  x &= 0x09249249u;
+  x = (x | (x >> 2)) & 0x030c30c3u;
+  x = (x | (x >> 4)) & 0x0300f00fu;
+  x = (x | (x >> 8)) & 0x030000ffu;
+  x = (x | (x >> 16)) & 0x3ffu;
+  return x;
+}
+
+// The head of a slot, i.e. the planes coded while n <= 2 coefficients are significant, has a simple
+// shape: RUNS of planes in which no further coefficient becomes significant -- each such plane is its n
+// verbatim bits followed by a 0 group test, n + 1 bits -- separated by EVENT planes, whose code comes from
+// the (n, nibble) table.  Runs are emitted / parsed many planes at a time with the spread / gather helpers
+// above, so the loops below make at most a handful of iterations whatever the data (each coefficient
+// causes at most one event).  From n >= 3 on the code of a plane IS its raw nibble: the bit of coefficient 3
+// doubles as the group test (its one is implicit), so the rest of the slot is the 4-way bit interleave.
+
 // ---------------------------------------------------------------------------------------------
 // encode: writes maxbits/32 words to out[]
 // ---------------------------------------------------------------------------------------------
@@ -153,29 +197,53 @@ ZFB_HD void encode_block(const float (&f)[4], unsigned maxbits, uint32_t (&out)[
 
   // bit position bookkeeping: bits are OR-ed into out[] at `pos`; everything past maxbits is dropped
   unsigned pos = 0;
+  uint64_t acc0 = 0, acc1 = 0;  // stream bits 0..63 and 64..127
   auto put = [&](uint32_t v, unsigned len) {  // len <= 32, v < 2^len
-    const unsigned w = pos >> 5, s = pos & 31u;
-    ZFB_UNROLL for (int i = 0; i < MAXW; i++) {
-      if ((unsigned)i == w) out[i] |= v << s;
-      if ((unsigned)i == w + 1) out[i] |= carry_out(v, s);
+    if (pos < 64u) acc0 |= (uint64_t)v << pos;
+    if (MAXW > 2) {
+      if (pos >= 64u) { if (pos < 128u) acc1 |= (uint64_t)v << (pos - 64u); }
+      else if (pos > 32u) acc1 |= (uint64_t)v >> (64u - pos);
     }
     pos += len;
   };
+  auto store = [&]() {
+    out[0] = (uint32_t)acc0;
+    if (MAXW > 1) out[1 % MAXW] = (uint32_t)(acc0 >> 32);
+    if (MAXW > 2) { out[2 % MAXW] = (uint32_t)acc1; out[3 % MAXW] = (uint32_t)(acc1 >> 32); }
+  };
   put(2u * (uint32_t)(E + 1) + 1u, 9);
   const uint32_t any = u[0] | u[1] | u[2] | u[3];
-  if (!any) return;  // cannot happen for finite input (the block maximum maps to >= 2^29); kept for safety
+  if (!any) { store(); return; }  // cannot happen for finite input (the block maximum maps to >= 2^29); kept for safety
   int k = 31 - clz32(any);
   pos += (unsigned)(31 - k);  // planes above k: one zero group-test bit each
   unsigned n = 0;
-  while (n < 4u && k >= 0 && pos < maxbits) {
+  while (n < 3u && k >= 0 && pos < maxbits) {
+    // run: planes k .. ke+1 in which coefficients n..3 are all zero
+    uint32_t rest = u[3] | u[2];
+    if (n < 2u) rest |= u[1];
+    if (n < 1u) rest |= u[0];
+    rest &= mask32((unsigned)k + 1u);
+    const int ke = rest ? 31 - clz32(rest) : -1;
+    unsigned L = (unsigned)(k - ke);
+    if (L) {
+      const unsigned cap = n == 0u ? 32u : (n == 1u ? 16u : 10u);  // planes whose codes fit one 32-bit put
+      if (L > cap) L = cap;
+      uint32_t code = 0u;
+      if (n == 1u) code = spread2(brev32(u[0] << (31 - k)) & mask32(L));
+      else if (n == 2u) code = spread3(brev32(u[0] << (31 - k)) & mask32(L)) | (spread3(brev32(u[1] << (31 - k)) & mask32(L)) << 1);
+      put(code, L * (n + 1u));
+      k -= (int)L;
+      continue;  // (a capped run is simply continued by the next iteration)
+    }
+    // event plane k
     const unsigned x = ((u[0] >> k) & 1u) | (((u[1] >> k) & 1u) << 1) | (((u[2] >> k) & 1u) << 2) | (((u[3] >> k) & 1u) << 3);
     const unsigned e = tb.enc[n * 16u + x];
     put(e & 0xffu, (e >> 8) & 15u);
     n = e >> 12;
     k--;
   }
-  if (n == 4u && k >= 0 && pos < maxbits) {
-    // planes k, k-1, ... : 4 verbatim bits each = interleave of the coefficients' bits below plane k+1
+  if (n >= 3u && k >= 0 && pos < maxbits) {
+    // planes k, k-1, ... : the raw nibble of every plane = interleave of the coefficients' bits below plane k+1
     uint32_t v[4];
     ZFB_UNROLL for (int i = 0; i < 4; i++) v[i] = brev32(u[i] << (31 - k));  // bit j = bit (k - j) of u[i]
     const unsigned planes = (unsigned)k + 1u;
@@ -189,8 +257,8 @@ ZFB_HD void encode_block(const float (&f)[4], unsigned maxbits, uint32_t (&out)[
       put(w & mask32(len), len);
     }
   }
-  // clear anything written past the budget (pos may have overshot inside the last word only if maxbits % 32 != 0,
-  // which this path does not accept; words beyond nw are simply not stored by the caller)
+  // bits past maxbits (a multiple of 32) live in words the caller does not store
+  store();
   (void)nw;
 }
 
@@ -207,14 +275,15 @@ ZFB_HD void decode_block(float (&f)[4], unsigned maxbits, const uint32_t (&in)[M
   }
   const int emax = (int)((in[0] >> 1) & 0xffu) - 127;
   unsigned pos = 9;
+  const uint64_t in0 = (uint64_t)in[0] | ((uint64_t)(MAXW > 1 ? in[1 % MAXW] : 0u) << 32);
+  const uint64_t in1 = MAXW > 2 ? ((uint64_t)in[2 % MAXW] | ((uint64_t)in[3 % MAXW] << 32)) : 0;
   auto peek = [&](unsigned p) -> uint32_t {  // 32 stream bits starting at p (zeros beyond the slot words)
-    const unsigned w = p >> 5, s = p & 31u;
-    uint32_t lo = 0u, hi = 0u;
-    ZFB_UNROLL for (int i = 0; i < MAXW; i++) {
-      if ((unsigned)i == w) lo = in[i];
-      if ((unsigned)i == w + 1) hi = in[i];
-    }
-    return fsr(lo, hi, s);
+    if (MAXW <= 2) return p < 64u ? (uint32_t)(in0 >> p) : 0u;
+    if (p >= 128u) return 0u;
+    if (p >= 64u) return (uint32_t)(in1 >> (p - 64u));
+    uint64_t v = in0 >> p;
+    if (p > 32u) v |= in1 << (64u - p);
+    return (uint32_t)v;
   };
   uint32_t u[4] = {0u, 0u, 0u, 0u};
   unsigned remaining = maxbits - 9u;
@@ -230,8 +299,30 @@ ZFB_HD void decode_block(float (&f)[4], unsigned maxbits, const uint32_t (&in)[M
     pos += sk; remaining -= sk; k -= (int)sk;
   }
   unsigned n = 0;
-  while (n < 4u && k >= 0 && remaining) {
+  while (n < 3u && k >= 0 && remaining) {
     const uint32_t w = peek(pos);
+    const unsigned cw = n + 1u;                                   // bits per run-plane code
+    unsigned R = (remaining < 32u ? remaining : 32u);
+    if (n == 2u && R > 30u) R = 30u;
+    R = n == 0u ? R : (n == 1u ? R >> 1 : (R * 11u) >> 5);         // whole codes in the window (n == 2: floor(R / 3) for R <= 30)
+    if (R > (unsigned)k + 1u) R = (unsigned)k + 1u;
+    // group-test bits of the run-plane codes: the last bit of every code
+    const uint32_t tests = (n == 0u ? 0xffffffffu : (n == 1u ? 0xaaaaaaaau : 0x24924924u)) & mask32(R * cw);
+    const uint32_t t = w & tests;
+    unsigned L = R;
+    if (t) { const unsigned z = (unsigned)ctz32(t); L = n == 0u ? z : (n == 1u ? z >> 1 : (z * 11u) >> 5); }
+    if (L) {
+      if (n == 1u) u[0] |= brev32(gather2(w) & mask32(L)) >> (31 - k);
+      else if (n == 2u) {
+        u[0] |= brev32(gather3(w) & mask32(L)) >> (31 - k);
+        u[1] |= brev32(gather3(w >> 1) & mask32(L)) >> (31 - k);
+      }
+      pos += L * cw; remaining -= L * cw; k -= (int)L;
+      continue;
+    }
+    if (R == 0u) {
+      // fewer than n + 1 bits are left: the budget ends inside this plane's code (handled exactly below)
+    }
     const unsigned e = tb.dec[n * 128u + (w & 127u)];
     const unsigned len = (e >> 4) & 15u;
     if (len <= remaining) {
@@ -241,16 +332,15 @@ ZFB_HD void decode_block(float (&f)[4], unsigned maxbits, const uint32_t (&in)[M
       pos += len; remaining -= len;
     } else {
       // the budget ends inside this plane's code: exact bit-serial steps (zfp's loop conditions)
-      unsigned bits = remaining, x = 0, m = n < bits ? n : bits, p = pos;
+      unsigned bits = remaining, x = 0, m = n < bits ? n : bits;
       bits -= m;
       x = w & ((1u << m) - 1u);
       uint32_t ww = w >> m;
-      p += m;
       unsigned nn = n;
       while (nn < 4u && bits) {
         bits--;
-        const unsigned t = ww & 1u; ww >>= 1;
-        if (!t) break;
+        const unsigned tt = ww & 1u; ww >>= 1;
+        if (!tt) break;
         while (nn < 3u && bits) {
           bits--;
           const unsigned b = ww & 1u; ww >>= 1;
@@ -266,7 +356,7 @@ ZFB_HD void decode_block(float (&f)[4], unsigned maxbits, const uint32_t (&in)[M
     }
     k--;
   }
-  if (n == 4u && k >= 0 && remaining) {
+  if (n >= 3u && k >= 0 && remaining) {
     const unsigned planes = (unsigned)k + 1u;
     uint32_t v[4] = {0u, 0u, 0u, 0u};
     for (unsigned c = 0; c * 8u < planes && remaining; c++) {
