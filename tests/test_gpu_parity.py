@@ -83,7 +83,9 @@ def test_small_fields_bit_exact(codec, pkg, oracle, dtype, shape):
                     check_metrics(pkg, oracle, part, f, g_ref, (label, rate, wra))
 
 
-TILE_SHAPES = [(8, 8, 256), (8, 8, 1028), (36, 40, 72), (64, 64, 64), (4, 4, 4), (12, 8, 516), (32, 256, 512)]
+TILE_SHAPES = [(8, 8, 256), (8, 8, 1028), (36, 40, 72), (64, 64, 64), (4, 4, 4), (12, 8, 516), (32, 256, 512),
+               # ny / nz not multiples of 4: tile kernels on the full block rows + edge kernel on the partial ones
+               (7, 9, 12), (10, 6, 256), (33, 34, 64), (5, 4, 1028), (4, 5, 260), (9, 130, 520)]
 
 
 @pytest.mark.parametrize("shape", TILE_SHAPES)

@@ -301,7 +301,7 @@ static bool tile_path_ok(const zfb_ctx* c, int dtype, int dims, const geom& g, u
 {
   if (c->force_generic || !c->encode_tiled) return false;
   if (dtype != ZFB_FLOAT || dims != 3) return false;
-  if ((g.nx | g.ny | g.nz) & 3) return false;
+  if ((g.nx & 3) || g.ny < 4 || g.nz < 4) return false;  // TMA needs 16-byte row strides; partial y/z rows go to the edge kernel
   if (maxbits & 63u) return false;
   const unsigned W = maxbits >> 6;
   if (!(W % 2 == 0 || g.bx % 2 == 0)) return false;  // bulk copies need 16-byte granularity
@@ -323,7 +323,8 @@ static bool line_path_ok(const zfb_ctx* c, int dtype, int dims, const geom& g, u
 static tile_geom make_tile_geom(const geom& g, unsigned maxbits)
 {
   tile_geom t;
-  t.nbx = (unsigned)g.bx; t.nby = (unsigned)g.by; t.nbz = (unsigned)g.bz;
+  t.nbx = (unsigned)g.bx; t.nby = (unsigned)(g.ny / 4); t.nbz = (unsigned)(g.nz / 4);
+  t.nby_t = (unsigned)g.by;
   t.bpr = (t.nbx + BOX_BLOCKS - 1) / BOX_BLOCKS;
   t.nboxes = t.bpr * t.nby * t.nbz;
   t.ntiles = (t.nboxes + BOXES_PER_TILE - 1) / BOXES_PER_TILE;
@@ -426,6 +427,7 @@ extern "C" int zfb_encode_dev(zfb_ctx* c, int dtype, int dims, size_t nx, size_t
     enc3_f32_tile_kernel<<<grid, TILE_THREADS, smem, c->stream>>>(tm, (uint64_t*)d_stream, tg, maxbits);
     c->launches++;
     CU_TRY(c, cudaGetLastError());
+    if ((g.ny | g.nz) & 3) return launch_enc_generic<float>(c, dims, g, maxbits, d_in, d_stream, 1);  // partial blocks
     return ZFB_OK;
   }
   if (line_path_ok(c, dtype, dims, g, maxbits) && ((uintptr_t)d_in & 15) == 0 && ((uintptr_t)d_stream & 15) == 0) {
@@ -483,7 +485,7 @@ extern "C" int zfb_decode_dev(zfb_ctx* c, int dtype, int dims, size_t nx, size_t
     }
     unsigned grid = (unsigned)c->sm_count * (unsigned)nb;
     if (grid > tg.ntiles) grid = tg.ntiles;
-    if ((int)grid > c->part_rows) grid = c->part_rows;
+    if ((int)grid > c->part_rows / 2) grid = c->part_rows / 2;
     if (metrics)
       dec3_f32_tile_kernel<true><<<grid, TILE_THREADS, smem, c->stream>>>(tm, (const uint64_t*)d_stream, (float*)d_out, tg, maxbits, c->part);
     else
@@ -491,6 +493,13 @@ extern "C" int zfb_decode_dev(zfb_ctx* c, int dtype, int dims, size_t nx, size_t
     c->launches++;
     CU_TRY(c, cudaGetLastError());
     rows = (int)grid;
+    if ((g.ny | g.nz) & 3) {  // partial blocks
+      int erows = 0;
+      rc = metrics ? launch_dec_generic<float, true>(c, dims, g, maxbits, d_stream, d_out, d_orig, 1, &erows, 0, rows)
+                   : launch_dec_generic<float, false>(c, dims, g, maxbits, d_stream, d_out, d_orig, 1, &erows, 0, rows);
+      if (rc) return rc;
+      rows += erows;
+    }
   } else if (line_path_ok(c, dtype, dims, g, maxbits) && ((uintptr_t)d_out & 15) == 0 && ((uintptr_t)d_stream & 15) == 0 &&
              (!metrics || ((uintptr_t)d_orig & 15) == 0)) {
     const size_t nfull = g.nx / 4;

@@ -436,7 +436,8 @@ constexpr int BOX_FLOATS = 256 * 4 * 4;        // 16 KiB
 constexpr int BOXES_PER_TILE = TILE_THREADS / BOX_BLOCKS;
 
 struct tile_geom {
-  unsigned nbx, nby, nbz;    // blocks per axis
+  unsigned nbx, nby, nbz;    // FULL blocks per axis handled by the tile kernels (ny/4, nz/4; nx % 4 == 0)
+  unsigned nby_t;            // block rows per z-slab in the stream, partial row included ((ny+3)/4)
   unsigned bpr;              // boxes per block-row = ceil(nbx / 64)
   unsigned nboxes;           // bpr * nby * nbz
   unsigned ntiles;           // ceil(nboxes / 2)
@@ -457,7 +458,7 @@ __device__ __forceinline__ box_info box_of(const tile_geom& tg, unsigned q)
   const unsigned row = q / tg.bpr, xb = q - row * tg.bpr;
   const unsigned iy = row % tg.nby, iz = row / tg.nby;
   b.x0 = xb * 256u; b.y0 = iy * 4u; b.z0 = iz * 4u;
-  b.blk0 = (size_t)row * tg.nbx + (size_t)xb * BOX_BLOCKS;
+  b.blk0 = ((size_t)iz * tg.nby_t + iy) * tg.nbx + (size_t)xb * BOX_BLOCKS;
   const unsigned rem = tg.nbx - xb * BOX_BLOCKS;
   b.nvalid = rem < (unsigned)BOX_BLOCKS ? rem : (unsigned)BOX_BLOCKS;
   return b;
@@ -539,8 +540,13 @@ enc3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t* __restr
     }
     __syncthreads();                       // tile buffer consumed, `out` complete, next descriptors published
     if (tid == 0) {
-      const unsigned nslots = b0.nvalid + b1.nvalid;
-      ptx::bulk_store(stream + b0.blk0 * tg.W, obuf, nslots * tg.W * 8u);
+      // the two boxes' slots are adjacent in the stream except across a partial block row
+      if (b1.nvalid && b1.blk0 != b0.blk0 + b0.nvalid) {
+        ptx::bulk_store(stream + b0.blk0 * tg.W, obuf, b0.nvalid * tg.W * 8u);
+        ptx::bulk_store(stream + b1.blk0 * tg.W, obuf + (size_t)b0.nvalid * tg.W, b1.nvalid * tg.W * 8u);
+      } else {
+        ptx::bulk_store(stream + b0.blk0 * tg.W, obuf, (b0.nvalid + b1.nvalid) * tg.W * 8u);
+      }
       ptx::bulk_commit();
       ptx::bulk_wait_read0();              // `out` may be rewritten once the next tile's loads have landed
       if (t + gridDim.x < tg.ntiles) issue_loads(sb[(it + 1) & 1]);
@@ -589,7 +595,12 @@ dec3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64
   auto issue_slots = [&](const box_info* bi) {
     const unsigned bytes = (bi[0].nvalid + bi[1].nvalid) * tg.W * 8u;
     ptx::mbar_expect_tx(&bars[0], bytes);
-    ptx::bulk_load(slots, stream + bi[0].blk0 * tg.W, bytes, &bars[0]);
+    if (bi[1].nvalid && bi[1].blk0 != bi[0].blk0 + bi[0].nvalid) {
+      ptx::bulk_load(slots, stream + bi[0].blk0 * tg.W, bi[0].nvalid * tg.W * 8u, &bars[0]);
+      ptx::bulk_load(slots + (size_t)bi[0].nvalid * tg.W, stream + bi[1].blk0 * tg.W, bi[1].nvalid * tg.W * 8u, &bars[0]);
+    } else {
+      ptx::bulk_load(slots, stream + bi[0].blk0 * tg.W, bytes, &bars[0]);
+    }
   };
   auto issue_orig = [&](const box_info* bi) {
 #pragma unroll
