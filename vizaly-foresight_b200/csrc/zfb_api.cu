@@ -152,7 +152,7 @@ static const size_t ENC_TILE_SMEM_BASE = BOXES_PER_TILE * BOX_FLOATS * sizeof(fl
 static size_t enc_tile_smem(unsigned W) { return ENC_TILE_SMEM_BASE + (size_t)TILE_THREADS * W * 8 + 2 * 8; }
 static size_t dec_tile_smem(unsigned W, bool /*metrics*/)
 {
-  return ENC_TILE_SMEM_BASE + (size_t)TILE_THREADS * W * 8 + 4 * 8;
+  return ENC_TILE_SMEM_BASE + 2 * (size_t)TILE_THREADS * W * 8 + 4 * 8;
 }
 
 extern "C" int zfb_create(zfb_ctx** out, int device)

@@ -133,18 +133,20 @@ template <> struct fast_scratch<true> {
 // ---------------------------------------------------------------------------------------------
 // metric accumulation (one thread)
 // ---------------------------------------------------------------------------------------------
-struct macc {
+template <typename MaxT> struct macc_t {
   double s_sq, s_abs, s_rel;
-  double m_abs, m_rel, m_o, m_no;  // maxima; m_no = max(-o)
+  MaxT m_abs, m_rel, m_o, m_no;  // maxima (float data keeps them in float: exact, and 4 registers fewer); m_no = max(-o)
   __device__ __forceinline__ void init()
   {
     s_sq = s_abs = s_rel = 0.0;
-    m_abs = 0.0;  // the reference's error vectors start with n zeros (absoluteError.hpp:66)
-    m_rel = 0.0;
-    m_o = -1.7976931348623157e308;
-    m_no = -1.7976931348623157e308;
+    m_abs = 0;  // the reference's error vectors start with n zeros (absoluteError.hpp:66)
+    m_rel = 0;
+    m_o = sizeof(MaxT) == 4 ? (MaxT)-3.402823466e38f : (MaxT)-1.7976931348623157e308;
+    m_no = m_o;
   }
 };
+typedef macc_t<double> macc;    // double fields, final reduction
+typedef macc_t<float> maccf;    // float fields
 
 // float: accumulates one row of 4 values into float partial sums (flushed to double by the caller)
 struct frow {
@@ -196,6 +198,13 @@ struct frow {
     mo = fmaxf(fmaxf(mo, o.x), o.y); mo = fmaxf(fmaxf(mo, o.z), o.w);
     mno = fmaxf(fmaxf(mno, -o.x), -o.y); mno = fmaxf(fmaxf(mno, -o.z), -o.w);
   }
+  // sums go to double; the maxima simply keep running in float (no reset needed)
+  __device__ __forceinline__ void flush(maccf& m)
+  {
+    m.s_sq += (double)ssq; m.s_abs += (double)sab; m.s_rel += (double)srl;
+    m.m_abs = fmaxf(m.m_abs, mab); m.m_rel = fmaxf(m.m_rel, mrl); m.m_o = fmaxf(m.m_o, mo); m.m_no = fmaxf(m.m_no, mno);
+    ssq = sab = srl = 0.f;
+  }
   __device__ __forceinline__ void flush(macc& m)
   {
     m.s_sq += (double)ssq; m.s_abs += (double)sab; m.s_rel += (double)srl;
@@ -223,8 +232,12 @@ __device__ __forceinline__ double shfl_xor_d(double v, int lane)
 
 // CTA-wide reduction of the per-thread accumulators; thread 0 writes one row of `part`.
 // red: shared scratch of 7 * (blockDim.x / 32) doubles.
-__device__ __forceinline__ void macc_block_store(macc m, double* red, double* part_row)
+template <typename MaxT>
+__device__ __forceinline__ void macc_block_store(const macc_t<MaxT>& mi, double* red, double* part_row)
 {
+  macc m;
+  m.s_sq = mi.s_sq; m.s_abs = mi.s_abs; m.s_rel = mi.s_rel;
+  m.m_abs = (double)mi.m_abs; m.m_rel = (double)mi.m_rel; m.m_o = (double)mi.m_o; m.m_no = (double)mi.m_no;
 #pragma unroll
   for (int o = 16; o; o >>= 1) {
     m.s_sq += shfl_xor_d(m.s_sq, o);
@@ -361,7 +374,7 @@ __global__ void __launch_bounds__(128) dec_generic_kernel(const uint64_t* __rest
   f3::tables tb;
   if (FAST) tb = build_coder_tables(cs);
   const f3::plane_rows ps = fsc.rows();
-  macc m;
+  macc_t<Scalar> m;
   m.init();
   for (size_t b = b_begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < g.nblocks; b += (size_t)gridDim.x * blockDim.x) {
     const size_t ix = b % g.bx, iy = (b / g.bx) % g.by, iz = b / (g.bx * g.by);
@@ -556,17 +569,16 @@ enc3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t* __restr
 }
 
 // dynamic shared memory layout (decode): [tile: 2 x 16 KiB plane scratch, then the original boxes]
-//                                        [slots: 128*W words][3 mbarriers]
-// Per tile: wait for the slot span (bulk copy) -> plane loop parses the slot into the thread's plane rows
-// -> rows back into registers -> __syncthreads -> thread 0 starts the bulk copy of the NEXT tile's slots
-// and the TMA load of this tile's ORIGINAL boxes into the plane-scratch buffer while all threads run the
-// inverse transform -> metrics against the original rows (LDS.128) -> 16 coalesced 128-bit stores of the
-// decoded rows -> __syncthreads.
-#ifndef ZFB_DEC_CTAS
-#define ZFB_DEC_CTAS 5
-#endif
+//                                        [slots: 2 x 128*W words][4 mbarriers]
+// Per tile: wait for the slot span (bulk copy, issued two tiles ahead into a double buffer) -> plane loop
+// parses the slot into the thread's plane rows -> rows back into registers -> __syncthreads -> thread 0
+// refills the slot buffer just consumed and starts the TMA load of this tile's ORIGINAL boxes into the
+// plane-scratch buffer while all threads run the inverse transform -> metrics against the original rows
+// (LDS.128) -> 16 coalesced 128-bit stores of the decoded rows -> __syncthreads.
+// 4 CTAs/SM at 128 registers: a 5-CTA / 96-register build runs at the same speed but its spills add
+// ~50 % DRAM write traffic (profiles/r01_notes.md), so the spill-free configuration is kept.
 template <bool METRICS>
-__global__ void __launch_bounds__(TILE_THREADS, ZFB_DEC_CTAS)
+__global__ void __launch_bounds__(TILE_THREADS, 4)
 dec3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64_t* __restrict__ stream,
                      float* __restrict__ out, tile_geom tg, unsigned maxbits, double* __restrict__ part)
 {
@@ -574,82 +586,90 @@ dec3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64
   float* tile = reinterpret_cast<float*>(smem_raw);
   uint64_t* slots = reinterpret_cast<uint64_t*>(smem_raw + BOXES_PER_TILE * BOX_FLOATS * sizeof(float));
   const unsigned slot_words = TILE_THREADS * tg.W;
-  uint64_t* bars = slots + (size_t)slot_words;  // [0] slots full, [1,2] orig boxes full
+  uint64_t* bars = slots + 2 * (size_t)slot_words;  // [0,1] slot buffers full, [2,3] orig boxes full
   __shared__ double red[7 * 4];
   __shared__ coder_smem cs;
+  __shared__ box_info sb[3][BOXES_PER_TILE];  // ring of box descriptors: current, next, next-next tile
 
   const unsigned tid = threadIdx.x;
   const unsigned box = tid >> 6, lb = tid & 63;
-
-  __shared__ box_info sb[2][BOXES_PER_TILE];  // box descriptors of the current / next tile (thread 0 computes)
   unsigned t = blockIdx.x;
   if (tid == 0) {
     if (METRICS) ptx::prefetch_tmap(&tmap_orig);
-    for (int i = 0; i < 3; i++) ptx::mbar_init(&bars[i], 1);
+    for (int i = 0; i < 4; i++) ptx::mbar_init(&bars[i], 1);
     ptx::fence_barrier_init();
-    sb[0][0] = box_of(tg, 2 * t);
-    sb[0][1] = box_of(tg, 2 * t + 1);
+    for (int j = 0; j < 2; j++) {
+      sb[j][0] = box_of(tg, 2 * (t + j * gridDim.x));
+      sb[j][1] = box_of(tg, 2 * (t + j * gridDim.x) + 1);
+    }
   }
-  const f3::tables tb = build_coder_tables(cs);  // includes the __syncthreads that publishes barriers and sb[0]
+  const f3::tables tb = build_coder_tables(cs);  // includes the __syncthreads that publishes barriers and sb
 
-  auto issue_slots = [&](const box_info* bi) {
+  auto issue_slots = [&](const box_info* bi, unsigned buf) {
+    uint64_t* dst = slots + (size_t)buf * slot_words;
     const unsigned bytes = (bi[0].nvalid + bi[1].nvalid) * tg.W * 8u;
-    ptx::mbar_expect_tx(&bars[0], bytes);
+    ptx::mbar_expect_tx(&bars[buf], bytes);
     if (bi[1].nvalid && bi[1].blk0 != bi[0].blk0 + bi[0].nvalid) {
-      ptx::bulk_load(slots, stream + bi[0].blk0 * tg.W, bi[0].nvalid * tg.W * 8u, &bars[0]);
-      ptx::bulk_load(slots + (size_t)bi[0].nvalid * tg.W, stream + bi[1].blk0 * tg.W, bi[1].nvalid * tg.W * 8u, &bars[0]);
+      ptx::bulk_load(dst, stream + bi[0].blk0 * tg.W, bi[0].nvalid * tg.W * 8u, &bars[buf]);
+      ptx::bulk_load(dst + (size_t)bi[0].nvalid * tg.W, stream + bi[1].blk0 * tg.W, bi[1].nvalid * tg.W * 8u, &bars[buf]);
     } else {
-      ptx::bulk_load(slots, stream + bi[0].blk0 * tg.W, bytes, &bars[0]);
+      ptx::bulk_load(dst, stream + bi[0].blk0 * tg.W, bytes, &bars[buf]);
     }
   };
   auto issue_orig = [&](const box_info* bi) {
 #pragma unroll
     for (int q = 0; q < BOXES_PER_TILE; q++) {
       if (bi[q].nvalid) {
-        ptx::mbar_expect_tx(&bars[1 + q], BOX_FLOATS * sizeof(float));
-        ptx::tma_load_3d(tile + q * BOX_FLOATS, &tmap_orig, (int)bi[q].x0, (int)bi[q].y0, (int)bi[q].z0, &bars[1 + q]);
+        ptx::mbar_expect_tx(&bars[2 + q], BOX_FLOATS * sizeof(float));
+        ptx::tma_load_3d(tile + q * BOX_FLOATS, &tmap_orig, (int)bi[q].x0, (int)bi[q].y0, (int)bi[q].z0, &bars[2 + q]);
       }
     }
   };
 
-  if (tid == 0 && t < tg.ntiles) issue_slots(sb[0]);
+  if (tid == 0) {
+    if (t < tg.ntiles) issue_slots(sb[0], 0);
+    if (t + gridDim.x < tg.ntiles) issue_slots(sb[1], 1);
+  }
 
   f3::plane_rows ps;
   ps.p = reinterpret_cast<f3::u32x4*>(tile + box * BOX_FLOATS) + lb;
   ps.stride = 64;
 
-  macc m;
+  maccf m;
   m.init();
-  for (unsigned it = 0; t < tg.ntiles; t += gridDim.x, it++) {
-    const box_info b0 = sb[it & 1][0], b1 = sb[it & 1][1];
+  unsigned cur = 0;  // it % 3
+  for (unsigned it = 0; t < tg.ntiles; t += gridDim.x, it++, cur = cur == 2 ? 0 : cur + 1) {
+    const unsigned buf = it & 1, nn = cur == 0 ? 2 : cur - 1;  // nn = (it + 2) % 3
+    const box_info b0 = sb[cur][0], b1 = sb[cur][1];
     const box_info mine = box ? b1 : b0;
     const bool active = lb < mine.nvalid;
     const unsigned nslots = b0.nvalid + b1.nvalid;
-    ptx::mbar_wait(&bars[0], it & 1);
+    ptx::mbar_wait(&bars[buf], (it >> 1) & 1);
     f3::planes64 P;
     int emax = 0;
     bool nonzero = false, low_used = false;
     if (active) {
       const unsigned p = (box ? b0.nvalid : 0u) + lb;
-      f3::reader32 r(reinterpret_cast<const uint32_t*>(slots + (size_t)p * tg.W), 2 * (nslots - p) * tg.W, 0);
+      f3::reader32 r(reinterpret_cast<const uint32_t*>(slots + (size_t)buf * slot_words + (size_t)p * tg.W),
+                     2 * (nslots - p) * tg.W, 0);
       nonzero = f3::decode_planes(P, emax, low_used, maxbits, r, tb, ps);
     }
     ptx::fence_proxy_async();  // plane-row writes (generic proxy) before the TMA load overwrites the buffer
     if (tid == 0) {
-      sb[(it + 1) & 1][0] = box_of(tg, 2 * (t + gridDim.x));
-      sb[(it + 1) & 1][1] = box_of(tg, 2 * (t + gridDim.x) + 1);
+      sb[nn][0] = box_of(tg, 2 * (t + 2 * gridDim.x));
+      sb[nn][1] = box_of(tg, 2 * (t + 2 * gridDim.x) + 1);
     }
-    __syncthreads();           // slots parsed; planes back in registers; next descriptors published
+    __syncthreads();           // slots[buf] parsed; planes back in registers; descriptors of tile it+2 published
     if (tid == 0) {
-      if (t + gridDim.x < tg.ntiles) issue_slots(sb[(it + 1) & 1]);
-      if (METRICS) issue_orig(sb[it & 1]);
+      if (t + 2 * gridDim.x < tg.ntiles) issue_slots(sb[nn], buf);
+      if (METRICS) issue_orig(sb[cur]);
     }
     if (active) {
       float f[64];
       f3::decode_finish(f, P, emax, nonzero, low_used);
       float* dst = out + ((size_t)mine.z0 * tg.ny + mine.y0) * tg.nx + mine.x0 + 4 * lb;
       if (METRICS) {
-        ptx::mbar_wait(&bars[1 + box], it & 1);
+        ptx::mbar_wait(&bars[2 + box], it & 1);
         const float4* src = reinterpret_cast<const float4*>(tile + box * BOX_FLOATS) + lb;
         frow fr;
         fr.init();
@@ -672,7 +692,7 @@ dec3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64
         }
       }
     } else if (METRICS && mine.nvalid) {
-      ptx::mbar_wait(&bars[1 + box], it & 1);  // keep every thread's view of the barrier phase in step
+      ptx::mbar_wait(&bars[2 + box], it & 1);  // keep every thread's view of the barrier phase in step
     }
     if (METRICS) __syncthreads();  // the original rows are consumed before the next tile's planes land there
   }
@@ -730,7 +750,7 @@ __global__ void __launch_bounds__(256) dec1_f32_kernel(const uint32_t* __restric
   __shared__ double red[7 * 8];
   const f1::tables tb = build_coder1_tables(cs);
   const unsigned nw = maxbits >> 5;
-  macc m;
+  maccf m;
   m.init();
   frow fr;
   fr.init();
@@ -766,7 +786,7 @@ __global__ void __launch_bounds__(256) metrics_kernel(const Scalar* __restrict__
                                                       size_t n, double* __restrict__ part)
 {
   __shared__ double red[7 * 8];
-  macc m;
+  macc_t<Scalar> m;
   m.init();
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
