@@ -321,7 +321,7 @@ def main():
             dist.all_reduce(wt, op=dist.ReduceOp.MAX)
         w = float(wt.item())
         e2e = {"value": world * field_bytes * args.e2e_steps / w / 1e9, "unit": "GB/s",
-               "h2d_bytes_per_step": field_bytes + cbytes, "d2h_bytes_per_step": field_bytes + cbytes,
+               "h2d_bytes_per_step": world * (field_bytes + cbytes), "d2h_bytes_per_step": world * (field_bytes + cbytes),
                "steps": args.e2e_steps, "ms_per_step": 1e3 * w / args.e2e_steps,
                "api": "zfb_compress_host + zfb_decompress_host (fused metrics), pinned host buffers"}
         codec.release()
@@ -349,6 +349,15 @@ def main():
                        "ms_per_launch": enc_ms},
             "round_trip": {"achieved": (enc_bytes + dec_bytes) / ((enc_ms + dec_ms) * 1e-3) / 1e9,
                            "bytes_per_value": (enc_bytes + dec_bytes) / n}}
+    # DRAM traffic of one launch, from the committed ncu --set full capture of this workload (null otherwise)
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic_nyx2048slab.json")))
+        if args.workload == "nyx2048-slab" and int(rate) == 8:
+            roof["traffic"] = tr["kernels"]["decode+metrics"]["traffic"]
+            roof["traffic_source"] = "profiles/r01_traffic_nyx2048slab.json (ncu dram__bytes_read.sum + dram__bytes_write.sum)"
+            roof["encode"]["traffic"] = tr["kernels"]["encode"]["traffic"]
+    except Exception:
+        pass
     roof["frac"] = roof["achieved"] / peak
     roof["encode"]["frac"] = roof["encode"]["achieved"] / peak
     roof["round_trip"]["frac"] = roof["round_trip"]["achieved"] / peak
