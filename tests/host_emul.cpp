@@ -8,6 +8,7 @@
 #include "../vizaly-foresight_b200/csrc/zfb_codec.cuh"
 #include "../vizaly-foresight_b200/csrc/zfb_codec_f3.cuh"
 #include "../vizaly-foresight_b200/csrc/zfb_codec_f1.cuh"
+#include "../vizaly-foresight_b200/csrc/zfb_codec_d3.cuh"
 #include <type_traits>
 
 using namespace zfb;
@@ -78,6 +79,23 @@ static void run(bool enc, size_t nx, size_t ny, size_t nz, unsigned maxbits, Sca
           continue;
         }
       }
+      if constexpr (std::is_same<Scalar, double>::value && DIMS == 3) {
+        if (g_use_f3) {
+          const f3::tables tb = host_tables();
+          uint32_t* s32 = reinterpret_cast<uint32_t*>(stream);
+          f3::u32x4 rows[32];
+          f3::plane_rows ps;
+          ps.p = rows; ps.stride = 1;
+          if (aligned) {
+            f3::sink32 sink(s32 + startbit / 32, maxbits / 32);
+            d3::encode_block(f, maxbits, sink, tb, ps);
+          } else {
+            f3::or_sink32 sink(s32, startbit, maxbits);
+            d3::encode_block(f, maxbits, sink, tb, ps);
+          }
+          continue;
+        }
+      }
       if constexpr (std::is_same<Scalar, float>::value && DIMS == 3) {
         if (g_use_f3) {
           const f3::tables tb = host_tables();
@@ -104,6 +122,18 @@ static void run(bool enc, size_t nx, size_t ny, size_t nz, unsigned maxbits, Sca
       }
     } else {
       bool done = false;
+      if constexpr (std::is_same<Scalar, double>::value && DIMS == 3) {
+        if (g_use_f3) {
+          const f3::tables tb = host_tables();
+          const uint32_t* s32 = reinterpret_cast<const uint32_t*>(stream);
+          f3::reader32 r(s32 + (startbit >> 5), (unsigned)(2 * stream_words - (startbit >> 5)), (unsigned)(startbit & 31));
+          f3::u32x4 rows[32];
+          f3::plane_rows ps;
+          ps.p = rows; ps.stride = 1;
+          d3::decode_block(f, maxbits, r, tb, ps);
+          done = true;
+        }
+      }
       if constexpr (std::is_same<Scalar, float>::value && DIMS == 1) {
         if (g_use_f3 && mx == 4 && (maxbits % 32) == 0 && maxbits <= 128) {
           const f1::tables tb = host_tables1();

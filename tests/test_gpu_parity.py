@@ -295,3 +295,29 @@ def test_bad_arguments_return_einval(codec, pkg):
     assert L.zfb_encode_dev(codec._h, 3, 1, 64, 1, 1, 64, t.data_ptr(), t.data_ptr()) == -1   # dtype
     assert L.zfb_encode_dev(codec._h, 1, 1, 64, 1, 1, 8, t.data_ptr(), t.data_ptr()) == -1    # maxbits < 1+EBITS
     assert L.zfb_encode_dev(codec._h, 1, 1, 64, 1, 1, 64, None, t.data_ptr()) == -1
+
+
+F64_TILE_SHAPES = [(8, 8, 256), (8, 8, 1028), (36, 40, 72), (4, 4, 4), (7, 9, 12), (9, 130, 520), (16, 64, 512)]
+
+
+@pytest.mark.parametrize("shape", F64_TILE_SHAPES)
+@pytest.mark.parametrize("rate", [1, 4, 8, 16, 32])
+def test_f64_tile_kernels_bit_exact(codec, pkg, oracle, shape, rate):
+    """3D double fields (nx % 4 == 0) take the f64 TMA tile kernels; metrics for doubles are computed in
+    double (documented deviation: the reference reinterprets the bytes as float)."""
+    f = np.exp(1.2 * smooth_field(shape, seed=rate + 3, dtype=np.float64))
+    mb = pkg.maxbits(np.float64, 3, rate)
+    s_ref = oracle.compress(f, mb)
+    g_ref = oracle.decompress(s_ref, shape, np.float64, mb)
+    s, g, part = gpu_roundtrip(codec, f, mb)
+    assert np.array_equal(s, s_ref)
+    assert_bits_equal(g, g_ref, "decoded")
+    d = f - g_ref
+    v = pkg.metric_values(part)
+    assert v["n"] == f.size
+    assert v["absolute_error"] == float(np.abs(d).max())
+    assert v["max"] == float(f.max()) and v["min"] == float(f.min())
+    mse = float(np.mean(d * d))
+    assert abs(v["mse"] - mse) <= 1e-9 * mse + 1e-300
+    s2, g2, _ = gpu_roundtrip(codec, f, mb, with_metrics=False)
+    assert_bits_equal(g2, g_ref, "decoded (no metrics)")

@@ -171,3 +171,28 @@ def test_fast_1d_coder(oracle):
             s, g = emul_roundtrip(O, f, mb)
             assert np.array_equal(s, s_ref), (label, mb)
             assert np.array_equal(g.view(np.uint8), O.decompress(s_ref, f.shape, np.float32, mb).view(np.uint8)), (label, mb)
+
+
+def test_fast_f64_coder_budget_boundaries(oracle):
+    """double/3D fast coder (zfb_codec_d3.cuh): budgets 12..4200 bits, lazily finished plane groups,
+    reduced precision for tiny exponents (kmin > 0)."""
+    O = oracle
+    rng = np.random.default_rng(43)
+    base = smooth_field((4, 8, 8), seed=5, dtype=np.float64, amp=7.0)
+    fields = [
+        base,
+        rng.standard_normal((4, 8, 8)) * 900,
+        base * (rng.random((4, 8, 8)) > 0.8),
+        np.where(rng.random((4, 8, 8)) > 0.97, 1.0e3, 1.0e-3),
+        np.full((4, 8, 8), -3.25),
+        rng.standard_normal((4, 8, 8)) * 1e-305,     # emax near the bottom: precision < 64 planes
+        rng.standard_normal((4, 8, 8)) * 4e-308,
+        rng.standard_normal((4, 8, 8)) * 1e300,
+    ]
+    for f in fields:
+        f = np.ascontiguousarray(f, dtype=np.float64)
+        for mb in list(range(12, 100, 3)) + list(range(100, 4200, 97)) + [64, 512, 1024, 2048, 4096]:
+            s_ref = O.compress(f, mb)
+            s, g = emul_roundtrip(O, f, mb)
+            assert np.array_equal(s, s_ref), mb
+            assert np.array_equal(g.view(np.uint8), O.decompress(s_ref, f.shape, np.float64, mb).view(np.uint8)), mb

@@ -200,6 +200,12 @@ extern "C" int zfb_create(zfb_ctx** out, int device)
     cudaGetLastError();
     c->encode_tiled = nullptr;  // tile kernels unusable: everything goes through the generic kernels
   }
+  if (cudaFuncSetAttribute(enc3_f64_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) != cudaSuccess ||
+      cudaFuncSetAttribute(dec3_f64_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) != cudaSuccess ||
+      cudaFuncSetAttribute(dec3_f64_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) != cudaSuccess) {
+    cudaGetLastError();
+    c->encode_tiled = nullptr;
+  }
   *out = c;
   return ZFB_OK;
 }
@@ -300,7 +306,7 @@ static geom make_geom(int dims, size_t nx, size_t ny, size_t nz, unsigned maxbit
 static bool tile_path_ok(const zfb_ctx* c, int dtype, int dims, const geom& g, unsigned maxbits, bool metrics)
 {
   if (c->force_generic || !c->encode_tiled) return false;
-  if (dtype != ZFB_FLOAT || dims != 3) return false;
+  if (dims != 3) return false;
   if ((g.nx & 3) || g.ny < 4 || g.nz < 4) return false;  // TMA needs 16-byte row strides; partial y/z rows go to the edge kernel
   if (maxbits & 63u) return false;
   const unsigned W = maxbits >> 6;
@@ -308,6 +314,7 @@ static bool tile_path_ok(const zfb_ctx* c, int dtype, int dims, const geom& g, u
   if (g.nx >= (1ull << 31) || g.ny >= (1ull << 31) || g.nz >= (1ull << 31)) return false;
   const size_t bpr = (g.bx + BOX_BLOCKS - 1) / BOX_BLOCKS;
   if (bpr * g.by * g.bz >= (1ull << 31)) return false;
+  if (dtype == ZFB_DOUBLE) return W <= 40;  // 32 KiB tile + 2 x 64*W*8 slot staging
   const size_t smem = metrics ? dec_tile_smem(W, true) : enc_tile_smem(W);
   if (smem > 100 * 1024 || enc_tile_smem(W) > 100 * 1024) return false;
   return true;
@@ -333,20 +340,26 @@ static tile_geom make_tile_geom(const geom& g, unsigned maxbits)
   return t;
 }
 
-static int make_tmap_3d_f32(zfb_ctx* c, CUtensorMap* tm, const void* base, const geom& g)
+static int make_tmap_3d(zfb_ctx* c, CUtensorMap* tm, const void* base, const geom& g, int dtype)
 {
+  const cuuint64_t es = dtype == ZFB_FLOAT ? 4 : 8;
   cuuint64_t gdim[3] = {(cuuint64_t)g.nx, (cuuint64_t)g.ny, (cuuint64_t)g.nz};
-  cuuint64_t gstr[2] = {(cuuint64_t)g.nx * 4, (cuuint64_t)g.nx * g.ny * 4};
+  cuuint64_t gstr[2] = {(cuuint64_t)g.nx * es, (cuuint64_t)g.nx * g.ny * es};
   cuuint32_t box[3] = {256, 4, 4};
   cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = c->encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gdim, gstr, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = c->encode_tiled(tm, dtype == ZFB_FLOAT ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3,
+                               const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     c->err = "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r);
     return ZFB_ECUDA;
   }
   return ZFB_OK;
+}
+static int make_tmap_3d_f32(zfb_ctx* c, CUtensorMap* tm, const void* base, const geom& g)
+{
+  return make_tmap_3d(c, tm, base, g, ZFB_FLOAT);
 }
 
 static int generic_grid(const zfb_ctx* c, size_t nblocks)
@@ -410,7 +423,22 @@ extern "C" int zfb_encode_dev(zfb_ctx* c, int dtype, int dims, size_t nx, size_t
   if (!d_in || !d_stream) { c->err = "null pointer"; return ZFB_EINVAL; }
   CU_TRY(c, cudaSetDevice(c->device));
   const geom g = make_geom(dims, nx, ny, nz, maxbits);
-  if (tile_path_ok(c, dtype, dims, g, maxbits, false) && ((uintptr_t)d_in & 15) == 0 && ((uintptr_t)d_stream & 15) == 0) {
+  if (dtype == ZFB_DOUBLE && tile_path_ok(c, dtype, dims, g, maxbits, false) && ((uintptr_t)d_in & 15) == 0 &&
+      ((uintptr_t)d_stream & 15) == 0) {
+    CUtensorMap tm;
+    rc = make_tmap_3d(c, &tm, d_in, g, ZFB_DOUBLE);
+    if (rc) return rc;
+    const tile_geom tg = make_tile_geom(g, maxbits);
+    const size_t smem = DBOX_DOUBLES * sizeof(double) + (size_t)DTILE_THREADS * tg.W * 8 + 16;
+    unsigned grid = (unsigned)c->sm_count * 4u;
+    if (grid > tg.nboxes) grid = tg.nboxes;
+    enc3_f64_tile_kernel<<<grid, DTILE_THREADS, smem, c->stream>>>(tm, (uint64_t*)d_stream, tg, maxbits);
+    c->launches++;
+    CU_TRY(c, cudaGetLastError());
+    if ((g.ny | g.nz) & 3) return launch_enc_generic<double>(c, dims, g, maxbits, d_in, d_stream, 1);
+    return ZFB_OK;
+  }
+  if (dtype == ZFB_FLOAT && tile_path_ok(c, dtype, dims, g, maxbits, false) && ((uintptr_t)d_in & 15) == 0 && ((uintptr_t)d_stream & 15) == 0) {
     CUtensorMap tm;
     rc = make_tmap_3d_f32(c, &tm, d_in, g);
     if (rc) return rc;
@@ -466,7 +494,34 @@ extern "C" int zfb_decode_dev(zfb_ctx* c, int dtype, int dims, size_t nx, size_t
   const size_t n = g.nx * g.ny * g.nz;
   const bool metrics = d_orig != nullptr;
   int rows = 0;
-  if (tile_path_ok(c, dtype, dims, g, maxbits, metrics) && ((uintptr_t)d_out & 15) == 0 &&
+  if (dtype == ZFB_DOUBLE && tile_path_ok(c, dtype, dims, g, maxbits, metrics) && ((uintptr_t)d_out & 15) == 0 &&
+      ((uintptr_t)d_stream & 15) == 0 && (!metrics || ((uintptr_t)d_orig & 15) == 0)) {
+    CUtensorMap tm;
+    memset(&tm, 0, sizeof tm);
+    if (metrics) {
+      rc = make_tmap_3d(c, &tm, d_orig, g, ZFB_DOUBLE);
+      if (rc) return rc;
+    }
+    const tile_geom tg = make_tile_geom(g, maxbits);
+    const size_t smem = DBOX_DOUBLES * sizeof(double) + 2 * (size_t)DTILE_THREADS * tg.W * 8 + 32;
+    unsigned grid = (unsigned)c->sm_count * 4u;
+    if (grid > tg.nboxes) grid = tg.nboxes;
+    if ((int)grid > c->part_rows / 2) grid = c->part_rows / 2;
+    if (metrics)
+      dec3_f64_tile_kernel<true><<<grid, DTILE_THREADS, smem, c->stream>>>(tm, (const uint64_t*)d_stream, (double*)d_out, tg, maxbits, c->part);
+    else
+      dec3_f64_tile_kernel<false><<<grid, DTILE_THREADS, smem, c->stream>>>(tm, (const uint64_t*)d_stream, (double*)d_out, tg, maxbits, c->part);
+    c->launches++;
+    CU_TRY(c, cudaGetLastError());
+    rows = (int)grid;
+    if ((g.ny | g.nz) & 3) {
+      int erows = 0;
+      rc = metrics ? launch_dec_generic<double, true>(c, dims, g, maxbits, d_stream, d_out, d_orig, 1, &erows, 0, rows)
+                   : launch_dec_generic<double, false>(c, dims, g, maxbits, d_stream, d_out, d_orig, 1, &erows, 0, rows);
+      if (rc) return rc;
+      rows += erows;
+    }
+  } else if (dtype == ZFB_FLOAT && tile_path_ok(c, dtype, dims, g, maxbits, metrics) && ((uintptr_t)d_out & 15) == 0 &&
       ((uintptr_t)d_stream & 15) == 0 && (!metrics || ((uintptr_t)d_orig & 15) == 0)) {
     CUtensorMap tm;
     memset(&tm, 0, sizeof tm);

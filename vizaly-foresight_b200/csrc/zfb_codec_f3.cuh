@@ -37,12 +37,16 @@ namespace f3 {
 struct alignas(16) u32x4 {
   uint32_t x, y, z, w;
 };
-struct plane_rows {
+// Row q lives at p[(q >> SH) * stride + (q & (2^SH - 1))]: SH = 0 for 16-byte columns (float tiles), SH = 1 for
+// the 32-byte columns of a double tile (two consecutive rows share one 32-byte row segment).
+template <int SH> struct plane_rows_t {
   u32x4* p;
   unsigned stride;
-  ZFB_HD u32x4 ld(int r) const { return p[(unsigned)r * stride]; }
-  ZFB_HD void st(int r, const u32x4& v) const { p[(unsigned)r * stride] = v; }
+  ZFB_HD unsigned at(int r) const { return SH ? ((unsigned)r >> SH) * stride + ((unsigned)r & ((1u << SH) - 1u)) : (unsigned)r * stride; }
+  ZFB_HD u32x4 ld(int r) const { return p[at(r)]; }
+  ZFB_HD void st(int r, const u32x4& v) const { p[at(r)] = v; }
 };
+typedef plane_rows_t<0> plane_rows;
 
 // ---------------------------------------------------------------------------------------------
 // small 32-bit helpers
@@ -200,6 +204,23 @@ struct planes64 {
   ZFB_HD void finish(int base) { stages_low(a, base); stages_low(b, base); }
 };
 
+// Finish (or, equally, un-finish: the stages are involutions) the transpose of the 16 planes parked in rows
+// r0 .. r0+7: both 16-word groups (coefficients 0..31 and 32..63) go through stages 8, 4, 2, 1.
+template <class PR> ZFB_HD void finish_rows(const PR& ps, int r0)
+{
+  planes64 Q;
+  ZFB_UNROLL for (int r = 0; r < 8; r++) {
+    const u32x4 v = ps.ld(r0 + r);
+    Q.a[2 * r] = v.x; Q.b[2 * r] = v.y; Q.a[2 * r + 1] = v.z; Q.b[2 * r + 1] = v.w;
+  }
+  Q.finish(0);
+  ZFB_UNROLL for (int r = 0; r < 8; r++) {
+    u32x4 v;
+    v.x = Q.a[2 * r]; v.y = Q.b[2 * r]; v.z = Q.a[2 * r + 1]; v.w = Q.b[2 * r + 1];
+    ps.st(r0 + r, v);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // 32-bit word sinks / writer
 // ---------------------------------------------------------------------------------------------
@@ -286,6 +307,62 @@ template <class Sink> struct writer32 {
 // ---------------------------------------------------------------------------------------------
 // encode
 // ---------------------------------------------------------------------------------------------
+// The embedded coder proper, shared by the float (NP = 32 planes) and double (NP = 64) front ends: planes
+// NP-1 .. kmin of 64 coefficients, read from the plane rows.  On entry the top 16 planes (rows NP/2-8 ..
+// NP/2-1) are finished; every lower group of 16 planes is still in its half-transposed form and is finished
+// only when the budget reaches it.
+template <int NP, class Sink, class PR>
+ZFB_HD void encode_planes(const PR& ps, unsigned maxbits, uint32_t header, unsigned hbits, int kmin, Sink& sink,
+                          const tables& tb)
+{
+  writer32<Sink> bw(sink);
+  bw.put(header, hbits);
+
+  unsigned n = 0;
+  u32x4 cur;
+  cur.x = cur.y = cur.z = cur.w = 0u;
+  ZFB_NOUNROLL for (int k = NP - 1; k >= kmin; k--) {
+    if (bw.total >= maxbits) break;
+    if (k < NP - 16 && (k & 15) == 15) finish_rows(ps, (k - 15) >> 1);  // next 16 planes: finish their transpose now
+    if (k & 1) cur = ps.ld(k >> 1);
+    const uint32_t xl = (k & 1) ? cur.z : cur.x, xh = (k & 1) ? cur.w : cur.y;
+    if (n == 64u) { bw.put64(xl, xh); continue; }  // every coefficient significant: the plane goes out verbatim
+    uint32_t yl, yh;
+    if (n == 0) { yl = xl; yh = xh; }
+    else if (n < 32) {
+      bw.put(xl & mask32(n), n);
+      yl = fsr(xl, xh, n); yh = xh >> n;
+    } else {
+      bw.put(xl, 32);
+      bw.put(xh & mask32(n - 32), n - 32);
+      yl = xh >> (n - 32); yh = 0u;
+    }
+    if ((yl | yh) == 0u) bw.put(0u, 1);
+    else {
+      const unsigned plast = yh ? 32u + (unsigned)msb32(yh) : (unsigned)msb32(yl);
+      const unsigned nfull = plast >> 3;                 // bytes before the one holding the last one-bit
+      uint32_t lead = 1u;                                // the first group test rides on the first byte's code
+      for (unsigned j = 0; j < nfull; j++) {
+        const uint32_t b = yl & 0xffu;
+        bw.put((tb.enc[b] << lead) | lead, 8u + (unsigned)popc32(b) + lead);
+        lead = 0u;
+        yl = fsr(yl, yh, 8); yh >>= 8;
+      }
+      {
+        const uint32_t b = yl & 0xffu;
+        uint32_t e = tb.enc[b];
+        unsigned len = (plast & 7u) + 1u + (unsigned)popc32(b);
+        if (n + plast == 63u) len -= 2;                  // the last coefficient's one is implicit, no test follows
+        else e &= ~(1u << (len - 1));                    // final group test: no more ones in this plane
+        bw.put(((e & mask32(len)) << lead) | lead, len + lead);
+      }
+      n += plast + 1u;
+    }
+  }
+  bw.flush();
+  sink.finish();
+}
+
 template <class Sink>
 ZFB_HD void encode_block(const float (&f)[64], unsigned maxbits, Sink& sink, const tables& tb, const plane_rows& ps)
 {
@@ -326,65 +403,9 @@ ZFB_HD void encode_block(const float (&f)[64], unsigned maxbits, Sink& sink, con
     ps.st(r, v);
   }
 
-  writer32<Sink> bw(sink);
-  bw.put(2u * (uint32_t)(E + 1) + 1u, 9);
-
-  unsigned n = 0;
-  u32x4 cur;
-  cur.x = cur.y = cur.z = cur.w = 0u;
-  ZFB_NOUNROLL for (int k = 31; k >= 0; k--) {
-    if (bw.total >= maxbits) break;
-    if (k == 15) {
-      planes64 Q;
-      ZFB_UNROLL for (int r = 0; r < 8; r++) {
-        const u32x4 v = ps.ld(r);
-        Q.a[2 * r] = v.x; Q.b[2 * r] = v.y; Q.a[2 * r + 1] = v.z; Q.b[2 * r + 1] = v.w;
-      }
-      Q.finish(0);
-      ZFB_UNROLL for (int r = 0; r < 8; r++) {
-        u32x4 v;
-        v.x = Q.a[2 * r]; v.y = Q.b[2 * r]; v.z = Q.a[2 * r + 1]; v.w = Q.b[2 * r + 1];
-        ps.st(r, v);
-      }
-    }
-    if (k & 1) cur = ps.ld(k >> 1);
-    const uint32_t xl = (k & 1) ? cur.z : cur.x, xh = (k & 1) ? cur.w : cur.y;
-    if (n == 64u) { bw.put64(xl, xh); continue; }  // every coefficient significant: the plane goes out verbatim
-    uint32_t yl, yh;
-    if (n == 0) { yl = xl; yh = xh; }
-    else if (n < 32) {
-      bw.put(xl & mask32(n), n);
-      yl = fsr(xl, xh, n); yh = xh >> n;
-    } else {
-      bw.put(xl, 32);
-      bw.put(xh & mask32(n - 32), n - 32);
-      yl = xh >> (n - 32); yh = 0u;
-    }
-    if ((yl | yh) == 0u) bw.put(0u, 1);
-    else {
-      const unsigned plast = yh ? 32u + (unsigned)msb32(yh) : (unsigned)msb32(yl);
-      const unsigned nfull = plast >> 3;                 // bytes before the one holding the last one-bit
-      uint32_t lead = 1u;                                // the first group test rides on the first byte's code
-      for (unsigned j = 0; j < nfull; j++) {
-        const uint32_t b = yl & 0xffu;
-        bw.put((tb.enc[b] << lead) | lead, 8u + (unsigned)popc32(b) + lead);
-        lead = 0u;
-        yl = fsr(yl, yh, 8); yh >>= 8;
-      }
-      {
-        const uint32_t b = yl & 0xffu;
-        uint32_t e = tb.enc[b];
-        unsigned len = (plast & 7u) + 1u + (unsigned)popc32(b);
-        if (n + plast == 63u) len -= 2;                  // the last coefficient's one is implicit, no test follows
-        else e &= ~(1u << (len - 1));                    // final group test: no more ones in this plane
-        bw.put(((e & mask32(len)) << lead) | lead, len + lead);
-      }
-      n += plast + 1u;
-    }
-  }
-  bw.flush();
-  sink.finish();
+  encode_planes<32>(ps, maxbits, 2u * (uint32_t)(E + 1) + 1u, 9u, 0, sink, tb);
 }
+
 
 // ---------------------------------------------------------------------------------------------
 // decode
@@ -446,32 +467,24 @@ struct reader32 {
   }
 };
 
-// Phase 1: parse the slot into bit planes (left in P).  Returns false for an all-zero block.
-template <class Reader>
-ZFB_HD bool decode_planes(planes64& P, int& emax, bool& low_used_out, unsigned maxbits, Reader& r, const tables& tb,
-                          const plane_rows& ps)
+// Shared slot parser (float: NP = 32 planes, 9 header bits; double: NP = 64, 12): fills the plane rows with
+// the decoded planes (finished form) and returns the first plane index that was NOT decoded (kmin - 1 .. NP-1),
+// so the caller knows which groups of 16 planes are non-zero.  `r` is positioned behind the header.
+template <int NP, class Reader, class PR>
+ZFB_HD int parse_planes(const PR& ps, unsigned maxbits, unsigned hbits, int kmin, Reader& r, const tables& tb)
 {
-  const uint32_t head = r.lo;
-  emax = 0;
-  low_used_out = false;
-  if (!(head & 1u)) return false;
-  emax = (int)((head >> 1) & 0xffu) - 127;
-  r.consume(9);
-
   {
     u32x4 z;
     z.x = z.y = z.z = z.w = 0u;
-    ZFB_UNROLL for (int q = 0; q < 16; q++) ps.st(q, z);
+    ZFB_UNROLL for (int q = 0; q < NP / 2; q++) ps.st(q, z);
   }
-  unsigned remaining = maxbits - 9u;
+  unsigned remaining = maxbits - hbits;
   unsigned n = 0;
-  bool low_used = false;
   u32x4 cur;
   cur.x = cur.y = cur.z = cur.w = 0u;
-  int k = 31;
-  ZFB_NOUNROLL for (; k >= 0; k--) {
+  int k = NP - 1;
+  ZFB_NOUNROLL for (; k >= kmin; k--) {
     if (!remaining) break;
-    if (k == 15) low_used = true;
     uint32_t xl = 0u, xh = 0u;
     if (n == 64u) {
       // every coefficient significant: the plane is the next min(64, remaining) stream bits
@@ -561,16 +574,31 @@ ZFB_HD bool decode_planes(planes64& P, int& emax, bool& low_used_out, unsigned m
     if (k & 1) { cur.z = xl; cur.w = xh; }
     else { cur.x = xl; cur.y = xh; ps.st(k >> 1, cur); }
   }
-  if (k >= 0 && !(k & 1)) {  // stopped with the odd plane of a row pending (k is the first plane NOT decoded)
+  if (k >= kmin && !(k & 1)) {  // stopped with the odd plane of a row pending (k is the first plane NOT decoded)
     cur.x = 0u; cur.y = 0u;
     ps.st(k >> 1, cur);
   }
 
+  return k;
+}
+
+// Phase 1: parse the slot into bit planes (left in P).  Returns false for an all-zero block.
+template <class Reader>
+ZFB_HD bool decode_planes(planes64& P, int& emax, bool& low_used_out, unsigned maxbits, Reader& r, const tables& tb,
+                          const plane_rows& ps)
+{
+  const uint32_t head = r.lo;
+  emax = 0;
+  low_used_out = false;
+  if (!(head & 1u)) return false;
+  emax = (int)((head >> 1) & 0xffu) - 127;
+  r.consume(9);
+  const int kend = parse_planes<32>(ps, maxbits, 9u, 0, r, tb);
   ZFB_UNROLL for (int q = 0; q < 16; q++) {
     const u32x4 v = ps.ld(q);
     P.a[2 * q] = v.x; P.b[2 * q] = v.y; P.a[2 * q + 1] = v.z; P.b[2 * q + 1] = v.w;
   }
-  low_used_out = low_used;
+  low_used_out = kend < 15;
   return true;
 }
 

@@ -23,6 +23,7 @@
 #include "zfb_codec.cuh"
 #include "zfb_codec_f3.cuh"
 #include "zfb_codec_f1.cuh"
+#include "zfb_codec_d3.cuh"
 
 namespace zfb {
 
@@ -695,6 +696,173 @@ dec3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64
       ptx::mbar_wait(&bars[2 + box], it & 1);  // keep every thread's view of the barrier phase in step
     }
     if (METRICS) __syncthreads();  // the original rows are consumed before the next tile's planes land there
+  }
+  if (METRICS) macc_block_store(m, red, part + (size_t)blockIdx.x * PART_STRIDE);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3D double tile kernels (nx % 4 == 0, whole-word slots): the float design with 64 threads per CTA and ONE
+// TMA box of 256x4x4 doubles (32 KiB, 64 x-consecutive blocks) per tile.  A block needs ~128 registers for
+// its 64 doubles alone, so CTAs are small and 4 fit per SM.  Plane rows are parked in place: a thread's 16
+// rows of 32 bytes hold its 32 plane rows of 16 bytes.
+// ---------------------------------------------------------------------------------------------
+constexpr int DTILE_THREADS = 64;
+constexpr int DBOX_DOUBLES = 256 * 4 * 4;  // 32 KiB
+
+// dynamic shared memory: [tile 32 KiB][out: 64*W words][1 mbarrier]
+__global__ void __launch_bounds__(DTILE_THREADS, 4)
+enc3_f64_tile_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t* __restrict__ stream, tile_geom tg,
+                     unsigned maxbits)
+{
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  double* tile = reinterpret_cast<double*>(smem_raw);
+  uint64_t* outw = reinterpret_cast<uint64_t*>(smem_raw + DBOX_DOUBLES * sizeof(double));
+  uint64_t* bars = outw + (size_t)DTILE_THREADS * tg.W;
+  __shared__ coder_smem cs;
+  __shared__ box_info sb[2];
+
+  const unsigned tid = threadIdx.x;
+  unsigned t = blockIdx.x;  // tile = box index
+  if (tid == 0) {
+    ptx::prefetch_tmap(&tmap);
+    ptx::mbar_init(&bars[0], 1);
+    ptx::fence_barrier_init();
+    sb[0] = box_of(tg, t);
+  }
+  const f3::tables tb = build_coder_tables(cs);
+
+  auto issue_load = [&](const box_info& bi) {
+    if (bi.nvalid) {
+      ptx::mbar_expect_tx(&bars[0], DBOX_DOUBLES * sizeof(double));
+      ptx::tma_load_3d(tile, &tmap, (int)bi.x0, (int)bi.y0, (int)bi.z0, &bars[0]);
+    }
+  };
+  if (tid == 0 && t < tg.nboxes) issue_load(sb[0]);
+
+  f3::plane_rows_t<1> ps;
+  ps.p = reinterpret_cast<f3::u32x4*>(tile) + 2 * tid;
+  ps.stride = 128;  // a row of the box is 256 doubles = 128 sixteen-byte units
+
+  for (unsigned it = 0; t < tg.nboxes; t += gridDim.x, it++) {
+    const box_info b0 = sb[it & 1];
+    const bool active = tid < b0.nvalid;
+    ptx::mbar_wait(&bars[0], it & 1);
+    if (active) {
+      double f[64];
+      const double2* src = reinterpret_cast<const double2*>(tile) + 2 * tid;
+#pragma unroll
+      for (int r = 0; r < 16; r++) {
+        const double2 v0 = src[r * 128], v1 = src[r * 128 + 1];
+        f[4 * r] = v0.x; f[4 * r + 1] = v0.y; f[4 * r + 2] = v1.x; f[4 * r + 3] = v1.y;
+      }
+      f3::sink32 sink(reinterpret_cast<uint32_t*>(outw + (size_t)tid * tg.W), 2 * tg.W);
+      d3::encode_block(f, maxbits, sink, tb, ps);
+    }
+    ptx::fence_proxy_async();
+    if (tid == 0) sb[(it + 1) & 1] = box_of(tg, t + gridDim.x);
+    __syncthreads();
+    if (tid == 0) {
+      ptx::bulk_store(stream + b0.blk0 * tg.W, outw, b0.nvalid * tg.W * 8u);
+      ptx::bulk_commit();
+      ptx::bulk_wait_read0();
+      if (t + gridDim.x < tg.nboxes) issue_load(sb[(it + 1) & 1]);
+    }
+  }
+  if (tid == 0) ptx::bulk_wait0();
+}
+
+// dynamic shared memory: [tile 32 KiB: plane scratch, then the original box][slots: 2 x 64*W words][3 mbarriers]
+template <bool METRICS>
+__global__ void __launch_bounds__(DTILE_THREADS, 4)
+dec3_f64_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64_t* __restrict__ stream,
+                     double* __restrict__ out, tile_geom tg, unsigned maxbits, double* __restrict__ part)
+{
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  double* tile = reinterpret_cast<double*>(smem_raw);
+  uint64_t* slots = reinterpret_cast<uint64_t*>(smem_raw + DBOX_DOUBLES * sizeof(double));
+  const unsigned slot_words = DTILE_THREADS * tg.W;
+  uint64_t* bars = slots + 2 * (size_t)slot_words;  // [0,1] slot buffers, [2] orig box
+  __shared__ double red[7 * 2];
+  __shared__ coder_smem cs;
+  __shared__ box_info sb[3];
+
+  const unsigned tid = threadIdx.x;
+  unsigned t = blockIdx.x;
+  if (tid == 0) {
+    if (METRICS) ptx::prefetch_tmap(&tmap_orig);
+    for (int i = 0; i < 3; i++) ptx::mbar_init(&bars[i], 1);
+    ptx::fence_barrier_init();
+    sb[0] = box_of(tg, t);
+    sb[1] = box_of(tg, t + gridDim.x);
+  }
+  const f3::tables tb = build_coder_tables(cs);
+
+  auto issue_slots = [&](const box_info& bi, unsigned buf) {
+    const unsigned bytes = bi.nvalid * tg.W * 8u;
+    ptx::mbar_expect_tx(&bars[buf], bytes);
+    ptx::bulk_load(slots + (size_t)buf * slot_words, stream + bi.blk0 * tg.W, bytes, &bars[buf]);
+  };
+  if (tid == 0) {
+    if (t < tg.nboxes) issue_slots(sb[0], 0);
+    if (t + gridDim.x < tg.nboxes) issue_slots(sb[1], 1);
+  }
+
+  f3::plane_rows_t<1> ps;
+  ps.p = reinterpret_cast<f3::u32x4*>(tile) + 2 * tid;
+  ps.stride = 128;
+
+  macc m;
+  m.init();
+  unsigned cur = 0;
+  for (unsigned it = 0; t < tg.nboxes; t += gridDim.x, it++, cur = cur == 2 ? 0 : cur + 1) {
+    const unsigned buf = it & 1, nn = cur == 0 ? 2 : cur - 1;
+    const box_info b0 = sb[cur];
+    const bool active = tid < b0.nvalid;
+    ptx::mbar_wait(&bars[buf], (it >> 1) & 1);
+    f3::planes64 PH, PL;
+    int emax = 0, kend = 63;
+    bool nonzero = false;
+    if (active) {
+      f3::reader32 r(reinterpret_cast<const uint32_t*>(slots + (size_t)buf * slot_words + (size_t)tid * tg.W),
+                     2 * (b0.nvalid - tid) * tg.W, 0);
+      nonzero = d3::decode_planes(PH, PL, emax, kend, maxbits, r, tb, ps);
+    }
+    ptx::fence_proxy_async();
+    if (tid == 0) sb[nn] = box_of(tg, t + 2 * gridDim.x);
+    __syncthreads();
+    if (tid == 0) {
+      if (t + 2 * gridDim.x < tg.nboxes) issue_slots(sb[nn], buf);
+      if (METRICS && b0.nvalid) {
+        ptx::mbar_expect_tx(&bars[2], DBOX_DOUBLES * sizeof(double));
+        ptx::tma_load_3d(tile, &tmap_orig, (int)b0.x0, (int)b0.y0, (int)b0.z0, &bars[2]);
+      }
+    }
+    if (active) {
+      double f[64];
+      d3::decode_finish(f, PH, PL, emax, nonzero, kend);
+      double* dst = out + ((size_t)b0.z0 * tg.ny + b0.y0) * tg.nx + b0.x0 + 4 * tid;
+      if (METRICS) {
+        ptx::mbar_wait(&bars[2], it & 1);
+        const double2* src = reinterpret_cast<const double2*>(tile) + 2 * tid;
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+          const double2 o0 = src[r * 128], o1 = src[r * 128 + 1];
+          macc_add(m, o0.x, f[4 * r]); macc_add(m, o0.y, f[4 * r + 1]); macc_add(m, o1.x, f[4 * r + 2]); macc_add(m, o1.y, f[4 * r + 3]);
+        }
+      }
+      const size_t rs = tg.nx, ps2 = (size_t)tg.ny * tg.nx;
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          double* rowp = dst + (size_t)k * ps2 + (size_t)j * rs;
+          __stcs(reinterpret_cast<double2*>(rowp), make_double2(f[16 * k + 4 * j], f[16 * k + 4 * j + 1]));
+          __stcs(reinterpret_cast<double2*>(rowp) + 1, make_double2(f[16 * k + 4 * j + 2], f[16 * k + 4 * j + 3]));
+        }
+    } else if (METRICS && b0.nvalid) {
+      ptx::mbar_wait(&bars[2], it & 1);
+    }
+    if (METRICS) __syncthreads();
   }
   if (METRICS) macc_block_store(m, red, part + (size_t)blockIdx.x * PART_STRIDE);
 }
