@@ -507,6 +507,21 @@ extern "C" int zfb_decode_dev(zfb_ctx* c, int dtype, int dims, size_t nx, size_t
     unsigned grid = (unsigned)c->sm_count * 4u;
     if (grid > tg.nboxes) grid = tg.nboxes;
     if ((int)grid > c->part_rows / 2) grid = c->part_rows / 2;
+    // float64: the metric arithmetic in double, unrolled over 64 values, makes the fused kernel 118 KiB of SASS
+    // and instruction-fetch bound (5.4 ms vs 3.2 ms for the 1 GiB-block benchmark slab), so the default is the
+    // lean decode kernel followed by the streaming metric kernel over (orig, out).  ZFB_F64_FUSED=1 fuses.
+    static const bool unfused = [] { const char* e = std::getenv("ZFB_F64_FUSED"); return !(e && e[0] == '1'); }();
+    if (metrics && unfused) {
+      dec3_f64_tile_kernel<false><<<grid, DTILE_THREADS, smem, c->stream>>>(tm, (const uint64_t*)d_stream, (double*)d_out, tg, maxbits, c->part);
+      c->launches++;
+      CU_TRY(c, cudaGetLastError());
+      if ((g.ny | g.nz) & 3) {
+        int er = 0;
+        rc = launch_dec_generic<double, false>(c, dims, g, maxbits, d_stream, d_out, d_orig, 1, &er, 0, 0);
+        if (rc) return rc;
+      }
+      return zfb_metrics_dev(c, dtype, d_orig, d_out, n);
+    }
     if (metrics)
       dec3_f64_tile_kernel<true><<<grid, DTILE_THREADS, smem, c->stream>>>(tm, (const uint64_t*)d_stream, (double*)d_out, tg, maxbits, c->part);
     else

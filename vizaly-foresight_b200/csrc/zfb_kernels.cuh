@@ -215,15 +215,30 @@ struct frow {
   }
 };
 
+// |d| / |o| for |o| >= 1 to ~1e-7 relative: both operands are scaled by the exact power of two that brings |o|
+// into [1, 2), then divided in float (MUFU.RCP).  An IEEE double division costs ~30 instructions per value and,
+// unrolled 64 times, pushed the double kernels out of the instruction cache.
+__device__ __forceinline__ double rel_quotient(double ad, double ao)
+{
+  int e = ((__double2hiint(ao) >> 20) & 0x7ff) - 1023;  // ao >= 1 -> e >= 0
+  e = e > 1022 ? 1022 : e;
+  const double sc = __hiloint2double((1023 - e) << 20, 0);  // 2^-e
+  const float aof = (float)(ao * sc), adf = (float)(ad * sc);
+  float q;
+  asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(q) : "f"(adf), "f"(aof));
+  return (double)q;
+}
+
 __device__ __forceinline__ void macc_add(macc& m, double o, double a)
 {
   // double fields: same formulas carried out in double (the reference reinterprets doubles as floats,
-  // which is meaningless)
+  // which is meaningless).  Maxima by compare-select (inputs are finite; fmax's NaN handling
+  // costs ~14 instructions each in double).
   const double d = o - a, ad = fabs(d), ao = fabs(o);
-  const double rl = ao < 1.0 ? ad : ad / ao;
-  m.s_sq += d * d; m.s_abs += ad; m.s_rel += rl;
-  m.m_abs = fmax(m.m_abs, ad); m.m_rel = fmax(m.m_rel, rl);
-  m.m_o = fmax(m.m_o, o); m.m_no = fmax(m.m_no, -o);
+  const double rl = ao < 1.0 ? ad : rel_quotient(ad, ao);
+  m.s_sq = fma(d, d, m.s_sq); m.s_abs += ad; m.s_rel += rl;
+  m.m_abs = ad > m.m_abs ? ad : m.m_abs; m.m_rel = rl > m.m_rel ? rl : m.m_rel;
+  m.m_o = o > m.m_o ? o : m.m_o; m.m_no = -o > m.m_no ? -o : m.m_no;
 }
 
 __device__ __forceinline__ double shfl_xor_d(double v, int lane)
