@@ -25,7 +25,7 @@ static f3::tables host_tables()
     built = true;
   }
   f3::tables t;
-  t.enc = g_enc; t.dec = g_dec;
+  t.enc = g_enc; t.dec = g_dec; t.enc_s = t.dec_s = 0;
   return t;
 }
 

@@ -556,6 +556,13 @@ extern "C" int zfb_decode_dev(zfb_ctx* c, int dtype, int dims, size_t nx, size_t
     unsigned grid = (unsigned)c->sm_count * (unsigned)nb;
     if (grid > tg.ntiles) grid = tg.ntiles;
     if ((int)grid > c->part_rows / 2) grid = c->part_rows / 2;
+    static const bool f32_unfused = [] { const char* e = std::getenv("ZFB_F32_UNFUSED"); return e && e[0] == '1'; }();
+    if (metrics && f32_unfused && !((g.ny | g.nz) & 3)) {  // experiment switch (fused is faster for float)
+      dec3_f32_tile_kernel<false><<<grid, TILE_THREADS, smem, c->stream>>>(tm, (const uint64_t*)d_stream, (float*)d_out, tg, maxbits, c->part);
+      c->launches++;
+      CU_TRY(c, cudaGetLastError());
+      return zfb_metrics_dev(c, dtype, d_orig, d_out, n);
+    }
     if (metrics)
       dec3_f32_tile_kernel<true><<<grid, TILE_THREADS, smem, c->stream>>>(tm, (const uint64_t*)d_stream, (float*)d_out, tg, maxbits, c->part);
     else

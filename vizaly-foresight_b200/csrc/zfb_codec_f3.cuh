@@ -157,7 +157,31 @@ ZFB_HD uint32_t dec_entry(unsigned state, unsigned v)
 struct tables {
   const uint16_t* enc;  // 256 entries
   const uint32_t* dec;  // 512 entries
+  uint32_t enc_s, dec_s;  // device: 32-bit shared-memory addresses of the two tables
 };
+// Table lookups.  On the device the tables live in shared memory and are read with ld.shared through a 32-bit
+// address: going through the generic pointer makes the compiler rebuild the shared window base
+// (S2UR SR_CgaCtaId -> ULEA) inside the coder loops, on their critical path.
+ZFB_HD uint32_t enc_at(const tables& tb, uint32_t i)
+{
+#if defined(__CUDA_ARCH__)
+  uint32_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(tb.enc_s + 2u * i));
+  return v;
+#else
+  return tb.enc[i];
+#endif
+}
+ZFB_HD uint32_t dec_at(const tables& tb, uint32_t i)
+{
+#if defined(__CUDA_ARCH__)
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(tb.dec_s + 4u * i));
+  return v;
+#else
+  return tb.dec[i];
+#endif
+}
 
 // ---------------------------------------------------------------------------------------------
 // bit planes of 64 x uint32 coefficients, finished lazily in two halves
@@ -344,13 +368,13 @@ ZFB_HD void encode_planes(const PR& ps, unsigned maxbits, uint32_t header, unsig
       uint32_t lead = 1u;                                // the first group test rides on the first byte's code
       for (unsigned j = 0; j < nfull; j++) {
         const uint32_t b = yl & 0xffu;
-        bw.put((tb.enc[b] << lead) | lead, 8u + (unsigned)popc32(b) + lead);
+        bw.put((enc_at(tb, b) << lead) | lead, 8u + (unsigned)popc32(b) + lead);
         lead = 0u;
         yl = fsr(yl, yh, 8); yh >>= 8;
       }
       {
         const uint32_t b = yl & 0xffu;
-        uint32_t e = tb.enc[b];
+        uint32_t e = enc_at(tb, b);
         unsigned len = (plast & 7u) + 1u + (unsigned)popc32(b);
         if (n + plast == 63u) len -= 2;                  // the last coefficient's one is implicit, no test follows
         else e &= ~(1u << (len - 1));                    // final group test: no more ones in this plane
@@ -504,7 +528,7 @@ ZFB_HD int parse_planes(const PR& ps, unsigned maxbits, unsigned hbits, int kmin
       // fast steps: far from the end of the budget (>= 16 bits) and of the block (n <= 48) a table step
       // (<= 8 stream bits, <= 8 coefficients) cannot run into either limit, so only "end of plane" is tested
       while (remaining >= 16u && n <= 48u) {
-        const uint32_t e = tb.dec[(state << 8) | (r.lo & 0xffu)];
+        const uint32_t e = dec_at(tb, (state << 8) | (r.lo & 0xffu));
         const unsigned npos = (e >> 8) & 15u, nbits = (e >> 12) & 15u;
         const uint32_t pat = e & 0xffu;
         if (n < 32) { xl |= pat << n; xh |= carry_out(pat, n); }
@@ -521,7 +545,7 @@ ZFB_HD int parse_planes(const PR& ps, unsigned maxbits, unsigned hbits, int kmin
         // at the end of the budget a terminator is forced behind the last valid bit: in state B it becomes
         // the one zfp's decoder deposits when the budget ends inside a zero run, in state A it deposits nothing
         if (forced) wb = (wb & mask32(remaining)) | (1u << remaining);
-        const uint32_t e = tb.dec[(state << 8) | (wb & 0xffu)];
+        const uint32_t e = dec_at(tb, (state << 8) | (wb & 0xffu));
         const unsigned npos = (e >> 8) & 15u, nbits = (e >> 12) & 15u;
         const uint32_t pat = e & 0xffu;
         if (n + npos <= 63u) {

@@ -118,6 +118,8 @@ __device__ __forceinline__ f3::tables build_coder_tables(coder_smem& cs)
   __syncthreads();
   f3::tables t;
   t.enc = cs.enc; t.dec = cs.dec;
+  t.enc_s = (uint32_t)__cvta_generic_to_shared(cs.enc);
+  t.dec_s = (uint32_t)__cvta_generic_to_shared(cs.dec);
   return t;
 }
 
