@@ -262,6 +262,36 @@ ZFB_HD void encode_block(const float (&f)[4], unsigned maxbits, uint32_t (&out)[
   (void)nw;
 }
 
+// One plane whose code is cut short by the end of the bit budget (`bits` < code length): zfp's decoder loop
+// conditions, bit by bit.  Returns the plane nibble | new n << 4.  Kept out of line: it runs at most once per
+// block and must not be if-converted into the table path.
+#if defined(__CUDACC__)
+__device__ __host__ __noinline__
+#else
+inline
+#endif
+unsigned truncated_plane(uint32_t w, unsigned bits, unsigned n)
+{
+  unsigned m = n < bits ? n : bits;
+  bits -= m;
+  unsigned x = w & ((1u << m) - 1u);
+  uint32_t ww = w >> m;
+  while (n < 4u && bits) {
+    bits--;
+    const unsigned tt = ww & 1u; ww >>= 1;
+    if (!tt) break;
+    while (n < 3u && bits) {
+      bits--;
+      const unsigned b = ww & 1u; ww >>= 1;
+      if (b) break;
+      n++;
+    }
+    x |= 1u << n;
+    n++;
+  }
+  return x | (n << 4);
+}
+
 // ---------------------------------------------------------------------------------------------
 // decode: reads maxbits/32 words from in[]
 // ---------------------------------------------------------------------------------------------
@@ -331,28 +361,12 @@ ZFB_HD void decode_block(float (&f)[4], unsigned maxbits, const uint32_t (&in)[M
       n = e >> 8;
       pos += len; remaining -= len;
     } else {
-      // the budget ends inside this plane's code: exact bit-serial steps (zfp's loop conditions)
-      unsigned bits = remaining, x = 0, m = n < bits ? n : bits;
-      bits -= m;
-      x = w & ((1u << m) - 1u);
-      uint32_t ww = w >> m;
-      unsigned nn = n;
-      while (nn < 4u && bits) {
-        bits--;
-        const unsigned tt = ww & 1u; ww >>= 1;
-        if (!tt) break;
-        while (nn < 3u && bits) {
-          bits--;
-          const unsigned b = ww & 1u; ww >>= 1;
-          if (b) break;
-          nn++;
-        }
-        x |= 1u << nn;
-        nn++;
-      }
+      // the budget ends inside this plane's code (at most once per block): exact bit-serial steps, out of line
+      const unsigned xn = truncated_plane(w, remaining, n);
+      const unsigned x = xn & 15u;
       ZFB_UNROLL for (int i = 0; i < 4; i++) u[i] |= ((x >> i) & 1u) << k;
       remaining = 0;
-      n = nn;
+      n = xn >> 4;
     }
     k--;
   }
