@@ -321,3 +321,50 @@ def test_f64_tile_kernels_bit_exact(codec, pkg, oracle, shape, rate):
     assert abs(v["mse"] - mse) <= 1e-9 * mse + 1e-300
     s2, g2, _ = gpu_roundtrip(codec, f, mb, with_metrics=False)
     assert_bits_equal(g2, g_ref, "decoded (no metrics)")
+
+
+def test_nyx_2048_full_size_properties(codec, pkg):
+    """BASELINE's headline field at FULL size on one GPU (2048^3 float32 = 32 GiB, ~70 GiB resident): the
+    size-independent properties -- the whole-field stream is the concatenation of the 8 slab streams, slab
+    decodes equal the whole-field decode, slab metric partials combine to the whole-field partials, and the
+    error obeys the fixed-rate bound seen on small fields."""
+    torch = _torch()
+    free, total = torch.cuda.mem_get_info()
+    if free < 76 * 2 ** 30:
+        pytest.skip("needs ~76 GiB of free device memory")
+    n = 2048
+    g = torch.Generator(device="cuda").manual_seed(7)
+    f = torch.empty((n, n, n), dtype=torch.float32, device="cuda")
+    xs = torch.arange(n, device="cuda", dtype=torch.float32) / n
+    for z0 in range(0, n, 64):
+        zz = (torch.arange(z0, z0 + 64, device="cuda", dtype=torch.float32) / n)[:, None, None]
+        a = torch.sin(6.2831853 * (3 * zz + 2 * xs[None, :, None] + 5 * xs[None, None, :]))
+        a = a + 0.5 * torch.cos(6.2831853 * (7 * zz - 4 * xs[None, :, None]))
+        a = a + 0.05 * torch.randn(a.shape, generator=g, device="cuda")
+        f[z0:z0 + 64] = torch.exp(1.5 * a)
+        del a
+    mb = pkg.maxbits(np.float32, 3, 8)
+    stream = codec.encode(f, mb)
+    assert stream.numel() == (n // 4) ** 3 * 64
+    out = codec.decode(stream, (n, n, n), torch.float32, mb, orig=f)
+    whole = codec.partials()
+    sl = n // 8
+    parts = []
+    sbytes = stream.numel() // 8
+    for r in range(8):
+        fs = f[r * sl:(r + 1) * sl]
+        ss = codec.encode(fs, mb)
+        assert torch.equal(ss, stream[r * sbytes:(r + 1) * sbytes]), r          # slab-concatenation identity
+        os_ = codec.decode(ss, (sl, n, n), torch.float32, mb, orig=fs)
+        assert torch.equal(os_, out[r * sl:(r + 1) * sl]), r
+        parts.append(codec.partials())
+        del ss, os_
+    comb = pkg.combine_partials(parts)
+    assert comb.n == whole.n == n ** 3
+    for k in ("max_abs", "max_rel", "max_orig", "neg_min_orig"):
+        assert getattr(comb, k) == getattr(whole, k), k
+    for k in ("sum_sq", "sum_abs", "sum_rel"):
+        assert abs(getattr(comb, k) - getattr(whole, k)) <= 1e-9 * abs(getattr(whole, k)), k
+    v = pkg.metric_values(whole)
+    assert v["absolute_error"] == float((f - out).abs().max().item())
+    assert v["psnr"] > 60.0
