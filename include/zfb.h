@@ -17,6 +17,8 @@
  *     to zfb_set_stream) without synchronising; "host" entry points take HOST pointers, do the
  *     host<->device copies themselves and return when the result is in host memory.
  *   - There is no CPU fallback: without a usable CUDA device every compute call returns ZFB_ENODEV.
+ *   - A context is not thread-safe: use it from one host thread at a time (CBench is single-threaded per rank,
+ *     one context per rank / GPU); distinct contexts are independent.
  */
 #ifndef ZFB_H
 #define ZFB_H

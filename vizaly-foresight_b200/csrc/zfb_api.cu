@@ -802,7 +802,14 @@ extern "C" int zfb_decompress_host(zfb_ctx* c, int dtype, int dims, size_t nx, s
   for (int i = 0; i < 2; i++) { cudaEventCreateWithFlags(&ev_up[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming); }
   std::vector<zfb_partials> slab_parts(metrics ? sp.nslabs : 0);
   partials_dev* d_slab_parts = nullptr;
-  if (metrics && cudaMalloc(&d_slab_parts, sp.nslabs * sizeof(partials_dev)) != cudaSuccess) { cudaGetLastError(); return ZFB_ENOMEM; }
+  if (metrics && cudaMalloc(&d_slab_parts, sp.nslabs * sizeof(partials_dev)) != cudaSuccess) {
+    cudaGetLastError();
+    for (int i = 0; i < 2; i++) { cudaEventDestroy(ev_up[i]); cudaEventDestroy(ev_k[i]); }
+    cudaStreamDestroy(up);
+    cudaStreamDestroy(down);
+    c->err = "cudaMalloc failed";
+    return ZFB_ENOMEM;
+  }
   int status = ZFB_OK;
   size_t row0 = 0, word0 = 0;
   for (size_t s = 0; s < sp.nslabs && status == ZFB_OK; s++) {
