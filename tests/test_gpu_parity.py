@@ -368,3 +368,37 @@ def test_nyx_2048_full_size_properties(codec, pkg):
     v = pkg.metric_values(whole)
     assert v["absolute_error"] == float((f - out).abs().max().item())
     assert v["psnr"] > 60.0
+
+
+GUARD_CASES = [("float32", (64, 64, 64), 8), ("float32", (36, 40, 72), 8), ("float32", (13, 9, 7), 8),
+               ("float32", (12, 8, 516), 4), ("float32", (4099,), 16), ("float32", (1 << 16,), 8),
+               ("float32", (33, 70), 8), ("float64", (16, 16, 64), 8), ("float64", (9, 10, 11), 16),
+               ("float64", (1001,), 16), ("float32", (20, 20, 20), 5.5)]
+
+
+@pytest.mark.parametrize("dtype,shape,rate", GUARD_CASES)
+def test_outputs_stay_inside_exact_size_buffers(codec, pkg, dtype, shape, rate):
+    """Every kernel family writes exactly stream_bytes / field bytes: guard bands on both sides stay intact
+    (the pool has no compute-sanitizer, so this is the out-of-bounds check)."""
+    torch = _torch()
+    G = 4096
+    tdt = getattr(torch, dtype)
+    mb = pkg.maxbits(dtype, len(shape), rate)
+    nbytes = pkg.stream_bytes(shape, mb)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    f = torch.randn(shape, dtype=tdt, device="cuda", generator=g)
+    sbuf = torch.full((nbytes + 2 * G,), 0xA5, dtype=torch.uint8, device="cuda")
+    s = codec.encode(f, mb, out=sbuf[G:G + nbytes])
+    assert s.data_ptr() == sbuf.data_ptr() + G
+    fbytes = f.numel() * f.element_size()
+    obuf = torch.full((fbytes + 2 * G,), 0x5A, dtype=torch.uint8, device="cuda")
+    out = obuf[G:G + fbytes].view(tdt).view(shape)
+    codec.decode(s, shape, tdt, mb, orig=f, out=out)
+    codec.synchronize()
+    assert bool((sbuf[:G] == 0xA5).all()) and bool((sbuf[G + nbytes:] == 0xA5).all()), "stream guard overwritten"
+    assert bool((obuf[:G] == 0x5A).all()) and bool((obuf[G + fbytes:] == 0x5A).all()), "field guard overwritten"
+    # and the guarded result equals the unguarded one
+    s2 = codec.encode(f, mb)
+    assert torch.equal(s, s2)
+    ref = codec.decode(s2, shape, tdt, mb)
+    assert torch.equal(out.contiguous().view(torch.uint8), ref.view(torch.uint8)), "guarded decode"
