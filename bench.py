@@ -46,8 +46,14 @@ def make_field(torch, shape, dtype, kind, seed, device):
     """Deterministic synthetic field generated on the device."""
     g = torch.Generator(device=device).manual_seed(20261019 + seed)
     tdt = torch.float32 if dtype == "float32" else torch.float64
-    if kind == "uniform":
+    if kind == "uniform":  # HACC positions: U[0, 256)
         return (256.0 * torch.rand(shape, generator=g, device=device, dtype=torch.float32)).to(tdt)
+    if kind == "velocity":  # HACC velocities: N(0, 900^2)
+        return (900.0 * torch.randn(shape, generator=g, device=device, dtype=torch.float32)).to(tdt)
+    if kind == "noise":  # coder worst case: white noise
+        return torch.randn(shape, generator=g, device=device, dtype=torch.float32).to(tdt)
+    if kind == "zero":  # coder best case: every block empty
+        return torch.zeros(shape, device=device, dtype=tdt)
     nz, ny, nx = shape
     cg = torch.Generator(device="cpu").manual_seed(1000 + seed)
     out = torch.empty(shape, device=device, dtype=tdt)
@@ -256,6 +262,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="nyx2048-slab", choices=sorted(WORKLOADS))
     ap.add_argument("--rate", type=float, default=0)
+    ap.add_argument("--wra", type=int, default=1, help="1 = CBench semantics (64-bit aligned slots), 0 = unaligned slots")
+    ap.add_argument("--field", default="", choices=["", "lognormal", "smooth", "uniform", "velocity", "noise", "zero"],
+                    help="override the workload's synthetic field kind (sweeps only)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
@@ -289,8 +298,8 @@ def main():
     npdt = np.float32 if dtype == "float32" else np.float64
     tdt = torch.float32 if dtype == "float32" else torch.float64
     esz = 4 if dtype == "float32" else 8
-    mb = pkg.maxbits(npdt, d, int(rate) if float(rate).is_integer() else rate)
-    field = make_field(torch, shape, dtype, wl["kind"], rank, dev)
+    mb = pkg.maxbits(npdt, d, int(rate) if float(rate).is_integer() else rate, args.wra)
+    field = make_field(torch, shape, dtype, args.field or wl["kind"], rank, dev)
     n = field.numel()
     field_bytes = n * esz
     cbytes = pkg.stream_bytes(shape, mb)
@@ -435,7 +444,8 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if dtype == "float32" else "f64", "data": "synthetic",
         "config": {"workload": args.workload, "description": wl["desc"], "shape_per_gpu": list(shape),
-                   "rate_bpv": rate, "maxbits": mb, "compressed_bytes_per_gpu": cbytes,
+                   "rate_bpv": rate, "maxbits": mb, "wra": args.wra, "field": args.field or wl["kind"],
+                   "compressed_bytes_per_gpu": cbytes,
                    "l2": "inputs (%.1f GiB per step) are far larger than the 126 MB L2; no flush needed" % (field_bytes / 2 ** 30),
                    "exchange": "NCCL all-reduce of metric partials (SUM f64[4], MAX f64[4])" if world > 1 else "none (1 GPU)"},
         "numa_binding": numa, "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,

@@ -2,6 +2,7 @@
 oracle's streams and decoded values bit for bit.  This pins the kernel arithmetic without a GPU."""
 import ctypes as C
 import os
+import glob
 import subprocess
 
 import numpy as np
@@ -17,9 +18,9 @@ def emul():
     if _lib is None:
         so = os.path.join(ROOT, "build", "libhost_emul.so")
         src = os.path.join(ROOT, "tests", "host_emul.cpp")
-        hdr = os.path.join(ROOT, "vizaly-foresight_b200", "csrc", "zfb_codec.cuh")
+        hdrs = glob.glob(os.path.join(ROOT, "vizaly-foresight_b200", "csrc", "*.cuh"))
         os.makedirs(os.path.dirname(so), exist_ok=True)
-        if (not os.path.exists(so)) or max(os.path.getmtime(src), os.path.getmtime(hdr)) > os.path.getmtime(so):
+        if (not os.path.exists(so)) or max(os.path.getmtime(p) for p in [src] + hdrs) > os.path.getmtime(so):
             cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
             subprocess.run([cxx, "-std=c++17", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-o", so, src],
                            check=True)

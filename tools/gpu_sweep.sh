@@ -4,9 +4,14 @@ for spec in "nyx512 4" "nyx512 8" "nyx512 16" "nyx2048-slab 4" "nyx2048-slab 16"
   set -- $spec
   timeout -k 10 300 python bench.py --workload $1 --rate $2 --steps 3 --warmup 3 --no-e2e --no-cpu 2>/dev/null | grep '^{' >> gpurun_out/sweep.jsonl
 done
+# coder best / worst cases, HACC velocities, unaligned (wra=0) 1D slots
+for spec in "nyx512 8 noise 1" "nyx512 8 zero 1" "hacc1d 8 velocity 1" "hacc1d 8 uniform 0" "hacc1d 16 uniform 0" "hacc1d 8 noise 1" "vpic1024-f64 8 noise 1" "vpic1024-f64 8 zero 1"; do
+  set -- $spec
+  timeout -k 10 300 python bench.py --workload $1 --rate $2 --field $3 --wra $4 --steps 3 --warmup 3 --no-e2e --no-cpu 2>/dev/null | grep '^{' >> gpurun_out/sweep.jsonl
+done
 python - <<'PY'
 import json
 for l in open("gpurun_out/sweep.jsonl"):
     d=json.loads(l); c=d["config"]
-    print(c["workload"], "rate", c["rate_bpv"], "maxbits", c["maxbits"], "GB/s", round(d["value"],1), "enc_ms", round(d["enc_ms"],3), "dec_ms", round(d["dec_ms"],3), "rt_frac", round(d["roofline"]["round_trip"]["frac"],3), "psnr", round(d["metrics_check"]["psnr"],2))
+    print(c["workload"], c.get("field"), "wra", c.get("wra"), "rate", c["rate_bpv"], "maxbits", c["maxbits"], "GB/s", round(d["value"],1), "enc_ms", round(d["enc_ms"],3), "dec_ms", round(d["dec_ms"],3), "rt_frac", round(d["roofline"]["round_trip"]["frac"],3), "psnr", round(d["metrics_check"]["psnr"],2))
 PY

@@ -267,6 +267,7 @@ struct sink32 {  // slot on a word boundary, whole number of 32-bit words (maxbi
   {
     for (; widx < nwords; widx++) dst[widx] = 0;
   }
+  ZFB_HD unsigned words() const { return widx; }
 };
 
 struct or_sink32 {  // arbitrary bit offset in a pre-zeroed stream (maxbits % 64 != 0)
@@ -297,20 +298,20 @@ struct or_sink32 {  // arbitrary bit offset in a pre-zeroed stream (maxbits % 64
   }
   ZFB_HD void word2(uint32_t w0, uint32_t w1) { word(w0); word(w1); }
   ZFB_HD void finish() {}
+  ZFB_HD unsigned words() const { return j; }
 };
 
 template <class Sink> struct writer32 {
   Sink& sink;
   uint32_t acc;
-  unsigned cnt;    // bits held in acc, < 32
-  unsigned total;  // bits emitted
-  ZFB_HD explicit writer32(Sink& s) : sink(s), acc(0), cnt(0), total(0) {}
+  unsigned cnt;  // bits held in acc, < 32
+  ZFB_HD explicit writer32(Sink& s) : sink(s), acc(0), cnt(0) {}
+  ZFB_HD unsigned bits() const { return 32u * sink.words() + cnt; }  // bits emitted so far
   ZFB_HD void put(uint32_t v, unsigned len)  // len in [0, 32]; bits of v above len are zero
   {
     acc |= v << cnt;
     const uint32_t c = carry_out(v, cnt);
     cnt += len;
-    total += len;
     if (cnt >= 32) { sink.word(acc); acc = c; cnt -= 32; }
   }
   ZFB_HD void put64(uint32_t xl, uint32_t xh)  // a whole plane of 64 significant coefficients
@@ -319,7 +320,6 @@ template <class Sink> struct writer32 {
     const uint32_t w1 = shl_pair(xl, xh, cnt);
     acc = carry_out(xh, cnt);
     sink.word2(w0, w1);
-    total += 64;
   }
   ZFB_HD void flush()
   {
@@ -346,39 +346,46 @@ ZFB_HD void encode_planes(const PR& ps, unsigned maxbits, uint32_t header, unsig
   u32x4 cur;
   cur.x = cur.y = cur.z = cur.w = 0u;
   ZFB_NOUNROLL for (int k = NP - 1; k >= kmin; k--) {
-    if (bw.total >= maxbits) break;
+    if (bw.bits() >= maxbits) break;
     if (k < NP - 16 && (k & 15) == 15) finish_rows(ps, (k - 15) >> 1);  // next 16 planes: finish their transpose now
     if (k & 1) cur = ps.ld(k >> 1);
     const uint32_t xl = (k & 1) ? cur.z : cur.x, xh = (k & 1) ? cur.w : cur.y;
     if (n == 64u) { bw.put64(xl, xh); continue; }  // every coefficient significant: the plane goes out verbatim
+    // y = the not yet significant coefficients; the first group test (y != 0) rides on the verbatim bits
     uint32_t yl, yh;
-    if (n == 0) { yl = xl; yh = xh; }
-    else if (n < 32) {
-      bw.put(xl & mask32(n), n);
-      yl = fsr(xl, xh, n); yh = xh >> n;
-    } else {
-      bw.put(xl, 32);
-      bw.put(xh & mask32(n - 32), n - 32);
-      yl = xh >> (n - 32); yh = 0u;
-    }
-    if ((yl | yh) == 0u) bw.put(0u, 1);
+    if (n < 32) { yl = fsr(xl, xh, n); yh = xh >> n; }
+    else { yl = xh >> (n - 32); yh = 0u; }
+    const uint32_t t = (yl | yh) ? 1u : 0u;
+    if (n < 32) bw.put((xl & mask32(n)) | (t << n), n + 1u);
     else {
+      bw.put(xl, 32);
+      bw.put((xh & mask32(n - 32)) | (t << (n - 32)), n - 31u);
+    }
+    if (t) {
+      // bytes of y up to the one holding the last one-bit, two table codes (<= 16 bits each) per put
       const unsigned plast = yh ? 32u + (unsigned)msb32(yh) : (unsigned)msb32(yl);
-      const unsigned nfull = plast >> 3;                 // bytes before the one holding the last one-bit
-      uint32_t lead = 1u;                                // the first group test rides on the first byte's code
-      for (unsigned j = 0; j < nfull; j++) {
-        const uint32_t b = yl & 0xffu;
-        bw.put((enc_at(tb, b) << lead) | lead, 8u + (unsigned)popc32(b) + lead);
-        lead = 0u;
-        yl = fsr(yl, yh, 8); yh >>= 8;
-      }
-      {
-        const uint32_t b = yl & 0xffu;
-        uint32_t e = enc_at(tb, b);
-        unsigned len = (plast & 7u) + 1u + (unsigned)popc32(b);
-        if (n + plast == 63u) len -= 2;                  // the last coefficient's one is implicit, no test follows
-        else e &= ~(1u << (len - 1));                    // final group test: no more ones in this plane
-        bw.put(((e & mask32(len)) << lead) | lead, len + lead);
+      const unsigned fpos = plast & 7u;
+      const bool implicit = n + plast == 63u;
+      unsigned nb = (plast >> 3) + 1u;
+      for (;;) {
+        const uint32_t b0 = yl & 0xffu, b1 = (yl >> 8) & 0xffu;
+        uint32_t e0 = enc_at(tb, b0), e1 = enc_at(tb, b1);
+        unsigned l0 = 8u + (unsigned)popc32(b0), l1 = 8u + (unsigned)popc32(b1);
+        if (nb <= 2u) {
+          // the final byte: its code stops behind the last one; the group test that follows is 0 (no more
+          // ones in this plane), or absent together with the one itself when that is coefficient 63
+          uint32_t e = nb == 1u ? e0 : e1;
+          unsigned l = (nb == 1u ? l0 : l1) - 7u + fpos;
+          if (implicit) l -= 2u;
+          else e &= ~(1u << (l - 1u));
+          e &= mask32(l);
+          if (nb == 1u) { e0 = e; l0 = l; e1 = 0u; l1 = 0u; }
+          else { e1 = e; l1 = l; }
+        }
+        bw.put(e0 | (e1 << l0), l0 + l1);
+        if (nb <= 2u) break;
+        nb -= 2u;
+        yl = fsr(yl, yh, 16); yh >>= 16;
       }
       n += plast + 1u;
     }
@@ -525,11 +532,13 @@ ZFB_HD int parse_planes(const PR& ps, unsigned maxbits, unsigned hbits, int kmin
       if (m > 32) { xl = r.take(32); xh = r.take(m - 32); }
       else if (m) xl = r.take(m);
       unsigned state = 0;
-      // fast steps: far from the end of the budget (>= 16 bits) and of the block (n <= 48) a table step
-      // (<= 8 stream bits, <= 8 coefficients) cannot run into either limit, so only "end of plane" is tested
-      while (remaining >= 16u && n <= 48u) {
+      // fast steps: with >= 8 bits of budget left a table step (<= 8 stream bits) cannot overrun it, and a
+      // step that stays below coefficient 63 (whose one is implicit) needs no end-of-block rule either; the
+      // first step that would touch coefficient 63 is left to the careful loop below
+      while (remaining >= 8u) {
         const uint32_t e = dec_at(tb, (state << 8) | (r.lo & 0xffu));
         const unsigned npos = (e >> 8) & 15u, nbits = (e >> 12) & 15u;
+        if (n + npos > 63u) break;
         const uint32_t pat = e & 0xffu;
         if (n < 32) { xl |= pat << n; xh |= carry_out(pat, n); }
         else xh |= pat << (n - 32);
