@@ -150,6 +150,50 @@ int zfb_histogram_host(zfb_ctx* ctx, int dtype, int which, double lo, double hi,
 /* Drop the resident device copies (called from CompressorInterface::close / between scalars). */
 int zfb_release_resident(zfb_ctx* ctx);
 
+/* ---- variable-rate streams: zfp's fixed-accuracy / fixed-precision modes ----------------------------
+ * What the CPU zfp plugin exposes as "abs" and "rel" (CBench/compressors/zfp/zfpCompressor.hpp:83-93,
+ * 117-120) and every shipped input uses (e.g. inputs/hacc/hacc_cbench_test.json).  Blocks have different
+ * lengths and are concatenated bit-tight, so a decoder needs the bit offset of every block (the index):
+ * zfb keeps it from the encode (as ZFPCompressor::decompress relies on state left by compress,
+ * zfpCompressor.hpp:22,160) or hands it to the caller; a bare stream is indexed by a sequential walk. */
+
+/* zfp_stream's four parameters */
+typedef struct zfb_mode {
+  unsigned minbits, maxbits, maxprec;
+  int minexp;
+} zfb_mode;
+
+int zfb_mode_rate(zfb_mode* m, int dtype, int dims, double rate, int wra); /* zfp_stream_set_rate      */
+int zfb_mode_accuracy(zfb_mode* m, double tolerance);                      /* zfp_stream_set_accuracy  (:118) */
+int zfb_mode_precision(zfb_mode* m, unsigned precision);                   /* zfp_stream_set_precision (:120) */
+
+/* Bytes zfp_stream_maximum_size() returns for this mode (buffer CBench mallocs, zfpCompressor.hpp:123-124). */
+size_t zfb_maximum_size(int dtype, int dims, size_t nx, size_t ny, size_t nz, const zfb_mode* m);
+/* Number of 4^d blocks; an index holds zfb_block_count() + 1 uint64 bit offsets. */
+size_t zfb_block_count(int dims, size_t nx, size_t ny, size_t nz);
+
+/* zfp_compress() in any mode on device buffers (zfpCompressor.hpp:132).  d_stream holds cap_bytes >=
+ * zfb_maximum_size().  d_index: nullable device array of zfb_block_count()+1 uint64 that receives the
+ * index (offset of every block, total bits last); with NULL the context keeps the index for the next
+ * zfb_decode_var_dev of the same d_stream.  *stream_bytes = what zfp_compress returns (the call
+ * synchronises: the size is data dependent). */
+int zfb_encode_var_dev(zfb_ctx* ctx, int dtype, int dims, size_t nx, size_t ny, size_t nz, const zfb_mode* m,
+                       const void* d_in, void* d_stream, size_t cap_bytes, uint64_t* d_index, size_t* stream_bytes);
+
+/* zfp_decompress() in any mode (zfpCompressor.hpp:224).  d_index: the index of this stream, or NULL: the
+ * context's index is used if it was built for this d_stream, else the stream is walked block by block
+ * to rebuild it (one thread: slow).  d_orig nullable: fuses the metrics as zfb_decode_dev does. */
+int zfb_decode_var_dev(zfb_ctx* ctx, int dtype, int dims, size_t nx, size_t ny, size_t nz, const zfb_mode* m,
+                       const void* d_stream, size_t stream_bytes, const uint64_t* d_index, void* d_out,
+                       const void* d_orig);
+
+/* Host-pointer forms (ZFPCompressor::compress / decompress bodies, zfpCompressor.hpp:96-141,186-234).
+ * The uploaded field, the stream and its index stay resident, keyed by h_in / h_stream. */
+int zfb_compress_var_host(zfb_ctx* ctx, int dtype, int dims, size_t nx, size_t ny, size_t nz, const zfb_mode* m,
+                          const void* h_in, void* h_stream, size_t cap_bytes, size_t* cbytes);
+int zfb_decompress_var_host(zfb_ctx* ctx, int dtype, int dims, size_t nx, size_t ny, size_t nz, const zfb_mode* m,
+                            const void* h_stream, size_t stream_bytes, void* h_out, const void* h_orig);
+
 /* ---- scalar metric values from (combined) partials: pure host arithmetic --------------------------- */
 double zfb_value_absolute_error(const zfb_partials* p); /* absoluteError.hpp:78-82   */
 double zfb_value_relative_error(const zfb_partials* p); /* relativeError.hpp:91-95   */

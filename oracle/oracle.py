@@ -33,6 +33,14 @@ def build(force=False):
         subprocess.run(["make", "-C", HERE, "ref"], check=True, capture_output=True)
 
 
+class Params(C.Structure):
+    """zfp_stream's four parameters (zfo_params in zfp_ref.c)."""
+    _fields_ = [("minbits", C.c_uint), ("maxbits", C.c_uint), ("maxprec", C.c_uint), ("minexp", C.c_int)]
+
+    def as_tuple(self):
+        return (self.minbits, self.maxbits, self.maxprec, self.minexp)
+
+
 def lib():
     global _lib
     if _lib is None:
@@ -49,6 +57,19 @@ def lib():
         L.zfo_compress.argtypes = [i, i, sz, sz, sz, u, vp, vp]
         L.zfo_decompress.restype = sz
         L.zfo_decompress.argtypes = [i, i, sz, sz, sz, u, vp, vp]
+        pp = C.POINTER(Params)
+        L.zfo_set_rate.restype = None
+        L.zfo_set_rate.argtypes = [pp, i, i, C.c_double, i]
+        L.zfo_set_accuracy.restype = None
+        L.zfo_set_accuracy.argtypes = [pp, C.c_double]
+        L.zfo_set_precision.restype = None
+        L.zfo_set_precision.argtypes = [pp, u]
+        L.zfo_maximum_size.restype = sz
+        L.zfo_maximum_size.argtypes = [i, i, sz, sz, sz, pp]
+        L.zfo_compress_ex.restype = sz
+        L.zfo_compress_ex.argtypes = [i, i, sz, sz, sz, pp, vp, vp, sz, vp]
+        L.zfo_decompress_ex.restype = sz
+        L.zfo_decompress_ex.argtypes = [i, i, sz, sz, sz, pp, vp, vp]
         L.zfo_perm.restype = C.POINTER(C.c_ubyte)
         L.zfo_perm.argtypes = [i]
         for name in ("zfo_fwd_xform_i32", "zfo_inv_xform_i32", "zfo_fwd_xform_i64", "zfo_inv_xform_i64"):
@@ -154,6 +175,58 @@ def decompress(stream, shape, dtype, mb):
     if not lib().zfo_decompress(t, d, nx, ny, nz, mb, buf.ctypes.data, out.ctypes.data):
         raise RuntimeError("oracle decompress failed")
     return out
+
+
+# ---- general stream parameters: fixed accuracy ("abs") / fixed precision ("rel") of the CPU zfp plugin
+def params_rate(dtype, dims, rate, wra=1):
+    p = Params()
+    lib().zfo_set_rate(C.byref(p), FLOAT if np.dtype(dtype) == np.float32 else DOUBLE, dims, float(rate), int(wra))
+    return p
+
+
+def params_accuracy(tolerance):
+    p = Params()
+    lib().zfo_set_accuracy(C.byref(p), float(tolerance))
+    return p
+
+
+def params_precision(precision):
+    p = Params()
+    lib().zfo_set_precision(C.byref(p), int(precision))
+    return p
+
+
+def maximum_size(shape, dtype, params):
+    d, nx, ny, nz = dims_of(shape)
+    t = FLOAT if np.dtype(dtype) == np.float32 else DOUBLE
+    return int(lib().zfo_maximum_size(t, d, nx, ny, nz, C.byref(params)))
+
+
+def compress_ex(a, params, with_offsets=False):
+    """Any mode.  Returns the uint8 stream (length = zfp_compress's return) [, block bit offsets (nblocks+1)]."""
+    a = np.ascontiguousarray(a)
+    d, nx, ny, nz = dims_of(a.shape)
+    cap = maximum_size(a.shape, a.dtype, params)
+    out = np.zeros(cap + 16, dtype=np.uint8)
+    nb = ((nx + 3) // 4) * ((ny + 3) // 4 if d >= 2 else 1) * ((nz + 3) // 4 if d >= 3 else 1)
+    offs = np.zeros(nb + 1, dtype=np.uint64) if with_offsets else None
+    got = int(lib().zfo_compress_ex(_type_of(a), d, nx, ny, nz, C.byref(params), a.ctypes.data, out.ctypes.data, cap,
+                                    offs.ctypes.data if with_offsets else None))
+    if not got or got > cap:
+        raise RuntimeError("oracle compress_ex failed")
+    return (out[:got], offs) if with_offsets else out[:got]
+
+
+def decompress_ex(stream, shape, dtype, params):
+    d, nx, ny, nz = dims_of(shape)
+    out = np.empty(shape, dtype=dtype)
+    buf = np.zeros(len(stream) + 64, dtype=np.uint8)
+    buf[: len(stream)] = stream
+    t = FLOAT if np.dtype(dtype) == np.float32 else DOUBLE
+    got = int(lib().zfo_decompress_ex(t, d, nx, ny, nz, C.byref(params), buf.ctypes.data, out.ctypes.data))
+    if not got:
+        raise RuntimeError("oracle decompress_ex failed")
+    return out, got
 
 
 def perm(dims):

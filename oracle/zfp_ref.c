@@ -1,8 +1,10 @@
 /*
  * oracle/zfp_ref.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
  *
- * Serial CPU restatement of the fixed-rate codec that CBench's zfp plugins call
- * (LLNL zfp 0.5.5, pinned by /root/reference/scripts/thirdparty/build_zfp.sh:6-8).
+ * Serial CPU restatement of the zfp codec that CBench's zfp plugins call (LLNL zfp 0.5.5,
+ * pinned by /root/reference/scripts/thirdparty/build_zfp.sh:6-8): fixed rate (zfp_gpu plugin)
+ * and, through zfo_compress_ex / zfo_decompress_ex, fixed accuracy and fixed precision (the
+ * CPU zfp plugin's "abs" / "rel", CBench/compressors/zfp/zfpCompressor.hpp:83-93,117-120).
  * zfp itself is NOT vendored in the reference tree and cannot be fetched here, so
  * this file restates the published algorithm and anchors on
  * the reference's own call sites:
@@ -133,6 +135,64 @@ size_t zfo_stream_capacity(int dims, size_t nx, size_t ny, size_t nz, unsigned m
 {
   size_t bits = 148 + nblocks(dims, nx, ny, nz) * (size_t)maxbits;
   return ((bits + 63) & ~(size_t)63) / 8;
+}
+
+/* ------------------------------------------------------------------------- */
+/* stream parameters (zfp_stream: minbits, maxbits, maxprec, minexp) and the   */
+/* three mode setters of zfp 0.5.5 [zfp-recall: src/zfp.c]                      */
+/* ------------------------------------------------------------------------- */
+#define ZFO_MIN_BITS 1u
+#define ZFO_MAX_BITS 16657u
+#define ZFO_MAX_PREC 64u
+#define ZFO_MIN_EXP (-1074)
+
+typedef struct {
+  unsigned minbits, maxbits, maxprec;
+  int minexp;
+} zfo_params;
+
+/* zfp_stream_set_rate(zfp, rate, type, dims, wra): zfpCompressorGpu.hpp:129 */
+void zfo_set_rate(zfo_params *zp, int type, int dims, double rate, int wra)
+{
+  zp->minbits = zp->maxbits = zfo_maxbits(type, dims, rate, wra);
+  zp->maxprec = ZFO_MAX_PREC;
+  zp->minexp = ZFO_MIN_EXP;
+}
+
+/* zfp_stream_set_accuracy(zfp, tolerance): zfp/zfpCompressor.hpp:118 ("abs").
+ * tolerance = x * 2^emin with 0.5 <= x < 1, then emin--, so 2^minexp <= tolerance */
+void zfo_set_accuracy(zfo_params *zp, double tolerance)
+{
+  int emin = ZFO_MIN_EXP;
+  if (tolerance > 0) {
+    frexp(tolerance, &emin);
+    emin--;
+  }
+  zp->minbits = ZFO_MIN_BITS;
+  zp->maxbits = ZFO_MAX_BITS;
+  zp->maxprec = ZFO_MAX_PREC;
+  zp->minexp = emin;
+}
+
+/* zfp_stream_set_precision(zfp, precision): zfp/zfpCompressor.hpp:120 ("rel") */
+void zfo_set_precision(zfo_params *zp, unsigned precision)
+{
+  zp->minbits = ZFO_MIN_BITS;
+  zp->maxbits = ZFO_MAX_BITS;
+  zp->maxprec = precision ? (precision < ZFO_MAX_PREC ? precision : ZFO_MAX_PREC) : ZFO_MAX_PREC;
+  zp->minexp = ZFO_MIN_EXP;
+}
+
+/* zfp_stream_maximum_size(zfp, field): zfp/zfpCompressor.hpp:123 mallocs this much */
+size_t zfo_maximum_size(int type, int dims, size_t nx, size_t ny, size_t nz, const zfo_params *zp)
+{
+  unsigned values = 1u << (2 * dims);
+  unsigned tprec = (type == ZFO_FLOAT) ? 32u : 64u;
+  unsigned maxbits = 1 + ((type == ZFO_FLOAT) ? 8u : 11u);
+  maxbits += values - 1 + values * (zp->maxprec < tprec ? zp->maxprec : tprec);
+  if (maxbits > zp->maxbits) maxbits = zp->maxbits;
+  if (maxbits < zp->minbits) maxbits = zp->minbits;
+  return ((148 + nblocks(dims, nx, ny, nz) * (size_t)maxbits + 63) & ~(size_t)63) / 8;
 }
 
 /* ------------------------------------------------------------------------- */
@@ -288,20 +348,22 @@ DEFINE_PAD(pad_d, double)
     return -EBIAS;                                                                                    \
   }                                                                                                   \
                                                                                                       \
-  static unsigned precision_##SFX(int maxexp, int dims)                                               \
+  /* precision(maxexp, maxprec, minexp, dims) = MIN(maxprec, MAX(0, maxexp - minexp + 2*(dims+1))) */  \
+  static unsigned precision_##SFX(int maxexp, const zfo_params *zp, int dims)                         \
   {                                                                                                   \
-    int p = maxexp - (-1074) + 2 * (dims + 1);                                                        \
+    int p = maxexp - zp->minexp + 2 * (dims + 1);                                                     \
     if (p < 0) p = 0;                                                                                 \
-    return p > 64 ? 64u : (unsigned)p;                                                                \
+    return (unsigned)p > zp->maxprec ? zp->maxprec : (unsigned)p;                                     \
   }                                                                                                   \
                                                                                                       \
-  /* A.5 encode one full block of 4^dims scalars into exactly maxbits bits */                         \
-  static void encode_block_##SFX(bitio *s, const Scalar *fblock, int dims, unsigned maxbits)          \
+  /* A.5 encode one full block of 4^dims scalars: at least minbits, at most maxbits bits */            \
+  static unsigned encode_block_##SFX(bitio *s, const Scalar *fblock, int dims, const zfo_params *zp)  \
   {                                                                                                   \
     unsigned size = 1u << (2 * dims);                                                                 \
     size_t start = s->pos;                                                                            \
+    unsigned bits = 1;                                                                                \
     int emax = exponent_block_##SFX(fblock, size);                                                    \
-    unsigned maxprec = precision_##SFX(emax, dims);                                                   \
+    unsigned maxprec = precision_##SFX(emax, zp, dims);                                               \
     unsigned e = maxprec ? (unsigned)(emax + EBIAS) : 0;                                              \
     if (e) {                                                                                          \
       Int iblock[64];                                                                                 \
@@ -309,7 +371,8 @@ DEFINE_PAD(pad_d, double)
       const unsigned char *perm = zfo_perm(dims);                                                     \
       unsigned i;                                                                                     \
       Scalar sc = LDEXP((Scalar)1, (8 * (int)sizeof(Scalar) - 2) - emax);                             \
-      put_bits(s, 2 * (uint64_t)e + 1, 1 + EBITS);                                                    \
+      bits += EBITS;                                                                                  \
+      put_bits(s, 2 * (uint64_t)e + 1, bits);                                                         \
       for (i = 0; i < size; i++) {                                                                    \
         volatile Scalar prod = sc * fblock[i]; /* product rounded to Scalar, then C truncation */     \
         iblock[i] = (Int)prod;                                                                        \
@@ -317,26 +380,33 @@ DEFINE_PAD(pad_d, double)
       fwd_xform_##SFX(iblock, dims);                                                                  \
       for (i = 0; i < size; i++)                                                                      \
         ublock[i] = ((UInt)iblock[perm[i]] + NBMASK) ^ NBMASK;                                        \
-      encode_ints_##SFX(s, maxbits - (1 + EBITS), maxprec, ublock, size);                             \
+      bits += encode_ints_##SFX(s, zp->maxbits - bits, maxprec, ublock, size);                        \
     } else {                                                                                          \
       put_bit(s, 0);                                                                                  \
     }                                                                                                 \
-    s->pos = start + maxbits; /* zero padding: the buffer is pre-zeroed */                            \
+    if (bits < zp->minbits)                                                                           \
+      bits = zp->minbits; /* stream_pad: the buffer is pre-zeroed */                                  \
+    s->pos = start + bits;                                                                            \
+    return bits;                                                                                      \
   }                                                                                                   \
                                                                                                       \
-  static void decode_block_##SFX(bitio *s, Scalar *fblock, int dims, unsigned maxbits)                \
+  static unsigned decode_block_##SFX(bitio *s, Scalar *fblock, int dims, const zfo_params *zp)        \
   {                                                                                                   \
     unsigned size = 1u << (2 * dims);                                                                 \
     size_t start = s->pos;                                                                            \
+    unsigned bits = 1;                                                                                \
     unsigned i;                                                                                       \
     if (get_bit(s)) {                                                                                 \
       Int iblock[64];                                                                                 \
       UInt ublock[64];                                                                                \
       const unsigned char *perm = zfo_perm(dims);                                                     \
-      int emax = (int)get_bits(s, EBITS) - EBIAS;                                                     \
-      unsigned maxprec = precision_##SFX(emax, dims);                                                 \
+      int emax;                                                                                       \
+      unsigned maxprec;                                                                               \
       Scalar sc;                                                                                      \
-      decode_ints_##SFX(s, maxbits - (1 + EBITS), maxprec, ublock, size);                             \
+      bits += EBITS;                                                                                  \
+      emax = (int)get_bits(s, EBITS) - EBIAS;                                                         \
+      maxprec = precision_##SFX(emax, zp, dims);                                                      \
+      bits += decode_ints_##SFX(s, zp->maxbits - bits, maxprec, ublock, size);                        \
       for (i = 0; i < size; i++)                                                                      \
         iblock[perm[i]] = (Int)((ublock[i] ^ NBMASK) - NBMASK);                                       \
       inv_xform_##SFX(iblock, dims);                                                                  \
@@ -350,7 +420,10 @@ DEFINE_PAD(pad_d, double)
       for (i = 0; i < size; i++)                                                                      \
         fblock[i] = 0;                                                                                \
     }                                                                                                 \
-    s->pos = start + maxbits;                                                                         \
+    if (bits < zp->minbits)                                                                           \
+      bits = zp->minbits; /* stream_skip */                                                           \
+    s->pos = start + bits;                                                                            \
+    return bits;                                                                                      \
   }                                                                                                   \
                                                                                                       \
   /* A.2/A.3 gather one (possibly partial) block at (x,y,z) */                                        \
@@ -390,29 +463,34 @@ DEFINE_PAD(pad_d, double)
           data[(x + i) + nx * ((y + j) + ny * (z + k))] = q[16 * k + 4 * j + i];                      \
   }                                                                                                   \
                                                                                                       \
+  /* zfp_compress: blocks in z, y, x order, then stream_flush (pad to a 64-bit word); returns the  */  \
+  /* stream size in bytes.  `out` must be pre-sized to zfo_maximum_size() and is zeroed here.      */  \
   static size_t compress_##SFX(const Scalar *data, int dims, size_t nx, size_t ny, size_t nz,         \
-                               unsigned maxbits, uint64_t *out)                                       \
+                               const zfo_params *zp, uint64_t *out, size_t cap_bytes,                 \
+                               uint64_t *block_offsets)                                               \
   {                                                                                                   \
     bitio s;                                                                                          \
-    size_t x, y, z;                                                                                   \
-    size_t bytes = zfo_stream_bytes(dims, nx, ny, nz, maxbits);                                       \
+    size_t x, y, z, b = 0;                                                                            \
     Scalar q[64];                                                                                     \
     if (dims < 2) ny = 1;                                                                             \
     if (dims < 3) nz = 1;                                                                             \
-    memset(out, 0, bytes);                                                                            \
+    memset(out, 0, cap_bytes);                                                                        \
     s.words = out;                                                                                    \
     s.pos = 0;                                                                                        \
     for (z = 0; z < nz; z += 4)                                                                       \
       for (y = 0; y < ny; y += 4)                                                                     \
         for (x = 0; x < nx; x += 4) {                                                                 \
+          if (block_offsets) block_offsets[b] = s.pos;                                                \
+          b++;                                                                                        \
           gather_##SFX(q, data, dims, nx, ny, nz, x, y, z);                                           \
-          encode_block_##SFX(&s, q, dims, maxbits);                                                   \
+          encode_block_##SFX(&s, q, dims, zp);                                                        \
         }                                                                                             \
-    return bytes;                                                                                     \
+    if (block_offsets) block_offsets[b] = s.pos;                                                      \
+    return ((s.pos + 63) / 64) * 8;                                                                   \
   }                                                                                                   \
                                                                                                       \
-  static void decompress_##SFX(Scalar *data, int dims, size_t nx, size_t ny, size_t nz,               \
-                               unsigned maxbits, const uint64_t *in)                                  \
+  static size_t decompress_##SFX(Scalar *data, int dims, size_t nx, size_t ny, size_t nz,             \
+                                 const zfo_params *zp, const uint64_t *in)                            \
   {                                                                                                   \
     bitio s;                                                                                          \
     size_t x, y, z;                                                                                   \
@@ -424,9 +502,10 @@ DEFINE_PAD(pad_d, double)
     for (z = 0; z < nz; z += 4)                                                                       \
       for (y = 0; y < ny; y += 4)                                                                     \
         for (x = 0; x < nx; x += 4) {                                                                 \
-          decode_block_##SFX(&s, q, dims, maxbits);                                                   \
+          decode_block_##SFX(&s, q, dims, zp);                                                        \
           scatter_##SFX(q, data, dims, nx, ny, nz, x, y, z);                                          \
         }                                                                                             \
+    return ((s.pos + 63) / 64) * 8;                                                                   \
   }
 
 DEFINE_CODEC(f, float, int32_t, uint32_t, 8, 127, 0xaaaaaaaau, frexpf, ldexpf, fabsf, pad_f)
@@ -436,39 +515,65 @@ DEFINE_CODEC(d, double, int64_t, uint64_t, 11, 1023, 0xaaaaaaaaaaaaaaaaull, frex
 /* public entry points (ctypes-friendly)                                       */
 /* ------------------------------------------------------------------------- */
 
-/* returns compressed bytes (what zfp_compress returns), 0 on bad arguments.
- * `out` must hold zfo_stream_bytes() bytes.                                   */
+/* General form: any (minbits, maxbits, maxprec, minexp).  `out` must hold cap_bytes >= zfo_maximum_size();
+ * returns the bytes zfp_compress returns (stream flushed to a 64-bit word), 0 on bad arguments.
+ * block_offsets (nullable): nblocks+1 absolute bit positions, [b] = first bit of block b.            */
+size_t zfo_compress_ex(int type, int dims, size_t nx, size_t ny, size_t nz, const zfo_params *zp,
+                       const void *in, void *out, size_t cap_bytes, uint64_t *block_offsets)
+{
+  if (dims < 1 || dims > 3 || !nx || !zp)
+    return 0;
+  if (type == ZFO_FLOAT) {
+    if (zp->maxbits < 9) return 0;
+    return compress_f((const float *)in, dims, nx, ny, nz, zp, (uint64_t *)out, cap_bytes, block_offsets);
+  }
+  if (type == ZFO_DOUBLE) {
+    if (zp->maxbits < 12) return 0;
+    return compress_d((const double *)in, dims, nx, ny, nz, zp, (uint64_t *)out, cap_bytes, block_offsets);
+  }
+  return 0;
+}
+
+/* returns the bytes consumed (zfp_decompress's return) */
+size_t zfo_decompress_ex(int type, int dims, size_t nx, size_t ny, size_t nz, const zfo_params *zp,
+                         const void *in, void *out)
+{
+  if (dims < 1 || dims > 3 || !nx || !zp)
+    return 0;
+  if (type == ZFO_FLOAT)
+    return decompress_f((float *)out, dims, nx, ny, nz, zp, (const uint64_t *)in);
+  if (type == ZFO_DOUBLE)
+    return decompress_d((double *)out, dims, nx, ny, nz, zp, (const uint64_t *)in);
+  return 0;
+}
+
+/* Fixed-rate form (zfp_gpu plugin): returns compressed bytes (what zfp_compress returns), 0 on bad
+ * arguments.  `out` must hold zfo_stream_bytes() bytes.                                             */
 size_t zfo_compress(int type, int dims, size_t nx, size_t ny, size_t nz, unsigned maxbits,
                     const void *in, void *out)
 {
+  zfo_params zp;
+  zp.minbits = zp.maxbits = maxbits;
+  zp.maxprec = ZFO_MAX_PREC;
+  zp.minexp = ZFO_MIN_EXP;
   if (dims < 1 || dims > 3 || !nx)
     return 0;
-  if (type == ZFO_FLOAT) {
-    if (maxbits < 9) return 0;
-    return compress_f((const float *)in, dims, nx, ny, nz, maxbits, (uint64_t *)out);
-  }
-  if (type == ZFO_DOUBLE) {
-    if (maxbits < 12) return 0;
-    return compress_d((const double *)in, dims, nx, ny, nz, maxbits, (uint64_t *)out);
-  }
-  return 0;
+  return zfo_compress_ex(type, dims, nx, ny, nz, &zp, in, out, zfo_stream_bytes(dims, nx, ny, nz, maxbits), NULL);
 }
 
 size_t zfo_decompress(int type, int dims, size_t nx, size_t ny, size_t nz, unsigned maxbits,
                       const void *in, void *out)
 {
-  if (dims < 1 || dims > 3 || !nx)
+  zfo_params zp;
+  zp.minbits = zp.maxbits = maxbits;
+  zp.maxprec = ZFO_MAX_PREC;
+  zp.minexp = ZFO_MIN_EXP;
+  if (dims < 1 || dims > 3 || !nx || (type != ZFO_FLOAT && type != ZFO_DOUBLE))
     return 0;
-  if (type == ZFO_FLOAT)
-    decompress_f((float *)out, dims, nx, ny, nz, maxbits, (const uint64_t *)in);
-  else if (type == ZFO_DOUBLE)
-    decompress_d((double *)out, dims, nx, ny, nz, maxbits, (const uint64_t *)in);
-  else
-    return 0;
+  zfo_decompress_ex(type, dims, nx, ny, nz, &zp, in, out);
   return zfo_stream_bytes(dims, nx, ny, nz, maxbits);
 }
 
-/* test hooks: the transform and coder in isolation */
 void zfo_fwd_xform_i32(int32_t *p, int dims) { fwd_xform_f(p, dims); }
 void zfo_inv_xform_i32(int32_t *p, int dims) { inv_xform_f(p, dims); }
 void zfo_fwd_xform_i64(int64_t *p, int dims) { fwd_xform_d(p, dims); }

@@ -180,7 +180,93 @@ static int dispatch(bool enc, int dims, size_t nx, size_t ny, size_t nz, unsigne
   return 0;
 }
 
+// Variable-rate emulation: the device codec's general encode_block / decode_block (stream_params) per block,
+// staged words appended bit-tight on the host (the device does that in compact_var_kernel).
+template <typename Scalar, int DIMS>
+static size_t run_var(bool enc, size_t nx, size_t ny, size_t nz, const stream_params& sp, Scalar* data, uint64_t* stream,
+                      size_t stream_words, uint64_t* offsets)
+{
+  constexpr int BS = 1 << (2 * DIMS);
+  if (DIMS < 2) ny = 1;
+  if (DIMS < 3) nz = 1;
+  const size_t bx = (nx + 3) / 4, by = (ny + 3) / 4, bz = (nz + 3) / 4;
+  if (enc) std::memset(stream, 0, stream_words * 8);
+  uint64_t pos = 0;
+  for (size_t b = 0; b < bx * by * bz; b++) {
+    const size_t ix = b % bx, iy = (b / bx) % by, iz = b / (bx * by);
+    const size_t x0 = 4 * ix, y0 = 4 * iy, z0 = 4 * iz;
+    const unsigned mx = (unsigned)(nx - x0 < 4 ? nx - x0 : 4);
+    const unsigned my = DIMS >= 2 ? (unsigned)(ny - y0 < 4 ? ny - y0 : 4) : 1;
+    const unsigned mz = DIMS >= 3 ? (unsigned)(nz - z0 < 4 ? nz - z0 : 4) : 1;
+    Scalar f[BS];
+    if (offsets) offsets[b] = pos;
+    if (enc) {
+      for (int i = 0; i < BS; i++) f[i] = 0;
+      for (unsigned k = 0; k < mz; k++)
+        for (unsigned j = 0; j < my; j++)
+          for (unsigned i = 0; i < mx; i++) f[16 * k + 4 * j + i] = data[(x0 + i) + nx * ((y0 + j) + ny * (z0 + k))];
+      if (mx < 4 || my < (DIMS >= 2 ? 4u : 1u) || mz < (DIMS >= 3 ? 4u : 1u)) pad_block<Scalar, DIMS>(f, mx, my, mz);
+      uint64_t stage[80];
+      std::memset(stage, 0xff, sizeof stage);  // garbage behind the written words must not leak into the stream
+      stage_sink sink(stage);
+      const unsigned bits = encode_block<Scalar, DIMS>(f, sp, sink);
+      for (unsigned j = 0; 64 * j < bits; j++) {
+        uint64_t w = stage[j];
+        const unsigned valid = bits - 64 * j;
+        if (valid < 64) w &= lowmask64(valid);
+        const uint64_t at = pos + 64 * j;
+        const unsigned sh = (unsigned)(at & 63);
+        if ((at >> 6) < stream_words) stream[at >> 6] |= w << sh;
+        if (sh && (at >> 6) + 1 < stream_words) stream[(at >> 6) + 1] |= w >> (64 - sh);
+      }
+      pos += bits;
+    } else {
+      slot_reader r(stream + (pos >> 6), (unsigned)(stream_words - (pos >> 6)), (unsigned)(pos & 63));
+      slot_reader r2 = r;
+      Scalar dummy[BS];
+      const unsigned bits = decode_block<Scalar, DIMS, false>(f, sp, r);
+      const unsigned bits2 = decode_block<Scalar, DIMS, true>(dummy, sp, r2);  // index walk must agree
+      if (bits != bits2) return 0;
+      pos += bits;
+      for (unsigned k = 0; k < mz; k++)
+        for (unsigned j = 0; j < my; j++)
+          for (unsigned i = 0; i < mx; i++) data[(x0 + i) + nx * ((y0 + j) + ny * (z0 + k))] = f[16 * k + 4 * j + i];
+    }
+  }
+  if (offsets) offsets[bx * by * bz] = pos;
+  return (size_t)((pos + 63) / 64) * 8;
+}
+
+template <typename Scalar>
+static size_t dispatch_var(bool enc, int dims, size_t nx, size_t ny, size_t nz, const stream_params& sp, void* data,
+                           void* stream, size_t stream_words, uint64_t* offsets)
+{
+  Scalar* d = (Scalar*)data;
+  uint64_t* s = (uint64_t*)stream;
+  if (dims == 1) return run_var<Scalar, 1>(enc, nx, ny, nz, sp, d, s, stream_words, offsets);
+  if (dims == 2) return run_var<Scalar, 2>(enc, nx, ny, nz, sp, d, s, stream_words, offsets);
+  if (dims == 3) return run_var<Scalar, 3>(enc, nx, ny, nz, sp, d, s, stream_words, offsets);
+  return 0;
+}
+
 extern "C" {
+// params: {minbits, maxbits, maxprec, minexp}; returns the stream size in bytes (0 = failure)
+size_t emul_compress_var(int type, int dims, size_t nx, size_t ny, size_t nz, const unsigned* params, const void* in,
+                         void* stream, size_t stream_words, uint64_t* offsets)
+{
+  stream_params sp;
+  sp.minbits = params[0]; sp.maxbits = params[1]; sp.maxprec = params[2]; sp.minexp = (int)params[3];
+  return type == 1 ? dispatch_var<float>(true, dims, nx, ny, nz, sp, (void*)in, stream, stream_words, offsets)
+                   : dispatch_var<double>(true, dims, nx, ny, nz, sp, (void*)in, stream, stream_words, offsets);
+}
+size_t emul_decompress_var(int type, int dims, size_t nx, size_t ny, size_t nz, const unsigned* params, const void* stream,
+                           void* out, size_t stream_words)
+{
+  stream_params sp;
+  sp.minbits = params[0]; sp.maxbits = params[1]; sp.maxprec = params[2]; sp.minexp = (int)params[3];
+  return type == 1 ? dispatch_var<float>(false, dims, nx, ny, nz, sp, out, (void*)stream, stream_words, nullptr)
+                   : dispatch_var<double>(false, dims, nx, ny, nz, sp, out, (void*)stream, stream_words, nullptr);
+}
 void emul_use_f3(int on) { g_use_f3 = on; }
 // type: 1 float, 2 double (same codes as the oracle and include/zfb.h)
 int emul_compress(int type, int dims, size_t nx, size_t ny, size_t nz, unsigned maxbits, const void* in, void* stream,

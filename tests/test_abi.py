@@ -106,3 +106,22 @@ def test_product_path_never_touches_the_oracle():
                     if "liboracle" in t or "zfo_" in t or "import oracle" in t or "oracle/" in t:
                         bad.append(os.path.join(dp, f))
     assert not bad, bad
+
+
+def test_mode_parameters_and_maximum_size_match_oracle(pkg, oracle):
+    """zfp_stream_set_accuracy / set_precision / set_rate and zfp_stream_maximum_size (pure host arithmetic)."""
+    for tol in (0.0, 1e-6, 0.003, 0.05, 0.5, 1.0, 3.0, 1000.0, 2.0 ** -20, 2.0 ** 10):
+        assert pkg.mode_accuracy(tol).as_tuple() == oracle.params_accuracy(tol).as_tuple(), tol
+    for prec in (0, 1, 8, 16, 23, 32, 40, 64, 100):
+        assert pkg.mode_precision(prec).as_tuple() == oracle.params_precision(prec).as_tuple(), prec
+    for dt in (np.float32, np.float64):
+        for dims, rate in ((1, 8), (2, 4.5), (3, 8), (3, 16)):
+            assert pkg.mode_rate(dt, dims, rate).as_tuple() == oracle.params_rate(dt, dims, rate).as_tuple()
+        for shape in [(10,), (4099,), (5, 7), (64, 64), (5, 6, 7), (33, 33, 33)]:
+            for m, p in ((pkg.mode_accuracy(0.01), oracle.params_accuracy(0.01)),
+                         (pkg.mode_precision(12), oracle.params_precision(12)),
+                         (pkg.mode_rate(dt, len(shape), 8), oracle.params_rate(dt, len(shape), 8))):
+                assert pkg.maximum_size(shape, dt, m) == oracle.maximum_size(shape, dt, p)
+    assert pkg.block_count((5, 6, 7)) == 2 * 2 * 2 and pkg.block_count((4099,)) == 1025
+    with pytest.raises(pkg.ZfbError):
+        pkg.mode_accuracy(-1.0)

@@ -197,3 +197,64 @@ def test_fast_f64_coder_budget_boundaries(oracle):
             s, g = emul_roundtrip(O, f, mb)
             assert np.array_equal(s, s_ref), mb
             assert np.array_equal(g.view(np.uint8), O.decompress(s_ref, f.shape, np.float64, mb).view(np.uint8)), mb
+
+
+# --------------------------------------------------------------------------- variable-rate modes
+def _var_protos():
+    L = emul()
+    L.emul_compress_var.restype = C.c_size_t
+    L.emul_compress_var.argtypes = [C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p,
+                                    C.c_void_p, C.c_size_t, C.c_void_p]
+    L.emul_decompress_var.restype = C.c_size_t
+    L.emul_decompress_var.argtypes = [C.c_int, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_size_t]
+    return L
+
+
+def emul_var_roundtrip(O, f, params):
+    L = _var_protos()
+    d, nx, ny, nz = O.dims_of(f.shape)
+    t = 1 if f.dtype == np.float32 else 2
+    cap = O.maximum_size(f.shape, f.dtype, params)
+    prm = np.array([params.minbits, params.maxbits, params.maxprec, params.minexp & 0xffffffff], dtype=np.uint32)
+    s = np.zeros(cap // 8 + 2, dtype=np.uint64)
+    nb = ((nx + 3) // 4) * ((ny + 3) // 4 if d >= 2 else 1) * ((nz + 3) // 4 if d >= 3 else 1)
+    offs = np.zeros(nb + 1, dtype=np.uint64)
+    got = L.emul_compress_var(t, d, nx, ny, nz, prm.ctypes.data, f.ctypes.data, s.ctypes.data, cap // 8, offs.ctypes.data)
+    assert got
+    g = np.empty_like(f)
+    used = L.emul_decompress_var(t, d, nx, ny, nz, prm.ctypes.data, s.ctypes.data, g.ctypes.data, cap // 8)
+    assert used == got
+    return s.view(np.uint8)[:got], g, offs
+
+
+VAR_MODES = [("accuracy", 1e-3), ("accuracy", 0.05), ("accuracy", 3.0), ("accuracy", 1e4), ("accuracy", 0.0),
+             ("precision", 1), ("precision", 7), ("precision", 16), ("precision", 23), ("precision", 32),
+             ("precision", 40), ("precision", 64)]
+
+
+def _var_params(O, kind, v):
+    return O.params_accuracy(v) if kind == "accuracy" else O.params_precision(v)
+
+
+@pytest.mark.parametrize("dtype,shape", CASES)
+def test_device_codec_variable_rate_equals_oracle(oracle, dtype, shape):
+    """The device codec's general (minbits, maxbits, maxprec, minexp) form, block lengths included, against the
+    oracle in zfp's fixed-accuracy and fixed-precision modes ("abs" / "rel" of the CPU zfp plugin)."""
+    O = oracle
+    rng = np.random.default_rng(len(shape) * 13 + np.dtype(dtype).itemsize)
+    f = (smooth_field(shape, seed=5, amp=40.0).astype(np.float64) + 0.01 * rng.standard_normal(shape)).astype(dtype)
+    f.ravel()[:: max(1, f.size // 9)] *= 1e-4  # mixed magnitudes: some blocks fall under the accuracy floor
+    f[tuple(slice(0, min(4, n)) for n in shape)] = 0  # an all-zero block
+    for kind, v in VAR_MODES:
+        p = _var_params(O, kind, v)
+        s_ref, offs_ref = O.compress_ex(f, p, with_offsets=True)
+        g_ref, used = O.decompress_ex(s_ref, f.shape, dtype, p)
+        assert used == len(s_ref)
+        s, g, offs = emul_var_roundtrip(O, f, p)
+        assert len(s) == len(s_ref), (kind, v)
+        assert np.array_equal(offs, offs_ref), (kind, v)
+        assert np.array_equal(s, s_ref), (kind, v)
+        assert np.array_equal(g.view(np.uint8), g_ref.view(np.uint8)), (kind, v)
+        if kind == "accuracy" and v > 0:
+            assert np.abs(g.astype(np.float64) - f.astype(np.float64)).max() <= v

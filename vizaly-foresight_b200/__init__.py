@@ -35,6 +35,14 @@ class Partials(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class Mode(C.Structure):
+    """zfb_mode of include/zfb.h: zfp_stream's (minbits, maxbits, maxprec, minexp)."""
+    _fields_ = [("minbits", C.c_uint), ("maxbits", C.c_uint), ("maxprec", C.c_uint), ("minexp", C.c_int)]
+
+    def as_tuple(self):
+        return (self.minbits, self.maxbits, self.maxprec, self.minexp)
+
+
 def build_library(force=False, verbose=False):
     """nvcc -> vizaly-foresight_b200/libzfb.so (in-tree, so it travels to the GPU box)."""
     csrc = os.path.join(HERE, "csrc")
@@ -72,6 +80,7 @@ def lib():
     L = C.CDLL(LIB_PATH)
     sz, u, i, vp, d = C.c_size_t, C.c_uint, C.c_int, C.c_void_p, C.c_double
     PP = C.POINTER(Partials)
+    MP = C.POINTER(Mode)
     sig = {
         "zfb_maxbits": (u, [i, i, d, i]),
         "zfb_stream_bytes": (sz, [i, sz, sz, sz, u]),
@@ -102,6 +111,15 @@ def lib():
         "zfb_value_psnr": (d, [PP]),
         "zfb_value_minmax": (d, [PP]),
         "zfb_partials_combine": (None, [PP, PP, i]),
+        "zfb_mode_rate": (i, [MP, i, i, d, i]),
+        "zfb_mode_accuracy": (i, [MP, d]),
+        "zfb_mode_precision": (i, [MP, u]),
+        "zfb_maximum_size": (sz, [i, i, sz, sz, sz, MP]),
+        "zfb_block_count": (sz, [i, sz, sz, sz]),
+        "zfb_encode_var_dev": (i, [vp, i, i, sz, sz, sz, MP, vp, vp, sz, vp, C.POINTER(sz)]),
+        "zfb_decode_var_dev": (i, [vp, i, i, sz, sz, sz, MP, vp, sz, vp, vp, vp]),
+        "zfb_compress_var_host": (i, [vp, i, i, sz, sz, sz, MP, vp, vp, sz, C.POINTER(sz)]),
+        "zfb_decompress_var_host": (i, [vp, i, i, sz, sz, sz, MP, vp, sz, vp, vp]),
     }
     for name, (res, args) in sig.items():
         f = getattr(L, name)
@@ -149,6 +167,39 @@ def stream_bytes(shape, mb):
 def stream_capacity(shape, mb):
     d, nx, ny, nz = dims_of(shape)
     return int(lib().zfb_stream_capacity(d, nx, ny, nz, mb))
+
+
+def mode_rate(dtype, dims, rate, wra=1):
+    m = Mode()
+    if lib().zfb_mode_rate(C.byref(m), _dtype_code(dtype), dims, float(rate), int(wra)):
+        raise ZfbError("zfb_mode_rate: bad arguments")
+    return m
+
+
+def mode_accuracy(tolerance):
+    """zfp_stream_set_accuracy: CBench's "abs" parameter (zfp/zfpCompressor.hpp:118)."""
+    m = Mode()
+    if lib().zfb_mode_accuracy(C.byref(m), float(tolerance)):
+        raise ZfbError("zfb_mode_accuracy: bad tolerance")
+    return m
+
+
+def mode_precision(precision):
+    """zfp_stream_set_precision: CBench's "rel" parameter (zfp/zfpCompressor.hpp:120)."""
+    m = Mode()
+    if lib().zfb_mode_precision(C.byref(m), int(precision)):
+        raise ZfbError("zfb_mode_precision: bad precision")
+    return m
+
+
+def maximum_size(shape, dtype, mode):
+    d, nx, ny, nz = dims_of(shape)
+    return int(lib().zfb_maximum_size(_dtype_code(dtype), d, nx, ny, nz, C.byref(mode)))
+
+
+def block_count(shape):
+    d, nx, ny, nz = dims_of(shape)
+    return int(lib().zfb_block_count(d, nx, ny, nz))
 
 
 def partition(rank, nranks, shape3):
@@ -285,6 +336,61 @@ class Codec:
                                             approx.numel(), counts.data_ptr(), counts.data_ptr() + 8 * NBINS),
                     "zfb_histogram_dev")
         return counts[:NBINS], counts[NBINS:]
+
+    # ---- variable-rate modes (fixed accuracy / fixed precision) --------------------------------
+    def encode_var(self, field, mode, out=None, index=None):
+        """Returns (stream[:nbytes], nbytes).  index: optional uint64 tensor of block_count()+1 entries that
+        receives the block offsets; without it the context keeps the index for decode_var of this stream."""
+        import torch
+
+        self.use_torch_stream()
+        d, nx, ny, nz = dims_of(field.shape)
+        cap = maximum_size(field.shape, field.dtype, mode)
+        if out is None:
+            out = torch.empty(cap, dtype=torch.uint8, device=field.device)
+        assert field.is_contiguous() and out.numel() >= cap
+        nbytes = C.c_size_t()
+        self._check(lib().zfb_encode_var_dev(self._h, _dtype_code(field.dtype), d, nx, ny, nz, C.byref(mode),
+                                             field.data_ptr(), out.data_ptr(), out.numel(),
+                                             index.data_ptr() if index is not None else None, C.byref(nbytes)),
+                    "zfb_encode_var_dev")
+        return out[: nbytes.value], nbytes.value
+
+    def decode_var(self, stream, shape, dtype, mode, index=None, orig=None, out=None):
+        import torch
+
+        self.use_torch_stream()
+        d, nx, ny, nz = dims_of(shape)
+        if out is None:
+            out = torch.empty(tuple(shape), dtype=dtype, device=stream.device)
+        self._check(lib().zfb_decode_var_dev(self._h, _dtype_code(dtype), d, nx, ny, nz, C.byref(mode), stream.data_ptr(),
+                                             stream.numel(), index.data_ptr() if index is not None else None,
+                                             out.data_ptr(), orig.data_ptr() if orig is not None else None),
+                    "zfb_decode_var_dev")
+        return out
+
+    def compress_var_host(self, a, mode):
+        import numpy as np
+
+        d, nx, ny, nz = dims_of(a.shape)
+        cap = maximum_size(a.shape, a.dtype, mode)
+        out = np.empty(cap, dtype=np.uint8)
+        cb = C.c_size_t()
+        self._check(lib().zfb_compress_var_host(self._h, _dtype_code(a.dtype), d, nx, ny, nz, C.byref(mode), a.ctypes.data,
+                                                out.ctypes.data, cap, C.byref(cb)), "zfb_compress_var_host")
+        return out[: cb.value]
+
+    def decompress_var_host(self, stream, shape, dtype, mode, orig=None, out=None):
+        import numpy as np
+
+        d, nx, ny, nz = dims_of(shape)
+        if out is None:
+            out = np.empty(tuple(shape), dtype=dtype)
+        self._check(lib().zfb_decompress_var_host(self._h, _dtype_code(dtype), d, nx, ny, nz, C.byref(mode),
+                                                  stream.ctypes.data, stream.size, out.ctypes.data,
+                                                  orig.ctypes.data if orig is not None else None),
+                    "zfb_decompress_var_host")
+        return out
 
     # ---- host path (what the CBench plugin calls) -------------------------------------------
     def compress_host(self, a, mb, out=None):

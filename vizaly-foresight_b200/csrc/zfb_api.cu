@@ -44,6 +44,13 @@ struct zfb_ctx {
   size_t out_bytes = 0;
   bool fused_valid = false;           // result holds metrics of (h_orig_key, h_out_key)
   int occ_enc[80] = {0}, occ_dec[80] = {0}, occ_decm[80] = {0};  // resident CTAs per SM, by slot words
+  // variable-rate path (zfb_api_var.cuh): scratch + the block index of the last encoded stream
+  devbuf var_stage, var_lens, var_chunks, var_index;
+  const void* var_index_key = nullptr;  // device stream the index in var_index describes
+  size_t var_index_blocks = 0;
+  uint64_t var_index_bits = 0;
+  const void* var_host_key = nullptr;   // host stream buffer the resident d_stream + index came from
+  size_t var_host_bytes = 0;
 };
 
 #define CU_TRY(ctx, call)                                                                   \
@@ -223,6 +230,8 @@ extern "C" int zfb_release_resident(zfb_ctx* c)
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   free_buf(c->d_orig); free_buf(c->d_stream); free_buf(c->d_out); free_buf(c->d_hist);
+  free_buf(c->var_stage); free_buf(c->var_lens); free_buf(c->var_chunks); free_buf(c->var_index);
+  c->var_index_key = c->var_host_key = nullptr;
   c->h_orig_key = c->h_out_key = nullptr;
   c->orig_bytes = c->out_bytes = 0;
   c->fused_valid = false;
@@ -921,3 +930,5 @@ extern "C" int zfb_histogram_host(zfb_ctx* c, int dtype, int which, double lo, d
   if (oob) *oob = tmp[ZFB_NBINS];
   return ZFB_OK;
 }
+
+#include "zfb_api_var.cuh"

@@ -1,0 +1,325 @@
+// zfb_api_var.cuh -- C ABI of the variable-rate (fixed-accuracy / fixed-precision) path; included at the end of
+// zfb_api.cu (shares its context and helpers).  Kernels: zfb_var.cuh.
+#pragma once
+#include "zfb_var.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// pure host arithmetic [zfp-recall: zfp 0.5.5 src/zfp.c]
+// ------------------------------------------------------------------------------------------------
+static const unsigned ZFB_MIN_BITS = 1u, ZFB_MAX_BITS = 16657u, ZFB_MAX_PREC = 64u;
+static const int ZFB_MIN_EXP = -1074;
+
+extern "C" int zfb_mode_rate(zfb_mode* m, int dtype, int dims, double rate, int wra)
+{
+  if (!m) return ZFB_EINVAL;
+  const unsigned mb = zfb_maxbits(dtype, dims, rate, wra);
+  if (!mb) return ZFB_EINVAL;
+  m->minbits = m->maxbits = mb;
+  m->maxprec = ZFB_MAX_PREC;
+  m->minexp = ZFB_MIN_EXP;
+  return ZFB_OK;
+}
+
+extern "C" int zfb_mode_accuracy(zfb_mode* m, double tolerance)
+{
+  if (!m || !(tolerance >= 0)) return ZFB_EINVAL;
+  int emin = ZFB_MIN_EXP;
+  if (tolerance > 0) {
+    frexp(tolerance, &emin);  // tolerance = x * 2^emin, 0.5 <= x < 1
+    emin--;                   // 2^emin <= tolerance < 2^(emin + 1)
+  }
+  m->minbits = ZFB_MIN_BITS;
+  m->maxbits = ZFB_MAX_BITS;
+  m->maxprec = ZFB_MAX_PREC;
+  m->minexp = emin;
+  return ZFB_OK;
+}
+
+extern "C" int zfb_mode_precision(zfb_mode* m, unsigned precision)
+{
+  if (!m) return ZFB_EINVAL;
+  m->minbits = ZFB_MIN_BITS;
+  m->maxbits = ZFB_MAX_BITS;
+  m->maxprec = precision ? (precision < ZFB_MAX_PREC ? precision : ZFB_MAX_PREC) : ZFB_MAX_PREC;
+  m->minexp = ZFB_MIN_EXP;
+  return ZFB_OK;
+}
+
+extern "C" size_t zfb_block_count(int dims, size_t nx, size_t ny, size_t nz)
+{
+  if (dims < 1 || dims > 3) return 0;
+  return count_blocks(dims, nx, ny, nz);
+}
+
+extern "C" size_t zfb_maximum_size(int dtype, int dims, size_t nx, size_t ny, size_t nz, const zfb_mode* m)
+{
+  if (!m || dims < 1 || dims > 3 || (dtype != ZFB_FLOAT && dtype != ZFB_DOUBLE)) return 0;
+  const unsigned values = 1u << (2 * dims);
+  const unsigned tprec = dtype == ZFB_FLOAT ? 32u : 64u;
+  unsigned maxbits = 1u + (dtype == ZFB_FLOAT ? 8u : 11u);
+  maxbits += values - 1u + values * (m->maxprec < tprec ? m->maxprec : tprec);
+  if (maxbits > m->maxbits) maxbits = m->maxbits;
+  if (maxbits < m->minbits) maxbits = m->minbits;
+  return ((148 + count_blocks(dims, nx, ny, nz) * (size_t)maxbits + 63) & ~(size_t)63) / 8;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device path
+// ------------------------------------------------------------------------------------------------
+static int check_var_args(zfb_ctx* c, int dtype, int dims, size_t nx, size_t ny, size_t nz, const zfb_mode* m)
+{
+  if (!c) return ZFB_EINVAL;
+  if (dims < 1 || dims > 3 || !nx || (dims >= 2 && !ny) || (dims >= 3 && !nz)) { c->err = "bad dims"; return ZFB_EINVAL; }
+  if (dtype != ZFB_FLOAT && dtype != ZFB_DOUBLE) { c->err = "bad dtype"; return ZFB_EINVAL; }
+  if (!m) { c->err = "null mode"; return ZFB_EINVAL; }
+  const unsigned hdr = dtype == ZFB_FLOAT ? 9u : 12u;
+  if (m->maxbits < hdr || m->minbits > m->maxbits || m->maxbits > ZFB_MAX_BITS || !m->maxprec || m->maxprec > 64u ||
+      m->minexp < ZFB_MIN_EXP || m->minexp > 2048) {
+    c->err = "bad mode parameters";
+    return ZFB_EINVAL;
+  }
+  return ZFB_OK;
+}
+
+static stream_params to_params(const zfb_mode* m)
+{
+  stream_params sp;
+  sp.minbits = m->minbits; sp.maxbits = m->maxbits; sp.maxprec = m->maxprec; sp.minexp = m->minexp;
+  return sp;
+}
+
+template <typename Scalar> static unsigned var_words(int dims)
+{
+  return dims == 1 ? var_caps<Scalar, 1>::WORDS : dims == 2 ? var_caps<Scalar, 2>::WORDS : var_caps<Scalar, 3>::WORDS;
+}
+
+static int var_grid(const zfb_ctx* c, size_t nblocks)
+{
+  const size_t want = (nblocks + 127) / 128, cap = (size_t)c->sm_count * 32;
+  return (int)(want < cap ? (want ? want : 1) : cap);
+}
+
+template <typename Scalar>
+static int launch_enc_var(zfb_ctx* c, int dims, const geom& g, const stream_params& sp, const void* d_in, uint64_t* stage,
+                          uint32_t* lens)
+{
+  const int grid = var_grid(c, g.nblocks);
+  const Scalar* in = (const Scalar*)d_in;
+  if (dims == 1) enc_var_kernel<Scalar, 1><<<grid, 128, 0, c->stream>>>(in, stage, lens, g, sp);
+  else if (dims == 2) enc_var_kernel<Scalar, 2><<<grid, 128, 0, c->stream>>>(in, stage, lens, g, sp);
+  else enc_var_kernel<Scalar, 3><<<grid, 128, 0, c->stream>>>(in, stage, lens, g, sp);
+  c->launches++;
+  CU_TRY(c, cudaGetLastError());
+  return ZFB_OK;
+}
+
+template <typename Scalar>
+static int launch_compact_var(zfb_ctx* c, int dims, const geom& g, const uint64_t* stage, const uint64_t* index,
+                              uint64_t* stream, size_t cap_words)
+{
+  const int grid = var_grid(c, g.nblocks);
+  if (dims == 1) compact_var_kernel<var_caps<Scalar, 1>::WORDS><<<grid, 128, 0, c->stream>>>(stage, index, g.nblocks, stream, cap_words);
+  else if (dims == 2) compact_var_kernel<var_caps<Scalar, 2>::WORDS><<<grid, 128, 0, c->stream>>>(stage, index, g.nblocks, stream, cap_words);
+  else compact_var_kernel<var_caps<Scalar, 3>::WORDS><<<grid, 128, 0, c->stream>>>(stage, index, g.nblocks, stream, cap_words);
+  c->launches++;
+  CU_TRY(c, cudaGetLastError());
+  return ZFB_OK;
+}
+
+extern "C" int zfb_encode_var_dev(zfb_ctx* c, int dtype, int dims, size_t nx, size_t ny, size_t nz, const zfb_mode* m,
+                                  const void* d_in, void* d_stream, size_t cap_bytes, uint64_t* d_index,
+                                  size_t* stream_bytes)
+{
+  int rc = check_var_args(c, dtype, dims, nx, ny, nz, m);
+  if (rc) return rc;
+  if (!d_in || !d_stream) { c->err = "null pointer"; return ZFB_EINVAL; }
+  if (cap_bytes < zfb_maximum_size(dtype, dims, nx, ny, nz, m)) { c->err = "stream buffer smaller than zfb_maximum_size()"; return ZFB_EINVAL; }
+  CU_TRY(c, cudaSetDevice(c->device));
+  geom g = make_geom(dims, nx, ny, nz, 64);
+  const size_t cap_words = cap_bytes / 8;
+  g.stream_words = cap_words;
+  const stream_params sp = to_params(m);
+  const unsigned words = dtype == ZFB_FLOAT ? var_words<float>(dims) : var_words<double>(dims);
+  const size_t groups = (g.nblocks + 31) / 32;
+  if ((rc = ensure(c, c->var_stage, groups * 32 * (size_t)words * 8))) return rc;
+  if ((rc = ensure(c, c->var_lens, g.nblocks * 4))) return rc;
+  const size_t nchunks = (g.nblocks + SCAN_CHUNK - 1) / SCAN_CHUNK;
+  if ((rc = ensure(c, c->var_chunks, (nchunks + 1) * 8))) return rc;
+  uint64_t* index = d_index;
+  c->var_index_key = nullptr;
+  if (!index) {
+    if ((rc = ensure(c, c->var_index, (g.nblocks + 1) * 8))) return rc;
+    index = (uint64_t*)c->var_index.p;
+  }
+  uint64_t* stage = (uint64_t*)c->var_stage.p;
+  uint32_t* lens = (uint32_t*)c->var_lens.p;
+  uint64_t* chunks = (uint64_t*)c->var_chunks.p;
+
+  rc = dtype == ZFB_FLOAT ? launch_enc_var<float>(c, dims, g, sp, d_in, stage, lens)
+                          : launch_enc_var<double>(c, dims, g, sp, d_in, stage, lens);
+  if (rc) return rc;
+  scan_sums_kernel<<<(unsigned)nchunks, SCAN_THREADS, 0, c->stream>>>(lens, g.nblocks, chunks);
+  scan_chunks_kernel<<<1, SCAN_THREADS, 0, c->stream>>>(chunks, nchunks);
+  scan_offsets_kernel<<<(unsigned)nchunks, SCAN_THREADS, 0, c->stream>>>(lens, g.nblocks, chunks, nchunks, index);
+  zero_stream_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>((uint64_t*)d_stream, index + g.nblocks, cap_words);
+  c->launches += 4;
+  CU_TRY(c, cudaGetLastError());
+  rc = dtype == ZFB_FLOAT ? launch_compact_var<float>(c, dims, g, stage, index, (uint64_t*)d_stream, cap_words)
+                          : launch_compact_var<double>(c, dims, g, stage, index, (uint64_t*)d_stream, cap_words);
+  if (rc) return rc;
+  uint64_t total_bits = 0;
+  CU_TRY(c, cudaMemcpyAsync(&total_bits, index + g.nblocks, 8, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  const size_t bytes = (size_t)((total_bits + 63) / 64) * 8;  // stream_flush pads to a word
+  if (bytes > cap_bytes) { c->err = "internal: stream longer than its bound"; return ZFB_ESTATE; }
+  if (stream_bytes) *stream_bytes = bytes;
+  if (!d_index) {
+    c->var_index_key = d_stream;
+    c->var_index_blocks = g.nblocks;
+    c->var_index_bits = total_bits;
+  }
+  return ZFB_OK;
+}
+
+template <typename Scalar>
+static int launch_index_var(zfb_ctx* c, int dims, const void* d_stream, size_t stream_words, size_t nblocks,
+                            const stream_params& sp, uint64_t* index)
+{
+  const uint64_t* st = (const uint64_t*)d_stream;
+  if (dims == 1) index_var_kernel<Scalar, 1><<<1, 32, 0, c->stream>>>(st, stream_words, nblocks, sp, index);
+  else if (dims == 2) index_var_kernel<Scalar, 2><<<1, 32, 0, c->stream>>>(st, stream_words, nblocks, sp, index);
+  else index_var_kernel<Scalar, 3><<<1, 32, 0, c->stream>>>(st, stream_words, nblocks, sp, index);
+  c->launches++;
+  CU_TRY(c, cudaGetLastError());
+  return ZFB_OK;
+}
+
+template <typename Scalar, bool METRICS>
+static int launch_dec_var(zfb_ctx* c, int dims, const geom& g, const stream_params& sp, const void* d_stream,
+                          const uint64_t* index, void* d_out, const void* d_orig, int* rows)
+{
+  int grid = var_grid(c, g.nblocks);
+  if (grid > c->part_rows) grid = c->part_rows;
+  const uint64_t* st = (const uint64_t*)d_stream;
+  Scalar* out = (Scalar*)d_out;
+  const Scalar* orig = (const Scalar*)d_orig;
+  if (dims == 1) dec_var_kernel<Scalar, 1, METRICS><<<grid, 128, 0, c->stream>>>(st, index, out, orig, g, sp, c->part);
+  else if (dims == 2) dec_var_kernel<Scalar, 2, METRICS><<<grid, 128, 0, c->stream>>>(st, index, out, orig, g, sp, c->part);
+  else dec_var_kernel<Scalar, 3, METRICS><<<grid, 128, 0, c->stream>>>(st, index, out, orig, g, sp, c->part);
+  c->launches++;
+  *rows = grid;
+  CU_TRY(c, cudaGetLastError());
+  return ZFB_OK;
+}
+
+extern "C" int zfb_decode_var_dev(zfb_ctx* c, int dtype, int dims, size_t nx, size_t ny, size_t nz, const zfb_mode* m,
+                                  const void* d_stream, size_t stream_bytes, const uint64_t* d_index, void* d_out,
+                                  const void* d_orig)
+{
+  int rc = check_var_args(c, dtype, dims, nx, ny, nz, m);
+  if (rc) return rc;
+  if (!d_stream || !d_out || !stream_bytes) { c->err = "null pointer"; return ZFB_EINVAL; }
+  CU_TRY(c, cudaSetDevice(c->device));
+  geom g = make_geom(dims, nx, ny, nz, 64);
+  g.stream_words = (stream_bytes + 7) / 8;
+  const stream_params sp = to_params(m);
+  const uint64_t* index = d_index;
+  if (!index) {
+    if (c->var_index_key == d_stream && c->var_index_blocks == g.nblocks && c->var_index.p &&
+        (size_t)((c->var_index_bits + 63) / 64) * 8 == g.stream_words * 8) {
+      index = (const uint64_t*)c->var_index.p;
+    } else {
+      c->var_index_key = nullptr;
+      if ((rc = ensure(c, c->var_index, (g.nblocks + 1) * 8))) return rc;
+      rc = dtype == ZFB_FLOAT ? launch_index_var<float>(c, dims, d_stream, g.stream_words, g.nblocks, sp, (uint64_t*)c->var_index.p)
+                              : launch_index_var<double>(c, dims, d_stream, g.stream_words, g.nblocks, sp, (uint64_t*)c->var_index.p);
+      if (rc) return rc;
+      index = (const uint64_t*)c->var_index.p;
+    }
+  }
+  int rows = 0;
+  const bool metrics = d_orig != nullptr;
+  if (dtype == ZFB_FLOAT) {
+    rc = metrics ? launch_dec_var<float, true>(c, dims, g, sp, d_stream, index, d_out, d_orig, &rows)
+                 : launch_dec_var<float, false>(c, dims, g, sp, d_stream, index, d_out, d_orig, &rows);
+  } else {
+    rc = metrics ? launch_dec_var<double, true>(c, dims, g, sp, d_stream, index, d_out, d_orig, &rows)
+                 : launch_dec_var<double, false>(c, dims, g, sp, d_stream, index, d_out, d_orig, &rows);
+  }
+  if (rc) return rc;
+  if (metrics) return finalize(c, rows, g.nx * g.ny * g.nz);
+  return ZFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-pointer forms
+// ------------------------------------------------------------------------------------------------
+extern "C" int zfb_compress_var_host(zfb_ctx* c, int dtype, int dims, size_t nx, size_t ny, size_t nz, const zfb_mode* m,
+                                     const void* h_in, void* h_stream, size_t cap_bytes, size_t* cbytes)
+{
+  int rc = check_var_args(c, dtype, dims, nx, ny, nz, m);
+  if (rc) return rc;
+  if (!h_in || !h_stream) { c->err = "null pointer"; return ZFB_EINVAL; }
+  const size_t need = zfb_maximum_size(dtype, dims, nx, ny, nz, m);
+  if (cap_bytes < need) { c->err = "stream buffer smaller than zfb_maximum_size()"; return ZFB_EINVAL; }
+  CU_TRY(c, cudaSetDevice(c->device));
+  const size_t esz = dtype == ZFB_FLOAT ? 4 : 8;
+  const size_t n = nx * (dims >= 2 ? ny : 1) * (dims >= 3 ? nz : 1);
+  if ((rc = ensure(c, c->d_orig, n * esz))) return rc;
+  if ((rc = ensure(c, c->d_stream, need + 16))) return rc;
+  c->fused_valid = false;
+  c->h_orig_key = nullptr;
+  c->var_host_key = nullptr;
+  CU_TRY(c, cudaMemcpyAsync(c->d_orig.p, h_in, n * esz, cudaMemcpyHostToDevice, c->stream));
+  size_t bytes = 0;
+  if ((rc = zfb_encode_var_dev(c, dtype, dims, nx, ny, nz, m, c->d_orig.p, c->d_stream.p, need, nullptr, &bytes))) return rc;
+  CU_TRY(c, cudaMemcpyAsync(h_stream, c->d_stream.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  if (cbytes) *cbytes = bytes;
+  c->h_orig_key = h_in;
+  c->orig_bytes = n * esz;
+  c->var_host_key = h_stream;   // the resident stream + index describe this host buffer
+  c->var_host_bytes = bytes;
+  return ZFB_OK;
+}
+
+extern "C" int zfb_decompress_var_host(zfb_ctx* c, int dtype, int dims, size_t nx, size_t ny, size_t nz, const zfb_mode* m,
+                                       const void* h_stream, size_t stream_bytes, void* h_out, const void* h_orig)
+{
+  int rc = check_var_args(c, dtype, dims, nx, ny, nz, m);
+  if (rc) return rc;
+  if (!h_out || !h_stream || !stream_bytes) { c->err = "null pointer"; return ZFB_EINVAL; }
+  CU_TRY(c, cudaSetDevice(c->device));
+  const size_t esz = dtype == ZFB_FLOAT ? 4 : 8;
+  const size_t n = nx * (dims >= 2 ? ny : 1) * (dims >= 3 ? nz : 1);
+  if ((rc = ensure(c, c->d_out, n * esz))) return rc;
+  const bool metrics = h_orig != nullptr;
+  const bool orig_resident = metrics && h_orig == c->h_orig_key && c->orig_bytes == n * esz && c->d_orig.p;
+  if (metrics && !orig_resident) {
+    if ((rc = ensure(c, c->d_orig, n * esz))) return rc;
+    CU_TRY(c, cudaMemcpyAsync(c->d_orig.p, h_orig, n * esz, cudaMemcpyHostToDevice, c->stream));
+  }
+  c->fused_valid = false;
+  // the index kept by zfb_compress_var_host is only trusted together with the bytes it was built from, so the
+  // stream is uploaded again (cheap next to the field) and the index reused when the host buffer is the same
+  const bool index_resident = c->var_host_key == h_stream && c->var_host_bytes == stream_bytes &&
+                              c->var_index_key == c->d_stream.p && c->d_stream.p;
+  if (!index_resident) {
+    if ((rc = ensure(c, c->d_stream, stream_bytes + 16))) return rc;
+    c->var_index_key = nullptr;
+  }
+  CU_TRY(c, cudaMemcpyAsync(c->d_stream.p, h_stream, stream_bytes, cudaMemcpyHostToDevice, c->stream));
+  if ((rc = zfb_decode_var_dev(c, dtype, dims, nx, ny, nz, m, c->d_stream.p, stream_bytes, nullptr, c->d_out.p,
+                               metrics ? c->d_orig.p : nullptr)))
+    return rc;
+  CU_TRY(c, cudaMemcpyAsync(h_out, c->d_out.p, n * esz, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  if (metrics) {
+    c->h_orig_key = h_orig;
+    c->orig_bytes = n * esz;
+    c->fused_valid = true;
+  }
+  c->h_out_key = h_out;
+  c->out_bytes = n * esz;
+  return ZFB_OK;
+}

@@ -490,14 +490,52 @@ struct slot_reader {
 };
 
 // ---------------------------------------------------------------------------------------------
+// zfp_stream's four parameters.  Fixed rate: minbits = maxbits, maxprec = 64, minexp = -1074
+// (zfp_stream_set_rate); fixed accuracy / precision (the CPU zfp plugin's "abs" / "rel",
+// zfp/zfpCompressor.hpp:117-120): minbits = 1, maxbits = 16657 and a per-block plane count
+// precision(emax) = min(maxprec, max(0, emax - minexp + 2 (dims + 1))).
+// ---------------------------------------------------------------------------------------------
+struct stream_params {
+  unsigned minbits, maxbits, maxprec;
+  int minexp;
+};
+
+ZFB_HD stream_params fixed_rate_params(unsigned maxbits)
+{
+  stream_params sp;
+  sp.minbits = maxbits; sp.maxbits = maxbits; sp.maxprec = 64u; sp.minexp = -1074;
+  return sp;
+}
+
+template <int DIMS> ZFB_HD int block_precision(int emax, const stream_params& sp)
+{
+  int p = emax - sp.minexp + 2 * (DIMS + 1);
+  p = p < 0 ? 0 : p;
+  return p > (int)sp.maxprec ? (int)sp.maxprec : p;
+}
+
+// Sink of the variable-rate path: whole words into a private staging area that is large enough for the longest
+// possible block (1 + EBITS + 4^d - 1 + 4^d * PBITS bits, zfp_stream_maximum_size's bound).
+struct stage_sink {
+  uint64_t* dst;
+  unsigned widx;
+  ZFB_HD explicit stage_sink(uint64_t* d) : dst(d), widx(0) {}
+  ZFB_HD void word(uint64_t w) { dst[widx++] = w; }
+  ZFB_HD void finish() {}
+};
+
+// ---------------------------------------------------------------------------------------------
 // encode one block (A.4, A.5, A.8).  Emits exactly maxbits bits into the sink (as whole words; the
 // sink drops anything past the slot and zero-fills the rest).  The fixed-rate stream is the first
 // maxbits bits of the unbounded embedded stream, so the coder runs without per-bit budget checks and
 // stops as soon as the budget is covered.
 // ---------------------------------------------------------------------------------------------
+// General form: returns the number of bits the block occupies (>= minbits, <= maxbits).  With minbits ==
+// maxbits the sink pads / truncates to the slot; otherwise the caller places the `bits` emitted bits.
 template <typename Scalar, int DIMS, class Sink>
-ZFB_HD void encode_block(const Scalar (&f)[1 << (2 * DIMS)], unsigned maxbits, Sink& sink)
+ZFB_HD unsigned encode_block(const Scalar (&f)[1 << (2 * DIMS)], const stream_params& sp, Sink& sink)
 {
+  const unsigned maxbits = sp.maxbits;
   typedef traits<Scalar> T;
   typedef typename T::Int Int;
   typedef typename T::UInt UInt;
@@ -509,14 +547,14 @@ ZFB_HD void encode_block(const Scalar (&f)[1 << (2 * DIMS)], unsigned maxbits, S
     Scalar a = f[i] < 0 ? -f[i] : f[i];
     mx = (mx < a) ? a : mx;
   }
-  if (!(mx > 0)) {  // all-zero block: a single 0 bit and padding
-    sink.finish();
-    return;
-  }
   const int E = T::expfield(mx);               // emax = E - (EBIAS - 1); biased e = E + 1
   const int emax = E - (T::EBIAS - 1);
-  int prec = emax + 1074 + 2 * (DIMS + 1);     // precision(emax, 64, -1074, dims); > 0 for any finite input
-  prec = prec > 64 ? 64 : prec;
+  const int prec = block_precision<DIMS>(emax, sp);  // > 0 for any finite non-zero input in fixed-rate mode
+  if (!(mx > 0) || prec == 0) {  // all-zero block, or nothing above the accuracy floor: a single 0 bit and padding
+    sink.word(0);
+    sink.finish();
+    return sp.minbits > 1u ? sp.minbits : 1u;
+  }
   const int kmin = T::PBITS > prec ? T::PBITS - prec : 0;
 
   // block-floating-point cast: i = (Int)(2^(p-2-emax) * f), truncation toward zero
@@ -564,15 +602,27 @@ ZFB_HD void encode_block(const Scalar (&f)[1 << (2 * DIMS)], unsigned maxbits, S
   }
   bw.flush();
   sink.finish();
+  const unsigned used = bw.total < maxbits ? bw.total : maxbits;
+  return used < sp.minbits ? sp.minbits : used;
+}
+
+// Fixed-rate form: exactly maxbits bits per block.
+template <typename Scalar, int DIMS, class Sink>
+ZFB_HD void encode_block(const Scalar (&f)[1 << (2 * DIMS)], unsigned maxbits, Sink& sink)
+{
+  encode_block<Scalar, DIMS>(f, fixed_rate_params(maxbits), sink);
 }
 
 // ---------------------------------------------------------------------------------------------
 // decode one block (A.5, A.8).  `r` is positioned at the first bit of the slot.
 // Budget bookkeeping is exact: zfp's decoder deposits a one when the budget ends inside a zero run.
 // ---------------------------------------------------------------------------------------------
-template <typename Scalar, int DIMS, class Reader>
-ZFB_HD void decode_block(Scalar (&f)[1 << (2 * DIMS)], unsigned maxbits, Reader& r)
+// General form: returns the number of bits the block occupied.  PARSE_ONLY skips the reconstruction (used to
+// rebuild the block index of a variable-rate stream).
+template <typename Scalar, int DIMS, bool PARSE_ONLY, class Reader>
+ZFB_HD unsigned decode_block(Scalar (&f)[1 << (2 * DIMS)], const stream_params& sp, Reader& r)
 {
+  const unsigned maxbits = sp.maxbits;
   typedef traits<Scalar> T;
   typedef typename T::Int Int;
   typedef typename T::UInt UInt;
@@ -580,14 +630,13 @@ ZFB_HD void decode_block(Scalar (&f)[1 << (2 * DIMS)], unsigned maxbits, Reader&
 
   uint64_t win = r.peek();
   if (!(win & 1)) {
-    ZFB_UNROLL for (int i = 0; i < BS; i++) f[i] = 0;
-    return;
+    if (!PARSE_ONLY) { ZFB_UNROLL for (int i = 0; i < BS; i++) f[i] = 0; }
+    return sp.minbits > 1u ? sp.minbits : 1u;
   }
   const int e = (int)((win >> 1) & (((uint64_t)1 << T::EBITS) - 1));
   const int emax = e - T::EBIAS;
   r.pos += 1 + T::EBITS;
-  int prec = emax + 1074 + 2 * (DIMS + 1);
-  prec = prec > 64 ? 64 : (prec < 0 ? 0 : prec);
+  const int prec = block_precision<DIMS>(emax, sp);
   const int kmin = T::PBITS > prec ? T::PBITS - prec : 0;
 
   planes<UInt, BS> P;
@@ -613,8 +662,10 @@ ZFB_HD void decode_block(Scalar (&f)[1 << (2 * DIMS)], unsigned maxbits, Reader&
       x |= (uint64_t)1 << n;
       n++;
     }
-    P.set(k, x);
+    if (!PARSE_ONLY) P.set(k, x);
   }
+  const unsigned used = maxbits - remaining;
+  if (PARSE_ONLY) return used < sp.minbits ? sp.minbits : used;
 
   UInt u[BS];
   P.to_coeffs(u);
@@ -623,6 +674,14 @@ ZFB_HD void decode_block(Scalar (&f)[1 << (2 * DIMS)], unsigned maxbits, Reader&
   inv_xform<Int, DIMS>(ib);
   const Scalar s = T::pow2(emax - (T::PBITS - 2));
   ZFB_UNROLL for (int i = 0; i < BS; i++) f[i] = s * T::to_scalar(ib[i]);
+  return used < sp.minbits ? sp.minbits : used;
+}
+
+// Fixed-rate form.
+template <typename Scalar, int DIMS, class Reader>
+ZFB_HD void decode_block(Scalar (&f)[1 << (2 * DIMS)], unsigned maxbits, Reader& r)
+{
+  decode_block<Scalar, DIMS, false>(f, fixed_rate_params(maxbits), r);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -1,0 +1,296 @@
+// zfb_var.cuh -- variable-rate streams: zfp's fixed-accuracy and fixed-precision modes, the ones the CPU zfp
+// plugin exposes as "abs" and "rel" (CBench/compressors/zfp/zfpCompressor.hpp:83-93,117-120).
+//
+// A variable-rate stream is the bit-tight concatenation of blocks of different lengths, so the encoder is three
+// steps instead of one:
+//   1. enc_var_kernel      every thread encodes one block into a private staging column (words of the 32 blocks of
+//                          a warp interleaved, so staging stores and loads are coalesced) and records its length
+//   2. scan_*_kernel       exclusive prefix sum of the lengths -> absolute bit offset of every block (the index)
+//   3. compact_var_kernel  every thread shifts its staged words to its bit offset in the (zeroed) stream: interior
+//                          words are plain stores, the two boundary words shared with the neighbours are OR-ed in
+// The decoder needs the index: dec_var_kernel takes the offsets array (kept by the caller from the encode, exactly
+// as CBench's decompress relies on state left by compress, zfpCompressor.hpp:22,160), and index_var_kernel rebuilds
+// it from a bare stream by walking the blocks in order (slow: the format has no resynchronisation points).
+#pragma once
+#include "zfb_kernels.cuh"
+
+namespace zfb {
+
+template <typename Scalar, int DIMS> struct var_caps {
+  static constexpr unsigned BS = 1u << (2 * DIMS);
+  // zfp_stream_maximum_size's per-block bound: 1 + EBITS + (4^d - 1) + 4^d * precision
+  static constexpr unsigned BITS = 1u + traits<Scalar>::EBITS + (BS - 1u) + BS * (unsigned)traits<Scalar>::PBITS;
+  static constexpr unsigned WORDS = (BITS + 63u) / 64u + 1u;
+};
+
+// staging column of one block: word j of block b lives at stage[(b / 32) * 32 * WORDS + j * 32 + b % 32]
+struct stage_col_sink {
+  uint64_t* dst;
+  unsigned widx;
+  ZFB_HD explicit stage_col_sink(uint64_t* d) : dst(d), widx(0) {}
+  ZFB_HD void word(uint64_t w) { dst[32u * widx++] = w; }
+  ZFB_HD void finish() {}
+};
+
+template <unsigned WORDS> __device__ __forceinline__ size_t stage_base(size_t b)
+{
+  return (b >> 5) * (size_t)(32u * WORDS) + (b & 31u);
+}
+
+// block b of the field -> 4^d values, partial blocks padded (A.3)
+template <typename Scalar, int DIMS>
+__device__ __forceinline__ void gather_block(const Scalar* __restrict__ in, const geom& g, size_t b,
+                                             Scalar (&f)[1 << (2 * DIMS)])
+{
+  constexpr int BS = 1 << (2 * DIMS);
+  const size_t ix = b % g.bx, iy = (b / g.bx) % g.by, iz = b / (g.bx * g.by);
+  const size_t x0 = 4 * ix, y0 = 4 * iy, z0 = 4 * iz;
+  const unsigned mx = (unsigned)(g.nx - x0 < 4 ? g.nx - x0 : 4);
+  const unsigned my = DIMS >= 2 ? (unsigned)(g.ny - y0 < 4 ? g.ny - y0 : 4) : 1u;
+  const unsigned mz = DIMS >= 3 ? (unsigned)(g.nz - z0 < 4 ? g.nz - z0 : 4) : 1u;
+  const bool full = mx == 4 && (DIMS < 2 || my == 4) && (DIMS < 3 || mz == 4);
+  const bool vec = ((g.nx & 3) == 0) && ((reinterpret_cast<size_t>(in) & 15) == 0) && sizeof(Scalar) == 4;
+  if (full && vec) {
+#pragma unroll
+    for (int k = 0; k < (DIMS >= 3 ? 4 : 1); k++)
+#pragma unroll
+      for (int j = 0; j < (DIMS >= 2 ? 4 : 1); j++) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(in + x0 + g.nx * ((y0 + j) + g.ny * (z0 + k))));
+        f[(16 * k + 4 * j + 0) & (BS - 1)] = (Scalar)v.x;
+        f[(16 * k + 4 * j + 1) & (BS - 1)] = (Scalar)v.y;
+        f[(16 * k + 4 * j + 2) & (BS - 1)] = (Scalar)v.z;
+        f[(16 * k + 4 * j + 3) & (BS - 1)] = (Scalar)v.w;
+      }
+    return;
+  }
+#pragma unroll
+  for (int k = 0; k < (DIMS >= 3 ? 4 : 1); k++)
+#pragma unroll
+    for (int j = 0; j < (DIMS >= 2 ? 4 : 1); j++)
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const bool ok = (unsigned)i < mx && (unsigned)j < my && (unsigned)k < mz;
+        f[(16 * k + 4 * j + i) & (BS - 1)] = ok ? __ldg(in + (x0 + i) + g.nx * ((y0 + j) + g.ny * (z0 + k))) : (Scalar)0;
+      }
+  if (!full) pad_block<Scalar, DIMS>(f, mx, my, mz);
+}
+
+// ---- step 1: encode into staging, record lengths ----------------------------------------------
+template <typename Scalar, int DIMS>
+__global__ void __launch_bounds__(128) enc_var_kernel(const Scalar* __restrict__ in, uint64_t* __restrict__ stage,
+                                                      uint32_t* __restrict__ lens, geom g, stream_params sp)
+{
+  constexpr int BS = 1 << (2 * DIMS);
+  constexpr unsigned WORDS = var_caps<Scalar, DIMS>::WORDS;
+  for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < g.nblocks; b += (size_t)gridDim.x * blockDim.x) {
+    Scalar f[BS];
+    gather_block<Scalar, DIMS>(in, g, b, f);
+    stage_col_sink sink(stage + stage_base<WORDS>(b));
+    lens[b] = encode_block<Scalar, DIMS>(f, sp, sink);
+  }
+}
+
+// ---- step 2: exclusive scan of the lengths (three small kernels, fixed order, no atomics) ----------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_CHUNK = SCAN_THREADS * SCAN_ITEMS;  // lengths per CTA
+
+__device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t v, uint64_t* sh, uint64_t& total)
+{
+  // sh: 32 + 1 words of shared memory
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  uint64_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) sh[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    uint64_t w = lane < nw ? sh[lane] : 0;
+    uint64_t winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint64_t t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += t;
+    }
+    if (lane < nw) sh[lane] = winc - w;
+    if (lane == nw - 1) sh[32] = winc;
+  }
+  __syncthreads();
+  const uint64_t r = sh[warp] + inc - v;
+  total = sh[32];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_sums_kernel(const uint32_t* __restrict__ lens, size_t n,
+                                                                 uint64_t* __restrict__ chunk_sums)
+{
+  __shared__ uint64_t sh[33];
+  const size_t base = (size_t)blockIdx.x * SCAN_CHUNK + (size_t)threadIdx.x * SCAN_ITEMS;
+  uint64_t s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++)
+    if (base + i < n) s += lens[base + i];
+  uint64_t total;
+  block_exclusive_scan(s, sh, total);
+  if (threadIdx.x == 0) chunk_sums[blockIdx.x] = total;
+}
+
+// one CTA: chunk sums -> exclusive chunk offsets (in place), grand total to chunk_sums[nchunks]
+__global__ void __launch_bounds__(SCAN_THREADS) scan_chunks_kernel(uint64_t* __restrict__ chunk_sums, size_t nchunks)
+{
+  __shared__ uint64_t sh[33];
+  uint64_t carry = 0;
+  for (size_t c0 = 0; c0 < nchunks; c0 += SCAN_THREADS) {
+    const size_t c = c0 + threadIdx.x;
+    const uint64_t v = c < nchunks ? chunk_sums[c] : 0;
+    uint64_t total;
+    const uint64_t ex = block_exclusive_scan(v, sh, total);
+    if (c < nchunks) chunk_sums[c] = carry + ex;
+    carry += total;
+  }
+  if (threadIdx.x == 0) chunk_sums[nchunks] = carry;
+}
+
+// offsets[b] = first bit of block b, offsets[n] = total bits
+__global__ void __launch_bounds__(SCAN_THREADS) scan_offsets_kernel(const uint32_t* __restrict__ lens, size_t n,
+                                                                    const uint64_t* __restrict__ chunk_sums,
+                                                                    size_t nchunks, uint64_t* __restrict__ offsets)
+{
+  __shared__ uint64_t sh[33];
+  const size_t base = (size_t)blockIdx.x * SCAN_CHUNK + (size_t)threadIdx.x * SCAN_ITEMS;
+  uint32_t l[SCAN_ITEMS];
+  uint64_t s = 0;
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) {
+    l[i] = base + i < n ? lens[base + i] : 0u;
+    s += l[i];
+  }
+  uint64_t total;
+  uint64_t ex = chunk_sums[blockIdx.x] + block_exclusive_scan(s, sh, total);
+#pragma unroll
+  for (int i = 0; i < SCAN_ITEMS; i++) {
+    if (base + i < n) offsets[base + i] = ex;
+    ex += l[i];
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) offsets[n] = chunk_sums[nchunks];
+}
+
+// zero the words the compaction will OR into: ceil(total_bits / 64) words, total read from the device
+__global__ void __launch_bounds__(256) zero_stream_kernel(uint64_t* __restrict__ stream, const uint64_t* __restrict__ total_bits,
+                                                          size_t cap_words)
+{
+  size_t nw = (size_t)((*total_bits + 63) >> 6);
+  if (nw > cap_words) nw = cap_words;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nw; i += (size_t)gridDim.x * blockDim.x) stream[i] = 0;
+}
+
+// ---- step 3: staged words -> bit-tight stream ---------------------------------------------------
+template <unsigned WORDS>
+__global__ void __launch_bounds__(128) compact_var_kernel(const uint64_t* __restrict__ stage, const uint64_t* __restrict__ offsets,
+                                                          size_t nblocks, uint64_t* __restrict__ stream, size_t cap_words)
+{
+  for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < nblocks; b += (size_t)gridDim.x * blockDim.x) {
+    const uint64_t off = offsets[b], end = offsets[b + 1];
+    const unsigned len = (unsigned)(end - off);
+    const unsigned nw = (len + 63u) >> 6;
+    const uint64_t* col = stage + stage_base<WORDS>(b);
+    const unsigned s = (unsigned)(off & 63u);
+    size_t wi = (size_t)(off >> 6);
+    uint64_t prev = 0;  // bits carried into the next output word
+    for (unsigned j = 0; j <= nw; j++) {
+      uint64_t w = 0;
+      if (j < nw) {
+        w = col[32u * j];
+        const unsigned valid = len - 64u * j;
+        if (valid < 64u) w &= lowmask64(valid);
+      }
+      const uint64_t o = s ? ((w << s) | prev) : w;
+      prev = s ? (w >> (64u - s)) : 0;
+      if (j == nw && !s) break;  // nothing carried over
+      const size_t i = wi + j;
+      if (i < cap_words && o) {
+        // words wholly inside [off, end) belong to this block alone; the first and the last are shared
+        const bool whole = (uint64_t)i * 64u >= off && (uint64_t)(i + 1) * 64u <= end;
+        if (whole) stream[i] = o;
+        else atomicOr(reinterpret_cast<unsigned long long*>(stream + i), (unsigned long long)o);
+      } else if (i < cap_words) {
+        const bool whole = (uint64_t)i * 64u >= off && (uint64_t)(i + 1) * 64u <= end;
+        (void)whole;  // zero contribution: the word was zeroed up front
+      }
+    }
+  }
+}
+
+// ---- decode with the index ---------------------------------------------------------------------
+template <typename Scalar, int DIMS, bool METRICS>
+__global__ void __launch_bounds__(128) dec_var_kernel(const uint64_t* __restrict__ stream, const uint64_t* __restrict__ offsets,
+                                                      Scalar* __restrict__ out, const Scalar* __restrict__ orig, geom g,
+                                                      stream_params sp, double* __restrict__ part)
+{
+  constexpr int BS = 1 << (2 * DIMS);
+  __shared__ double red[7 * 4];
+  macc_t<Scalar> m;
+  m.init();
+  for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < g.nblocks; b += (size_t)gridDim.x * blockDim.x) {
+    const size_t ix = b % g.bx, iy = (b / g.bx) % g.by, iz = b / (g.bx * g.by);
+    const size_t x0 = 4 * ix, y0 = 4 * iy, z0 = 4 * iz;
+    const unsigned mx = (unsigned)(g.nx - x0 < 4 ? g.nx - x0 : 4);
+    const unsigned my = DIMS >= 2 ? (unsigned)(g.ny - y0 < 4 ? g.ny - y0 : 4) : 1u;
+    const unsigned mz = DIMS >= 3 ? (unsigned)(g.nz - z0 < 4 ? g.nz - z0 : 4) : 1u;
+    const uint64_t startbit = offsets[b];
+    const size_t w0 = (size_t)(startbit >> 6);
+    const size_t left = g.stream_words > w0 ? g.stream_words - w0 : 0;
+    Scalar f[BS];
+    slot_reader r(stream + w0, left > 0xffffffffull ? 0xffffffffu : (unsigned)left, (unsigned)(startbit & 63));
+    decode_block<Scalar, DIMS, false>(f, sp, r);
+#pragma unroll
+    for (int k = 0; k < (DIMS >= 3 ? 4 : 1); k++)
+#pragma unroll
+      for (int j = 0; j < (DIMS >= 2 ? 4 : 1); j++)
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const bool ok = (unsigned)i < mx && (unsigned)j < my && (unsigned)k < mz;
+          if (ok) {
+            const size_t idx = (x0 + i) + g.nx * ((y0 + j) + g.ny * (z0 + k));
+            const Scalar a = f[(16 * k + 4 * j + i) & (BS - 1)];
+            out[idx] = a;
+            if (METRICS) {
+              if constexpr (sizeof(Scalar) == 4) {
+                frow fr;
+                fr.init();
+                fr.add(__ldg(orig + idx), a);
+                fr.flush(m);
+              } else {
+                macc_add(m, (double)__ldg(orig + idx), (double)a);
+              }
+            }
+          }
+        }
+  }
+  if (METRICS) macc_block_store(m, red, part + (size_t)blockIdx.x * PART_STRIDE);
+}
+
+// ---- index rebuild: walk a bare stream block by block (one thread; the format is strictly sequential) ----
+template <typename Scalar, int DIMS>
+__global__ void index_var_kernel(const uint64_t* __restrict__ stream, size_t stream_words, size_t nblocks, stream_params sp,
+                                 uint64_t* __restrict__ offsets)
+{
+  if (blockIdx.x || threadIdx.x) return;
+  constexpr int BS = 1 << (2 * DIMS);
+  uint64_t pos = 0;
+  Scalar f[BS];
+  for (size_t b = 0; b < nblocks; b++) {
+    offsets[b] = pos;
+    const size_t w0 = (size_t)(pos >> 6);
+    const size_t left = stream_words > w0 ? stream_words - w0 : 0;
+    slot_reader r(stream + w0, left > 0xffffffffull ? 0xffffffffu : (unsigned)left, (unsigned)(pos & 63));
+    pos += decode_block<Scalar, DIMS, true>(f, sp, r);
+  }
+  offsets[nblocks] = pos;
+}
+
+}  // namespace zfb
