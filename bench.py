@@ -265,6 +265,8 @@ def main():
     ap.add_argument("--wra", type=int, default=1, help="1 = CBench semantics (64-bit aligned slots), 0 = unaligned slots")
     ap.add_argument("--field", default="", choices=["", "lognormal", "smooth", "uniform", "velocity", "noise", "zero"],
                     help="override the workload's synthetic field kind (sweeps only)")
+    ap.add_argument("--mode", default="", help="variable-rate sweep only: abs:<tolerance> (zfp fixed accuracy) or "
+                                               "rel:<precision> (fixed precision); default = fixed rate")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
@@ -303,6 +305,12 @@ def main():
     n = field.numel()
     field_bytes = n * esz
     cbytes = pkg.stream_bytes(shape, mb)
+    var_mode = None
+    if args.mode:
+        kind, _, val = args.mode.partition(":")
+        var_mode = pkg.mode_accuracy(float(val)) if kind == "abs" else pkg.mode_precision(int(val))
+        cbytes = pkg.maximum_size(shape, npdt, var_mode)  # capacity; the real size is data dependent (set below)
+        args.no_e2e = args.no_cpu = True
     stream = torch.empty(cbytes + 16, dtype=torch.uint8, device=dev)
     out = torch.empty(shape, dtype=tdt, device=dev)
 
@@ -321,13 +329,21 @@ def main():
 
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
 
+    var_bytes = [0]
+
     def step(i=None):
         if i is not None:
             ev[i][0].record()
-        codec.encode(field, mb, out=stream)
+        if var_mode is not None:
+            s_var, var_bytes[0] = codec.encode_var(field, var_mode, out=stream)
+        else:
+            codec.encode(field, mb, out=stream)
         if i is not None:
             ev[i][1].record()
-        codec.decode(stream, shape, tdt, mb, orig=field if want_metrics else None, out=out)
+        if var_mode is not None:
+            codec.decode_var(s_var, shape, tdt, var_mode, orig=field, out=out)
+        else:
+            codec.decode(stream, shape, tdt, mb, orig=field if want_metrics else None, out=out)
         if i is not None:
             ev[i][2].record()
         if world > 1:
@@ -388,6 +404,8 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    if var_mode is not None:
+        cbytes = var_bytes[0]
     dec_bytes = cbytes + 2 * field_bytes
     enc_bytes = cbytes + field_bytes
     roof = {"bound": "hbm", "kernel": "decode+metrics", "achieved": dec_bytes / (dec_ms * 1e-3) / 1e9, "peak": peak,
@@ -444,7 +462,8 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if dtype == "float32" else "f64", "data": "synthetic",
         "config": {"workload": args.workload, "description": wl["desc"], "shape_per_gpu": list(shape),
-                   "rate_bpv": rate, "maxbits": mb, "wra": args.wra, "field": args.field or wl["kind"],
+                   "rate_bpv": rate if var_mode is None else 8.0 * cbytes / n, "maxbits": mb if var_mode is None else None,
+                   "mode": args.mode or "rate", "wra": args.wra, "field": args.field or wl["kind"],
                    "compressed_bytes_per_gpu": cbytes,
                    "l2": "inputs (%.1f GiB per step) are far larger than the 126 MB L2; no flush needed" % (field_bytes / 2 ** 30),
                    "exchange": "NCCL all-reduce of metric partials (SUM f64[4], MAX f64[4])" if world > 1 else "none (1 GPU)"},

@@ -208,8 +208,23 @@ static size_t run_var(bool enc, size_t nx, size_t ny, size_t nz, const stream_pa
       if (mx < 4 || my < (DIMS >= 2 ? 4u : 1u) || mz < (DIMS >= 3 ? 4u : 1u)) pad_block<Scalar, DIMS>(f, mx, my, mz);
       uint64_t stage[80];
       std::memset(stage, 0xff, sizeof stage);  // garbage behind the written words must not leak into the stream
-      stage_sink sink(stage);
-      const unsigned bits = encode_block<Scalar, DIMS>(f, sp, sink);
+      unsigned bits = 0;
+      bool done = false;
+      if constexpr (std::is_same<Scalar, float>::value && DIMS == 3) {
+        if (g_use_f3) {  // the fast float/3D coder, as enc_var_kernel uses it
+          const f3::tables tb = host_tables();
+          f3::u32x4 rows[16];
+          f3::plane_rows ps;
+          ps.p = rows; ps.stride = 1;
+          f3::sink32 sink(reinterpret_cast<uint32_t*>(stage), 160);
+          bits = f3::encode_block(f, sp, sink, tb, ps);
+          done = true;
+        }
+      }
+      if (!done) {
+        stage_sink sink(stage);
+        bits = encode_block<Scalar, DIMS>(f, sp, sink);
+      }
       for (unsigned j = 0; 64 * j < bits; j++) {
         uint64_t w = stage[j];
         const unsigned valid = bits - 64 * j;
@@ -223,10 +238,22 @@ static size_t run_var(bool enc, size_t nx, size_t ny, size_t nz, const stream_pa
     } else {
       slot_reader r(stream + (pos >> 6), (unsigned)(stream_words - (pos >> 6)), (unsigned)(pos & 63));
       slot_reader r2 = r;
-      Scalar dummy[BS];
+      Scalar dummy[BS], f2[BS];
       const unsigned bits = decode_block<Scalar, DIMS, false>(f, sp, r);
       const unsigned bits2 = decode_block<Scalar, DIMS, true>(dummy, sp, r2);  // index walk must agree
       if (bits != bits2) return 0;
+      if constexpr (std::is_same<Scalar, float>::value && DIMS == 3) {
+        if (g_use_f3) {  // the fast float/3D decoder must reproduce the generic one bit for bit
+          const f3::tables tb = host_tables();
+          const uint32_t* s32 = reinterpret_cast<const uint32_t*>(stream);
+          f3::reader32 r3(s32 + (pos >> 5), (unsigned)(2 * stream_words - (pos >> 5)), (unsigned)(pos & 31));
+          f3::u32x4 rows[16];
+          f3::plane_rows ps;
+          ps.p = rows; ps.stride = 1;
+          f3::decode_block(f2, sp, r3, tb, ps);
+          if (std::memcmp(f, f2, sizeof f2)) return 0;
+        }
+      }
       pos += bits;
       for (unsigned k = 0; k < mz; k++)
         for (unsigned j = 0; j < my; j++)

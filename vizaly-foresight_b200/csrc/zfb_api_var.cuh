@@ -118,9 +118,10 @@ static int launch_compact_var(zfb_ctx* c, int dims, const geom& g, const uint64_
                               uint64_t* stream, size_t cap_words)
 {
   const int grid = var_grid(c, g.nblocks);
-  if (dims == 1) compact_var_kernel<var_caps<Scalar, 1>::WORDS><<<grid, 128, 0, c->stream>>>(stage, index, g.nblocks, stream, cap_words);
-  else if (dims == 2) compact_var_kernel<var_caps<Scalar, 2>::WORDS><<<grid, 128, 0, c->stream>>>(stage, index, g.nblocks, stream, cap_words);
-  else compact_var_kernel<var_caps<Scalar, 3>::WORDS><<<grid, 128, 0, c->stream>>>(stage, index, g.nblocks, stream, cap_words);
+  constexpr bool COL32 = sizeof(Scalar) == 4;  // float/3D is staged by the 32-bit table coder
+  if (dims == 1) compact_var_kernel<var_caps<Scalar, 1>::WORDS, false><<<grid, 128, 0, c->stream>>>(stage, index, g.nblocks, stream, cap_words);
+  else if (dims == 2) compact_var_kernel<var_caps<Scalar, 2>::WORDS, false><<<grid, 128, 0, c->stream>>>(stage, index, g.nblocks, stream, cap_words);
+  else compact_var_kernel<var_caps<Scalar, 3>::WORDS, COL32><<<grid, 128, 0, c->stream>>>(stage, index, g.nblocks, stream, cap_words);
   c->launches++;
   CU_TRY(c, cudaGetLastError());
   return ZFB_OK;

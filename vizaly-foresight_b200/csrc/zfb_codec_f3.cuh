@@ -336,8 +336,8 @@ template <class Sink> struct writer32 {
 // NP/2-1) are finished; every lower group of 16 planes is still in its half-transposed form and is finished
 // only when the budget reaches it.
 template <int NP, class Sink, class PR>
-ZFB_HD void encode_planes(const PR& ps, unsigned maxbits, uint32_t header, unsigned hbits, int kmin, Sink& sink,
-                          const tables& tb)
+ZFB_HD unsigned encode_planes(const PR& ps, unsigned maxbits, uint32_t header, unsigned hbits, int kmin, Sink& sink,
+                              const tables& tb)
 {
   writer32<Sink> bw(sink);
   bw.put(header, hbits);
@@ -390,14 +390,19 @@ ZFB_HD void encode_planes(const PR& ps, unsigned maxbits, uint32_t header, unsig
       n += plast + 1u;
     }
   }
+  const unsigned total = bw.bits();  // bits emitted (the fixed-rate sinks truncate / pad to the slot)
   bw.flush();
   sink.finish();
+  return total;
 }
 
+// General form (zfp_stream's minbits / maxbits / maxprec / minexp): returns the bits the block occupies.
 template <class Sink>
-ZFB_HD void encode_block(const float (&f)[64], unsigned maxbits, Sink& sink, const tables& tb, const plane_rows& ps)
+ZFB_HD unsigned encode_block(const float (&f)[64], const stream_params& sp, Sink& sink, const tables& tb,
+                             const plane_rows& ps)
 {
   typedef traits<float> T;
+  const unsigned maxbits = sp.maxbits;
   float mx = 0.f;
   ZFB_UNROLL for (int i = 0; i < 64; i++) {
 #if defined(__CUDA_ARCH__)
@@ -407,9 +412,15 @@ ZFB_HD void encode_block(const float (&f)[64], unsigned maxbits, Sink& sink, con
     mx = (mx < a) ? a : mx;
 #endif
   }
-  if (!(mx > 0.f)) { sink.finish(); return; }
   const int E = T::expfield(mx);
   const int emax = E - 126;
+  const int prec = block_precision<3>(emax, sp);
+  if (!(mx > 0.f) || prec == 0) {  // all zero, or nothing above the accuracy floor: a single 0 bit
+    sink.word(0u);
+    sink.finish();
+    return sp.minbits > 1u ? sp.minbits : 1u;
+  }
+  const int kmin = prec < 32 ? 32 - prec : 0;
 
   planes64 P;
   {
@@ -434,7 +445,16 @@ ZFB_HD void encode_block(const float (&f)[64], unsigned maxbits, Sink& sink, con
     ps.st(r, v);
   }
 
-  encode_planes<32>(ps, maxbits, 2u * (uint32_t)(E + 1) + 1u, 9u, 0, sink, tb);
+  unsigned used = encode_planes<32>(ps, maxbits, 2u * (uint32_t)(E + 1) + 1u, 9u, kmin, sink, tb);
+  used = used < maxbits ? used : maxbits;
+  return used < sp.minbits ? sp.minbits : used;
+}
+
+// Fixed-rate form.
+template <class Sink>
+ZFB_HD void encode_block(const float (&f)[64], unsigned maxbits, Sink& sink, const tables& tb, const plane_rows& ps)
+{
+  encode_block(f, fixed_rate_params(maxbits), sink, tb, ps);
 }
 
 
@@ -607,7 +627,7 @@ ZFB_HD int parse_planes(const PR& ps, unsigned maxbits, unsigned hbits, int kmin
     if (k & 1) { cur.z = xl; cur.w = xh; }
     else { cur.x = xl; cur.y = xh; ps.st(k >> 1, cur); }
   }
-  if (k >= kmin && !(k & 1)) {  // stopped with the odd plane of a row pending (k is the first plane NOT decoded)
+  if (k >= 0 && !(k & 1)) {  // stopped (budget, or an odd kmin) with the odd plane of a row pending; k = first plane NOT decoded
     cur.x = 0u; cur.y = 0u;
     ps.st(k >> 1, cur);
   }
@@ -617,8 +637,8 @@ ZFB_HD int parse_planes(const PR& ps, unsigned maxbits, unsigned hbits, int kmin
 
 // Phase 1: parse the slot into bit planes (left in P).  Returns false for an all-zero block.
 template <class Reader>
-ZFB_HD bool decode_planes(planes64& P, int& emax, bool& low_used_out, unsigned maxbits, Reader& r, const tables& tb,
-                          const plane_rows& ps)
+ZFB_HD bool decode_planes(planes64& P, int& emax, bool& low_used_out, const stream_params& sp, Reader& r,
+                          const tables& tb, const plane_rows& ps)
 {
   const uint32_t head = r.lo;
   emax = 0;
@@ -626,13 +646,21 @@ ZFB_HD bool decode_planes(planes64& P, int& emax, bool& low_used_out, unsigned m
   if (!(head & 1u)) return false;
   emax = (int)((head >> 1) & 0xffu) - 127;
   r.consume(9);
-  const int kend = parse_planes<32>(ps, maxbits, 9u, 0, r, tb);
+  const int prec = block_precision<3>(emax, sp);
+  const int kend = parse_planes<32>(ps, sp.maxbits, 9u, prec < 32 ? 32 - prec : 0, r, tb);
   ZFB_UNROLL for (int q = 0; q < 16; q++) {
     const u32x4 v = ps.ld(q);
     P.a[2 * q] = v.x; P.b[2 * q] = v.y; P.a[2 * q + 1] = v.z; P.b[2 * q + 1] = v.w;
   }
   low_used_out = kend < 15;
   return true;
+}
+
+template <class Reader>
+ZFB_HD bool decode_planes(planes64& P, int& emax, bool& low_used_out, unsigned maxbits, Reader& r, const tables& tb,
+                          const plane_rows& ps)
+{
+  return decode_planes(P, emax, low_used_out, fixed_rate_params(maxbits), r, tb, ps);
 }
 
 // Phase 2: planes -> coefficients -> inverse transform -> floats.
@@ -657,13 +685,19 @@ ZFB_HD void decode_finish(float (&f)[64], planes64& P, int emax, bool nonzero, b
 }
 
 template <class Reader>
-ZFB_HD void decode_block(float (&f)[64], unsigned maxbits, Reader& r, const tables& tb, const plane_rows& ps)
+ZFB_HD void decode_block(float (&f)[64], const stream_params& sp, Reader& r, const tables& tb, const plane_rows& ps)
 {
   planes64 P;
   int emax;
   bool low_used;
-  const bool nonzero = decode_planes(P, emax, low_used, maxbits, r, tb, ps);
+  const bool nonzero = decode_planes(P, emax, low_used, sp, r, tb, ps);
   decode_finish(f, P, emax, nonzero, low_used);
+}
+
+template <class Reader>
+ZFB_HD void decode_block(float (&f)[64], unsigned maxbits, Reader& r, const tables& tb, const plane_rows& ps)
+{
+  decode_block(f, fixed_rate_params(maxbits), r, tb, ps);
 }
 
 }  // namespace f3

@@ -32,6 +32,17 @@ struct stage_col_sink {
   ZFB_HD void finish() {}
 };
 
+// the same column seen as 32-bit words (fast float/3D coder): 32-bit word j at stage32[2 * base + j * 32]
+struct stage_col_sink32 {
+  uint32_t* dst;
+  unsigned widx;
+  ZFB_HD explicit stage_col_sink32(uint32_t* d) : dst(d), widx(0) {}
+  ZFB_HD void word(uint32_t w) { dst[32u * widx++] = w; }
+  ZFB_HD void word2(uint32_t w0, uint32_t w1) { word(w0); word(w1); }
+  ZFB_HD void finish() {}
+  ZFB_HD unsigned words() const { return widx; }
+};
+
 template <unsigned WORDS> __device__ __forceinline__ size_t stage_base(size_t b)
 {
   return (b >> 5) * (size_t)(32u * WORDS) + (b & 31u);
@@ -82,11 +93,23 @@ __global__ void __launch_bounds__(128) enc_var_kernel(const Scalar* __restrict__
 {
   constexpr int BS = 1 << (2 * DIMS);
   constexpr unsigned WORDS = var_caps<Scalar, DIMS>::WORDS;
+  constexpr bool FAST = sizeof(Scalar) == 4 && DIMS == 3;  // table coder with the planes parked in shared memory
+  __shared__ coder_smem cs;
+  __shared__ fast_scratch<FAST> fsc;
+  f3::tables tb;
+  if (FAST) tb = build_coder_tables(cs);
+  const f3::plane_rows ps = fsc.rows();
   for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < g.nblocks; b += (size_t)gridDim.x * blockDim.x) {
     Scalar f[BS];
     gather_block<Scalar, DIMS>(in, g, b, f);
-    stage_col_sink sink(stage + stage_base<WORDS>(b));
-    lens[b] = encode_block<Scalar, DIMS>(f, sp, sink);
+    if constexpr (FAST) {
+      // 32-bit word j of the column: the two halves of 64-bit word j/2 sit 32 words apart, see compact_var_kernel
+      stage_col_sink32 sink(reinterpret_cast<uint32_t*>(stage) + 2 * ((b >> 5) * (size_t)(32u * WORDS)) + (b & 31u));
+      lens[b] = f3::encode_block(f, sp, sink, tb, ps);
+    } else {
+      stage_col_sink sink(stage + stage_base<WORDS>(b));
+      lens[b] = encode_block<Scalar, DIMS>(f, sp, sink);
+    }
   }
 }
 
@@ -189,7 +212,7 @@ __global__ void __launch_bounds__(256) zero_stream_kernel(uint64_t* __restrict__
 }
 
 // ---- step 3: staged words -> bit-tight stream ---------------------------------------------------
-template <unsigned WORDS>
+template <unsigned WORDS, bool COL32>
 __global__ void __launch_bounds__(128) compact_var_kernel(const uint64_t* __restrict__ stage, const uint64_t* __restrict__ offsets,
                                                           size_t nblocks, uint64_t* __restrict__ stream, size_t cap_words)
 {
@@ -198,13 +221,15 @@ __global__ void __launch_bounds__(128) compact_var_kernel(const uint64_t* __rest
     const unsigned len = (unsigned)(end - off);
     const unsigned nw = (len + 63u) >> 6;
     const uint64_t* col = stage + stage_base<WORDS>(b);
+    const uint32_t* col32 = reinterpret_cast<const uint32_t*>(stage) + 2 * ((b >> 5) * (size_t)(32u * WORDS)) + (b & 31u);
     const unsigned s = (unsigned)(off & 63u);
     size_t wi = (size_t)(off >> 6);
     uint64_t prev = 0;  // bits carried into the next output word
     for (unsigned j = 0; j <= nw; j++) {
       uint64_t w = 0;
       if (j < nw) {
-        w = col[32u * j];
+        if (COL32) w = (uint64_t)col32[64u * j] | ((uint64_t)col32[64u * j + 32u] << 32);
+        else w = col[32u * j];
         const unsigned valid = len - 64u * j;
         if (valid < 64u) w &= lowmask64(valid);
       }
@@ -212,14 +237,11 @@ __global__ void __launch_bounds__(128) compact_var_kernel(const uint64_t* __rest
       prev = s ? (w >> (64u - s)) : 0;
       if (j == nw && !s) break;  // nothing carried over
       const size_t i = wi + j;
-      if (i < cap_words && o) {
+      if (i < cap_words && o) {  // a zero contribution needs no write: the words were zeroed up front
         // words wholly inside [off, end) belong to this block alone; the first and the last are shared
         const bool whole = (uint64_t)i * 64u >= off && (uint64_t)(i + 1) * 64u <= end;
         if (whole) stream[i] = o;
         else atomicOr(reinterpret_cast<unsigned long long*>(stream + i), (unsigned long long)o);
-      } else if (i < cap_words) {
-        const bool whole = (uint64_t)i * 64u >= off && (uint64_t)(i + 1) * 64u <= end;
-        (void)whole;  // zero contribution: the word was zeroed up front
       }
     }
   }
@@ -232,9 +254,17 @@ __global__ void __launch_bounds__(128) dec_var_kernel(const uint64_t* __restrict
                                                       stream_params sp, double* __restrict__ part)
 {
   constexpr int BS = 1 << (2 * DIMS);
+  constexpr bool FAST = sizeof(Scalar) == 4 && DIMS == 3;
   __shared__ double red[7 * 4];
+  __shared__ coder_smem cs;
+  __shared__ fast_scratch<FAST> fsc;
+  f3::tables tb;
+  if (FAST) tb = build_coder_tables(cs);
+  const f3::plane_rows ps = fsc.rows();
   macc_t<Scalar> m;
   m.init();
+  const bool vec = FAST && ((g.nx & 3) == 0) && ((reinterpret_cast<size_t>(out) & 15) == 0) &&
+                   (!METRICS || (reinterpret_cast<size_t>(orig) & 15) == 0);
   for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < g.nblocks; b += (size_t)gridDim.x * blockDim.x) {
     const size_t ix = b % g.bx, iy = (b / g.bx) % g.by, iz = b / (g.bx * g.by);
     const size_t x0 = 4 * ix, y0 = 4 * iy, z0 = 4 * iz;
@@ -245,8 +275,34 @@ __global__ void __launch_bounds__(128) dec_var_kernel(const uint64_t* __restrict
     const size_t w0 = (size_t)(startbit >> 6);
     const size_t left = g.stream_words > w0 ? g.stream_words - w0 : 0;
     Scalar f[BS];
-    slot_reader r(stream + w0, left > 0xffffffffull ? 0xffffffffu : (unsigned)left, (unsigned)(startbit & 63));
-    decode_block<Scalar, DIMS, false>(f, sp, r);
+    if constexpr (FAST) {
+      const size_t v0 = (size_t)(startbit >> 5);
+      const size_t left32 = 2 * g.stream_words > v0 ? 2 * g.stream_words - v0 : 0;
+      f3::reader32 r(reinterpret_cast<const uint32_t*>(stream) + v0, left32 > 0xffffffffull ? 0xffffffffu : (unsigned)left32,
+                     (unsigned)(startbit & 31));
+      f3::decode_block(f, sp, r, tb, ps);
+      if (vec && my == 4 && mz == 4) {  // whole block, 16-byte rows: vector stores, four values per metric step
+        frow fr;
+        fr.init();
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const size_t idx = x0 + g.nx * ((y0 + j) + g.ny * (z0 + k));
+            const int q = 16 * k + 4 * j;
+            float4 v;
+            v.x = f[q]; v.y = f[q + 1]; v.z = f[q + 2]; v.w = f[q + 3];
+            if (METRICS) fr.add4(__ldg(reinterpret_cast<const float4*>(orig + idx)), v.x, v.y, v.z, v.w);
+            *reinterpret_cast<float4*>(out + idx) = v;
+          }
+          if (METRICS) fr.flush(m);
+        }
+        continue;
+      }
+    } else {
+      slot_reader r(stream + w0, left > 0xffffffffull ? 0xffffffffu : (unsigned)left, (unsigned)(startbit & 63));
+      decode_block<Scalar, DIMS, false>(f, sp, r);
+    }
 #pragma unroll
     for (int k = 0; k < (DIMS >= 3 ? 4 : 1); k++)
 #pragma unroll
