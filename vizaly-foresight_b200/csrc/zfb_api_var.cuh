@@ -206,7 +206,11 @@ static int launch_dec_var(zfb_ctx* c, int dims, const geom& g, const stream_para
   const Scalar* orig = (const Scalar*)d_orig;
   if (dims == 1) dec_var_kernel<Scalar, 1, METRICS><<<grid, 128, 0, c->stream>>>(st, index, out, orig, g, sp, c->part);
   else if (dims == 2) dec_var_kernel<Scalar, 2, METRICS><<<grid, 128, 0, c->stream>>>(st, index, out, orig, g, sp, c->part);
-  else dec_var_kernel<Scalar, 3, METRICS><<<grid, 128, 0, c->stream>>>(st, index, out, orig, g, sp, c->part);
+  else if constexpr (sizeof(Scalar) == 4) {
+    const int persistent = c->sm_count * 4;  // 4 resident CTAs per SM, tiles of 128 blocks taken round-robin
+    if (grid > persistent) grid = persistent;
+    dec_var_f32_kernel<METRICS><<<grid, 128, 0, c->stream>>>(st, index, (float*)d_out, (const float*)d_orig, g, sp, c->part);
+  } else dec_var_kernel<Scalar, 3, METRICS><<<grid, 128, 0, c->stream>>>(st, index, out, orig, g, sp, c->part);
   c->launches++;
   *rows = grid;
   CU_TRY(c, cudaGetLastError());

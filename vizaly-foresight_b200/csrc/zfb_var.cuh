@@ -248,23 +248,48 @@ __global__ void __launch_bounds__(128) compact_var_kernel(const uint64_t* __rest
 }
 
 // ---- decode with the index ---------------------------------------------------------------------
+// scatter one decoded block (partial blocks: only the values inside the field), metrics fused
+template <typename Scalar, int DIMS, bool METRICS>
+__device__ __forceinline__ void scatter_block(const Scalar (&f)[1 << (2 * DIMS)], Scalar* __restrict__ out,
+                                              const Scalar* __restrict__ orig, const geom& g, size_t x0, size_t y0,
+                                              size_t z0, unsigned mx, unsigned my, unsigned mz, macc_t<Scalar>& m)
+{
+  constexpr int BS = 1 << (2 * DIMS);
+#pragma unroll
+  for (int k = 0; k < (DIMS >= 3 ? 4 : 1); k++)
+#pragma unroll
+    for (int j = 0; j < (DIMS >= 2 ? 4 : 1); j++)
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const bool ok = (unsigned)i < mx && (unsigned)j < my && (unsigned)k < mz;
+        if (ok) {
+          const size_t idx = (x0 + i) + g.nx * ((y0 + j) + g.ny * (z0 + k));
+          const Scalar a = f[(16 * k + 4 * j + i) & (BS - 1)];
+          out[idx] = a;
+          if (METRICS) {
+            if constexpr (sizeof(Scalar) == 4) {
+              frow fr;
+              fr.init();
+              fr.add(__ldg(orig + idx), a);
+              fr.flush(m);
+            } else {
+              macc_add(m, (double)__ldg(orig + idx), (double)a);
+            }
+          }
+        }
+      }
+}
+
+// any type / dims: thread per block, the block's bits read straight from the stream
 template <typename Scalar, int DIMS, bool METRICS>
 __global__ void __launch_bounds__(128) dec_var_kernel(const uint64_t* __restrict__ stream, const uint64_t* __restrict__ offsets,
                                                       Scalar* __restrict__ out, const Scalar* __restrict__ orig, geom g,
                                                       stream_params sp, double* __restrict__ part)
 {
   constexpr int BS = 1 << (2 * DIMS);
-  constexpr bool FAST = sizeof(Scalar) == 4 && DIMS == 3;
   __shared__ double red[7 * 4];
-  __shared__ coder_smem cs;
-  __shared__ fast_scratch<FAST> fsc;
-  f3::tables tb;
-  if (FAST) tb = build_coder_tables(cs);
-  const f3::plane_rows ps = fsc.rows();
   macc_t<Scalar> m;
   m.init();
-  const bool vec = FAST && ((g.nx & 3) == 0) && ((reinterpret_cast<size_t>(out) & 15) == 0) &&
-                   (!METRICS || (reinterpret_cast<size_t>(orig) & 15) == 0);
   for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < g.nblocks; b += (size_t)gridDim.x * blockDim.x) {
     const size_t ix = b % g.bx, iy = (b / g.bx) % g.by, iz = b / (g.bx * g.by);
     const size_t x0 = 4 * ix, y0 = 4 * iy, z0 = 4 * iz;
@@ -275,12 +300,68 @@ __global__ void __launch_bounds__(128) dec_var_kernel(const uint64_t* __restrict
     const size_t w0 = (size_t)(startbit >> 6);
     const size_t left = g.stream_words > w0 ? g.stream_words - w0 : 0;
     Scalar f[BS];
-    if constexpr (FAST) {
+    slot_reader r(stream + w0, left > 0xffffffffull ? 0xffffffffu : (unsigned)left, (unsigned)(startbit & 63));
+    decode_block<Scalar, DIMS, false>(f, sp, r);
+    scatter_block<Scalar, DIMS, METRICS>(f, out, orig, g, x0, y0, z0, mx, my, mz, m);
+  }
+  if (METRICS) macc_block_store(m, red, part + (size_t)blockIdx.x * PART_STRIDE);
+}
+
+// float / 3D: a CTA takes 128 consecutive blocks, whose bits are one contiguous piece of the stream: the piece is
+// staged in shared memory with coalesced loads (when it fits: VAR_STAGE_WORDS covers ~12 bits per value on average)
+// and parsed from there by the table coder; whole blocks go out as 16-byte rows with the metrics fused.
+constexpr unsigned VAR_STAGE_WORDS = 3072;  // 32-bit words; static shared memory stays under 48 KiB
+
+template <bool METRICS>
+__global__ void __launch_bounds__(128, 4) dec_var_f32_kernel(const uint64_t* __restrict__ stream,
+                                                             const uint64_t* __restrict__ offsets, float* __restrict__ out,
+                                                             const float* __restrict__ orig, geom g, stream_params sp,
+                                                             double* __restrict__ part)
+{
+  __shared__ double red[7 * 4];
+  __shared__ coder_smem cs;
+  __shared__ fast_scratch<true> fsc;
+  __shared__ uint32_t piece[VAR_STAGE_WORDS];
+  __shared__ uint64_t range[2];
+  const f3::tables tb = build_coder_tables(cs);
+  const f3::plane_rows ps = fsc.rows();
+  maccf m;
+  m.init();
+  const bool vec = ((g.nx & 3) == 0) && ((reinterpret_cast<size_t>(out) & 15) == 0) &&
+                   (!METRICS || (reinterpret_cast<size_t>(orig) & 15) == 0);
+  const uint32_t* s32 = reinterpret_cast<const uint32_t*>(stream);
+  const size_t total32 = 2 * g.stream_words;
+  const size_t ntiles = (g.nblocks + 127) / 128;
+  for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const size_t b = tile * 128 + threadIdx.x;
+    const bool active = b < g.nblocks;
+    const uint64_t startbit = active ? offsets[b] : 0;
+    if (threadIdx.x == 0) range[0] = startbit;
+    if (active && (threadIdx.x == 127 || b + 1 == g.nblocks)) range[1] = offsets[b + 1];
+    __syncthreads();
+    const size_t v_begin = (size_t)(range[0] >> 5);
+    const size_t v_end = (size_t)((range[1] + 31) >> 5) + 2;  // + the reader's two look-ahead words
+    const bool staged = v_end - v_begin <= VAR_STAGE_WORDS;
+    if (staged) {
+      for (size_t i = threadIdx.x; i < v_end - v_begin; i += 128) piece[i] = v_begin + i < total32 ? __ldg(s32 + v_begin + i) : 0u;
+    }
+    __syncthreads();
+    if (active) {
+      const size_t ix = b % g.bx, iy = (b / g.bx) % g.by, iz = b / (g.bx * g.by);
+      const size_t x0 = 4 * ix, y0 = 4 * iy, z0 = 4 * iz;
+      const unsigned mx = (unsigned)(g.nx - x0 < 4 ? g.nx - x0 : 4);
+      const unsigned my = (unsigned)(g.ny - y0 < 4 ? g.ny - y0 : 4);
+      const unsigned mz = (unsigned)(g.nz - z0 < 4 ? g.nz - z0 : 4);
       const size_t v0 = (size_t)(startbit >> 5);
-      const size_t left32 = 2 * g.stream_words > v0 ? 2 * g.stream_words - v0 : 0;
-      f3::reader32 r(reinterpret_cast<const uint32_t*>(stream) + v0, left32 > 0xffffffffull ? 0xffffffffu : (unsigned)left32,
-                     (unsigned)(startbit & 31));
-      f3::decode_block(f, sp, r, tb, ps);
+      float f[64];
+      {
+        // one call site (generic loads): the staged piece, or the stream itself when the piece was too long
+        const size_t left32 = total32 > v0 ? total32 - v0 : 0;
+        const uint32_t* src = staged ? piece + (v0 - v_begin) : s32 + v0;
+        const unsigned navail = staged ? (unsigned)(v_end - v0) : (left32 > 0xffffffffull ? 0xffffffffu : (unsigned)left32);
+        f3::reader32 r(src, navail, (unsigned)(startbit & 31));
+        f3::decode_block(f, sp, r, tb, ps);
+      }
       if (vec && my == 4 && mz == 4) {  // whole block, 16-byte rows: vector stores, four values per metric step
         frow fr;
         fr.init();
@@ -293,39 +374,15 @@ __global__ void __launch_bounds__(128) dec_var_kernel(const uint64_t* __restrict
             float4 v;
             v.x = f[q]; v.y = f[q + 1]; v.z = f[q + 2]; v.w = f[q + 3];
             if (METRICS) fr.add4(__ldg(reinterpret_cast<const float4*>(orig + idx)), v.x, v.y, v.z, v.w);
-            *reinterpret_cast<float4*>(out + idx) = v;
+            __stcs(reinterpret_cast<float4*>(out + idx), v);
           }
           if (METRICS) fr.flush(m);
         }
-        continue;
+      } else {
+        scatter_block<float, 3, METRICS>(f, out, orig, g, x0, y0, z0, mx, my, mz, m);
       }
-    } else {
-      slot_reader r(stream + w0, left > 0xffffffffull ? 0xffffffffu : (unsigned)left, (unsigned)(startbit & 63));
-      decode_block<Scalar, DIMS, false>(f, sp, r);
     }
-#pragma unroll
-    for (int k = 0; k < (DIMS >= 3 ? 4 : 1); k++)
-#pragma unroll
-      for (int j = 0; j < (DIMS >= 2 ? 4 : 1); j++)
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const bool ok = (unsigned)i < mx && (unsigned)j < my && (unsigned)k < mz;
-          if (ok) {
-            const size_t idx = (x0 + i) + g.nx * ((y0 + j) + g.ny * (z0 + k));
-            const Scalar a = f[(16 * k + 4 * j + i) & (BS - 1)];
-            out[idx] = a;
-            if (METRICS) {
-              if constexpr (sizeof(Scalar) == 4) {
-                frow fr;
-                fr.init();
-                fr.add(__ldg(orig + idx), a);
-                fr.flush(m);
-              } else {
-                macc_add(m, (double)__ldg(orig + idx), (double)a);
-              }
-            }
-          }
-        }
+    __syncthreads();  // the piece and the range are rewritten by the next tile
   }
   if (METRICS) macc_block_store(m, red, part + (size_t)blockIdx.x * PART_STRIDE);
 }
