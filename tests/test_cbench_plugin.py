@@ -89,3 +89,26 @@ def test_dropin_check_runs_on_gpu_if_built():
         pytest.skip("dropin_check is built only where the reference tree exists")
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and "compress rc 1" in r.stdout
+
+
+@pytest.mark.gpu
+def test_mini_driver_abs_and_rel_modes_match_oracle(oracle):
+    """The CPU zfp plugin's parameters ("abs", "rel": zfp/zfpCompressor.hpp:83-93) through the same plugin class."""
+    exe = build_mini()
+    f = np.fromfile(os.path.join(GOLD, "nyx_z255_32_baryon_density.f32"), dtype=np.float32).reshape(32, 32, 32)
+    for arg, p in (("abs=0.01", oracle.params_accuracy(0.01)), ("rel=18", oracle.params_precision(18)),
+                   ("abs=1.5", oracle.params_accuracy(1.5))):
+        r = subprocess.run([exe, os.path.join(GOLD, "nyx_z255_32_baryon_density.f32"), "32", "32", "32", arg,
+                            "--field", "baryon_density", "--name", "zfp"], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        row = [t.strip() for t in r.stdout.splitlines()[1].split(",")]
+        assert row[0] == "zfp_baryon_density__" + arg.replace("=", "")
+        s = oracle.compress_ex(f, p)
+        g, _ = oracle.decompress_ex(s, f.shape, np.float32, p)
+        m = oracle.metrics(f, g)
+        got = [float(t) for t in row[2:7]]
+        want = [m["absolute_error"], m["relative_error"], m["mse"], m["psnr"], m["minmax"]]
+        for a, b in zip(got, want):
+            assert abs(a - b) <= 1.01e-5 * abs(b), (arg, got, want)
+        assert abs(float(row[9]) - f.nbytes / len(s)) <= 1e-5 * f.nbytes / len(s) + 1e-3, (arg, row[9], f.nbytes / len(s))
+    # no parameters at all under the name "zfp": the CPU plugin's default abs = 1E-3 (zfpCompressor.hpp:80)

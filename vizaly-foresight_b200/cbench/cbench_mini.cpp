@@ -3,7 +3,8 @@
 // loop, then the CSV row and the human-readable log.  File I/O, JSON and MPI launch stay with the real
 // CBench (out of scope); this driver exists so the plugin classes can be exercised and tested here.
 //
-//   cbench_mini <raw float32 file | synth> <n0> <n1> <n2> <bits> [--hist] [--prefix P] [--field NAME]
+//   cbench_mini <raw float32 file | synth> <n0> <n1> <n2> <bits | abs=TOL | rel=PREC> [--hist] [--prefix P]
+//               [--field NAME] [--name zfp|zfp_gpu]
 //     dims with extent 0 are unused (CBench's size_t n[5] convention), n0 slowest.
 //   prints:  CSV header, CSV row, then the metric log (same text main.cpp appends to its metrics file)
 #include <cmath>
@@ -22,18 +23,19 @@
 int main(int argc, char** argv)
 {
   if (argc < 6) {
-    std::cerr << "usage: cbench_mini <file.f32|synth> n0 n1 n2 bits [--hist] [--prefix P] [--field NAME]\n";
+    std::cerr << "usage: cbench_mini <file.f32|synth> n0 n1 n2 <bits|abs=TOL|rel=PREC> [--hist] [--prefix P] [--field NAME] [--name zfp|zfp_gpu]\n";
     return 2;
   }
   const std::string src = argv[1];
   size_t n[5] = {(size_t)atoll(argv[2]), (size_t)atoll(argv[3]), (size_t)atoll(argv[4]), 0, 0};
   const std::string bits = argv[5];
   bool hist = false;
-  std::string prefix = "zfp_gpu_" + bits + "_", field = "field";
+  std::string prefix = "zfp_gpu_" + bits + "_", field = "field", cname = "zfp_gpu";
   for (int i = 6; i < argc; i++) {
     if (!strcmp(argv[i], "--hist")) hist = true;
     else if (!strcmp(argv[i], "--prefix") && i + 1 < argc) prefix = argv[++i];
     else if (!strcmp(argv[i], "--field") && i + 1 < argc) field = argv[++i];
+    else if (!strcmp(argv[i], "--name") && i + 1 < argc) cname = argv[++i];
   }
   size_t numel = n[0];
   for (int i = 1; i < 3; i++)
@@ -55,9 +57,12 @@ int main(int argc, char** argv)
   for (const auto& m : metrics) csv << m << ", ";
   csv << "Compression Throughput(MB/s), DeCompression Throughput(MB/s), Compression Ratio\n";
 
-  CompressorInterface* comp = new ZFPCompressorB200();
+  CompressorInterface* comp = new ZFPCompressorB200(cname.c_str());
   comp->init();
-  comp->compressorParameters["bits"] = bits;  // strConvert::toStr of the JSON value, main.cpp:196-204
+  // strConvert::toStr of the JSON value, main.cpp:196-204; "abs=0.003" / "rel=16" set that key instead of "bits"
+  const size_t eq = bits.find('=');
+  if (eq == std::string::npos) comp->compressorParameters["bits"] = bits;
+  else comp->compressorParameters[bits.substr(0, eq)] = bits.substr(eq + 1);
   csv << comp->getCompressorName() << "_" << field << "__" << comp->getParamsInfo() << ", " << prefix << ", ";
 
   Timer cclock, dclock;

@@ -6,9 +6,13 @@
 // rate semantics (zfp_stream_set_rate(zfp, bits, type, dims, 8), :129), malloc'd outputs that main.cpp
 // std::free()s (main.cpp:395), return 1 / 0, messages on std::cout.  Differences, all documented in
 // "rate" (double) and "wra" are accepted as extensions; the compressed input buffer is
-// freed in decompress() (ZFPCompressorGpu leaks it); abs / rel modes are rejected loudly (libzfp's CUDA
-// backend is fixed-rate only as well: zfp_compress returns 0 there and the plugin prints
-// "compression failed", zfpCompressorGpu.hpp:145-150).
+// freed in decompress() (ZFPCompressorGpu leaks it).
+//
+// The same class also stands in for CBench/compressors/zfp/zfpCompressor.hpp (class ZFPCompressor, factory
+// name "zfp"): "abs" selects zfp's fixed-accuracy mode (zfp_stream_set_accuracy, zfpCompressor.hpp:83-87,118)
+// and "rel" its fixed-precision mode (zfp_stream_set_precision, :88-92,120), "abs" winning when both are
+// present, and an object constructed under the name "zfp" defaults to abs = 1E-3 as that plugin does (:80-82).
+// libzfp's own CUDA backend cannot do these modes (zfp_compress returns 0 there, zfpCompressorGpu.hpp:145-150).
 #ifndef ZFB_ZFP_B200_COMPRESSOR_HPP
 #define ZFB_ZFP_B200_COMPRESSOR_HPP
 
@@ -87,14 +91,21 @@ class ZFPCompressorB200 : public CompressorInterface {
     if (t == "double") return ZFB_DOUBLE;
     return 0;
   }
+  // "abs" / "rel" (variable rate) or neither; false = fixed rate
+  bool variable_mode(zfb_mode& mode)
+  {
+    auto a = compressorParameters.find("abs");
+    if (a != compressorParameters.end()) return zfb_mode_accuracy(&mode, zfb_cbench::to_double(a->second)) == ZFB_OK;
+    auto r = compressorParameters.find("rel");
+    if (r != compressorParameters.end()) return zfb_mode_precision(&mode, (unsigned)(int)zfb_cbench::to_double(r->second)) == ZFB_OK;
+    if (compressorName == "zfp" && compressorParameters.find("bits") == compressorParameters.end() &&
+        compressorParameters.find("rate") == compressorParameters.end())
+      return zfb_mode_accuracy(&mode, 1E-3) == ZFB_OK;  // the CPU plugin's default
+    return false;
+  }
   // bits-per-value -> bits per block, CBench semantics
   bool maxbits_of(int dtype, int dims, unsigned& mb)
   {
-    if (compressorParameters.find("abs") != compressorParameters.end() ||
-        compressorParameters.find("rel") != compressorParameters.end()) {
-      std::cout << "zfp_gpu (B200): only fixed-rate (\"bits\") is supported on the GPU path\n";
-      return false;
-    }
     double rate = 4;  // default of the reference plugin (int bits = 4)
     int wra = 8;
     auto it = compressorParameters.find("bits");
@@ -108,7 +119,7 @@ class ZFPCompressorB200 : public CompressorInterface {
   }
 
  public:
-  ZFPCompressorB200() : compressedSize(0) { compressorName = "zfp_gpu"; }
+  explicit ZFPCompressorB200(const char* name = "zfp_gpu") : compressedSize(0) { compressorName = name; }
   ~ZFPCompressorB200() {}
 
   void init()
@@ -123,15 +134,28 @@ class ZFPCompressorB200 : public CompressorInterface {
     Shape s;
     const int dtype = dtype_of(dataType);
     unsigned mb = 0;
-    if (sh.ensure() != ZFB_OK || !shape_of(n, s) || !dtype || !maxbits_of(dtype, s.dims, mb)) {
+    zfb_mode mode;
+    if (sh.ensure() != ZFB_OK || !shape_of(n, s) || !dtype) {
+      std::cout << "compression failed\n";
+      return 0;
+    }
+    const bool var = variable_mode(mode);
+    if (!var && !maxbits_of(dtype, s.dims, mb)) {
       std::cout << "compression failed\n";
       return 0;
     }
     Timer cTime;
     cTime.start();
-    output = std::malloc(zfb_stream_capacity(s.dims, s.nx, s.ny, s.nz, mb));
     size_t got = 0;
-    const int rc = output ? zfb_compress_host(sh.ctx, dtype, s.dims, s.nx, s.ny, s.nz, mb, input, output, &got) : ZFB_ENOMEM;
+    int rc;
+    if (var) {
+      const size_t cap = zfb_maximum_size(dtype, s.dims, s.nx, s.ny, s.nz, &mode);
+      output = std::malloc(cap);
+      rc = output ? zfb_compress_var_host(sh.ctx, dtype, s.dims, s.nx, s.ny, s.nz, &mode, input, output, cap, &got) : ZFB_ENOMEM;
+    } else {
+      output = std::malloc(zfb_stream_capacity(s.dims, s.nx, s.ny, s.nz, mb));
+      rc = output ? zfb_compress_host(sh.ctx, dtype, s.dims, s.nx, s.ny, s.nz, mb, input, output, &got) : ZFB_ENOMEM;
+    }
     if (rc != ZFB_OK || !got) {
       std::cout << "compression failed\n";
       return 0;
@@ -152,16 +176,26 @@ class ZFPCompressorB200 : public CompressorInterface {
     Shape s;
     const int dtype = dtype_of(dataType);
     unsigned mb = 0;
-    if (sh.ensure() != ZFB_OK || !shape_of(n, s) || !dtype || !maxbits_of(dtype, s.dims, mb) || !input) {
+    zfb_mode mode;
+    if (sh.ensure() != ZFB_OK || !shape_of(n, s) || !dtype || !input) {
+      std::cout << "decompression failed\n";
+      return 0;
+    }
+    const bool var = variable_mode(mode);
+    if (!var && !maxbits_of(dtype, s.dims, mb)) {
       std::cout << "decompression failed\n";
       return 0;
     }
     Timer dTime;
     dTime.start();
     output = std::malloc(s.numel * dataTypeSize);
-    // the field uploaded by compress() is still resident: the metric partials are fused into this pass
-    const int rc = output ? zfb_decompress_host(sh.ctx, dtype, s.dims, s.nx, s.ny, s.nz, mb, input, output, sh.last_orig)
-                          : ZFB_ENOMEM;
+    // the field uploaded by compress() is still resident: the metric partials are fused into this pass.
+    // Variable rate: the stream length is the state compress() left behind (zfpCompressor.hpp:22,145,211).
+    int rc = ZFB_ENOMEM;
+    if (output && var)
+      rc = zfb_decompress_var_host(sh.ctx, dtype, s.dims, s.nx, s.ny, s.nz, &mode, input, compressedSize, output, sh.last_orig);
+    else if (output)
+      rc = zfb_decompress_host(sh.ctx, dtype, s.dims, s.nx, s.ny, s.nz, mb, input, output, sh.last_orig);
     if (rc != ZFB_OK) {
       std::cout << "decompression failed\n";
       return 0;
