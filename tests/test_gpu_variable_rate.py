@@ -160,3 +160,29 @@ def test_variable_rate_outputs_stay_in_bounds_and_bad_arguments(codec, pkg):
                                           small.numel(), None, C.byref(nb))
         assert rc == -1
         raise pkg.ZfbError("EINVAL as expected")
+
+
+def test_expert_parameters_and_fixed_rate_through_the_general_path(codec, pkg, oracle):
+    """Budget, padding floor, plane limit and accuracy floor together (zfp_stream_set_params), and fixed rate run
+    through the general path: the stream must be the one the fixed-rate kernels write."""
+    torch = _torch()
+    rng = np.random.default_rng(77)
+    for dtype, shape in ((np.float32, (9, 10, 11)), (np.float32, (16, 16, 32)), (np.float64, (6, 9, 10)),
+                         (np.float32, (37,)), (np.float64, (11, 13))):
+        f = (smooth_field(shape, seed=8, amp=300.0).astype(np.float64) * (rng.random(shape) > 0.3)).astype(dtype)
+        d_f = torch.from_numpy(f).cuda()
+        tdt = torch.float32 if dtype == np.float32 else torch.float64
+        for prm in ((64, 300, 20, -20), (1, 130, 64, -1074), (200, 200, 9, -5), (17, 2000, 31, -30), (96, 97, 64, -1074)):
+            m, p = pkg.Mode(*prm), oracle.Params(*prm)
+            s_ref = oracle.compress_ex(f, p)
+            g_ref, _ = oracle.decompress_ex(s_ref, shape, dtype, p)
+            s, _ = codec.encode_var(d_f, m)
+            assert np.array_equal(s.cpu().numpy(), s_ref), (dtype, shape, prm)
+            out = codec.decode_var(s, shape, tdt, m)
+            assert np.array_equal(out.cpu().numpy().view(np.uint8), g_ref.view(np.uint8)), (dtype, shape, prm)
+        m = pkg.mode_rate(dtype, len(shape), 8)
+        s, nbytes = codec.encode_var(d_f, m)
+        s_fixed = codec.encode(d_f, m.maxbits)
+        assert nbytes == s_fixed.numel() and torch.equal(s, s_fixed), (dtype, shape)
+    with pytest.raises(pkg.ZfbError):  # minbits > maxbits
+        codec.encode_var(d_f, pkg.Mode(9000, 300, 64, -1074))

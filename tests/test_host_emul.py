@@ -258,3 +258,25 @@ def test_device_codec_variable_rate_equals_oracle(oracle, dtype, shape):
         assert np.array_equal(g.view(np.uint8), g_ref.view(np.uint8)), (kind, v)
         if kind == "accuracy" and v > 0:
             assert np.abs(g.astype(np.float64) - f.astype(np.float64)).max() <= v
+
+
+def test_device_codec_expert_parameters(oracle):
+    """zfp's expert mode (zfp_stream_set_params): budget, padding floor, plane limit and accuracy floor all active
+    at once -- every exit of the coder loops in one stream."""
+    O = oracle
+    rng = np.random.default_rng(77)
+    for dtype, shape in ((np.float32, (9, 10, 11)), (np.float32, (16, 16, 16)), (np.float64, (6, 9, 10)),
+                         (np.float32, (37,)), (np.float64, (11, 13))):
+        f = (smooth_field(shape, seed=8, amp=300.0).astype(np.float64) * (rng.random(shape) > 0.3)).astype(dtype)
+        for minbits, maxbits, maxprec, minexp in ((64, 300, 20, -20), (1, 130, 64, -1074), (200, 200, 9, -5),
+                                                  (17, 2000, 31, -30), (1, 16657, 13, -2), (96, 97, 64, -1074)):
+            p = O.Params(minbits, maxbits, maxprec, minexp)
+            s_ref, offs_ref = O.compress_ex(f, p, with_offsets=True)
+            g_ref, used = O.decompress_ex(s_ref, f.shape, dtype, p)
+            assert used == len(s_ref)
+            lens = np.diff(offs_ref.astype(np.int64))
+            assert lens.min() >= minbits and lens.max() <= max(maxbits, minbits)
+            s, g, offs = emul_var_roundtrip(O, f, p)
+            assert np.array_equal(offs, offs_ref), (dtype, shape, minbits, maxbits, maxprec, minexp)
+            assert np.array_equal(s, s_ref), (dtype, shape, minbits, maxbits, maxprec, minexp)
+            assert np.array_equal(g.view(np.uint8), g_ref.view(np.uint8)), (dtype, shape, minbits, maxbits, maxprec, minexp)

@@ -413,6 +413,7 @@ struct aligned_sink {
   {
     for (; widx < nwords; widx++) dst[widx] = 0;
   }
+  ZFB_HD void pad_to(unsigned) {}  // finish() already zero-filled the slot
 };
 
 // Slot at an arbitrary bit offset of a pre-zeroed stream (maxbits not a multiple of 64, i.e. the
@@ -443,6 +444,7 @@ struct or_sink {
     if (s && (w >> (64 - s))) or64(base + (pos >> 6) + 1, w >> (64 - s));
   }
   ZFB_HD void finish() {}
+  ZFB_HD void pad_to(unsigned) {}  // the stream is pre-zeroed
 };
 
 // Accumulates emitted bit strings into 64-bit words and hands completed words to the sink.
@@ -522,6 +524,7 @@ struct stage_sink {
   ZFB_HD explicit stage_sink(uint64_t* d) : dst(d), widx(0) {}
   ZFB_HD void word(uint64_t w) { dst[widx++] = w; }
   ZFB_HD void finish() {}
+  ZFB_HD void pad_to(unsigned bits) { while (64u * widx < bits) word(0); }  // minbits padding is part of the block
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -553,6 +556,7 @@ ZFB_HD unsigned encode_block(const Scalar (&f)[1 << (2 * DIMS)], const stream_pa
   if (!(mx > 0) || prec == 0) {  // all-zero block, or nothing above the accuracy floor: a single 0 bit and padding
     sink.word(0);
     sink.finish();
+    sink.pad_to(sp.minbits);
     return sp.minbits > 1u ? sp.minbits : 1u;
   }
   const int kmin = T::PBITS > prec ? T::PBITS - prec : 0;
@@ -603,6 +607,7 @@ ZFB_HD unsigned encode_block(const Scalar (&f)[1 << (2 * DIMS)], const stream_pa
   bw.flush();
   sink.finish();
   const unsigned used = bw.total < maxbits ? bw.total : maxbits;
+  sink.pad_to(sp.minbits);
   return used < sp.minbits ? sp.minbits : used;
 }
 

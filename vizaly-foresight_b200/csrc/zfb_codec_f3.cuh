@@ -268,6 +268,7 @@ struct sink32 {  // slot on a word boundary, whole number of 32-bit words (maxbi
     for (; widx < nwords; widx++) dst[widx] = 0;
   }
   ZFB_HD unsigned words() const { return widx; }
+  ZFB_HD void pad_to(unsigned bits) { while (32u * widx < bits && widx < nwords) dst[widx++] = 0; }
 };
 
 struct or_sink32 {  // arbitrary bit offset in a pre-zeroed stream (maxbits % 64 != 0)
@@ -299,6 +300,7 @@ struct or_sink32 {  // arbitrary bit offset in a pre-zeroed stream (maxbits % 64
   ZFB_HD void word2(uint32_t w0, uint32_t w1) { word(w0); word(w1); }
   ZFB_HD void finish() {}
   ZFB_HD unsigned words() const { return j; }
+  ZFB_HD void pad_to(unsigned) {}  // the stream is pre-zeroed
 };
 
 template <class Sink> struct writer32 {
@@ -418,6 +420,7 @@ ZFB_HD unsigned encode_block(const float (&f)[64], const stream_params& sp, Sink
   if (!(mx > 0.f) || prec == 0) {  // all zero, or nothing above the accuracy floor: a single 0 bit
     sink.word(0u);
     sink.finish();
+    sink.pad_to(sp.minbits);
     return sp.minbits > 1u ? sp.minbits : 1u;
   }
   const int kmin = prec < 32 ? 32 - prec : 0;
@@ -447,6 +450,7 @@ ZFB_HD unsigned encode_block(const float (&f)[64], const stream_params& sp, Sink
 
   unsigned used = encode_planes<32>(ps, maxbits, 2u * (uint32_t)(E + 1) + 1u, 9u, kmin, sink, tb);
   used = used < maxbits ? used : maxbits;
+  sink.pad_to(sp.minbits);
   return used < sp.minbits ? sp.minbits : used;
 }
 

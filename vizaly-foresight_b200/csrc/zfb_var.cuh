@@ -24,23 +24,27 @@ template <typename Scalar, int DIMS> struct var_caps {
 };
 
 // staging column of one block: word j of block b lives at stage[(b / 32) * 32 * WORDS + j * 32 + b % 32]
+// (a minbits floor above the longest codable block is padding only: the column holds `cap` words, the compaction
+// copies at most that many and the rest of the block stays zero in the pre-zeroed stream)
 struct stage_col_sink {
   uint64_t* dst;
-  unsigned widx;
-  ZFB_HD explicit stage_col_sink(uint64_t* d) : dst(d), widx(0) {}
+  unsigned widx, cap;
+  ZFB_HD stage_col_sink(uint64_t* d, unsigned cap_words) : dst(d), widx(0), cap(cap_words) {}
   ZFB_HD void word(uint64_t w) { dst[32u * widx++] = w; }
   ZFB_HD void finish() {}
+  ZFB_HD void pad_to(unsigned bits) { while (64u * widx < bits && widx < cap) word(0); }
 };
 
 // the same column seen as 32-bit words (fast float/3D coder): 32-bit word j at stage32[2 * base + j * 32]
 struct stage_col_sink32 {
   uint32_t* dst;
-  unsigned widx;
-  ZFB_HD explicit stage_col_sink32(uint32_t* d) : dst(d), widx(0) {}
+  unsigned widx, cap;
+  ZFB_HD stage_col_sink32(uint32_t* d, unsigned cap_words32) : dst(d), widx(0), cap(cap_words32) {}
   ZFB_HD void word(uint32_t w) { dst[32u * widx++] = w; }
   ZFB_HD void word2(uint32_t w0, uint32_t w1) { word(w0); word(w1); }
   ZFB_HD void finish() {}
   ZFB_HD unsigned words() const { return widx; }
+  ZFB_HD void pad_to(unsigned bits) { while (32u * widx < bits && widx < cap) word(0u); }
 };
 
 template <unsigned WORDS> __device__ __forceinline__ size_t stage_base(size_t b)
@@ -104,10 +108,10 @@ __global__ void __launch_bounds__(128) enc_var_kernel(const Scalar* __restrict__
     gather_block<Scalar, DIMS>(in, g, b, f);
     if constexpr (FAST) {
       // 32-bit word j of the column: the two halves of 64-bit word j/2 sit 32 words apart, see compact_var_kernel
-      stage_col_sink32 sink(reinterpret_cast<uint32_t*>(stage) + 2 * ((b >> 5) * (size_t)(32u * WORDS)) + (b & 31u));
+      stage_col_sink32 sink(reinterpret_cast<uint32_t*>(stage) + 2 * ((b >> 5) * (size_t)(32u * WORDS)) + (b & 31u), 2u * WORDS);
       lens[b] = f3::encode_block(f, sp, sink, tb, ps);
     } else {
-      stage_col_sink sink(stage + stage_base<WORDS>(b));
+      stage_col_sink sink(stage + stage_base<WORDS>(b), WORDS);
       lens[b] = encode_block<Scalar, DIMS>(f, sp, sink);
     }
   }
@@ -219,7 +223,8 @@ __global__ void __launch_bounds__(128) compact_var_kernel(const uint64_t* __rest
   for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < nblocks; b += (size_t)gridDim.x * blockDim.x) {
     const uint64_t off = offsets[b], end = offsets[b + 1];
     const unsigned len = (unsigned)(end - off);
-    const unsigned nw = (len + 63u) >> 6;
+    const unsigned nw_all = (len + 63u) >> 6;
+    const unsigned nw = nw_all < WORDS ? nw_all : WORDS;  // beyond the column there is only minbits padding (zeros)
     const uint64_t* col = stage + stage_base<WORDS>(b);
     const uint32_t* col32 = reinterpret_cast<const uint32_t*>(stage) + 2 * ((b >> 5) * (size_t)(32u * WORDS)) + (b & 31u);
     const unsigned s = (unsigned)(off & 63u);
