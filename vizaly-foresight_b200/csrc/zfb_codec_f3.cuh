@@ -137,8 +137,15 @@ ZFB_HD uint16_t enc_entry(unsigned b)
 
 // DEC[state][v]: run zfp's group-test parser over the 8 stream bits v (LSB first) from `state`
 //   state 0 (A) = expecting a test bit, state 1 (B) = inside a zero run (next bit is a coefficient bit).
-// Entry: bits 0-7 ones deposited (relative to the current coefficient index), 8-11 coefficients advanced,
-//        12-15 stream bits consumed, 16-17 next state (0 A, 1 B, 2 END = a zero test bit was consumed).
+// Entry, laid out for the parse loop's critical path (table load -> window shift -> next table load):
+//   bits 0-4   stream bits consumed: the entry itself is the shift amount of wrap-mode funnel shifts
+//   bits 8-15  ones deposited (relative to the current coefficient index), bits 16-19 coefficients advanced
+//   bits 30-31 next state (0 A, 1 B, 2 END = a zero test bit was consumed): e >> 20 is the byte offset of the
+//              next state's half of the table, bit 31 alone says END
+ZFB_HD unsigned dec_nbits(uint32_t e) { return e & 31u; }
+ZFB_HD uint32_t dec_pat(uint32_t e) { return (e >> 8) & 0xffu; }
+ZFB_HD unsigned dec_npos(uint32_t e) { return (e >> 16) & 15u; }
+ZFB_HD unsigned dec_state(uint32_t e) { return e >> 30; }
 ZFB_HD uint32_t dec_entry(unsigned state, unsigned v)
 {
   unsigned pattern = 0, npos = 0, nbits = 0;
@@ -151,7 +158,7 @@ ZFB_HD uint32_t dec_entry(unsigned state, unsigned v)
       npos++;
     }
   }
-  return pattern | (npos << 8) | (nbits << 12) | (state << 16);
+  return nbits | (pattern << 8) | (npos << 16) | (state << 30);
 }
 
 struct tables {
@@ -170,6 +177,17 @@ ZFB_HD uint32_t enc_at(const tables& tb, uint32_t i)
   return v;
 #else
   return tb.enc[i];
+#endif
+}
+// DEC entry at a byte address inside the table (device: shared-memory address; host: offset from tb.dec)
+ZFB_HD uint32_t dec_load(const tables& tb, uint32_t addr)
+{
+#if defined(__CUDA_ARCH__)
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+#else
+  return tb.dec[(addr - tb.dec_s) >> 2];
 #endif
 }
 ZFB_HD uint32_t dec_at(const tables& tb, uint32_t i)
@@ -505,6 +523,25 @@ struct reader32 {
       avail += 32;
     }
   }
+  ZFB_HD void consume_entry(uint32_t e)  // consume dec_nbits(e) <= 8 bits; e's upper bits are ignored by the shifts
+  {
+#if defined(__CUDA_ARCH__)
+    lo = __funnelshift_r(lo, hi, e);
+    hi = __funnelshift_r(hi, 0u, e);
+#else
+    const unsigned k = e & 31u;
+    lo = fsr(lo, hi, k);
+    hi >>= k;
+#endif
+    avail -= e & 31u;
+    if (avail < 32) {
+      const uint32_t nw = widx < nwords ? w[widx] : 0u;
+      widx++;
+      lo |= nw << avail;
+      hi = carry_out(nw, avail);
+      avail += 32;
+    }
+  }
   ZFB_HD uint32_t take(unsigned k)  // k in [0, 32]
   {
     const uint32_t v = lo & mask32(k);
@@ -559,18 +596,20 @@ ZFB_HD int parse_planes(const PR& ps, unsigned maxbits, unsigned hbits, int kmin
       // fast steps: with >= 8 bits of budget left a table step (<= 8 stream bits) cannot overrun it, and a
       // step that stays below coefficient 63 (whose one is implicit) needs no end-of-block rule either; the
       // first step that would touch coefficient 63 is left to the careful loop below
+      uint32_t half = tb.dec_s;  // address of the current state's half of the table
       while (remaining >= 8u) {
-        const uint32_t e = dec_at(tb, (state << 8) | (r.lo & 0xffu));
-        const unsigned npos = (e >> 8) & 15u, nbits = (e >> 12) & 15u;
+        const uint32_t e = dec_load(tb, half + ((r.lo & 0xffu) << 2));
+        const unsigned npos = dec_npos(e);
         if (n + npos > 63u) break;
-        const uint32_t pat = e & 0xffu;
+        const uint32_t pat = dec_pat(e);
         if (n < 32) { xl |= pat << n; xh |= carry_out(pat, n); }
         else xh |= pat << (n - 32);
         n += npos;
-        remaining -= nbits;
-        r.consume_small(nbits);
-        state = (e >> 16) & 3u;
-        if (state == 2u) break;
+        remaining -= dec_nbits(e);
+        r.consume_entry(e);
+        half = tb.dec_s + (e >> 20);
+        state = dec_state(e);
+        if ((int32_t)e < 0) break;  // END
       }
       while (state != 2u && n < 64u && remaining) {
         uint32_t wb = r.lo;
@@ -579,8 +618,8 @@ ZFB_HD int parse_planes(const PR& ps, unsigned maxbits, unsigned hbits, int kmin
         // the one zfp's decoder deposits when the budget ends inside a zero run, in state A it deposits nothing
         if (forced) wb = (wb & mask32(remaining)) | (1u << remaining);
         const uint32_t e = dec_at(tb, (state << 8) | (wb & 0xffu));
-        const unsigned npos = (e >> 8) & 15u, nbits = (e >> 12) & 15u;
-        const uint32_t pat = e & 0xffu;
+        const unsigned npos = dec_npos(e), nbits = dec_nbits(e);
+        const uint32_t pat = dec_pat(e);
         if (n + npos <= 63u) {
           // table step: deposit up to 8 coefficient bits at once
           if (n < 32) { xl |= pat << n; xh |= carry_out(pat, n); }
@@ -589,7 +628,7 @@ ZFB_HD int parse_planes(const PR& ps, unsigned maxbits, unsigned hbits, int kmin
           if (nbits > remaining) { remaining = 0u; state = 0u; break; }  // ran into the forced terminator
           remaining -= nbits;
           r.consume(nbits);
-          state = (e >> 16) & 3u;
+          state = dec_state(e);
           if (state == 2u) break;
         } else if (!forced) {
           // the step would read a bit for coefficient 63, whose one is implicit: keep the L = 63 - n positions

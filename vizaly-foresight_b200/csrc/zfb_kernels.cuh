@@ -120,6 +120,10 @@ __device__ __forceinline__ f3::tables build_coder_tables(coder_smem& cs)
   t.enc = cs.enc; t.dec = cs.dec;
   t.enc_s = (uint32_t)__cvta_generic_to_shared(cs.enc);
   t.dec_s = (uint32_t)__cvta_generic_to_shared(cs.dec);
+  // opaque to the compiler: otherwise it rebuilds the shared window address (S2UR SR_CgaCtaId, ULEA, ...) in front
+  // of every table load inside the coder loops instead of keeping it in a register
+  asm volatile("mov.u32 %0, %0;" : "+r"(t.enc_s));
+  asm volatile("mov.u32 %0, %0;" : "+r"(t.dec_s));
   return t;
 }
 
