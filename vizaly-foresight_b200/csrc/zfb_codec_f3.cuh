@@ -142,9 +142,17 @@ ZFB_HD uint16_t enc_entry(unsigned b)
 //   bits 8-15  ones deposited (relative to the current coefficient index), bits 16-19 coefficients advanced
 //   bits 30-31 next state (0 A, 1 B, 2 END = a zero test bit was consumed): e >> 20 is the byte offset of the
 //              next state's half of the table, bit 31 alone says END
+ZFB_HD uint32_t byte_of(uint32_t v, int i)  // byte i of v, zero extended (one PRMT on the device)
+{
+#if defined(__CUDA_ARCH__)
+  return __byte_perm(v, 0u, 0x4440u + (unsigned)i);
+#else
+  return (v >> (8 * i)) & 0xffu;
+#endif
+}
 ZFB_HD unsigned dec_nbits(uint32_t e) { return e & 31u; }
-ZFB_HD uint32_t dec_pat(uint32_t e) { return (e >> 8) & 0xffu; }
-ZFB_HD unsigned dec_npos(uint32_t e) { return (e >> 16) & 15u; }
+ZFB_HD uint32_t dec_pat(uint32_t e) { return byte_of(e, 1); }
+ZFB_HD unsigned dec_npos(uint32_t e) { return byte_of(e, 2); }  // bits 20-23 are zero
 ZFB_HD unsigned dec_state(uint32_t e) { return e >> 30; }
 ZFB_HD uint32_t dec_entry(unsigned state, unsigned v)
 {
@@ -597,8 +605,9 @@ ZFB_HD int parse_planes(const PR& ps, unsigned maxbits, unsigned hbits, int kmin
       // step that stays below coefficient 63 (whose one is implicit) needs no end-of-block rule either; the
       // first step that would touch coefficient 63 is left to the careful loop below
       uint32_t half = tb.dec_s;  // address of the current state's half of the table
+      uint32_t last = 0u;        // last entry applied (state A before the first)
       while (remaining >= 8u) {
-        const uint32_t e = dec_load(tb, half + ((r.lo & 0xffu) << 2));
+        const uint32_t e = dec_load(tb, half + 4u * byte_of(r.lo, 0));
         const unsigned npos = dec_npos(e);
         if (n + npos > 63u) break;
         const uint32_t pat = dec_pat(e);
@@ -608,9 +617,10 @@ ZFB_HD int parse_planes(const PR& ps, unsigned maxbits, unsigned hbits, int kmin
         remaining -= dec_nbits(e);
         r.consume_entry(e);
         half = tb.dec_s + (e >> 20);
-        state = dec_state(e);
+        last = e;
         if ((int32_t)e < 0) break;  // END
       }
+      state = dec_state(last);
       while (state != 2u && n < 64u && remaining) {
         uint32_t wb = r.lo;
         const bool forced = remaining < 8u;
