@@ -283,6 +283,11 @@ struct sink32 {  // slot on a word boundary, whole number of 32-bit words (maxbi
     if (widx < nwords) dst[widx] = w;
     widx++;
   }
+  ZFB_HD void word_if(bool on, uint32_t w)
+  {
+    if (on & (widx < nwords)) dst[widx] = w;
+    widx += on ? 1u : 0u;
+  }
   ZFB_HD void word2(uint32_t w0, uint32_t w1)
   {
     if (widx + 2 <= nwords) { dst[widx] = w0; dst[widx + 1] = w1; }
@@ -323,6 +328,7 @@ struct or_sink32 {  // arbitrary bit offset in a pre-zeroed stream (maxbits % 64
     const uint32_t c = carry_out(w, s);
     if (c) or32(base + (pos >> 5) + 1, c);
   }
+  ZFB_HD void word_if(bool on, uint32_t w) { if (on) word(w); }
   ZFB_HD void word2(uint32_t w0, uint32_t w1) { word(w0); word(w1); }
   ZFB_HD void finish() {}
   ZFB_HD unsigned words() const { return j; }
@@ -340,7 +346,12 @@ template <class Sink> struct writer32 {
     acc |= v << cnt;
     const uint32_t c = carry_out(v, cnt);
     cnt += len;
-    if (cnt >= 32) { sink.word(acc); acc = c; cnt -= 32; }
+    // no branch: the lanes of a warp fill their words at different times, so a flush branch would be taken by a
+    // few lanes on nearly every call
+    const bool full = cnt >= 32;
+    sink.word_if(full, acc);
+    acc = full ? c : acc;
+    cnt &= 31u;
   }
   ZFB_HD void put64(uint32_t xl, uint32_t xh)  // a whole plane of 64 significant coefficients
   {

@@ -41,6 +41,11 @@ struct stage_col_sink32 {
   unsigned widx, cap;
   ZFB_HD stage_col_sink32(uint32_t* d, unsigned cap_words32) : dst(d), widx(0), cap(cap_words32) {}
   ZFB_HD void word(uint32_t w) { dst[32u * widx++] = w; }
+  ZFB_HD void word_if(bool on, uint32_t w)
+  {
+    if (on) dst[32u * widx] = w;
+    widx += on ? 1u : 0u;
+  }
   ZFB_HD void word2(uint32_t w0, uint32_t w1) { word(w0); word(w1); }
   ZFB_HD void finish() {}
   ZFB_HD unsigned words() const { return widx; }
