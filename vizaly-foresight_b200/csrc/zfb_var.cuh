@@ -233,25 +233,38 @@ __global__ void __launch_bounds__(128) compact_var_kernel(const uint64_t* __rest
     const uint64_t* col = stage + stage_base<WORDS>(b);
     const uint32_t* col32 = reinterpret_cast<const uint32_t*>(stage) + 2 * ((b >> 5) * (size_t)(32u * WORDS)) + (b & 31u);
     const unsigned s = (unsigned)(off & 63u);
-    size_t wi = (size_t)(off >> 6);
+    const size_t wi = (size_t)(off >> 6);
     uint64_t prev = 0;  // bits carried into the next output word
-    for (unsigned j = 0; j <= nw; j++) {
-      uint64_t w = 0;
-      if (j < nw) {
-        if (COL32) w = (uint64_t)col32[64u * j] | ((uint64_t)col32[64u * j + 32u] << 32);
-        else w = col[32u * j];
-        const unsigned valid = len - 64u * j;
-        if (valid < 64u) w &= lowmask64(valid);
+    // four staged words per step: the loads of a step are independent, so their latencies overlap
+    for (unsigned j0 = 0; j0 <= nw; j0 += 4) {
+      uint64_t w[4];
+#pragma unroll
+      for (unsigned q = 0; q < 4; q++) {
+        const unsigned j = j0 + q;
+        w[q] = 0;
+        if (j < nw) {
+          if (COL32) w[q] = (uint64_t)col32[64u * j] | ((uint64_t)col32[64u * j + 32u] << 32);
+          else w[q] = col[32u * j];
+        }
       }
-      const uint64_t o = s ? ((w << s) | prev) : w;
-      prev = s ? (w >> (64u - s)) : 0;
-      if (j == nw && !s) break;  // nothing carried over
-      const size_t i = wi + j;
-      if (i < cap_words && o) {  // a zero contribution needs no write: the words were zeroed up front
-        // words wholly inside [off, end) belong to this block alone; the first and the last are shared
-        const bool whole = (uint64_t)i * 64u >= off && (uint64_t)(i + 1) * 64u <= end;
-        if (whole) stream[i] = o;
-        else atomicOr(reinterpret_cast<unsigned long long*>(stream + i), (unsigned long long)o);
+#pragma unroll
+      for (unsigned q = 0; q < 4; q++) {
+        const unsigned j = j0 + q;
+        if (j > nw) break;
+        uint64_t v = w[q];
+        if (j < nw) {
+          const unsigned valid = len - 64u * j;
+          if (valid < 64u) v &= lowmask64(valid);
+        }
+        const uint64_t o = s ? ((v << s) | prev) : v;
+        prev = s ? (v >> (64u - s)) : 0;
+        const size_t i = wi + j;
+        if (i < cap_words && o) {  // a zero contribution needs no write: the words were zeroed up front
+          // words wholly inside [off, end) belong to this block alone; the first and the last are shared
+          const bool whole = (uint64_t)i * 64u >= off && (uint64_t)(i + 1) * 64u <= end;
+          if (whole) stream[i] = o;
+          else atomicOr(reinterpret_cast<unsigned long long*>(stream + i), (unsigned long long)o);
+        }
       }
     }
   }
