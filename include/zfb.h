@@ -104,7 +104,8 @@ int zfb_decode_dev(zfb_ctx* ctx, int dtype, int dims, size_t nx, size_t ny, size
                    const void* d_stream, void* d_out, const void* d_orig);
 
 /* Stand-alone streaming metric pass over two device arrays (any compressor's output):
- * absoluteError/relativeError/meansquareError/psnrError/minmaxMetric::execute first loops. */
+ * absoluteError/relativeError/meansquareError/psnrError/minmaxMetric::execute first loops.
+ * Both pointers must be 16-byte aligned (any cudaMalloc'ed array is). */
 int zfb_metrics_dev(zfb_ctx* ctx, int dtype, const void* d_orig, const void* d_approx, size_t n);
 
 /* Device address of the context's zfb_partials (valid after the stream reaches the producing call);

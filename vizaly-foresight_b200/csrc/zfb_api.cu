@@ -636,8 +636,8 @@ extern "C" int zfb_metrics_dev(zfb_ctx* c, int dtype, const void* d_orig, const 
   size_t want = (n / 4 + 255) / 256;
   int grid = (int)(want < (size_t)c->sm_count * 8 ? (want ? want : 1) : (size_t)c->sm_count * 8);
   if (grid > c->part_rows) grid = c->part_rows;
+  if (((uintptr_t)d_orig | (uintptr_t)d_approx) & 15) { c->err = "metrics: pointers must be 16-byte aligned"; return ZFB_EINVAL; }
   if (dtype == ZFB_FLOAT) {
-    if (((uintptr_t)d_orig | (uintptr_t)d_approx) & 15) { c->err = "metrics: pointers must be 16-byte aligned"; return ZFB_EINVAL; }
     metrics_kernel<float><<<grid, 256, 0, c->stream>>>((const float*)d_orig, (const float*)d_approx, n, c->part);
   } else {
     metrics_kernel<double><<<grid, 256, 0, c->stream>>>((const double*)d_orig, (const double*)d_approx, n, c->part);

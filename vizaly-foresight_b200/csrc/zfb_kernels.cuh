@@ -995,7 +995,21 @@ __global__ void __launch_bounds__(256) metrics_kernel(const Scalar* __restrict__
     if (tail < n) fr.add(orig[tail], approx[tail]);
     fr.flush(m);
   } else {
-    for (; i < n; i += stride) macc_add(m, (double)orig[i], (double)approx[i]);
+    // 16-byte loads, two independent pairs in flight per thread and iteration
+    const size_t n2 = n / 2;
+    const double2* o2 = reinterpret_cast<const double2*>(orig);
+    const double2* a2 = reinterpret_cast<const double2*>(approx);
+    for (; i + stride < n2; i += 2 * stride) {
+      const double2 o0 = __ldcs(o2 + i), a0 = __ldcs(a2 + i);
+      const double2 o1 = __ldcs(o2 + i + stride), a1 = __ldcs(a2 + i + stride);
+      macc_add(m, o0.x, a0.x); macc_add(m, o0.y, a0.y);
+      macc_add(m, o1.x, a1.x); macc_add(m, o1.y, a1.y);
+    }
+    if (i < n2) {
+      const double2 o0 = __ldcs(o2 + i), a0 = __ldcs(a2 + i);
+      macc_add(m, o0.x, a0.x); macc_add(m, o0.y, a0.y);
+    }
+    if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) macc_add(m, (double)orig[n - 1], (double)approx[n - 1]);
   }
   macc_block_store(m, red, part + (size_t)blockIdx.x * PART_STRIDE);
 }
