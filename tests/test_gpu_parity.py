@@ -402,3 +402,29 @@ def test_outputs_stay_inside_exact_size_buffers(codec, pkg, dtype, shape, rate):
     assert torch.equal(s, s2)
     ref = codec.decode(s2, shape, tdt, mb)
     assert torch.equal(out.contiguous().view(torch.uint8), ref.view(torch.uint8)), "guarded decode"
+
+
+def test_cbench_brick_partition_against_oracle(codec, pkg, oracle):
+    """CBench-parity sharding (getPartition, dataLoaderInterface.hpp:123-215): the 8 ranks of a 2x2x2 split each
+    compress their own brick as a contiguous local array; every brick matches the oracle bit for bit (odd brick
+    extents: partial blocks), and the ranks' partials combine to the metrics of the whole field."""
+    torch = _torch()
+    ext = (40, 52, 60)  # 2x2x2 bricks of 20 x 26 x 30
+    f = smooth_field(ext, seed=21, amp=25.0)
+    mb = pkg.maxbits(np.float32, 3, 8)
+    parts, g_all = [], np.empty_like(f)
+    for r in range(8):
+        cnt, off = pkg.partition(r, 8, ext)
+        sl = tuple(slice(o, o + c) for o, c in zip(off, cnt))
+        brick = np.ascontiguousarray(f[sl])
+        d_b = torch.from_numpy(brick).cuda()
+        s = codec.encode(d_b, mb)
+        s_ref = oracle.compress(brick, mb)
+        assert np.array_equal(s.cpu().numpy(), s_ref), r
+        out = codec.decode(s, brick.shape, torch.float32, mb, orig=d_b)
+        g_ref = oracle.decompress(s_ref, brick.shape, np.float32, mb)
+        assert_bits_equal(out.cpu().numpy(), g_ref, "brick %d" % r)
+        parts.append(codec.partials())
+        g_all[sl] = g_ref
+    total = pkg.combine_partials(parts)
+    check_metrics(pkg, oracle, total, f, g_all, "8 bricks combined")
