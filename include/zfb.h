@@ -170,12 +170,17 @@ int zfb_mode_precision(zfb_mode* m, unsigned precision);                   /* zf
 
 /* Bytes zfp_stream_maximum_size() returns for this mode (buffer CBench mallocs, zfpCompressor.hpp:123-124). */
 size_t zfb_maximum_size(int dtype, int dims, size_t nx, size_t ny, size_t nz, const zfb_mode* m);
-/* Number of 4^d blocks; an index holds zfb_block_count() + 1 uint64 bit offsets. */
+/* Number of 4^d blocks. */
 size_t zfb_block_count(int dims, size_t nx, size_t ny, size_t nz);
+/* The index: zfb_index_count() + 1 uint64 bit offsets, one per zfb_index_unit(dims) consecutive blocks
+ * (2D/3D: every block; 1D: every 8th block -- a 1D block is 16 bytes of data, finer bookkeeping would cost
+ * more than the data), the total number of bits last. */
+size_t zfb_index_unit(int dims);
+size_t zfb_index_count(int dims, size_t nx, size_t ny, size_t nz);
 
 /* zfp_compress() in any mode on device buffers (zfpCompressor.hpp:132).  d_stream holds cap_bytes >=
- * zfb_maximum_size().  d_index: nullable device array of zfb_block_count()+1 uint64 that receives the
- * index (offset of every block, total bits last); with NULL the context keeps the index for the next
+ * zfb_maximum_size().  d_index: nullable device array of zfb_index_count()+1 uint64 that receives the
+ * index; with NULL the context keeps the index for the next
  * zfb_decode_var_dev of the same d_stream.  *stream_bytes = what zfp_compress returns (the call
  * synchronises: the size is data dependent). */
 int zfb_encode_var_dev(zfb_ctx* ctx, int dtype, int dims, size_t nx, size_t ny, size_t nz, const zfb_mode* m,

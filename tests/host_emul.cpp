@@ -221,6 +221,32 @@ static size_t run_var(bool enc, size_t nx, size_t ny, size_t nz, const stream_pa
           done = true;
         }
       }
+      if constexpr (std::is_same<Scalar, float>::value && DIMS == 1) {
+        if (g_use_f3 && f1::var_params_ok(sp)) {  // per-plane table coder of the float/1D variable-rate kernels
+          const f1::tables tb = host_tables1();
+          stage_sink sink(stage);
+          bit_writer<stage_sink> bw(sink);
+          bits = f1::encode_block_var(f, sp, bw, tb);
+          bw.flush();
+          done = true;
+        }
+      }
+      if (!done && DIMS == 1) {  // append form, as enc_var1_kernel strings the blocks of a group together
+        stage_sink sink(stage);
+        bit_writer<stage_sink> bw(sink);
+        bw.put(0x2au, 7);  // something already in the writer: the block must land behind it untouched
+        bits = encode_block_append<Scalar, DIMS>(f, sp, bw);
+        bw.flush();
+        uint64_t carry = 0;  // drop the 7 leading bits again
+        const unsigned nwords = (bits + 7 + 63) / 64;
+        for (unsigned j = nwords; j-- > 0;) {
+          const uint64_t w = stage[j];
+          stage[j] = (w >> 7) | (carry << 57);
+          carry = w & 0x7fu;
+        }
+        if ((stage[0], carry) != 0x2au) return 0;
+        done = true;
+      }
       if (!done) {
         stage_sink sink(stage);
         bits = encode_block<Scalar, DIMS>(f, sp, sink);
@@ -242,6 +268,15 @@ static size_t run_var(bool enc, size_t nx, size_t ny, size_t nz, const stream_pa
       const unsigned bits = decode_block<Scalar, DIMS, false>(f, sp, r);
       const unsigned bits2 = decode_block<Scalar, DIMS, true>(dummy, sp, r2);  // index walk must agree
       if (bits != bits2) return 0;
+      if constexpr (std::is_same<Scalar, float>::value && DIMS == 1) {
+        if (g_use_f3 && f1::var_params_ok(sp)) {  // the float/1D table decoder must reproduce the generic one
+          const f1::tables tb = host_tables1();
+          const uint32_t* s32 = reinterpret_cast<const uint32_t*>(stream);
+          f3::reader32 r3(s32 + (pos >> 5), (unsigned)(2 * stream_words - (pos >> 5)), (unsigned)(pos & 31));
+          const unsigned bits3 = f1::decode_block_var(f2, sp, r3, tb);
+          if (bits3 != bits || std::memcmp(f, f2, 4 * sizeof(float))) return 0;
+        }
+      }
       if constexpr (std::is_same<Scalar, float>::value && DIMS == 3) {
         if (g_use_f3) {  // the fast float/3D decoder must reproduce the generic one bit for bit
           const f3::tables tb = host_tables();

@@ -38,7 +38,7 @@ def _modes(pkg, oracle):
     return out
 
 
-SHAPES = [(np.float32, (10,)), (np.float32, (4099,)), (np.float32, (5, 7)), (np.float32, (64, 64)),
+SHAPES = [(np.float32, (10,)), (np.float32, (4099,)), (np.float32, (70001,)), (np.float64, (33,)), (np.float32, (5, 7)), (np.float32, (64, 64)),
           (np.float32, (5, 6, 7)), (np.float32, (33, 33, 33)), (np.float32, (16, 32, 64)), (np.float32, (64, 64, 64)),
           (np.float64, (1001,)), (np.float64, (17, 19)), (np.float64, (5, 6, 7)), (np.float64, (16, 16, 32))]
 
@@ -49,14 +49,17 @@ def test_variable_rate_bit_exact(codec, pkg, oracle, dtype, shape):
     f = _field(shape, dtype)
     d_f = torch.from_numpy(f).cuda()
     tdt = torch.float32 if dtype == np.float32 else torch.float64
-    nb = pkg.block_count(shape)
+    ni, unit = pkg.index_count(shape), pkg.index_unit(len(shape))
+    assert ni == -(-pkg.block_count(shape) // unit) and unit == (8 if len(shape) == 1 else 1)
     for name, m, p in _modes(pkg, oracle):
         s_ref, offs_ref = oracle.compress_ex(f, p, with_offsets=True)
         g_ref, _ = oracle.decompress_ex(s_ref, shape, dtype, p)
-        index = torch.zeros(nb + 1, dtype=torch.int64, device="cuda")
+        index = torch.zeros(ni + 1, dtype=torch.int64, device="cuda")
         s, nbytes = codec.encode_var(d_f, m, index=index)
         assert nbytes == len(s_ref), name
-        assert np.array_equal(index.cpu().numpy().view(np.uint64), offs_ref), name
+        # one entry per `unit` blocks (1D: groups of 8), the total number of bits last
+        want = np.concatenate([offs_ref[:-1][::unit], offs_ref[-1:]])
+        assert np.array_equal(index.cpu().numpy().view(np.uint64), want), name
         assert np.array_equal(s.cpu().numpy(), s_ref), name
         # decode with the caller's index, fused metrics
         out = codec.decode_var(s, shape, tdt, m, index=index, orig=d_f)
@@ -173,6 +176,8 @@ def test_expert_parameters_and_fixed_rate_through_the_general_path(codec, pkg, o
         d_f = torch.from_numpy(f).cuda()
         tdt = torch.float32 if dtype == np.float32 else torch.float64
         for prm in ((64, 300, 20, -20), (1, 130, 64, -1074), (200, 200, 9, -5), (17, 2000, 31, -30), (96, 97, 64, -1074)):
+            if len(shape) == 1 and prm[0] > 140:
+                continue  # 1D: a padding floor above the longest codable block is rejected (see below)
             m, p = pkg.Mode(*prm), oracle.Params(*prm)
             s_ref = oracle.compress_ex(f, p)
             g_ref, _ = oracle.decompress_ex(s_ref, shape, dtype, p)
@@ -186,3 +191,5 @@ def test_expert_parameters_and_fixed_rate_through_the_general_path(codec, pkg, o
         assert nbytes == s_fixed.numel() and torch.equal(s, s_fixed), (dtype, shape)
     with pytest.raises(pkg.ZfbError):  # minbits > maxbits
         codec.encode_var(d_f, pkg.Mode(9000, 300, 64, -1074))
+    with pytest.raises(pkg.ZfbError):  # 1D float: padding floor above the 140-bit block bound
+        codec.encode_var(torch.zeros(64, device="cuda"), pkg.Mode(200, 200, 9, -5))

@@ -116,6 +116,8 @@ def lib():
         "zfb_mode_precision": (i, [MP, u]),
         "zfb_maximum_size": (sz, [i, i, sz, sz, sz, MP]),
         "zfb_block_count": (sz, [i, sz, sz, sz]),
+        "zfb_index_unit": (sz, [i]),
+        "zfb_index_count": (sz, [i, sz, sz, sz]),
         "zfb_encode_var_dev": (i, [vp, i, i, sz, sz, sz, MP, vp, vp, sz, vp, C.POINTER(sz)]),
         "zfb_decode_var_dev": (i, [vp, i, i, sz, sz, sz, MP, vp, sz, vp, vp, vp]),
         "zfb_compress_var_host": (i, [vp, i, i, sz, sz, sz, MP, vp, vp, sz, C.POINTER(sz)]),
@@ -200,6 +202,17 @@ def maximum_size(shape, dtype, mode):
 def block_count(shape):
     d, nx, ny, nz = dims_of(shape)
     return int(lib().zfb_block_count(d, nx, ny, nz))
+
+
+def index_unit(dims):
+    """Blocks per index entry of a variable-rate stream (1 for 2D/3D, 8 for 1D)."""
+    return int(lib().zfb_index_unit(int(dims)))
+
+
+def index_count(shape):
+    """Index entries of a variable-rate stream; the index array holds index_count() + 1 uint64 bit offsets."""
+    d, nx, ny, nz = dims_of(shape)
+    return int(lib().zfb_index_count(d, nx, ny, nz))
 
 
 def partition(rank, nranks, shape3):
@@ -339,8 +352,8 @@ class Codec:
 
     # ---- variable-rate modes (fixed accuracy / fixed precision) --------------------------------
     def encode_var(self, field, mode, out=None, index=None):
-        """Returns (stream[:nbytes], nbytes).  index: optional uint64 tensor of block_count()+1 entries that
-        receives the block offsets; without it the context keeps the index for decode_var of this stream."""
+        """Returns (stream[:nbytes], nbytes).  index: optional uint64 tensor of index_count()+1 entries that
+        receives the bit offsets; without it the context keeps the index for decode_var of this stream."""
         import torch
 
         self.use_torch_stream()

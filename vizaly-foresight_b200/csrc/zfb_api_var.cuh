@@ -51,6 +51,17 @@ extern "C" size_t zfb_block_count(int dims, size_t nx, size_t ny, size_t nz)
   return count_blocks(dims, nx, ny, nz);
 }
 
+static size_t index_unit(int dims) { return dims == 1 ? (size_t)VAR1_GROUP : 1; }
+
+extern "C" size_t zfb_index_unit(int dims) { return dims >= 1 && dims <= 3 ? index_unit(dims) : 0; }
+
+extern "C" size_t zfb_index_count(int dims, size_t nx, size_t ny, size_t nz)
+{
+  if (dims < 1 || dims > 3) return 0;
+  const size_t u = index_unit(dims);
+  return (count_blocks(dims, nx, ny, nz) + u - 1) / u;
+}
+
 extern "C" size_t zfb_maximum_size(int dtype, int dims, size_t nx, size_t ny, size_t nz, const zfb_mode* m)
 {
   if (!m || dims < 1 || dims > 3 || (dtype != ZFB_FLOAT && dtype != ZFB_DOUBLE)) return 0;
@@ -88,9 +99,9 @@ static stream_params to_params(const zfb_mode* m)
   return sp;
 }
 
-template <typename Scalar> static unsigned var_words(int dims)
+template <typename Scalar> static unsigned var_words(int dims)  // staging words per index unit
 {
-  return dims == 1 ? var_caps<Scalar, 1>::WORDS : dims == 2 ? var_caps<Scalar, 2>::WORDS : var_caps<Scalar, 3>::WORDS;
+  return dims == 1 ? var1_caps<Scalar>::WORDS : dims == 2 ? var_caps<Scalar, 2>::WORDS : var_caps<Scalar, 3>::WORDS;
 }
 
 static int var_grid(const zfb_ctx* c, size_t nblocks)
@@ -103,9 +114,9 @@ template <typename Scalar>
 static int launch_enc_var(zfb_ctx* c, int dims, const geom& g, const stream_params& sp, const void* d_in, uint64_t* stage,
                           uint32_t* lens)
 {
-  const int grid = var_grid(c, g.nblocks);
+  const int grid = var_grid(c, (g.nblocks + index_unit(dims) - 1) / index_unit(dims));
   const Scalar* in = (const Scalar*)d_in;
-  if (dims == 1) enc_var_kernel<Scalar, 1><<<grid, 128, 0, c->stream>>>(in, stage, lens, g, sp);
+  if (dims == 1) enc_var1_kernel<Scalar><<<grid, 128, 0, c->stream>>>(in, stage, lens, g, sp);
   else if (dims == 2) enc_var_kernel<Scalar, 2><<<grid, 128, 0, c->stream>>>(in, stage, lens, g, sp);
   else enc_var_kernel<Scalar, 3><<<grid, 128, 0, c->stream>>>(in, stage, lens, g, sp);
   c->launches++;
@@ -117,11 +128,12 @@ template <typename Scalar>
 static int launch_compact_var(zfb_ctx* c, int dims, const geom& g, const uint64_t* stage, const uint64_t* index,
                               uint64_t* stream, size_t cap_words)
 {
-  const int grid = var_grid(c, g.nblocks);
+  const size_t units = (g.nblocks + index_unit(dims) - 1) / index_unit(dims);
+  const int grid = var_grid(c, units);
   constexpr bool COL32 = sizeof(Scalar) == 4;  // float/3D is staged by the 32-bit table coder
-  if (dims == 1) compact_var_kernel<var_caps<Scalar, 1>::WORDS, false><<<grid, 128, 0, c->stream>>>(stage, index, g.nblocks, stream, cap_words);
-  else if (dims == 2) compact_var_kernel<var_caps<Scalar, 2>::WORDS, false><<<grid, 128, 0, c->stream>>>(stage, index, g.nblocks, stream, cap_words);
-  else compact_var_kernel<var_caps<Scalar, 3>::WORDS, COL32><<<grid, 128, 0, c->stream>>>(stage, index, g.nblocks, stream, cap_words);
+  if (dims == 1) compact_var_kernel<var1_caps<Scalar>::WORDS, false><<<grid, 128, 0, c->stream>>>(stage, index, units, stream, cap_words);
+  else if (dims == 2) compact_var_kernel<var_caps<Scalar, 2>::WORDS, false><<<grid, 128, 0, c->stream>>>(stage, index, units, stream, cap_words);
+  else compact_var_kernel<var_caps<Scalar, 3>::WORDS, COL32><<<grid, 128, 0, c->stream>>>(stage, index, units, stream, cap_words);
   c->launches++;
   CU_TRY(c, cudaGetLastError());
   return ZFB_OK;
@@ -141,15 +153,20 @@ extern "C" int zfb_encode_var_dev(zfb_ctx* c, int dtype, int dims, size_t nx, si
   g.stream_words = cap_words;
   const stream_params sp = to_params(m);
   const unsigned words = dtype == ZFB_FLOAT ? var_words<float>(dims) : var_words<double>(dims);
-  const size_t groups = (g.nblocks + 31) / 32;
+  const size_t units = (g.nblocks + index_unit(dims) - 1) / index_unit(dims);  // index entries (1D: groups of blocks)
+  if (dims == 1 && m->minbits > (dtype == ZFB_FLOAT ? var_caps<float, 1>::BITS : var_caps<double, 1>::BITS)) {
+    c->err = "1D: minbits above the longest codable block is not supported";
+    return ZFB_EINVAL;
+  }
+  const size_t groups = (units + 31) / 32;
   if ((rc = ensure(c, c->var_stage, groups * 32 * (size_t)words * 8))) return rc;
-  if ((rc = ensure(c, c->var_lens, g.nblocks * 4))) return rc;
-  const size_t nchunks = (g.nblocks + SCAN_CHUNK - 1) / SCAN_CHUNK;
+  if ((rc = ensure(c, c->var_lens, units * 4))) return rc;
+  const size_t nchunks = (units + SCAN_CHUNK - 1) / SCAN_CHUNK;
   if ((rc = ensure(c, c->var_chunks, (nchunks + 1) * 8))) return rc;
   uint64_t* index = d_index;
   c->var_index_key = nullptr;
   if (!index) {
-    if ((rc = ensure(c, c->var_index, (g.nblocks + 1) * 8))) return rc;
+    if ((rc = ensure(c, c->var_index, (units + 1) * 8))) return rc;
     index = (uint64_t*)c->var_index.p;
   }
   uint64_t* stage = (uint64_t*)c->var_stage.p;
@@ -159,24 +176,24 @@ extern "C" int zfb_encode_var_dev(zfb_ctx* c, int dtype, int dims, size_t nx, si
   rc = dtype == ZFB_FLOAT ? launch_enc_var<float>(c, dims, g, sp, d_in, stage, lens)
                           : launch_enc_var<double>(c, dims, g, sp, d_in, stage, lens);
   if (rc) return rc;
-  scan_sums_kernel<<<(unsigned)nchunks, SCAN_THREADS, 0, c->stream>>>(lens, g.nblocks, chunks);
+  scan_sums_kernel<<<(unsigned)nchunks, SCAN_THREADS, 0, c->stream>>>(lens, units, chunks);
   scan_chunks_kernel<<<1, SCAN_THREADS, 0, c->stream>>>(chunks, nchunks);
-  scan_offsets_kernel<<<(unsigned)nchunks, SCAN_THREADS, 0, c->stream>>>(lens, g.nblocks, chunks, nchunks, index);
-  zero_stream_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>((uint64_t*)d_stream, index + g.nblocks, cap_words);
+  scan_offsets_kernel<<<(unsigned)nchunks, SCAN_THREADS, 0, c->stream>>>(lens, units, chunks, nchunks, index);
+  zero_stream_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>((uint64_t*)d_stream, index + units, cap_words);
   c->launches += 4;
   CU_TRY(c, cudaGetLastError());
   rc = dtype == ZFB_FLOAT ? launch_compact_var<float>(c, dims, g, stage, index, (uint64_t*)d_stream, cap_words)
                           : launch_compact_var<double>(c, dims, g, stage, index, (uint64_t*)d_stream, cap_words);
   if (rc) return rc;
   uint64_t total_bits = 0;
-  CU_TRY(c, cudaMemcpyAsync(&total_bits, index + g.nblocks, 8, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(&total_bits, index + units, 8, cudaMemcpyDeviceToHost, c->stream));
   CU_TRY(c, cudaStreamSynchronize(c->stream));
   const size_t bytes = (size_t)((total_bits + 63) / 64) * 8;  // stream_flush pads to a word
   if (bytes > cap_bytes) { c->err = "internal: stream longer than its bound"; return ZFB_ESTATE; }
   if (stream_bytes) *stream_bytes = bytes;
   if (!d_index) {
     c->var_index_key = d_stream;
-    c->var_index_blocks = g.nblocks;
+    c->var_index_blocks = units;
     c->var_index_bits = total_bits;
   }
   return ZFB_OK;
@@ -199,12 +216,12 @@ template <typename Scalar, bool METRICS>
 static int launch_dec_var(zfb_ctx* c, int dims, const geom& g, const stream_params& sp, const void* d_stream,
                           const uint64_t* index, void* d_out, const void* d_orig, int* rows)
 {
-  int grid = var_grid(c, g.nblocks);
+  int grid = var_grid(c, (g.nblocks + index_unit(dims) - 1) / index_unit(dims));
   if (grid > c->part_rows) grid = c->part_rows;
   const uint64_t* st = (const uint64_t*)d_stream;
   Scalar* out = (Scalar*)d_out;
   const Scalar* orig = (const Scalar*)d_orig;
-  if (dims == 1) dec_var_kernel<Scalar, 1, METRICS><<<grid, 128, 0, c->stream>>>(st, index, out, orig, g, sp, c->part);
+  if (dims == 1) dec_var1_kernel<Scalar, METRICS><<<grid, 128, 0, c->stream>>>(st, index, out, orig, g, sp, c->part);
   else if (dims == 2) dec_var_kernel<Scalar, 2, METRICS><<<grid, 128, 0, c->stream>>>(st, index, out, orig, g, sp, c->part);
   else if constexpr (sizeof(Scalar) == 4) {
     const int persistent = c->sm_count * 4;  // 4 resident CTAs per SM, tiles of 128 blocks taken round-robin
@@ -229,13 +246,14 @@ extern "C" int zfb_decode_var_dev(zfb_ctx* c, int dtype, int dims, size_t nx, si
   g.stream_words = (stream_bytes + 7) / 8;
   const stream_params sp = to_params(m);
   const uint64_t* index = d_index;
+  const size_t units = (g.nblocks + index_unit(dims) - 1) / index_unit(dims);
   if (!index) {
-    if (c->var_index_key == d_stream && c->var_index_blocks == g.nblocks && c->var_index.p &&
+    if (c->var_index_key == d_stream && c->var_index_blocks == units && c->var_index.p &&
         (size_t)((c->var_index_bits + 63) / 64) * 8 == g.stream_words * 8) {
       index = (const uint64_t*)c->var_index.p;
     } else {
       c->var_index_key = nullptr;
-      if ((rc = ensure(c, c->var_index, (g.nblocks + 1) * 8))) return rc;
+      if ((rc = ensure(c, c->var_index, (units + 1) * 8))) return rc;
       rc = dtype == ZFB_FLOAT ? launch_index_var<float>(c, dims, d_stream, g.stream_words, g.nblocks, sp, (uint64_t*)c->var_index.p)
                               : launch_index_var<double>(c, dims, d_stream, g.stream_words, g.nblocks, sp, (uint64_t*)c->var_index.p);
       if (rc) return rc;

@@ -611,6 +611,78 @@ ZFB_HD unsigned encode_block(const Scalar (&f)[1 << (2 * DIMS)], const stream_pa
   return used < sp.minbits ? sp.minbits : used;
 }
 
+// Append form: the block's bits (exactly the returned count, padding and truncation included) go to a bit writer
+// the caller owns, behind whatever it already holds.  Used where one thread strings several small blocks
+// together (1D variable rate: a block is 16 bytes of data, so per-block bookkeeping would dominate).
+template <typename Scalar, int DIMS, class Writer>
+ZFB_HD unsigned encode_block_append(const Scalar (&f)[1 << (2 * DIMS)], const stream_params& sp, Writer& bw)
+{
+  typedef traits<Scalar> T;
+  typedef typename T::Int Int;
+  typedef typename T::UInt UInt;
+  constexpr int BS = 1 << (2 * DIMS);
+  const unsigned maxbits = sp.maxbits;
+  unsigned used = 0;
+  auto put = [&](uint64_t v, unsigned len) {  // never beyond the block's budget
+    const unsigned room = maxbits - used;
+    if (len > room) { v &= lowmask64(room); len = room; }
+    bw.put(v, len);
+    used += len;
+  };
+  auto pad = [&]() {
+    while (used < sp.minbits) {
+      const unsigned l = sp.minbits - used < 64u ? sp.minbits - used : 64u;
+      bw.put(0, l);
+      used += l;
+    }
+  };
+
+  Scalar mx = 0;
+  ZFB_UNROLL for (int i = 0; i < BS; i++) {
+    Scalar a = f[i] < 0 ? -f[i] : f[i];
+    mx = (mx < a) ? a : mx;
+  }
+  const int E = T::expfield(mx);
+  const int emax = E - (T::EBIAS - 1);
+  const int prec = block_precision<DIMS>(emax, sp);
+  if (!(mx > 0) || prec == 0) {
+    put(0, 1);
+    pad();
+    return used;
+  }
+  const int kmin = T::PBITS > prec ? T::PBITS - prec : 0;
+  Int ib[BS];
+  {
+    const int se = (T::PBITS - 2) - emax;
+    const Scalar s = T::pow2(se);
+    ZFB_UNROLL for (int i = 0; i < BS; i++) ib[i] = T::trunc_cast(s * f[i]);
+    if (se > T::EBIAS) { ZFB_UNROLL for (int i = 0; i < BS; i++) ib[i] = T::int_min(); }  // see encode_block
+  }
+  fwd_xform<Int, DIMS>(ib);
+  UInt u[BS];
+  ZFB_UNROLL for (int i = 0; i < BS; i++) u[i] = ((UInt)ib[order<DIMS>::at(i)] + T::NBMASK) ^ T::NBMASK;
+  planes<UInt, BS> P;
+  P.from_coeffs(u);
+  put(2 * (uint64_t)(E + 1) + 1, 1 + T::EBITS);
+  unsigned n = 0;
+  ZFB_ROLLED for (int k = T::PBITS - 1; k >= 0; k--) {
+    if (used >= maxbits || k < kmin) break;
+    uint64_t x = P.get(k);
+    put(x & lowmask64(n), n);
+    x = n < 64 ? x >> n : 0;
+    while (n < (unsigned)BS && used < maxbits) {
+      if (!x) { put(0, 1); break; }
+      const unsigned z = (unsigned)ctz64(x);
+      const unsigned one = (n + z < (unsigned)(BS - 1));
+      put((uint64_t)1 | ((uint64_t)one << (z + 1)), z + 1 + one);
+      x = (z + 1 < 64) ? x >> (z + 1) : 0;
+      n += z + 1;
+    }
+  }
+  pad();
+  return used;
+}
+
 // Fixed-rate form: exactly maxbits bits per block.
 template <typename Scalar, int DIMS, class Sink>
 ZFB_HD void encode_block(const Scalar (&f)[1 << (2 * DIMS)], unsigned maxbits, Sink& sink)

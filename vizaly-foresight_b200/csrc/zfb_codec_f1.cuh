@@ -391,5 +391,126 @@ ZFB_HD void decode_block(float (&f)[4], unsigned maxbits, const uint32_t (&in)[M
   ZFB_UNROLL for (int i = 0; i < 4; i++) f[i] = s * T::to_scalar(ib[i]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Variable rate (zfp fixed accuracy / precision, no bit budget in the way): one table step per bit plane.
+// Valid when sp.maxbits covers the longest codable block (1 + 8 + 3 + 4 * 32 = 140 bits) and sp.minbits <= 1,
+// which is what zfp_stream_set_accuracy / set_precision give; other parameter sets take the generic coder.
+// ---------------------------------------------------------------------------------------------
+ZFB_HD bool var_params_ok(const stream_params& sp) { return sp.maxbits >= 140u && sp.minbits <= 1u; }
+
+// Appends the block to the caller's bit writer (put(v, len) with len <= 64); returns its length in bits.
+template <class Writer>
+ZFB_HD unsigned encode_block_var(const float (&f)[4], const stream_params& sp, Writer& bw, const tables& tb)
+{
+  typedef traits<float> T;
+  float mx = 0.f;
+  ZFB_UNROLL for (int i = 0; i < 4; i++) {
+    const float a = f[i] < 0 ? -f[i] : f[i];
+    mx = (mx < a) ? a : mx;
+  }
+  const int E = T::expfield(mx);
+  const int emax = E - 126;
+  const int prec = block_precision<1>(emax, sp);
+  if (!(mx > 0.f) || prec == 0) { bw.put(0, 1); return 1u; }
+  const int kmin = prec < 32 ? 32 - prec : 0;
+  int32_t ib[4];
+  {
+    const int se = 30 - emax;
+    const float s = T::pow2(se);
+    ZFB_UNROLL for (int i = 0; i < 4; i++) ib[i] = T::trunc_cast(s * f[i]);
+    if (se > 127) { ZFB_UNROLL for (int i = 0; i < 4; i++) ib[i] = T::int_min(); }  // see zfb_codec.cuh
+  }
+  fwd_xform<int32_t, 1>(ib);
+  uint32_t u[4];
+  ZFB_UNROLL for (int i = 0; i < 4; i++) u[i] = ((uint32_t)ib[i] + T::NBMASK) ^ T::NBMASK;
+  bw.put(2u * (uint32_t)(E + 1) + 1u, 9);
+  unsigned used = 9;
+  int k = 31;
+  // planes above every coefficient's top bit: one zero test bit each
+  const uint32_t any = u[0] | u[1] | u[2] | u[3];
+  const int ktop = any ? 31 - clz32(any) : -1;
+  {
+    const int stop = ktop + 1 > kmin ? ktop + 1 : kmin;  // first plane that is not skipped
+    const unsigned z = (unsigned)(32 - stop);
+    if (z) { bw.put(0, z); used += z; k = stop - 1; }
+  }
+  // head: one table step per plane until all four coefficients are significant
+  unsigned n = 0;
+  ZFB_NOUNROLL for (; k >= kmin && n < 4u; k--) {
+    const unsigned x = ((u[0] >> k) & 1u) | (((u[1] >> k) & 1u) << 1) | (((u[2] >> k) & 1u) << 2) | (((u[3] >> k) & 1u) << 3);
+    const unsigned e = tb.enc[n * 16u + x];
+    const unsigned len = (e >> 8) & 15u;
+    n = e >> 12;
+    bw.put(e & 0xffu, len);
+    used += len;
+  }
+  // tail: every further plane is its four bits verbatim, i.e. the rest of the block is the 4-way bit interleave of
+  // the coefficients' bits k .. kmin, most significant first: 32 stream bits per step through the byte spread table
+  if (k >= kmin) {
+    const unsigned R = (unsigned)(k - kmin + 1);
+    uint32_t v[4];
+    ZFB_UNROLL for (int c = 0; c < 4; c++) v[c] = (brev32(u[c]) >> (31 - k)) & mask32(R);  // bit i = bit k - i of u[c]
+    ZFB_UNROLL for (unsigned w = 0; w < 4; w++) {
+      if (8u * w < R) {
+        const uint32_t t = tb.spread[(v[0] >> (8u * w)) & 0xffu] | (tb.spread[(v[1] >> (8u * w)) & 0xffu] << 1) |
+                           (tb.spread[(v[2] >> (8u * w)) & 0xffu] << 2) | (tb.spread[(v[3] >> (8u * w)) & 0xffu] << 3);
+        const unsigned left = 4u * R - 32u * w;
+        bw.put(t, left < 32u ? left : 32u);
+      }
+    }
+    used += 4u * R;
+  }
+  return used;
+}
+
+// Decodes the block that starts at the reader's position (an f3::reader32-like window: lo, consume(k), take(k));
+// returns its length in bits.
+template <class Reader>
+ZFB_HD unsigned decode_block_var(float (&f)[4], const stream_params& sp, Reader& r, const tables& tb)
+{
+  typedef traits<float> T;
+  const uint32_t head = r.lo;
+  if (!(head & 1u)) {
+    ZFB_UNROLL for (int i = 0; i < 4; i++) f[i] = 0.f;
+    r.consume(1);
+    return 1u;
+  }
+  const int emax = (int)((head >> 1) & 0xffu) - 127;
+  r.consume(9);
+  unsigned used = 9;
+  const int prec = block_precision<1>(emax, sp);
+  const int kmin = prec < 32 ? 32 - prec : 0;
+  uint32_t u[4] = {0u, 0u, 0u, 0u};
+  unsigned n = 0;
+  int k = 31;
+  ZFB_NOUNROLL for (; k >= kmin && n < 4u; k--) {  // head: one table step per plane
+    const unsigned e = tb.dec[n * 128u + (r.lo & 127u)];
+    const unsigned x = e & 15u, len = (e >> 4) & 15u;
+    n = e >> 8;
+    r.consume(len);
+    used += len;
+    u[0] |= (x & 1u) << k; u[1] |= ((x >> 1) & 1u) << k; u[2] |= ((x >> 2) & 1u) << k; u[3] |= (x >> 3) << k;
+  }
+  if (k >= kmin) {  // tail: de-interleave the remaining 4 R bits, 32 at a time
+    const unsigned R = (unsigned)(k - kmin + 1);
+    uint32_t v[4] = {0u, 0u, 0u, 0u};
+    ZFB_UNROLL for (unsigned w = 0; w < 4; w++) {
+      if (8u * w < R) {
+        const unsigned left = 4u * R - 32u * w;
+        const uint32_t t = r.take(left < 32u ? left : 32u);
+        ZFB_UNROLL for (int c = 0; c < 4; c++) v[c] |= gather4(t >> c) << (8u * w);
+      }
+    }
+    ZFB_UNROLL for (int c = 0; c < 4; c++) u[c] |= brev32(v[c]) >> (31 - k);
+    used += 4u * R;
+  }
+  int32_t ib[4];
+  ZFB_UNROLL for (int i = 0; i < 4; i++) ib[i] = (int32_t)((u[i] ^ T::NBMASK) - T::NBMASK);
+  inv_xform<int32_t, 1>(ib);
+  const float s = T::pow2(emax - 30);
+  ZFB_UNROLL for (int i = 0; i < 4; i++) f[i] = s * T::to_scalar(ib[i]);
+  return used;
+}
+
 }  // namespace f1
 }  // namespace zfb

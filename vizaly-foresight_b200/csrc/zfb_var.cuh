@@ -23,6 +23,13 @@ template <typename Scalar, int DIMS> struct var_caps {
   static constexpr unsigned WORDS = (BITS + 63u) / 64u + 1u;
 };
 
+// 1D: a block is four values, so one thread strings VAR1_GROUP consecutive blocks together and the index has one
+// entry per group (per-block lengths, offsets and boundary atomics would cost more than the data itself)
+constexpr unsigned VAR1_GROUP = 8;
+template <typename Scalar> struct var1_caps {
+  static constexpr unsigned WORDS = (VAR1_GROUP * var_caps<Scalar, 1>::BITS + 63u) / 64u + 1u;
+};
+
 // staging column of one block: word j of block b lives at stage[(b / 32) * 32 * WORDS + j * 32 + b % 32]
 // (a minbits floor above the longest codable block is padding only: the column holds `cap` words, the compaction
 // copies at most that many and the rest of the block stays zero in the pre-zeroed stream)
@@ -30,7 +37,11 @@ struct stage_col_sink {
   uint64_t* dst;
   unsigned widx, cap;
   ZFB_HD stage_col_sink(uint64_t* d, unsigned cap_words) : dst(d), widx(0), cap(cap_words) {}
-  ZFB_HD void word(uint64_t w) { dst[32u * widx++] = w; }
+  ZFB_HD void word(uint64_t w)
+  {
+    if (widx < cap) dst[32u * widx] = w;
+    widx++;
+  }
   ZFB_HD void finish() {}
   ZFB_HD void pad_to(unsigned bits) { while (64u * widx < bits && widx < cap) word(0); }
 };
@@ -120,6 +131,127 @@ __global__ void __launch_bounds__(128) enc_var_kernel(const Scalar* __restrict__
       lens[b] = encode_block<Scalar, DIMS>(f, sp, sink);
     }
   }
+}
+
+template <typename Scalar, int DIMS, bool METRICS>
+__device__ __forceinline__ void scatter_block(const Scalar (&f)[1 << (2 * DIMS)], Scalar* __restrict__ out,
+                                              const Scalar* __restrict__ orig, const geom& g, size_t x0, size_t y0,
+                                              size_t z0, unsigned mx, unsigned my, unsigned mz, macc_t<Scalar>& m);
+
+// 1D: one thread = one group of VAR1_GROUP blocks = one staging column = one index entry
+template <typename Scalar>
+__global__ void __launch_bounds__(128) enc_var1_kernel(const Scalar* __restrict__ in, uint64_t* __restrict__ stage,
+                                                       uint32_t* __restrict__ lens, geom g, stream_params sp)
+{
+  constexpr unsigned WORDS = var1_caps<Scalar>::WORDS;
+  constexpr bool F32 = sizeof(Scalar) == 4;
+  __shared__ coder1_smem cs;
+  f1::tables tb;
+  if (F32) tb = build_coder1_tables(cs);
+  const bool fast = F32 && f1::var_params_ok(sp);  // per-plane table coder (accuracy / precision modes)
+  const size_t ngroups = (g.nblocks + VAR1_GROUP - 1) / VAR1_GROUP;
+  const bool vec = (reinterpret_cast<size_t>(in) & 15) == 0;
+  for (size_t grp = (size_t)blockIdx.x * blockDim.x + threadIdx.x; grp < ngroups; grp += (size_t)gridDim.x * blockDim.x) {
+    stage_col_sink sink(stage + stage_base<WORDS>(grp), WORDS);
+    bit_writer<stage_col_sink> bw(sink);
+    unsigned total = 0;
+    for (unsigned q = 0; q < VAR1_GROUP; q++) {
+      const size_t b = grp * VAR1_GROUP + q;
+      if (b >= g.nblocks) break;
+      const size_t x0 = 4 * b;
+      Scalar f[4];
+      if (x0 + 4 <= g.nx && vec) {
+        if constexpr (sizeof(Scalar) == 4) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(in + x0));
+          f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+        } else {
+          const double2 v0 = __ldg(reinterpret_cast<const double2*>(in + x0));
+          const double2 v1 = __ldg(reinterpret_cast<const double2*>(in + x0 + 2));
+          f[0] = v0.x; f[1] = v0.y; f[2] = v1.x; f[3] = v1.y;
+        }
+      } else {
+        const unsigned mx = (unsigned)(g.nx - x0 < 4 ? g.nx - x0 : 4);
+#pragma unroll
+        for (int i = 0; i < 4; i++) f[i] = (unsigned)i < mx ? __ldg(in + x0 + i) : (Scalar)0;
+        if (mx < 4) pad_block<Scalar, 1>(f, mx, 1u, 1u);
+      }
+      if constexpr (F32) {
+        if (fast) { total += f1::encode_block_var(f, sp, bw, tb); continue; }
+      }
+      total += encode_block_append<Scalar, 1>(f, sp, bw);
+    }
+    bw.flush();
+    lens[grp] = total;
+  }
+}
+
+template <typename Scalar, bool METRICS>
+__global__ void __launch_bounds__(128) dec_var1_kernel(const uint64_t* __restrict__ stream, const uint64_t* __restrict__ offsets,
+                                                       Scalar* __restrict__ out, const Scalar* __restrict__ orig, geom g,
+                                                       stream_params sp, double* __restrict__ part)
+{
+  __shared__ double red[7 * 4];
+  constexpr bool F32 = sizeof(Scalar) == 4;
+  __shared__ coder1_smem cs;
+  f1::tables tb;
+  if (F32) tb = build_coder1_tables(cs);
+  const bool fast = F32 && f1::var_params_ok(sp);
+  macc_t<Scalar> m;
+  m.init();
+  const size_t ngroups = (g.nblocks + VAR1_GROUP - 1) / VAR1_GROUP;
+  const bool vec = ((reinterpret_cast<size_t>(out) & 15) == 0) && (!METRICS || (reinterpret_cast<size_t>(orig) & 15) == 0);
+  for (size_t grp = (size_t)blockIdx.x * blockDim.x + threadIdx.x; grp < ngroups; grp += (size_t)gridDim.x * blockDim.x) {
+    uint64_t pos = offsets[grp];
+    for (unsigned q = 0; q < VAR1_GROUP; q++) {
+      const size_t b = grp * VAR1_GROUP + q;
+      if (b >= g.nblocks) break;
+      Scalar f[4];
+      bool done = false;
+      if constexpr (F32) {
+        if (fast) {
+          const size_t v0 = (size_t)(pos >> 5);
+          const size_t left32 = 2 * g.stream_words > v0 ? 2 * g.stream_words - v0 : 0;
+          f3::reader32 r(reinterpret_cast<const uint32_t*>(stream) + v0, left32 > 0xffffffffull ? 0xffffffffu : (unsigned)left32,
+                         (unsigned)(pos & 31));
+          pos += f1::decode_block_var(f, sp, r, tb);
+          done = true;
+        }
+      }
+      if (!done) {
+        const size_t w0 = (size_t)(pos >> 6);
+        const size_t left = g.stream_words > w0 ? g.stream_words - w0 : 0;
+        slot_reader r(stream + w0, left > 0xffffffffull ? 0xffffffffu : (unsigned)left, (unsigned)(pos & 63));
+        pos += decode_block<Scalar, 1, false>(f, sp, r);
+      }
+      const size_t x0 = 4 * b;
+      if (x0 + 4 <= g.nx && vec) {
+        if constexpr (sizeof(Scalar) == 4) {
+          float4 v;
+          v.x = f[0]; v.y = f[1]; v.z = f[2]; v.w = f[3];
+          if (METRICS) {
+            frow fr;
+            fr.init();
+            fr.add4(__ldg(reinterpret_cast<const float4*>(orig + x0)), v.x, v.y, v.z, v.w);
+            fr.flush(m);
+          }
+          *reinterpret_cast<float4*>(out + x0) = v;
+        } else {
+          if (METRICS) {
+            const double2 o0 = __ldg(reinterpret_cast<const double2*>(orig + x0));
+            const double2 o1 = __ldg(reinterpret_cast<const double2*>(orig + x0 + 2));
+            macc_add(m, o0.x, (double)f[0]); macc_add(m, o0.y, (double)f[1]);
+            macc_add(m, o1.x, (double)f[2]); macc_add(m, o1.y, (double)f[3]);
+          }
+          *reinterpret_cast<double2*>(out + x0) = make_double2((double)f[0], (double)f[1]);
+          *reinterpret_cast<double2*>(out + x0 + 2) = make_double2((double)f[2], (double)f[3]);
+        }
+      } else {
+        const unsigned mx = (unsigned)(g.nx - x0 < 4 ? g.nx - x0 : 4);
+        scatter_block<Scalar, 1, METRICS>(f, out, orig, g, x0, 0, 0, mx, 1u, 1u, m);
+      }
+    }
+  }
+  if (METRICS) macc_block_store(m, red, part + (size_t)blockIdx.x * PART_STRIDE);
 }
 
 // ---- step 2: exclusive scan of the lengths (three small kernels, fixed order, no atomics) ----------
@@ -417,16 +549,17 @@ __global__ void index_var_kernel(const uint64_t* __restrict__ stream, size_t str
 {
   if (blockIdx.x || threadIdx.x) return;
   constexpr int BS = 1 << (2 * DIMS);
+  constexpr size_t UNIT = DIMS == 1 ? VAR1_GROUP : 1;  // blocks per index entry
   uint64_t pos = 0;
   Scalar f[BS];
   for (size_t b = 0; b < nblocks; b++) {
-    offsets[b] = pos;
+    if (b % UNIT == 0) offsets[b / UNIT] = pos;
     const size_t w0 = (size_t)(pos >> 6);
     const size_t left = stream_words > w0 ? stream_words - w0 : 0;
     slot_reader r(stream + w0, left > 0xffffffffull ? 0xffffffffu : (unsigned)left, (unsigned)(pos & 63));
     pos += decode_block<Scalar, DIMS, true>(f, sp, r);
   }
-  offsets[nblocks] = pos;
+  offsets[(nblocks + UNIT - 1) / UNIT] = pos;
 }
 
 }  // namespace zfb
