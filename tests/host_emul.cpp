@@ -206,7 +206,7 @@ static size_t run_var(bool enc, size_t nx, size_t ny, size_t nz, const stream_pa
         for (unsigned j = 0; j < my; j++)
           for (unsigned i = 0; i < mx; i++) f[16 * k + 4 * j + i] = data[(x0 + i) + nx * ((y0 + j) + ny * (z0 + k))];
       if (mx < 4 || my < (DIMS >= 2 ? 4u : 1u) || mz < (DIMS >= 3 ? 4u : 1u)) pad_block<Scalar, DIMS>(f, mx, my, mz);
-      uint64_t stage[80];
+      uint64_t stage[96];
       std::memset(stage, 0xff, sizeof stage);  // garbage behind the written words must not leak into the stream
       unsigned bits = 0;
       bool done = false;
@@ -218,6 +218,17 @@ static size_t run_var(bool enc, size_t nx, size_t ny, size_t nz, const stream_pa
           ps.p = rows; ps.stride = 1;
           f3::sink32 sink(reinterpret_cast<uint32_t*>(stage), 160);
           bits = f3::encode_block(f, sp, sink, tb, ps);
+          done = true;
+        }
+      }
+      if constexpr (std::is_same<Scalar, double>::value && DIMS == 3) {
+        if (g_use_f3) {  // the double/3D table coder, as enc_var_f64_kernel uses it
+          const f3::tables tb = host_tables();
+          f3::u32x4 rows[32];
+          f3::plane_rows ps;
+          ps.p = rows; ps.stride = 1;
+          f3::sink32 sink(reinterpret_cast<uint32_t*>(stage), 160);
+          bits = d3::encode_block(f, sp, sink, tb, ps);
           done = true;
         }
       }
@@ -268,6 +279,18 @@ static size_t run_var(bool enc, size_t nx, size_t ny, size_t nz, const stream_pa
       const unsigned bits = decode_block<Scalar, DIMS, false>(f, sp, r);
       const unsigned bits2 = decode_block<Scalar, DIMS, true>(dummy, sp, r2);  // index walk must agree
       if (bits != bits2) return 0;
+      if constexpr (std::is_same<Scalar, double>::value && DIMS == 3) {
+        if (g_use_f3) {  // the double/3D table decoder must reproduce the generic one bit for bit
+          const f3::tables tb = host_tables();
+          const uint32_t* s32 = reinterpret_cast<const uint32_t*>(stream);
+          f3::reader32 r3(s32 + (pos >> 5), (unsigned)(2 * stream_words - (pos >> 5)), (unsigned)(pos & 31));
+          f3::u32x4 rows[32];
+          f3::plane_rows ps;
+          ps.p = rows; ps.stride = 1;
+          d3::decode_block(f2, sp, r3, tb, ps);
+          if (std::memcmp(f, f2, sizeof f2)) return 0;
+        }
+      }
       if constexpr (std::is_same<Scalar, float>::value && DIMS == 1) {
         if (g_use_f3 && f1::var_params_ok(sp)) {  // the float/1D table decoder must reproduce the generic one
           const f1::tables tb = host_tables1();

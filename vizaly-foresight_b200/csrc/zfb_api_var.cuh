@@ -118,7 +118,10 @@ static int launch_enc_var(zfb_ctx* c, int dims, const geom& g, const stream_para
   const Scalar* in = (const Scalar*)d_in;
   if (dims == 1) enc_var1_kernel<Scalar><<<grid, 128, 0, c->stream>>>(in, stage, lens, g, sp);
   else if (dims == 2) enc_var_kernel<Scalar, 2><<<grid, 128, 0, c->stream>>>(in, stage, lens, g, sp);
-  else enc_var_kernel<Scalar, 3><<<grid, 128, 0, c->stream>>>(in, stage, lens, g, sp);
+  else if constexpr (sizeof(Scalar) == 8) {
+    const size_t want = (g.nblocks + VAR64_THREADS - 1) / VAR64_THREADS, cap = (size_t)c->sm_count * 32;
+    enc_var_f64_kernel<<<(unsigned)(want < cap ? (want ? want : 1) : cap), VAR64_THREADS, 0, c->stream>>>((const double*)d_in, stage, lens, g, sp);
+  } else enc_var_kernel<Scalar, 3><<<grid, 128, 0, c->stream>>>(in, stage, lens, g, sp);
   c->launches++;
   CU_TRY(c, cudaGetLastError());
   return ZFB_OK;
@@ -130,7 +133,7 @@ static int launch_compact_var(zfb_ctx* c, int dims, const geom& g, const uint64_
 {
   const size_t units = (g.nblocks + index_unit(dims) - 1) / index_unit(dims);
   const int grid = var_grid(c, units);
-  constexpr bool COL32 = sizeof(Scalar) == 4;  // float/3D is staged by the 32-bit table coder
+  constexpr bool COL32 = true;  // 3D blocks are staged by the 32-bit table coders
   if (dims == 1) compact_var_kernel<var1_caps<Scalar>::WORDS, false><<<grid, 128, 0, c->stream>>>(stage, index, units, stream, cap_words);
   else if (dims == 2) compact_var_kernel<var_caps<Scalar, 2>::WORDS, false><<<grid, 128, 0, c->stream>>>(stage, index, units, stream, cap_words);
   else compact_var_kernel<var_caps<Scalar, 3>::WORDS, COL32><<<grid, 128, 0, c->stream>>>(stage, index, units, stream, cap_words);
@@ -262,6 +265,14 @@ extern "C" int zfb_decode_var_dev(zfb_ctx* c, int dtype, int dims, size_t nx, si
   }
   int rows = 0;
   const bool metrics = d_orig != nullptr;
+  if (dtype == ZFB_DOUBLE && dims == 3 && (!metrics || ((((uintptr_t)d_orig | (uintptr_t)d_out) & 15) == 0))) {
+    const size_t want = (g.nblocks + VAR64_THREADS - 1) / VAR64_THREADS, cap = (size_t)c->sm_count * 32;
+    dec_var_f64_kernel<<<(unsigned)(want < cap ? (want ? want : 1) : cap), VAR64_THREADS, 0, c->stream>>>(
+        (const uint64_t*)d_stream, index, (double*)d_out, g, sp);
+    c->launches++;
+    CU_TRY(c, cudaGetLastError());
+    return metrics ? zfb_metrics_dev(c, dtype, d_orig, d_out, g.nx * g.ny * g.nz) : ZFB_OK;
+  }
   if (dtype == ZFB_FLOAT) {
     rc = metrics ? launch_dec_var<float, true>(c, dims, g, sp, d_stream, index, d_out, d_orig, &rows)
                  : launch_dec_var<float, false>(c, dims, g, sp, d_stream, index, d_out, d_orig, &rows);

@@ -18,17 +18,12 @@ using f3::planes64;
 using f3::tables;
 using f3::u32x4;
 
-ZFB_HD int kmin_of(int emax)  // 64 - precision(emax, 64, -1074, 3)
-{
-  int prec = emax + 1074 + 8;
-  prec = prec > 64 ? 64 : (prec < 0 ? 0 : prec);
-  return 64 - prec;
-}
-
+// General form (zfp_stream's minbits / maxbits / maxprec / minexp): returns the bits the block occupies.
 template <class Sink, class PR>
-ZFB_HD void encode_block(const double (&f)[64], unsigned maxbits, Sink& sink, const tables& tb, const PR& ps)
+ZFB_HD unsigned encode_block(const double (&f)[64], const stream_params& sp, Sink& sink, const tables& tb, const PR& ps)
 {
   typedef traits<double> T;
+  const unsigned maxbits = sp.maxbits;
   double mx = 0.0;
   ZFB_UNROLL for (int i = 0; i < 64; i++) {
 #if defined(__CUDA_ARCH__)
@@ -38,10 +33,16 @@ ZFB_HD void encode_block(const double (&f)[64], unsigned maxbits, Sink& sink, co
     mx = (mx < a) ? a : mx;
 #endif
   }
-  if (!(mx > 0.0)) { sink.finish(); return; }
   const int E = T::expfield(mx);
   const int emax = E - 1022;
-  const int kmin = kmin_of(emax);
+  const int prec = block_precision<3>(emax, sp);
+  if (!(mx > 0.0) || prec == 0) {  // all zero, or nothing above the accuracy floor: a single 0 bit
+    sink.word(0u);
+    sink.finish();
+    sink.pad_to(sp.minbits);
+    return sp.minbits > 1u ? sp.minbits : 1u;
+  }
+  const int kmin = 64 - prec;
 
   planes64 PH, PL;  // upper / lower words of the negabinary coefficients in sequency order
   {
@@ -68,13 +69,23 @@ ZFB_HD void encode_block(const double (&f)[64], unsigned maxbits, Sink& sink, co
     v.x = PH.a[2 * r]; v.y = PH.b[2 * r]; v.z = PH.a[2 * r + 1]; v.w = PH.b[2 * r + 1];
     ps.st(16 + r, v);
   }
-  f3::encode_planes<64>(ps, maxbits, 2u * (uint32_t)(E + 1) + 1u, 12u, kmin, sink, tb);
+  unsigned used = f3::encode_planes<64>(ps, maxbits, 2u * (uint32_t)(E + 1) + 1u, 12u, kmin, sink, tb);
+  used = used < maxbits ? used : maxbits;
+  sink.pad_to(sp.minbits);
+  return used < sp.minbits ? sp.minbits : used;
+}
+
+// Fixed-rate form.
+template <class Sink, class PR>
+ZFB_HD void encode_block(const double (&f)[64], unsigned maxbits, Sink& sink, const tables& tb, const PR& ps)
+{
+  encode_block(f, fixed_rate_params(maxbits), sink, tb, ps);
 }
 
 // Phase 1: parse the slot; planes come back in PH (63..32) and PL (31..0).  kend = first plane not decoded.
 template <class Reader, class PR>
-ZFB_HD bool decode_planes(planes64& PH, planes64& PL, int& emax, int& kend, unsigned maxbits, Reader& r, const tables& tb,
-                          const PR& ps)
+ZFB_HD bool decode_planes(planes64& PH, planes64& PL, int& emax, int& kend, const stream_params& sp, Reader& r,
+                          const tables& tb, const PR& ps)
 {
   const uint32_t head = r.lo;
   emax = 0;
@@ -82,7 +93,7 @@ ZFB_HD bool decode_planes(planes64& PH, planes64& PL, int& emax, int& kend, unsi
   if (!(head & 1u)) return false;
   emax = (int)((head >> 1) & 0x7ffu) - 1023;
   r.consume(12);
-  kend = f3::parse_planes<64>(ps, maxbits, 12u, kmin_of(emax), r, tb);
+  kend = f3::parse_planes<64>(ps, sp.maxbits, 12u, 64 - block_precision<3>(emax, sp), r, tb);
   ZFB_UNROLL for (int q = 0; q < 16; q++) {
     u32x4 v = ps.ld(q);
     PL.a[2 * q] = v.x; PL.b[2 * q] = v.y; PL.a[2 * q + 1] = v.z; PL.b[2 * q + 1] = v.w;
@@ -90,6 +101,13 @@ ZFB_HD bool decode_planes(planes64& PH, planes64& PL, int& emax, int& kend, unsi
     PH.a[2 * q] = v.x; PH.b[2 * q] = v.y; PH.a[2 * q + 1] = v.z; PH.b[2 * q + 1] = v.w;
   }
   return true;
+}
+
+template <class Reader, class PR>
+ZFB_HD bool decode_planes(planes64& PH, planes64& PL, int& emax, int& kend, unsigned maxbits, Reader& r, const tables& tb,
+                          const PR& ps)
+{
+  return decode_planes(PH, PL, emax, kend, fixed_rate_params(maxbits), r, tb, ps);
 }
 
 // Phase 2: planes -> coefficients -> inverse transform -> doubles.
@@ -119,12 +137,18 @@ ZFB_HD void decode_finish(double (&f)[64], planes64& PH, planes64& PL, int emax,
 }
 
 template <class Reader, class PR>
-ZFB_HD void decode_block(double (&f)[64], unsigned maxbits, Reader& r, const tables& tb, const PR& ps)
+ZFB_HD void decode_block(double (&f)[64], const stream_params& sp, Reader& r, const tables& tb, const PR& ps)
 {
   planes64 PH, PL;
   int emax, kend;
-  const bool nonzero = decode_planes(PH, PL, emax, kend, maxbits, r, tb, ps);
+  const bool nonzero = decode_planes(PH, PL, emax, kend, sp, r, tb, ps);
   decode_finish(f, PH, PL, emax, nonzero, kend);
+}
+
+template <class Reader, class PR>
+ZFB_HD void decode_block(double (&f)[64], unsigned maxbits, Reader& r, const tables& tb, const PR& ps)
+{
+  decode_block(f, fixed_rate_params(maxbits), r, tb, ps);
 }
 
 }  // namespace d3

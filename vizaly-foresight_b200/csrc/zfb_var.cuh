@@ -542,6 +542,58 @@ __global__ void __launch_bounds__(128, 4) dec_var_f32_kernel(const uint64_t* __r
   if (METRICS) macc_block_store(m, red, part + (size_t)blockIdx.x * PART_STRIDE);
 }
 
+// double / 3D: the table coder with 64 planes parked in shared memory (32 rows x 16 bytes per block, so 64 threads
+// per CTA).  Decode leaves the metrics to the streaming pass (zfb_api_var.cuh), as the fixed-rate double path does.
+constexpr int VAR64_THREADS = 64;
+
+__global__ void __launch_bounds__(VAR64_THREADS) enc_var_f64_kernel(const double* __restrict__ in, uint64_t* __restrict__ stage,
+                                                                    uint32_t* __restrict__ lens, geom g, stream_params sp)
+{
+  constexpr unsigned WORDS = var_caps<double, 3>::WORDS;
+  __shared__ coder_smem cs;
+  __shared__ f3::u32x4 rows[32 * VAR64_THREADS];
+  const f3::tables tb = build_coder_tables(cs);
+  f3::plane_rows ps;
+  ps.p = rows + threadIdx.x;
+  ps.stride = VAR64_THREADS;
+  for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < g.nblocks; b += (size_t)gridDim.x * blockDim.x) {
+    double f[64];
+    gather_block<double, 3>(in, g, b, f);
+    stage_col_sink32 sink(reinterpret_cast<uint32_t*>(stage) + 2 * ((b >> 5) * (size_t)(32u * WORDS)) + (b & 31u), 2u * WORDS);
+    lens[b] = d3::encode_block(f, sp, sink, tb, ps);
+  }
+}
+
+__global__ void __launch_bounds__(VAR64_THREADS) dec_var_f64_kernel(const uint64_t* __restrict__ stream,
+                                                                    const uint64_t* __restrict__ offsets, double* __restrict__ out,
+                                                                    geom g, stream_params sp)
+{
+  __shared__ coder_smem cs;
+  __shared__ f3::u32x4 rows[32 * VAR64_THREADS];
+  const f3::tables tb = build_coder_tables(cs);
+  f3::plane_rows ps;
+  ps.p = rows + threadIdx.x;
+  ps.stride = VAR64_THREADS;
+  macc m;  // unused (METRICS = false), scatter_block's signature
+  m.init();
+  const uint32_t* s32 = reinterpret_cast<const uint32_t*>(stream);
+  const size_t total32 = 2 * g.stream_words;
+  for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < g.nblocks; b += (size_t)gridDim.x * blockDim.x) {
+    const size_t ix = b % g.bx, iy = (b / g.bx) % g.by, iz = b / (g.bx * g.by);
+    const size_t x0 = 4 * ix, y0 = 4 * iy, z0 = 4 * iz;
+    const unsigned mx = (unsigned)(g.nx - x0 < 4 ? g.nx - x0 : 4);
+    const unsigned my = (unsigned)(g.ny - y0 < 4 ? g.ny - y0 : 4);
+    const unsigned mz = (unsigned)(g.nz - z0 < 4 ? g.nz - z0 : 4);
+    const uint64_t startbit = offsets[b];
+    const size_t v0 = (size_t)(startbit >> 5);
+    const size_t left32 = total32 > v0 ? total32 - v0 : 0;
+    f3::reader32 r(s32 + v0, left32 > 0xffffffffull ? 0xffffffffu : (unsigned)left32, (unsigned)(startbit & 31));
+    double f[64];
+    d3::decode_block(f, sp, r, tb, ps);
+    scatter_block<double, 3, false>(f, out, nullptr, g, x0, y0, z0, mx, my, mz, m);
+  }
+}
+
 // ---- index rebuild: walk a bare stream block by block (one thread; the format is strictly sequential) ----
 template <typename Scalar, int DIMS>
 __global__ void index_var_kernel(const uint64_t* __restrict__ stream, size_t stream_words, size_t nblocks, stream_params sp,
