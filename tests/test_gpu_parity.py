@@ -199,6 +199,48 @@ def test_histograms_match_oracle(codec, pkg, oracle):
     assert int(oob.item()) == m["minmax_oob"]
 
 
+def test_histogram_bin_edges_are_exact(codec):
+    """Values on and next to bin edges: the reciprocal estimate in hist_kernel must fall back to the reference's
+    exact double division wherever a few ulp could move a value across an edge (absoluteError.hpp:119-121,
+    minmaxMetric.hpp:112)."""
+    torch = _torch()
+    rng = np.random.default_rng(3)
+    for hi in (1.0, 0.3, 7.123456789, 1e-3, 123456.0):
+        binw = hi / 1024.0
+        j = rng.integers(0, 1025, size=60000)
+        base = (j * binw).astype(np.float32)
+        err = np.concatenate([base, np.nextafter(base, np.float32(0)), np.nextafter(base, np.float32(np.inf)),
+                              (rng.random(60000) * hi).astype(np.float32), np.zeros(1000, np.float32),
+                              np.full(1000, hi, np.float32)]).astype(np.float32)
+        err = err[(err >= 0)]
+        # which = 0: |o - a| with a = 0 is exactly err
+        q = err.astype(np.float64) / binw
+        pos = q.astype(np.int64)
+        bad = (q >= 1025.0) | ((pos - (pos >= 1024)) >= 1024)
+        pos = np.where(pos >= 1024, pos - 1, pos)
+        pos = np.where(pos >= 1024, 1023, pos)
+        want = np.bincount(pos, minlength=1024)
+        d_o = torch.from_numpy(err).cuda()
+        d_a = torch.zeros_like(d_o)
+        cnt, oob = codec.histogram(0, 0.0, hi, d_o, d_a)
+        assert np.array_equal(cnt.cpu().numpy().astype(np.int64), want), hi
+        assert int(oob.item()) == int(bad.sum()), hi
+        # which = 2: values over [lo, hi]
+        lo = -0.25 * hi
+        v = (err.astype(np.float64) * 1.25 + lo).astype(np.float32)
+        rng_ = hi - lo
+        q = (rng_ * ((v.astype(np.float64) - lo) / rng_)) / (rng_ / 1024.0)
+        ok = q >= 0
+        pos = np.where(ok, q, 0).astype(np.int64)
+        over = ok & (q >= 1025.0)
+        pos = np.where(over, 1023, pos)
+        pos = np.where(~over & (pos >= 1024), pos - 1, pos)
+        pos = np.where(pos >= 1024, 1023, pos)
+        want = np.bincount(pos, minlength=1024)
+        cnt, oob = codec.histogram(2, lo, hi, None, torch.from_numpy(v).cuda())
+        assert np.array_equal(cnt.cpu().numpy().astype(np.int64), want), ("minmax", hi)
+
+
 def test_generic_and_tile_paths_agree(pkg, oracle):
     """ZFB_FORCE_GENERIC=1 routes a tile-eligible field through the generic kernels: same bits."""
     torch = _torch()

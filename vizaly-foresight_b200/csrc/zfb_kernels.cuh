@@ -1017,6 +1017,47 @@ __global__ void __launch_bounds__(256) metrics_kernel(const Scalar* __restrict__
 // which: 0 abs error, 1 rel error, 2 approx value.  Binning follows the reference expression by
 // expression (double arithmetic, int truncation, `if (pos >= numBins) pos = pos - 1`), with out-of-range
 // positions clamped and counted instead of indexing out of bounds.
+// One value -> its bin, exactly as the reference computes it (counts out-of-range values in `bad`).
+template <typename Scalar>
+__device__ __forceinline__ int hist_bin(int which, Scalar ov, Scalar av, double lo, double range, double bin, double rbin,
+                                        double rrange, unsigned int* bad)
+{
+  // The reference divides in double and truncates.  An IEEE division is ~40 instructions, so the quotient is first
+  // estimated with reciprocal multiplies (a few ulp off); only when the estimate lies within 1e-9 (relative) of an
+  // integer -- where a few ulp could change the truncation -- is the reference's exact expression evaluated.
+  double q;
+  if (which == 2) {
+    const double v = (double)av;
+    q = (range * ((v - lo) * rrange)) * rbin;
+    const double k = rint(q);
+    if (fabs(q - k) <= 1e-9 * (k + 1.0)) q = (range * ((v - lo) / range)) / bin;  // minmaxMetric.hpp:112
+  } else {
+    double err;
+    if constexpr (sizeof(Scalar) == 4) {
+      const float o = ov, a = av;
+      const float ad = fabsf(o - a);
+      if (which == 0) err = (double)ad;                                                    // absoluteError.hpp:119
+      else err = (double)(fabsf(o) < 1.0f ? ad : (float)((double)ad / (double)fabsf(o)));  // relativeError.hpp:131
+    } else {
+      const double o = (double)ov, a = (double)av;
+      const double ad = fabs(o - a);
+      err = (which == 0 || fabs(o) < 1.0) ? ad : ad / fabs(o);
+    }
+    q = err * rbin;
+    const double k = rint(q);
+    if (fabs(q - k) <= 1e-9 * (k + 1.0)) q = err / bin;  // absoluteError.hpp:119-121, relativeError.hpp:131-133
+  }
+  int pos;
+  if (!(q >= 0.0)) { pos = 0; atomicAdd(bad, 1u); }
+  else if (q >= 1025.0) { pos = 1023; atomicAdd(bad, 1u); }
+  else {
+    pos = (int)q;
+    if (pos >= 1024) pos = pos - 1;
+    if (pos >= 1024) { pos = 1023; atomicAdd(bad, 1u); }
+  }
+  return pos;
+}
+
 template <typename Scalar>
 __global__ void __launch_bounds__(256) hist_kernel(int which, double lo, double hi, const Scalar* __restrict__ orig,
                                                    const Scalar* __restrict__ approx, size_t n,
@@ -1030,35 +1071,34 @@ __global__ void __launch_bounds__(256) hist_kernel(int which, double lo, double 
   __syncthreads();
   const double range = hi - lo;
   const double bin = range / 1024.0;
+  const double rbin = 1.0 / bin, rrange = 1.0 / range;
   // a CTA handles at most 2^31 values between flushes, so 32-bit shared counters cannot overflow
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    double q;
-    if (which == 2) {
-      const double v = (double)approx[i];
-      q = (range * ((v - lo) / range)) / bin;  // minmaxMetric.hpp:112
-    } else {
-      double err;
-      if constexpr (sizeof(Scalar) == 4) {
-        const float o = orig[i], a = approx[i];
-        const float ad = fabsf(o - a);
-        if (which == 0) err = (double)ad;                                                    // absoluteError.hpp:119
-        else err = (double)(fabsf(o) < 1.0f ? ad : (float)((double)ad / (double)fabsf(o)));  // relativeError.hpp:131
-      } else {
-        const double o = (double)orig[i], a = (double)approx[i];
-        const double ad = fabs(o - a);
-        err = (which == 0 || fabs(o) < 1.0) ? ad : ad / fabs(o);
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  size_t done = 0;
+  if constexpr (sizeof(Scalar) == 4) {
+    // 16-byte loads, four values per thread and step (the loop is otherwise latency bound on 4-byte loads)
+    const bool vec = ((reinterpret_cast<size_t>(approx) | (which == 2 ? 0 : reinterpret_cast<size_t>(orig))) & 15) == 0;
+    if (vec) {
+      const size_t n4 = n / 4;
+      const float4* o4 = reinterpret_cast<const float4*>(orig);
+      const float4* a4 = reinterpret_cast<const float4*>(approx);
+      for (size_t i = tid; i < n4; i += stride) {
+        const float4 a = __ldcs(a4 + i);
+        float4 o = a;
+        if (which != 2) o = __ldcs(o4 + i);
+        const int p0 = hist_bin<float>(which, o.x, a.x, lo, range, bin, rbin, rrange, &bad);
+        const int p1 = hist_bin<float>(which, o.y, a.y, lo, range, bin, rbin, rrange, &bad);
+        const int p2 = hist_bin<float>(which, o.z, a.z, lo, range, bin, rbin, rrange, &bad);
+        const int p3 = hist_bin<float>(which, o.w, a.w, lo, range, bin, rbin, rrange, &bad);
+        atomicAdd(&h[p0], 1u); atomicAdd(&h[p1], 1u); atomicAdd(&h[p2], 1u); atomicAdd(&h[p3], 1u);
       }
-      q = err / bin;
+      done = n4 * 4;
     }
-    int pos;
-    if (!(q >= 0.0)) { pos = 0; atomicAdd(&bad, 1u); }
-    else if (q >= 1025.0) { pos = 1023; atomicAdd(&bad, 1u); }
-    else {
-      pos = (int)q;
-      if (pos >= 1024) pos = pos - 1;
-      if (pos >= 1024) { pos = 1023; atomicAdd(&bad, 1u); }
-    }
-    atomicAdd(&h[pos], 1u);
+  }
+  for (size_t i = done + tid; i < n; i += stride) {
+    const Scalar a = approx[i];
+    const Scalar o = which == 2 ? a : orig[i];
+    atomicAdd(&h[hist_bin<Scalar>(which, o, a, lo, range, bin, rbin, rrange, &bad)], 1u);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 1024; i += blockDim.x)
