@@ -986,10 +986,16 @@ __global__ void __launch_bounds__(256) metrics_kernel(const Scalar* __restrict__
     frow fr;
     fr.init();
     int cnt = 0;
-    for (; i < n4; i += stride) {
+    for (; i + stride < n4; i += 2 * stride) {  // two independent 16-byte pairs in flight
+      const float4 o0 = __ldcs(o4 + i), a0 = __ldcs(a4 + i);
+      const float4 o1 = __ldcs(o4 + i + stride), a1 = __ldcs(a4 + i + stride);
+      fr.add4(o0, a0.x, a0.y, a0.z, a0.w);
+      fr.add4(o1, a1.x, a1.y, a1.z, a1.w);
+      if (++cnt == 2) { fr.flush(m); cnt = 0; }
+    }
+    if (i < n4) {
       const float4 o = __ldcs(o4 + i), a = __ldcs(a4 + i);
       fr.add4(o, a.x, a.y, a.z, a.w);
-      if (++cnt == 4) { fr.flush(m); cnt = 0; }
     }
     const size_t tail = n4 * 4 + ((size_t)blockIdx.x * blockDim.x + threadIdx.x);
     if (tail < n) fr.add(orig[tail], approx[tail]);
