@@ -193,3 +193,33 @@ def test_expert_parameters_and_fixed_rate_through_the_general_path(codec, pkg, o
         codec.encode_var(d_f, pkg.Mode(9000, 300, 64, -1074))
     with pytest.raises(pkg.ZfbError):  # 1D float: padding floor above the 140-bit block bound
         codec.encode_var(torch.zeros(64, device="cuda"), pkg.Mode(200, 200, 9, -5))
+
+
+def test_variable_rate_extreme_values(codec, pkg, oracle):
+    """Denormals, values around the float range limits, mixed magnitudes, negative-only and all-zero fields in the
+    accuracy / precision modes, float and double, 1D and 3D."""
+    torch = _torch()
+    rng = np.random.default_rng(3)
+    cases = {
+        "zeros": np.zeros((8, 8, 8), np.float32),
+        "tiny": (rng.standard_normal((8, 8, 8)) * 1e-35).astype(np.float32),
+        "denorm": (rng.standard_normal((8, 8, 8)) * 1e-42).astype(np.float32),
+        "huge": (rng.standard_normal((8, 8, 8)) * 1e37).astype(np.float32),
+        "mixed": (rng.standard_normal((8, 8, 8)) * 10.0 ** rng.integers(-30, 30, (8, 8, 8))).astype(np.float32),
+        "neg": -np.abs(rng.standard_normal((8, 8, 8))).astype(np.float32),
+        "line": (rng.standard_normal(4099) * 10.0 ** rng.integers(-20, 20, 4099)).astype(np.float32),
+        "dmixed": rng.standard_normal((6, 8, 12)) * 10.0 ** rng.integers(-200, 200, (6, 8, 12)),
+        "ddenorm": rng.standard_normal((4, 8, 8)) * 1e-310,
+    }
+    for label, f in cases.items():
+        d_f = torch.from_numpy(f).cuda()
+        tdt = torch.float32 if f.dtype == np.float32 else torch.float64
+        for m, p in ((pkg.mode_accuracy(1e-3), oracle.params_accuracy(1e-3)), (pkg.mode_accuracy(1e-40), oracle.params_accuracy(1e-40)),
+                     (pkg.mode_accuracy(1e30), oracle.params_accuracy(1e30)), (pkg.mode_precision(11), oracle.params_precision(11)),
+                     (pkg.mode_precision(64), oracle.params_precision(64))):
+            s_ref = oracle.compress_ex(f, p)
+            g_ref, _ = oracle.decompress_ex(s_ref, f.shape, f.dtype, p)
+            s, _ = codec.encode_var(d_f, m)
+            assert np.array_equal(s.cpu().numpy(), s_ref), (label, m.as_tuple())
+            out = codec.decode_var(s, f.shape, tdt, m)
+            assert np.array_equal(out.cpu().numpy().view(np.uint8), g_ref.view(np.uint8)), (label, m.as_tuple())
