@@ -13,8 +13,11 @@
 //     are conflict-free 128-bit LDS; compressed slots of a tile are contiguous in the stream and move
 //     with one bulk copy (cp.async.bulk) in each direction; decoded rows leave as coalesced 128-bit
 //     stores (a warp writes 512 contiguous bytes per row).
-//   * generic kernels (1D, 2D, partial blocks, unaligned slots, double): same codec, direct global
-//     access; 1D full blocks use one 128-bit load per block.
+//   * enc3/dec3 f64 tile kernels: the same design with 64 threads and one 32 KiB box per CTA (a block of
+//     doubles needs ~128 registers for its values alone); metrics run as the streaming pass by default.
+//   * enc1/dec1 kernels (1D float, HACC): one 4-value block per thread, one 128-bit load / store per block.
+//   * generic kernels (2D, partial blocks, unaligned slots, anything else): same codec, direct global access.
+//   * variable-rate kernels (fixed accuracy / precision): zfb_var.cuh.
 // Metric partials: per-thread -> warp shuffle -> CTA -> one row of `part` per CTA -> fixed-order
 // final reduction (deterministic for a given grid).
 #pragma once
