@@ -434,15 +434,25 @@ ZFB_HD unsigned encode_block_var(const float (&f)[4], const stream_params& sp, W
     const unsigned z = (unsigned)(32 - stop);
     if (z) { bw.put(0, z); used += z; k = stop - 1; }
   }
-  // head: one table step per plane until all four coefficients are significant
+  // head: one table step per plane until all four coefficients are significant, eight planes per batch: their
+  // nibbles come from one byte of each coefficient through the spread table (plane k in the top nibble of W), and
+  // the batch's codes (<= 7 bits each) are collected in a 64-bit word before they go to the writer
   unsigned n = 0;
-  ZFB_NOUNROLL for (; k >= kmin && n < 4u; k--) {
-    const unsigned x = ((u[0] >> k) & 1u) | (((u[1] >> k) & 1u) << 1) | (((u[2] >> k) & 1u) << 2) | (((u[3] >> k) & 1u) << 3);
-    const unsigned e = tb.enc[n * 16u + x];
-    const unsigned len = (e >> 8) & 15u;
-    n = e >> 12;
-    bw.put(e & 0xffu, len);
-    used += len;
+  while (k >= kmin && n < 4u) {
+    const unsigned sh = 31u - (unsigned)k;
+    const uint32_t W = tb.spread[(u[0] << sh) >> 24] | (tb.spread[(u[1] << sh) >> 24] << 1) |
+                       (tb.spread[(u[2] << sh) >> 24] << 2) | (tb.spread[(u[3] << sh) >> 24] << 3);
+    uint64_t acc = 0;
+    unsigned cnt = 0;
+    ZFB_NOUNROLL for (unsigned i = 0; i < 8u && k >= kmin && n < 4u; i++, k--) {
+      const unsigned x = (W >> (28u - 4u * i)) & 15u;
+      const unsigned e = tb.enc[n * 16u + x];
+      acc |= (uint64_t)(e & 0xffu) << cnt;
+      cnt += (e >> 8) & 15u;
+      n = e >> 12;
+    }
+    bw.put(acc, cnt);
+    used += cnt;
   }
   // tail: every further plane is its four bits verbatim, i.e. the rest of the block is the 4-way bit interleave of
   // the coefficients' bits k .. kmin, most significant first: 32 stream bits per step through the byte spread table
@@ -483,13 +493,19 @@ ZFB_HD unsigned decode_block_var(float (&f)[4], const stream_params& sp, Reader&
   uint32_t u[4] = {0u, 0u, 0u, 0u};
   unsigned n = 0;
   int k = 31;
-  ZFB_NOUNROLL for (; k >= kmin && n < 4u; k--) {  // head: one table step per plane
-    const unsigned e = tb.dec[n * 128u + (r.lo & 127u)];
-    const unsigned x = e & 15u, len = (e >> 4) & 15u;
-    n = e >> 8;
-    r.consume(len);
-    used += len;
-    u[0] |= (x & 1u) << k; u[1] |= ((x >> 1) & 1u) << k; u[2] |= ((x >> 2) & 1u) << k; u[3] |= (x >> 3) << k;
+  while (k >= kmin && n < 4u) {  // head: one table step per plane, the nibbles of eight planes collected in W
+    const int kb = k;
+    uint32_t W = 0u;
+    ZFB_NOUNROLL for (unsigned i = 0; i < 8u && k >= kmin && n < 4u; i++, k--) {
+      const unsigned e = tb.dec[n * 128u + (r.lo & 127u)];
+      const unsigned len = (e >> 4) & 15u;
+      W |= (e & 15u) << (28u - 4u * i);  // plane kb - i in nibble 7 - i
+      n = e >> 8;
+      r.consume(len);
+      used += len;
+    }
+    // de-interleave: gather4(W >> c) has plane kb - 7 + j of coefficient c in bit j
+    ZFB_UNROLL for (int c = 0; c < 4; c++) u[c] |= (gather4(W >> c) << 24) >> (31 - kb);
   }
   if (k >= kmin) {  // tail: de-interleave the remaining 4 R bits, 32 at a time
     const unsigned R = (unsigned)(k - kmin + 1);

@@ -185,6 +185,8 @@ __global__ void __launch_bounds__(128) enc_var1_kernel(const Scalar* __restrict_
   }
 }
 
+constexpr unsigned VAR1_STAGE_WORDS = 3072;  // 32-bit words of stream staged per CTA tile (128 groups)
+
 template <typename Scalar, bool METRICS>
 __global__ void __launch_bounds__(128) dec_var1_kernel(const uint64_t* __restrict__ stream, const uint64_t* __restrict__ offsets,
                                                        Scalar* __restrict__ out, const Scalar* __restrict__ orig, geom g,
@@ -193,6 +195,8 @@ __global__ void __launch_bounds__(128) dec_var1_kernel(const uint64_t* __restric
   __shared__ double red[7 * 4];
   constexpr bool F32 = sizeof(Scalar) == 4;
   __shared__ coder1_smem cs;
+  __shared__ uint32_t piece[F32 ? VAR1_STAGE_WORDS : 1];
+  __shared__ uint64_t range[2];
   f1::tables tb;
   if (F32) tb = build_coder1_tables(cs);
   const bool fast = F32 && f1::var_params_ok(sp);
@@ -200,56 +204,81 @@ __global__ void __launch_bounds__(128) dec_var1_kernel(const uint64_t* __restric
   m.init();
   const size_t ngroups = (g.nblocks + VAR1_GROUP - 1) / VAR1_GROUP;
   const bool vec = ((reinterpret_cast<size_t>(out) & 15) == 0) && (!METRICS || (reinterpret_cast<size_t>(orig) & 15) == 0);
-  for (size_t grp = (size_t)blockIdx.x * blockDim.x + threadIdx.x; grp < ngroups; grp += (size_t)gridDim.x * blockDim.x) {
-    uint64_t pos = offsets[grp];
-    for (unsigned q = 0; q < VAR1_GROUP; q++) {
-      const size_t b = grp * VAR1_GROUP + q;
-      if (b >= g.nblocks) break;
-      Scalar f[4];
-      bool done = false;
-      if constexpr (F32) {
-        if (fast) {
-          const size_t v0 = (size_t)(pos >> 5);
-          const size_t left32 = 2 * g.stream_words > v0 ? 2 * g.stream_words - v0 : 0;
-          f3::reader32 r(reinterpret_cast<const uint32_t*>(stream) + v0, left32 > 0xffffffffull ? 0xffffffffu : (unsigned)left32,
-                         (unsigned)(pos & 31));
-          pos += f1::decode_block_var(f, sp, r, tb);
-          done = true;
-        }
-      }
-      if (!done) {
-        const size_t w0 = (size_t)(pos >> 6);
-        const size_t left = g.stream_words > w0 ? g.stream_words - w0 : 0;
-        slot_reader r(stream + w0, left > 0xffffffffull ? 0xffffffffu : (unsigned)left, (unsigned)(pos & 63));
-        pos += decode_block<Scalar, 1, false>(f, sp, r);
-      }
-      const size_t x0 = 4 * b;
-      if (x0 + 4 <= g.nx && vec) {
-        if constexpr (sizeof(Scalar) == 4) {
-          float4 v;
-          v.x = f[0]; v.y = f[1]; v.z = f[2]; v.w = f[3];
-          if (METRICS) {
-            frow fr;
-            fr.init();
-            fr.add4(__ldg(reinterpret_cast<const float4*>(orig + x0)), v.x, v.y, v.z, v.w);
-            fr.flush(m);
+  const uint32_t* s32 = reinterpret_cast<const uint32_t*>(stream);
+  const size_t total32 = 2 * g.stream_words;
+  const size_t ntiles = (ngroups + 127) / 128;
+  // a CTA takes 128 consecutive groups: their bits are one contiguous piece of the stream, staged in shared memory
+  // with coalesced loads when it fits (a thread reading its own words from global memory waits a full DRAM
+  // latency at every 32 bits)
+  for (size_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const size_t grp = tile * 128 + threadIdx.x;
+    const bool active = grp < ngroups;
+    uint64_t pos = active ? offsets[grp] : 0;
+    bool staged = false;
+    size_t v_begin = 0, v_end = 0;
+    if (fast) {
+      if (threadIdx.x == 0) range[0] = pos;
+      if (active && (threadIdx.x == 127 || grp + 1 == ngroups)) range[1] = offsets[grp + 1];
+      __syncthreads();
+      v_begin = (size_t)(range[0] >> 5);
+      v_end = (size_t)((range[1] + 31) >> 5) + 2;  // + the reader's two look-ahead words
+      staged = v_end - v_begin <= VAR1_STAGE_WORDS;
+      if (staged)
+        for (size_t i = threadIdx.x; i < v_end - v_begin; i += 128) piece[i] = v_begin + i < total32 ? __ldg(s32 + v_begin + i) : 0u;
+      __syncthreads();
+    }
+    if (active) {
+      for (unsigned q = 0; q < VAR1_GROUP; q++) {
+        const size_t b = grp * VAR1_GROUP + q;
+        if (b >= g.nblocks) break;
+        Scalar f[4];
+        bool done = false;
+        if constexpr (F32) {
+          if (fast) {
+            const size_t v0 = (size_t)(pos >> 5);
+            const size_t left32 = total32 > v0 ? total32 - v0 : 0;
+            const uint32_t* src = staged ? piece + (v0 - v_begin) : s32 + v0;
+            const unsigned navail = staged ? (unsigned)(v_end - v0) : (left32 > 0xffffffffull ? 0xffffffffu : (unsigned)left32);
+            f3::reader32 r(src, navail, (unsigned)(pos & 31));
+            pos += f1::decode_block_var(f, sp, r, tb);
+            done = true;
           }
-          *reinterpret_cast<float4*>(out + x0) = v;
+        }
+        if (!done) {
+          const size_t w0 = (size_t)(pos >> 6);
+          const size_t left = g.stream_words > w0 ? g.stream_words - w0 : 0;
+          slot_reader r(stream + w0, left > 0xffffffffull ? 0xffffffffu : (unsigned)left, (unsigned)(pos & 63));
+          pos += decode_block<Scalar, 1, false>(f, sp, r);
+        }
+        const size_t x0 = 4 * b;
+        if (x0 + 4 <= g.nx && vec) {
+          if constexpr (sizeof(Scalar) == 4) {
+            float4 v;
+            v.x = f[0]; v.y = f[1]; v.z = f[2]; v.w = f[3];
+            if (METRICS) {
+              frow fr;
+              fr.init();
+              fr.add4(__ldg(reinterpret_cast<const float4*>(orig + x0)), v.x, v.y, v.z, v.w);
+              fr.flush(m);
+            }
+            *reinterpret_cast<float4*>(out + x0) = v;
+          } else {
+            if (METRICS) {
+              const double2 o0 = __ldg(reinterpret_cast<const double2*>(orig + x0));
+              const double2 o1 = __ldg(reinterpret_cast<const double2*>(orig + x0 + 2));
+              macc_add(m, o0.x, (double)f[0]); macc_add(m, o0.y, (double)f[1]);
+              macc_add(m, o1.x, (double)f[2]); macc_add(m, o1.y, (double)f[3]);
+            }
+            *reinterpret_cast<double2*>(out + x0) = make_double2((double)f[0], (double)f[1]);
+            *reinterpret_cast<double2*>(out + x0 + 2) = make_double2((double)f[2], (double)f[3]);
+          }
         } else {
-          if (METRICS) {
-            const double2 o0 = __ldg(reinterpret_cast<const double2*>(orig + x0));
-            const double2 o1 = __ldg(reinterpret_cast<const double2*>(orig + x0 + 2));
-            macc_add(m, o0.x, (double)f[0]); macc_add(m, o0.y, (double)f[1]);
-            macc_add(m, o1.x, (double)f[2]); macc_add(m, o1.y, (double)f[3]);
-          }
-          *reinterpret_cast<double2*>(out + x0) = make_double2((double)f[0], (double)f[1]);
-          *reinterpret_cast<double2*>(out + x0 + 2) = make_double2((double)f[2], (double)f[3]);
+          const unsigned mx = (unsigned)(g.nx - x0 < 4 ? g.nx - x0 : 4);
+          scatter_block<Scalar, 1, METRICS>(f, out, orig, g, x0, 0, 0, mx, 1u, 1u, m);
         }
-      } else {
-        const unsigned mx = (unsigned)(g.nx - x0 < 4 ? g.nx - x0 : 4);
-        scatter_block<Scalar, 1, METRICS>(f, out, orig, g, x0, 0, 0, mx, 1u, 1u, m);
       }
     }
+    if (fast) __syncthreads();  // the piece and the range are rewritten by the next tile
   }
   if (METRICS) macc_block_store(m, red, part + (size_t)blockIdx.x * PART_STRIDE);
 }
