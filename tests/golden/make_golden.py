@@ -1,4 +1,4 @@
-"""Generates tests/golden/codec_kat.json and tests/golden/metrics_kat.json.
+"""Generates tests/golden/codec_kat.json, tests/golden/codec_var_kat.json and tests/golden/metrics_kat.json.
 
 * codec_kat.json   -- SHA-256 of stream and decoded bytes from oracle/zfp_ref.c on seeded inputs
                       (regression pins of OUR restatement: the reference ships no codec vectors).
@@ -48,6 +48,22 @@ CASES = [
 ]
 
 
+VAR_CASES = [
+    # name, dtype, shape, mode ("abs" tolerance | "rel" precision), value, kind, seed
+    ("f32_1d_n4099_abs1e-2", "float32", [4099], "abs", 1e-2, "uniform256", 31),
+    ("f32_1d_n1000_rel12", "float32", [1000], "rel", 12, "normal900", 32),
+    ("f32_2d_33x70_abs0.5", "float32", [33, 70], "abs", 0.5, "smooth", 33),
+    ("f32_3d_5x6x7_abs1e-3", "float32", [5, 6, 7], "abs", 1e-3, "smooth", 34),
+    ("f32_3d_33_abs0.05", "float32", [33, 33, 33], "abs", 0.05, "lognormal", 35),
+    ("f32_3d_64_rel16", "float32", [64, 64, 64], "rel", 16, "smooth", 36),
+    ("f32_3d_32_noise_abs10", "float32", [32, 32, 32], "abs", 10.0, "normal900", 37),
+    ("f32_3d_16_zero_abs1", "float32", [16, 16, 16], "abs", 1.0, "zero", 0),
+    ("f64_3d_9x10x11_abs1e-6", "float64", [9, 10, 11], "abs", 1e-6, "smooth", 38),
+    ("f64_3d_32_rel30", "float64", [32, 32, 32], "rel", 30, "smooth", 39),
+    ("f64_1d_n1001_abs1e-3", "float64", [1001], "abs", 1e-3, "normal900", 40),
+]
+
+
 def case_input(case):
     from conftest import smooth_field
 
@@ -87,6 +103,25 @@ def main():
         case["decoded_sha256"] = hashlib.sha256(g.tobytes()).hexdigest()
         out["cases"].append(case)
     json.dump(out, open(os.path.join(HERE, "codec_kat.json"), "w"), indent=1)
+
+    # variable-rate modes (zfp fixed accuracy / precision: the CPU zfp plugin's "abs" / "rel")
+    vout = {"generator": "tests/golden/make_golden.py", "oracle": "oracle/zfp_ref.c zfo_compress_ex (restatement; parity unpinned)",
+            "cases": []}
+    for name, dt, shape, mode, value, kind, seed in VAR_CASES:
+        case = {"name": name, "dtype": dt, "shape": shape, "mode": mode, "value": value, "kind": kind, "seed": seed}
+        f = case_input(case)
+        p = O.params_accuracy(value) if mode == "abs" else O.params_precision(value)
+        s, offs = O.compress_ex(f, p, with_offsets=True)
+        g, _ = O.decompress_ex(s, f.shape, f.dtype, p)
+        case["params"] = list(p.as_tuple())
+        case["stream_bytes"] = int(len(s))
+        case["total_bits"] = int(offs[-1])
+        case["input_sha256"] = hashlib.sha256(f.tobytes()).hexdigest()
+        case["stream_sha256"] = hashlib.sha256(s.tobytes()).hexdigest()
+        case["index_sha256"] = hashlib.sha256(offs.tobytes()).hexdigest()
+        case["decoded_sha256"] = hashlib.sha256(g.tobytes()).hexdigest()
+        vout["cases"].append(case)
+    json.dump(vout, open(os.path.join(HERE, "codec_var_kat.json"), "w"), indent=1)
 
     # real-data inputs out of the reference's toy files
     ref = "/root/reference/testing/data"

@@ -223,3 +223,26 @@ def test_variable_rate_extreme_values(codec, pkg, oracle):
             assert np.array_equal(s.cpu().numpy(), s_ref), (label, m.as_tuple())
             out = codec.decode_var(s, f.shape, tdt, m)
             assert np.array_equal(out.cpu().numpy().view(np.uint8), g_ref.view(np.uint8)), (label, m.as_tuple())
+
+
+def test_variable_rate_known_answer_hashes_on_gpu(codec, pkg):
+    """The committed known-answer vectors (tests/golden/codec_var_kat.json) without the oracle in the loop."""
+    import hashlib
+    import json
+
+    import make_golden
+
+    torch = _torch()
+    kat = json.load(open(os.path.join(GOLD, "codec_var_kat.json")))
+    for case in kat["cases"]:
+        f = make_golden.case_input(case)
+        assert hashlib.sha256(f.tobytes()).hexdigest() == case["input_sha256"], case["name"]
+        m = pkg.mode_accuracy(case["value"]) if case["mode"] == "abs" else pkg.mode_precision(case["value"])
+        assert list(m.as_tuple()) == case["params"], case["name"]
+        d_f = torch.from_numpy(f).cuda()
+        tdt = torch.float32 if f.dtype == np.float32 else torch.float64
+        s, nbytes = codec.encode_var(d_f, m)
+        assert nbytes == case["stream_bytes"], case["name"]
+        assert hashlib.sha256(s.cpu().numpy().tobytes()).hexdigest() == case["stream_sha256"], case["name"]
+        out = codec.decode_var(s, f.shape, tdt, m)
+        assert hashlib.sha256(out.cpu().numpy().tobytes()).hexdigest() == case["decoded_sha256"], case["name"]
