@@ -280,3 +280,48 @@ def test_device_codec_expert_parameters(oracle):
             assert np.array_equal(offs, offs_ref), (dtype, shape, minbits, maxbits, maxprec, minexp)
             assert np.array_equal(s, s_ref), (dtype, shape, minbits, maxbits, maxprec, minexp)
             assert np.array_equal(g.view(np.uint8), g_ref.view(np.uint8)), (dtype, shape, minbits, maxbits, maxprec, minexp)
+
+
+def test_device_codec_random_sweep(oracle):
+    """Seeded random shapes / types / parameter sets through the CPU build of the device codec (fixed rate, accuracy,
+    precision, expert) against the oracle: the GPU-less counterpart of tests/test_gpu_fuzz.py."""
+    O = oracle
+    rng = np.random.default_rng(424242)
+    for case in range(120):
+        d = int(rng.integers(1, 4))
+        shape = tuple(int(rng.integers(1, 14 if d == 3 else (40 if d == 2 else 300))) for _ in range(d))
+        dtype = np.float32 if rng.random() < 0.6 else np.float64
+        kind = int(rng.integers(0, 4))
+        if kind == 0:
+            f = rng.standard_normal(shape) * 10.0 ** int(rng.integers(-8, 9))
+        elif kind == 1:
+            f = smooth_field(shape, seed=case, amp=float(10.0 ** rng.uniform(-2, 3))).astype(np.float64)
+        elif kind == 2:
+            f = rng.standard_normal(shape) * (rng.random(shape) > 0.75)
+        else:
+            f = np.exp(rng.standard_normal(shape) * 5.0)
+        f = np.ascontiguousarray(f.astype(dtype))
+        sel = rng.random()
+        if sel < 0.35:
+            rate = float(rng.choice([1, 2.5, 4, 8, 13, 16, 32]))
+            mb = O.maxbits(dtype, d, rate, int(rng.random() < 0.7))
+            s_ref = O.compress(f, mb)
+            s, g = emul_roundtrip(O, f, mb)
+            assert np.array_equal(s, s_ref), (case, shape, dtype, mb)
+            assert np.array_equal(g.view(np.uint8), O.decompress(s_ref, shape, dtype, mb).view(np.uint8)), (case, shape, mb)
+            continue
+        if sel < 0.6:
+            p = O.params_accuracy(float(10.0 ** rng.uniform(-8, 4)))
+        elif sel < 0.8:
+            p = O.params_precision(int(rng.integers(1, 66)))
+        else:
+            hdr = 9 if dtype == np.float32 else 12
+            maxbits = int(rng.integers(hdr, 700))
+            cap = 140 if (d == 1 and dtype == np.float32) else 4000
+            p = O.Params(int(rng.integers(0, min(maxbits, cap) + 1)), maxbits, int(rng.integers(1, 65)), int(rng.integers(-60, 10)))
+        s_ref, offs_ref = O.compress_ex(f, p, with_offsets=True)
+        g_ref, _ = O.decompress_ex(s_ref, shape, dtype, p)
+        s, g, offs = emul_var_roundtrip(O, f, p)
+        assert np.array_equal(offs, offs_ref), (case, shape, dtype, p.as_tuple())
+        assert np.array_equal(s, s_ref), (case, shape, dtype, p.as_tuple())
+        assert np.array_equal(g.view(np.uint8), g_ref.view(np.uint8)), (case, shape, dtype, p.as_tuple())
