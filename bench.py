@@ -254,6 +254,42 @@ def run_e2e(torch, dist, codec, pkg, field, shape, dtype, tdt, mb, cbytes, field
             "api": "zfb_compress_host + zfb_decompress_host (fused metrics), pinned host buffers; PCIe bound"}
 
 
+def run_e2e_var(torch, codec, pkg, field, shape, dtype, tdt, mode, field_bytes, args):
+    """The same end-to-end measurement for a variable-rate mode (N = 1 sweeps): zfb_compress_var_host +
+    zfb_decompress_var_host on pinned host buffers, stream length as the state between the two calls."""
+    import ctypes as C
+
+    h_in = torch.empty(shape, dtype=tdt, pin_memory=True)
+    h_in.copy_(field)
+    cap = pkg.maximum_size(shape, "float32" if dtype == "float32" else "float64", mode)
+    h_stream = torch.empty(cap, dtype=torch.uint8, pin_memory=True)
+    h_out = torch.empty(shape, dtype=tdt, pin_memory=True)
+    code = 1 if dtype == "float32" else 2
+    d, nx, ny, nz = pkg.dims_of(shape)
+    L = pkg.lib()
+    nbytes = C.c_size_t()
+
+    def e2e_step():
+        codec._check(L.zfb_compress_var_host(codec._h, code, d, nx, ny, nz, C.byref(mode), h_in.data_ptr(), h_stream.data_ptr(),
+                                             cap, C.byref(nbytes)), "zfb_compress_var_host")
+        codec._check(L.zfb_decompress_var_host(codec._h, code, d, nx, ny, nz, C.byref(mode), h_stream.data_ptr(), nbytes.value,
+                                               h_out.data_ptr(), h_in.data_ptr()), "zfb_decompress_var_host")
+        return codec.partials()
+
+    e2e_step()
+    torch.cuda.synchronize()
+    w0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    w = time.perf_counter() - w0
+    codec.release()
+    cb = int(nbytes.value)
+    return {"value": field_bytes * args.e2e_steps / w / 1e9, "unit": "GB/s", "h2d_bytes_per_step": field_bytes + cb,
+            "d2h_bytes_per_step": field_bytes + cb, "steps": args.e2e_steps, "ms_per_step": 1e3 * w / args.e2e_steps,
+            "api": "zfb_compress_var_host + zfb_decompress_var_host (fused metrics), pinned host buffers, no slab pipeline"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -310,7 +346,7 @@ def main():
         kind, _, val = args.mode.partition(":")
         var_mode = pkg.mode_accuracy(float(val)) if kind == "abs" else pkg.mode_precision(int(val))
         cbytes = pkg.maximum_size(shape, npdt, var_mode)  # capacity; the real size is data dependent (set below)
-        args.no_e2e = args.no_cpu = True
+        args.no_cpu = True
     stream = torch.empty(cbytes + 16, dtype=torch.uint8, device=dev)
     out = torch.empty(shape, dtype=tdt, device=dev)
 
@@ -383,7 +419,10 @@ def main():
     e2e = None
     if not args.no_e2e:
         try:
-            e2e = run_e2e(torch, dist, codec, pkg, field, shape, dtype, tdt, mb, cbytes, field_bytes, world, dev, args)
+            if var_mode is not None:
+                e2e = run_e2e_var(torch, codec, pkg, field, shape, dtype, tdt, var_mode, field_bytes, args) if world == 1 else None
+            else:
+                e2e = run_e2e(torch, dist, codec, pkg, field, shape, dtype, tdt, mb, cbytes, field_bytes, world, dev, args)
         except Exception as ex:  # e.g. pinned host memory exhausted with many ranks: report, do not lose the bench line
             e2e = {"value": None, "unit": "GB/s", "error": str(ex)[:200]}
         ok = torch.tensor([0 if e2e.get("value") is None else 1], device=dev)

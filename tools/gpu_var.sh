@@ -9,5 +9,5 @@ import json
 for l in open("gpurun_out/var_sweep.jsonl"):
     if not l.startswith("{"): print(l.strip()[:300]); continue
     d=json.loads(l); c=d["config"]
-    print(c["workload"], c["mode"], "bpv", round(c["rate_bpv"],3), "GB/s", round(d["value"],1), "enc_ms", round(d["enc_ms"],3), "dec_ms", round(d["dec_ms"],3), "rt_frac", round(d["roofline"]["round_trip"]["frac"],3), "maxabs", d["metrics_check"]["absolute_error"], "psnr", round(d["metrics_check"]["psnr"],2), "launches", d["gpu_launches"])
+    print(c["workload"], c["mode"], "bpv", round(c["rate_bpv"],3), "GB/s", round(d["value"],1), "enc_ms", round(d["enc_ms"],3), "dec_ms", round(d["dec_ms"],3), "rt_frac", round(d["roofline"]["round_trip"]["frac"],3), "maxabs", d["metrics_check"]["absolute_error"], "psnr", round(d["metrics_check"]["psnr"],2), "launches", d["gpu_launches"], "e2e", round(d["e2e"]["value"],1) if d.get("e2e") and d["e2e"].get("value") else None)
 PY
