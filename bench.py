@@ -287,7 +287,7 @@ def run_e2e_var(torch, codec, pkg, field, shape, dtype, tdt, mode, field_bytes, 
     cb = int(nbytes.value)
     return {"value": field_bytes * args.e2e_steps / w / 1e9, "unit": "GB/s", "h2d_bytes_per_step": field_bytes + cb,
             "d2h_bytes_per_step": field_bytes + cb, "steps": args.e2e_steps, "ms_per_step": 1e3 * w / args.e2e_steps,
-            "api": "zfb_compress_var_host + zfb_decompress_var_host (fused metrics), pinned host buffers, no slab pipeline"}
+            "api": "zfb_compress_var_host + zfb_decompress_var_host (fused metrics), pinned host buffers, slab pipeline"}
 
 
 def main():

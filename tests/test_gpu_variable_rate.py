@@ -246,3 +246,46 @@ def test_variable_rate_known_answer_hashes_on_gpu(codec, pkg):
         assert hashlib.sha256(s.cpu().numpy().tobytes()).hexdigest() == case["stream_sha256"], case["name"]
         out = codec.decode_var(s, f.shape, tdt, m)
         assert hashlib.sha256(out.cpu().numpy().tobytes()).hexdigest() == case["decoded_sha256"], case["name"]
+
+
+_SLAB_SCRIPT = r"""
+import sys, os
+import numpy as np
+sys.path.insert(0, os.getcwd())
+sys.path.insert(0, os.path.join(os.getcwd(), "oracle"))
+sys.path.insert(0, os.path.join(os.getcwd(), "tests"))
+import __graft_entry__ as g
+import oracle as O
+from conftest import smooth_field
+pkg = g.load_package()
+codec = pkg.Codec(0)
+rng = np.random.default_rng(5)
+cases = [(np.float32, (70, 96, 128)), (np.float32, (3000001,)), (np.float64, (37, 64, 96)), (np.float32, (301, 1500))]
+for dtype, shape in cases:
+    f = (smooth_field(shape, seed=3, amp=20.0).astype(np.float64) + 0.01 * rng.standard_normal(shape)).astype(dtype)
+    for m, p in ((pkg.mode_accuracy(0.01), O.params_accuracy(0.01)), (pkg.mode_precision(13), O.params_precision(13))):
+        s_ref = O.compress_ex(f, p)
+        g_ref, _ = O.decompress_ex(s_ref, shape, dtype, p)
+        s = codec.compress_var_host(f, m)
+        assert np.array_equal(s, s_ref), ("stream", dtype, shape)
+        out = codec.decompress_var_host(s, shape, dtype, m, orig=f)
+        assert np.array_equal(out.view(np.uint8), g_ref.view(np.uint8)), ("decoded", dtype, shape)
+        if dtype == np.float32:
+            v = pkg.metric_values(codec.metrics_host(f, out)); r = O.metrics(f, g_ref)
+            assert v["absolute_error"] == r["absolute_error"] and abs(v["mse"] - r["mse"]) <= 1e-6 * r["mse"], (v, r)
+        out2 = codec.decompress_var_host(s.copy(), shape, dtype, m)   # foreign buffer: whole-stream path
+        assert np.array_equal(out2.view(np.uint8), g_ref.view(np.uint8)), ("decoded bare", dtype, shape)
+print("SLABS OK", len(cases))
+"""
+
+
+def test_variable_rate_host_pipeline_with_many_slabs():
+    """The host entry points cut a field into slabs whose streams join at arbitrary bits; with 1 MiB slabs
+    (ZFB_SLAB_MB, read once per process, hence the subprocess) a 3-12 MiB field becomes 3-12 chained slabs."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, ZFB_SLAB_MB="1")
+    r = subprocess.run([sys.executable, "-c", _SLAB_SCRIPT], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "SLABS OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]

@@ -44,6 +44,7 @@ struct zfb_ctx {
   size_t out_bytes = 0;
   bool fused_valid = false;           // result holds metrics of (h_orig_key, h_out_key)
   int occ_enc[80] = {0}, occ_dec[80] = {0}, occ_decm[80] = {0};  // resident CTAs per SM, by slot words
+  std::vector<uint64_t> var_slab_bits;  // host copy: bit offset at which every slab of the resident stream starts (+ total)
   // variable-rate path (zfb_api_var.cuh): scratch + the block index of the last encoded stream
   devbuf var_stage, var_lens, var_chunks, var_index;
   const void* var_index_key = nullptr;  // device stream the index in var_index describes
@@ -699,7 +700,12 @@ static slab_plan plan_slabs(int dims, size_t nx, size_t ny, size_t nz, unsigned 
   p.slowest = dims == 1 ? nx : dims == 2 ? ny : nz;
   p.row_elems = dims == 1 ? 1 : dims == 2 ? nx : nx * ny;
   p.blocks_per_4rows = dims == 1 ? 1 : dims == 2 ? (nx + 3) / 4 : ((nx + 3) / 4) * ((ny + 3) / 4);
-  const size_t target = (size_t)64 << 20;  // ~64 MiB of field per slab
+  static const size_t target_mb = [] {  // ~64 MiB of field per slab; ZFB_SLAB_MB overrides (tests use small slabs)
+    const char* e = std::getenv("ZFB_SLAB_MB");
+    const long v = e ? std::atol(e) : 0;
+    return (size_t)(v > 0 ? v : 64);
+  }();
+  const size_t target = target_mb << 20;
   size_t thick = target / (p.row_elems * esz);
   // a slab must be a whole number of block rows (4) and its piece of the stream a whole number of
   // 16-byte units, so that every slab keeps the fast path's alignment: q*blocks*maxbits % 128 == 0

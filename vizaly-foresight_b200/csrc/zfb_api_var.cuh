@@ -142,6 +142,50 @@ static int launch_compact_var(zfb_ctx* c, int dims, const geom& g, const uint64_
   return ZFB_OK;
 }
 
+// One (sub-)field -> its part of the stream, no host synchronisation.  `index` points at this part's first entry of
+// the (global) index; with `chained` the bit count already sitting there (the total of the parts before) is the
+// base of this part, so consecutive slabs of a field can be queued back to back.
+static int encode_var_part(zfb_ctx* c, int dtype, int dims, size_t nx, size_t ny, size_t nz, const zfb_mode* m,
+                           const void* d_in, void* d_stream, size_t cap_words, uint64_t* index, bool chained)
+{
+  int rc;
+  geom g = make_geom(dims, nx, ny, nz, 64);
+  g.stream_words = cap_words;
+  const stream_params sp = to_params(m);
+  const unsigned words = dtype == ZFB_FLOAT ? var_words<float>(dims) : var_words<double>(dims);
+  const size_t units = (g.nblocks + index_unit(dims) - 1) / index_unit(dims);  // index entries (1D: groups of blocks)
+  const size_t groups = (units + 31) / 32;
+  if ((rc = ensure(c, c->var_stage, groups * 32 * (size_t)words * 8))) return rc;
+  if ((rc = ensure(c, c->var_lens, units * 4))) return rc;
+  const size_t nchunks = (units + SCAN_CHUNK - 1) / SCAN_CHUNK;
+  if ((rc = ensure(c, c->var_chunks, (nchunks + 1) * 8))) return rc;
+  uint64_t* stage = (uint64_t*)c->var_stage.p;
+  uint32_t* lens = (uint32_t*)c->var_lens.p;
+  uint64_t* chunks = (uint64_t*)c->var_chunks.p;
+  const uint64_t* base = chained ? index : nullptr;
+
+  rc = dtype == ZFB_FLOAT ? launch_enc_var<float>(c, dims, g, sp, d_in, stage, lens)
+                          : launch_enc_var<double>(c, dims, g, sp, d_in, stage, lens);
+  if (rc) return rc;
+  scan_sums_kernel<<<(unsigned)nchunks, SCAN_THREADS, 0, c->stream>>>(lens, units, chunks);
+  scan_chunks_kernel<<<1, SCAN_THREADS, 0, c->stream>>>(chunks, nchunks);
+  scan_offsets_kernel<<<(unsigned)nchunks, SCAN_THREADS, 0, c->stream>>>(lens, units, chunks, nchunks, index, base);
+  zero_stream_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>((uint64_t*)d_stream, base, index + units, cap_words);
+  c->launches += 4;
+  CU_TRY(c, cudaGetLastError());
+  return dtype == ZFB_FLOAT ? launch_compact_var<float>(c, dims, g, stage, index, (uint64_t*)d_stream, cap_words)
+                            : launch_compact_var<double>(c, dims, g, stage, index, (uint64_t*)d_stream, cap_words);
+}
+
+static int check_var_minbits(zfb_ctx* c, int dtype, int dims, const zfb_mode* m)
+{
+  if (dims == 1 && m->minbits > (dtype == ZFB_FLOAT ? var_caps<float, 1>::BITS : var_caps<double, 1>::BITS)) {
+    c->err = "1D: minbits above the longest codable block is not supported";
+    return ZFB_EINVAL;
+  }
+  return ZFB_OK;
+}
+
 extern "C" int zfb_encode_var_dev(zfb_ctx* c, int dtype, int dims, size_t nx, size_t ny, size_t nz, const zfb_mode* m,
                                   const void* d_in, void* d_stream, size_t cap_bytes, uint64_t* d_index,
                                   size_t* stream_bytes)
@@ -150,44 +194,16 @@ extern "C" int zfb_encode_var_dev(zfb_ctx* c, int dtype, int dims, size_t nx, si
   if (rc) return rc;
   if (!d_in || !d_stream) { c->err = "null pointer"; return ZFB_EINVAL; }
   if (cap_bytes < zfb_maximum_size(dtype, dims, nx, ny, nz, m)) { c->err = "stream buffer smaller than zfb_maximum_size()"; return ZFB_EINVAL; }
+  if ((rc = check_var_minbits(c, dtype, dims, m))) return rc;
   CU_TRY(c, cudaSetDevice(c->device));
-  geom g = make_geom(dims, nx, ny, nz, 64);
-  const size_t cap_words = cap_bytes / 8;
-  g.stream_words = cap_words;
-  const stream_params sp = to_params(m);
-  const unsigned words = dtype == ZFB_FLOAT ? var_words<float>(dims) : var_words<double>(dims);
-  const size_t units = (g.nblocks + index_unit(dims) - 1) / index_unit(dims);  // index entries (1D: groups of blocks)
-  if (dims == 1 && m->minbits > (dtype == ZFB_FLOAT ? var_caps<float, 1>::BITS : var_caps<double, 1>::BITS)) {
-    c->err = "1D: minbits above the longest codable block is not supported";
-    return ZFB_EINVAL;
-  }
-  const size_t groups = (units + 31) / 32;
-  if ((rc = ensure(c, c->var_stage, groups * 32 * (size_t)words * 8))) return rc;
-  if ((rc = ensure(c, c->var_lens, units * 4))) return rc;
-  const size_t nchunks = (units + SCAN_CHUNK - 1) / SCAN_CHUNK;
-  if ((rc = ensure(c, c->var_chunks, (nchunks + 1) * 8))) return rc;
+  const size_t units = zfb_index_count(dims, nx, ny, nz);
   uint64_t* index = d_index;
   c->var_index_key = nullptr;
   if (!index) {
     if ((rc = ensure(c, c->var_index, (units + 1) * 8))) return rc;
     index = (uint64_t*)c->var_index.p;
   }
-  uint64_t* stage = (uint64_t*)c->var_stage.p;
-  uint32_t* lens = (uint32_t*)c->var_lens.p;
-  uint64_t* chunks = (uint64_t*)c->var_chunks.p;
-
-  rc = dtype == ZFB_FLOAT ? launch_enc_var<float>(c, dims, g, sp, d_in, stage, lens)
-                          : launch_enc_var<double>(c, dims, g, sp, d_in, stage, lens);
-  if (rc) return rc;
-  scan_sums_kernel<<<(unsigned)nchunks, SCAN_THREADS, 0, c->stream>>>(lens, units, chunks);
-  scan_chunks_kernel<<<1, SCAN_THREADS, 0, c->stream>>>(chunks, nchunks);
-  scan_offsets_kernel<<<(unsigned)nchunks, SCAN_THREADS, 0, c->stream>>>(lens, units, chunks, nchunks, index);
-  zero_stream_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>((uint64_t*)d_stream, index + units, cap_words);
-  c->launches += 4;
-  CU_TRY(c, cudaGetLastError());
-  rc = dtype == ZFB_FLOAT ? launch_compact_var<float>(c, dims, g, stage, index, (uint64_t*)d_stream, cap_words)
-                          : launch_compact_var<double>(c, dims, g, stage, index, (uint64_t*)d_stream, cap_words);
-  if (rc) return rc;
+  if ((rc = encode_var_part(c, dtype, dims, nx, ny, nz, m, d_in, d_stream, cap_bytes / 8, index, false))) return rc;
   uint64_t total_bits = 0;
   CU_TRY(c, cudaMemcpyAsync(&total_bits, index + units, 8, cudaMemcpyDeviceToHost, c->stream));
   CU_TRY(c, cudaStreamSynchronize(c->stream));
@@ -237,32 +253,14 @@ static int launch_dec_var(zfb_ctx* c, int dims, const geom& g, const stream_para
   return ZFB_OK;
 }
 
-extern "C" int zfb_decode_var_dev(zfb_ctx* c, int dtype, int dims, size_t nx, size_t ny, size_t nz, const zfb_mode* m,
-                                  const void* d_stream, size_t stream_bytes, const uint64_t* d_index, void* d_out,
-                                  const void* d_orig)
+// Decode one (sub-)field whose index entries start at `index`; metrics (d_orig != NULL) end in the context's partials.
+static int decode_var_part(zfb_ctx* c, int dtype, int dims, size_t nx, size_t ny, size_t nz, const zfb_mode* m,
+                           const void* d_stream, size_t stream_words, const uint64_t* index, void* d_out, const void* d_orig)
 {
-  int rc = check_var_args(c, dtype, dims, nx, ny, nz, m);
-  if (rc) return rc;
-  if (!d_stream || !d_out || !stream_bytes) { c->err = "null pointer"; return ZFB_EINVAL; }
-  CU_TRY(c, cudaSetDevice(c->device));
+  int rc;
   geom g = make_geom(dims, nx, ny, nz, 64);
-  g.stream_words = (stream_bytes + 7) / 8;
+  g.stream_words = stream_words;
   const stream_params sp = to_params(m);
-  const uint64_t* index = d_index;
-  const size_t units = (g.nblocks + index_unit(dims) - 1) / index_unit(dims);
-  if (!index) {
-    if (c->var_index_key == d_stream && c->var_index_blocks == units && c->var_index.p &&
-        (size_t)((c->var_index_bits + 63) / 64) * 8 == g.stream_words * 8) {
-      index = (const uint64_t*)c->var_index.p;
-    } else {
-      c->var_index_key = nullptr;
-      if ((rc = ensure(c, c->var_index, (units + 1) * 8))) return rc;
-      rc = dtype == ZFB_FLOAT ? launch_index_var<float>(c, dims, d_stream, g.stream_words, g.nblocks, sp, (uint64_t*)c->var_index.p)
-                              : launch_index_var<double>(c, dims, d_stream, g.stream_words, g.nblocks, sp, (uint64_t*)c->var_index.p);
-      if (rc) return rc;
-      index = (const uint64_t*)c->var_index.p;
-    }
-  }
   int rows = 0;
   const bool metrics = d_orig != nullptr;
   if (dtype == ZFB_DOUBLE && dims == 3 && (!metrics || ((((uintptr_t)d_orig | (uintptr_t)d_out) & 15) == 0))) {
@@ -285,9 +283,53 @@ extern "C" int zfb_decode_var_dev(zfb_ctx* c, int dtype, int dims, size_t nx, si
   return ZFB_OK;
 }
 
+extern "C" int zfb_decode_var_dev(zfb_ctx* c, int dtype, int dims, size_t nx, size_t ny, size_t nz, const zfb_mode* m,
+                                  const void* d_stream, size_t stream_bytes, const uint64_t* d_index, void* d_out,
+                                  const void* d_orig)
+{
+  int rc = check_var_args(c, dtype, dims, nx, ny, nz, m);
+  if (rc) return rc;
+  if (!d_stream || !d_out || !stream_bytes) { c->err = "null pointer"; return ZFB_EINVAL; }
+  CU_TRY(c, cudaSetDevice(c->device));
+  const size_t stream_words = (stream_bytes + 7) / 8;
+  const size_t nblocks = count_blocks(dims, nx, ny, nz);
+  const uint64_t* index = d_index;
+  const size_t units = (nblocks + index_unit(dims) - 1) / index_unit(dims);
+  if (!index) {
+    if (c->var_index_key == d_stream && c->var_index_blocks == units && c->var_index.p &&
+        (size_t)((c->var_index_bits + 63) / 64) == stream_words) {
+      index = (const uint64_t*)c->var_index.p;
+    } else {
+      c->var_index_key = nullptr;
+      const stream_params sp = to_params(m);
+      if ((rc = ensure(c, c->var_index, (units + 1) * 8))) return rc;
+      rc = dtype == ZFB_FLOAT ? launch_index_var<float>(c, dims, d_stream, stream_words, nblocks, sp, (uint64_t*)c->var_index.p)
+                              : launch_index_var<double>(c, dims, d_stream, stream_words, nblocks, sp, (uint64_t*)c->var_index.p);
+      if (rc) return rc;
+      index = (const uint64_t*)c->var_index.p;
+    }
+  }
+  return decode_var_part(c, dtype, dims, nx, ny, nz, m, d_stream, stream_words, index, d_out, d_orig);
+}
+
 // ------------------------------------------------------------------------------------------------
-// host-pointer forms
+// host-pointer forms: slabs along the slowest axis, pipelined like the fixed-rate entry points.  The slabs of a
+// variable-rate stream join at arbitrary bits, so slab s+1 is queued with the running bit count that slab s leaves
+// in the index as its base (no host round trip), and the host only learns the slab boundaries one slab late, which
+// is when it queues that slab's share of the download.
 // ------------------------------------------------------------------------------------------------
+static slab_plan plan_var_slabs(int dims, size_t nx, size_t ny, size_t nz, size_t esz)
+{
+  slab_plan sp = plan_slabs(dims, nx, ny, nz, 128, esz);  // thickness a multiple of 4
+  if (dims == 1 && sp.nslabs > 1) {  // 1D: whole index units (8 blocks = 32 values)
+    size_t t = sp.thick / 32 * 32;
+    if (t < 32) t = 32;
+    sp.thick = t >= sp.slowest ? sp.slowest : t;
+    sp.nslabs = (sp.slowest + sp.thick - 1) / sp.thick;
+  }
+  return sp;
+}
+
 extern "C" int zfb_compress_var_host(zfb_ctx* c, int dtype, int dims, size_t nx, size_t ny, size_t nz, const zfb_mode* m,
                                      const void* h_in, void* h_stream, size_t cap_bytes, size_t* cbytes)
 {
@@ -296,22 +338,82 @@ extern "C" int zfb_compress_var_host(zfb_ctx* c, int dtype, int dims, size_t nx,
   if (!h_in || !h_stream) { c->err = "null pointer"; return ZFB_EINVAL; }
   const size_t need = zfb_maximum_size(dtype, dims, nx, ny, nz, m);
   if (cap_bytes < need) { c->err = "stream buffer smaller than zfb_maximum_size()"; return ZFB_EINVAL; }
+  if ((rc = check_var_minbits(c, dtype, dims, m))) return rc;
   CU_TRY(c, cudaSetDevice(c->device));
   const size_t esz = dtype == ZFB_FLOAT ? 4 : 8;
   const size_t n = nx * (dims >= 2 ? ny : 1) * (dims >= 3 ? nz : 1);
+  const size_t units = zfb_index_count(dims, nx, ny, nz);
   if ((rc = ensure(c, c->d_orig, n * esz))) return rc;
   if ((rc = ensure(c, c->d_stream, need + 16))) return rc;
+  if ((rc = ensure(c, c->var_index, (units + 1) * 8))) return rc;
   c->fused_valid = false;
   c->h_orig_key = nullptr;
   c->var_host_key = nullptr;
-  CU_TRY(c, cudaMemcpyAsync(c->d_orig.p, h_in, n * esz, cudaMemcpyHostToDevice, c->stream));
-  size_t bytes = 0;
-  if ((rc = zfb_encode_var_dev(c, dtype, dims, nx, ny, nz, m, c->d_orig.p, c->d_stream.p, need, nullptr, &bytes))) return rc;
-  CU_TRY(c, cudaMemcpyAsync(h_stream, c->d_stream.p, bytes, cudaMemcpyDeviceToHost, c->stream));
-  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  c->var_index_key = nullptr;
+  c->var_slab_bits.clear();
+
+  const slab_plan sp = plan_var_slabs(dims, nx, ny, nz, esz);
+  uint64_t* index = (uint64_t*)c->var_index.p;
+  uint64_t* h_tot = nullptr;  // pinned: running bit count after every slab
+  if (cudaMallocHost(&h_tot, (sp.nslabs + 1) * 8) != cudaSuccess) { cudaGetLastError(); c->err = "cudaMallocHost failed"; return ZFB_ENOMEM; }
+  cudaStream_t up, down;
+  std::vector<cudaEvent_t> ev_up(sp.nslabs), ev_k(sp.nslabs);
+  cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&down, cudaStreamNonBlocking);
+  for (size_t i = 0; i < sp.nslabs; i++) { cudaEventCreateWithFlags(&ev_up[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming); }
+  int status = ZFB_OK;
+  size_t row0 = 0, u0 = 0, sent_words = 0;
+  c->var_slab_bits.push_back(0);
+  auto download_upto = [&](size_t slab) {  // queue the words that slab `slab` (already finished on the device) completed
+    if (cudaEventSynchronize(ev_k[slab]) != cudaSuccess) { status = ZFB_ECUDA; return; }
+    const uint64_t bits = h_tot[slab];
+    c->var_slab_bits.push_back(bits);
+    const bool last = slab + 1 == sp.nslabs;
+    const size_t upto = last ? (size_t)((bits + 63) / 64) : (size_t)(bits / 64);  // the word a later slab still ORs into stays
+    if (upto > sent_words) {
+      if (cudaMemcpyAsync((char*)h_stream + sent_words * 8, (char*)c->d_stream.p + sent_words * 8, (upto - sent_words) * 8,
+                          cudaMemcpyDeviceToHost, down) != cudaSuccess) status = ZFB_ECUDA;
+      sent_words = upto;
+    }
+  };
+  for (size_t s = 0; s < sp.nslabs && status == ZFB_OK; s++) {
+    const size_t rows = (row0 + sp.thick <= sp.slowest) ? sp.thick : sp.slowest - row0;
+    size_t sx, sy, sz;
+    slab_dims(dims, nx, ny, nz, rows, sx, sy, sz);
+    const size_t off_e = row0 * sp.row_elems;
+    char* dsrc = (char*)c->d_orig.p + off_e * esz;
+    if (cudaMemcpyAsync(dsrc, (const char*)h_in + off_e * esz, rows * sp.row_elems * esz, cudaMemcpyHostToDevice, up) != cudaSuccess) { status = ZFB_ECUDA; break; }
+    cudaEventRecord(ev_up[s], up);
+    cudaStreamWaitEvent(c->stream, ev_up[s], 0);
+    status = encode_var_part(c, dtype, dims, sx, sy, sz, m, dsrc, c->d_stream.p, need / 8, index + u0, s > 0);
+    if (status) break;
+    u0 += zfb_index_count(dims, sx, sy, sz);
+    cudaMemcpyAsync(&h_tot[s], index + u0, 8, cudaMemcpyDeviceToHost, c->stream);
+    cudaEventRecord(ev_k[s], c->stream);
+    if (s > 0) download_upto(s - 1);  // one slab late: the upload and the kernels of slab s are already queued
+    row0 += rows;
+  }
+  if (status == ZFB_OK) download_upto(sp.nslabs - 1);
+  cudaError_t e1 = cudaStreamSynchronize(up), e2 = cudaStreamSynchronize(c->stream), e3 = cudaStreamSynchronize(down);
+  for (size_t i = 0; i < sp.nslabs; i++) { cudaEventDestroy(ev_up[i]); cudaEventDestroy(ev_k[i]); }
+  cudaStreamDestroy(up);
+  cudaStreamDestroy(down);
+  const uint64_t total_bits = status == ZFB_OK ? h_tot[sp.nslabs - 1] : 0;
+  cudaFreeHost(h_tot);
+  if (status == ZFB_OK && (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)) {
+    c->err = std::string("compress_var_host: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3);
+    status = ZFB_ECUDA;
+  }
+  if (status) { c->var_slab_bits.clear(); return status; }
+  if (u0 != units) { c->err = "internal: slabs do not tile the index"; return ZFB_ESTATE; }
+  const size_t bytes = (size_t)((total_bits + 63) / 64) * 8;
+  if (bytes > cap_bytes) { c->err = "internal: stream longer than its bound"; return ZFB_ESTATE; }
   if (cbytes) *cbytes = bytes;
   c->h_orig_key = h_in;
   c->orig_bytes = n * esz;
+  c->var_index_key = c->d_stream.p;
+  c->var_index_blocks = units;
+  c->var_index_bits = total_bits;
   c->var_host_key = h_stream;   // the resident stream + index describe this host buffer
   c->var_host_bytes = bytes;
   return ZFB_OK;
@@ -326,28 +428,94 @@ extern "C" int zfb_decompress_var_host(zfb_ctx* c, int dtype, int dims, size_t n
   CU_TRY(c, cudaSetDevice(c->device));
   const size_t esz = dtype == ZFB_FLOAT ? 4 : 8;
   const size_t n = nx * (dims >= 2 ? ny : 1) * (dims >= 3 ? nz : 1);
+  const size_t units = zfb_index_count(dims, nx, ny, nz);
   if ((rc = ensure(c, c->d_out, n * esz))) return rc;
   const bool metrics = h_orig != nullptr;
   const bool orig_resident = metrics && h_orig == c->h_orig_key && c->orig_bytes == n * esz && c->d_orig.p;
   if (metrics && !orig_resident) {
     if ((rc = ensure(c, c->d_orig, n * esz))) return rc;
-    CU_TRY(c, cudaMemcpyAsync(c->d_orig.p, h_orig, n * esz, cudaMemcpyHostToDevice, c->stream));
   }
   c->fused_valid = false;
+  const slab_plan sp = plan_var_slabs(dims, nx, ny, nz, esz);
   // the index kept by zfb_compress_var_host is only trusted together with the bytes it was built from, so the
   // stream is uploaded again (cheap next to the field) and the index reused when the host buffer is the same
   const bool index_resident = c->var_host_key == h_stream && c->var_host_bytes == stream_bytes &&
-                              c->var_index_key == c->d_stream.p && c->d_stream.p;
+                              c->var_index_key == c->d_stream.p && c->d_stream.p && c->var_index_blocks == units &&
+                              c->var_slab_bits.size() == sp.nslabs + 1;
   if (!index_resident) {
+    // a stream from elsewhere: upload it whole, rebuild the index on the device, decode in one piece
     if ((rc = ensure(c, c->d_stream, stream_bytes + 16))) return rc;
     c->var_index_key = nullptr;
+    c->var_host_key = nullptr;
+    CU_TRY(c, cudaMemcpyAsync(c->d_stream.p, h_stream, stream_bytes, cudaMemcpyHostToDevice, c->stream));
+    if (metrics && !orig_resident) CU_TRY(c, cudaMemcpyAsync(c->d_orig.p, h_orig, n * esz, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = zfb_decode_var_dev(c, dtype, dims, nx, ny, nz, m, c->d_stream.p, stream_bytes, nullptr, c->d_out.p,
+                                 metrics ? c->d_orig.p : nullptr)))
+      return rc;
+    CU_TRY(c, cudaMemcpyAsync(h_out, c->d_out.p, n * esz, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+  } else {
+    const size_t stream_words = (stream_bytes + 7) / 8;
+    const uint64_t* index = (const uint64_t*)c->var_index.p;
+    cudaStream_t up, down;
+    std::vector<cudaEvent_t> ev_up(sp.nslabs), ev_k(sp.nslabs);
+    cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags(&down, cudaStreamNonBlocking);
+    for (size_t i = 0; i < sp.nslabs; i++) { cudaEventCreateWithFlags(&ev_up[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming); }
+    std::vector<zfb_partials> slab_parts(metrics ? sp.nslabs : 0);
+    partials_dev* d_slab_parts = nullptr;
+    int status = ZFB_OK;
+    if (metrics && cudaMalloc(&d_slab_parts, sp.nslabs * sizeof(partials_dev)) != cudaSuccess) { cudaGetLastError(); c->err = "cudaMalloc failed"; status = ZFB_ENOMEM; }
+    size_t row0 = 0, u0 = 0, sent_words = 0;
+    for (size_t s = 0; s < sp.nslabs && status == ZFB_OK; s++) {
+      const size_t rows = (row0 + sp.thick <= sp.slowest) ? sp.thick : sp.slowest - row0;
+      size_t sx, sy, sz;
+      slab_dims(dims, nx, ny, nz, rows, sx, sy, sz);
+      const size_t off_e = row0 * sp.row_elems, slab_bytes = rows * sp.row_elems * esz;
+      // the words this slab's blocks read: up to its last bit, plus the decoders' look-ahead
+      size_t upto = (size_t)((c->var_slab_bits[s + 1] + 63) / 64) + 2;
+      if (upto > stream_words || s + 1 == sp.nslabs) upto = stream_words;
+      if (upto > sent_words) {
+        if (cudaMemcpyAsync((char*)c->d_stream.p + sent_words * 8, (const char*)h_stream + sent_words * 8, (upto - sent_words) * 8,
+                            cudaMemcpyHostToDevice, up) != cudaSuccess) { status = ZFB_ECUDA; break; }
+        sent_words = upto;
+      }
+      char* dorig = metrics ? (char*)c->d_orig.p + off_e * esz : nullptr;
+      if (metrics && !orig_resident &&
+          cudaMemcpyAsync(dorig, (const char*)h_orig + off_e * esz, slab_bytes, cudaMemcpyHostToDevice, up) != cudaSuccess) { status = ZFB_ECUDA; break; }
+      cudaEventRecord(ev_up[s], up);
+      cudaStreamWaitEvent(c->stream, ev_up[s], 0);
+      char* dout = (char*)c->d_out.p + off_e * esz;
+      status = decode_var_part(c, dtype, dims, sx, sy, sz, m, c->d_stream.p, stream_words, index + u0, dout, dorig);
+      if (status) break;
+      if (metrics) cudaMemcpyAsync(d_slab_parts + s, c->result, sizeof(partials_dev), cudaMemcpyDeviceToDevice, c->stream);
+      cudaEventRecord(ev_k[s], c->stream);
+      cudaStreamWaitEvent(down, ev_k[s], 0);
+      if (cudaMemcpyAsync((char*)h_out + off_e * esz, dout, slab_bytes, cudaMemcpyDeviceToHost, down) != cudaSuccess) { status = ZFB_ECUDA; break; }
+      u0 += zfb_index_count(dims, sx, sy, sz);
+      row0 += rows;
+    }
+    cudaError_t e1 = cudaStreamSynchronize(up), e2 = cudaStreamSynchronize(c->stream), e3 = cudaStreamSynchronize(down);
+    if (status == ZFB_OK && metrics &&
+        cudaMemcpy(slab_parts.data(), d_slab_parts, sp.nslabs * sizeof(partials_dev), cudaMemcpyDeviceToHost) != cudaSuccess) status = ZFB_ECUDA;
+    if (d_slab_parts) cudaFree(d_slab_parts);
+    for (size_t i = 0; i < sp.nslabs; i++) { cudaEventDestroy(ev_up[i]); cudaEventDestroy(ev_k[i]); }
+    cudaStreamDestroy(up);
+    cudaStreamDestroy(down);
+    if (status == ZFB_OK && (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)) {
+      c->err = std::string("decompress_var_host: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3);
+      status = ZFB_ECUDA;
+    }
+    if (status) return status;
+    if (metrics) {
+      zfb_partials total;
+      memset(&total, 0, sizeof total);
+      total.max_orig = -1.7976931348623157e308;
+      total.neg_min_orig = -1.7976931348623157e308;
+      zfb_partials_combine(&total, slab_parts.data(), (int)sp.nslabs);
+      if ((rc = zfb_partials_set(c, &total))) return rc;
+    }
   }
-  CU_TRY(c, cudaMemcpyAsync(c->d_stream.p, h_stream, stream_bytes, cudaMemcpyHostToDevice, c->stream));
-  if ((rc = zfb_decode_var_dev(c, dtype, dims, nx, ny, nz, m, c->d_stream.p, stream_bytes, nullptr, c->d_out.p,
-                               metrics ? c->d_orig.p : nullptr)))
-    return rc;
-  CU_TRY(c, cudaMemcpyAsync(h_out, c->d_out.p, n * esz, cudaMemcpyDeviceToHost, c->stream));
-  CU_TRY(c, cudaStreamSynchronize(c->stream));
   if (metrics) {
     c->h_orig_key = h_orig;
     c->orig_bytes = n * esz;

@@ -349,11 +349,15 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_chunks_kernel(uint64_t* __r
 }
 
 // offsets[b] = first bit of block b, offsets[n] = total bits
+// base (nullable): device scalar added to every offset -- the bits of the slabs encoded before this one.  It may be
+// offsets[0] itself (the total the previous slab's scan left there): every thread then writes back what it read.
 __global__ void __launch_bounds__(SCAN_THREADS) scan_offsets_kernel(const uint32_t* __restrict__ lens, size_t n,
                                                                     const uint64_t* __restrict__ chunk_sums,
-                                                                    size_t nchunks, uint64_t* __restrict__ offsets)
+                                                                    size_t nchunks, uint64_t* offsets,
+                                                                    const uint64_t* base_ptr)
 {
   __shared__ uint64_t sh[33];
+  const uint64_t bit0 = base_ptr ? *base_ptr : 0;
   const size_t base = (size_t)blockIdx.x * SCAN_CHUNK + (size_t)threadIdx.x * SCAN_ITEMS;
   uint32_t l[SCAN_ITEMS];
   uint64_t s = 0;
@@ -363,22 +367,24 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_offsets_kernel(const uint32
     s += l[i];
   }
   uint64_t total;
-  uint64_t ex = chunk_sums[blockIdx.x] + block_exclusive_scan(s, sh, total);
+  uint64_t ex = bit0 + chunk_sums[blockIdx.x] + block_exclusive_scan(s, sh, total);
 #pragma unroll
   for (int i = 0; i < SCAN_ITEMS; i++) {
     if (base + i < n) offsets[base + i] = ex;
     ex += l[i];
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) offsets[n] = chunk_sums[nchunks];
+  if (blockIdx.x == 0 && threadIdx.x == 0) offsets[n] = bit0 + chunk_sums[nchunks];
 }
 
 // zero the words the compaction will OR into: ceil(total_bits / 64) words, total read from the device
-__global__ void __launch_bounds__(256) zero_stream_kernel(uint64_t* __restrict__ stream, const uint64_t* __restrict__ total_bits,
-                                                          size_t cap_words)
+// (a later slab starts behind the word that holds the previous slab's last bits: that word is already in use)
+__global__ void __launch_bounds__(256) zero_stream_kernel(uint64_t* __restrict__ stream, const uint64_t* base_bits,
+                                                          const uint64_t* __restrict__ total_bits, size_t cap_words)
 {
+  const size_t first = base_bits ? (size_t)((*base_bits + 63) >> 6) : 0;
   size_t nw = (size_t)((*total_bits + 63) >> 6);
   if (nw > cap_words) nw = cap_words;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nw; i += (size_t)gridDim.x * blockDim.x) stream[i] = 0;
+  for (size_t i = first + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nw; i += (size_t)gridDim.x * blockDim.x) stream[i] = 0;
 }
 
 // ---- step 3: staged words -> bit-tight stream ---------------------------------------------------
