@@ -195,6 +195,15 @@ int zfb_decode_var_dev(zfb_ctx* ctx, int dtype, int dims, size_t nx, size_t ny, 
                        const void* d_stream, size_t stream_bytes, const uint64_t* d_index, void* d_out,
                        const void* d_orig);
 
+/* A stream kept for later needs its index, but not all of it: keep every `stride`-th entry (entries 0, stride,
+ * 2*stride, ... of the index, then the total number of bits: ceil(zfb_index_count()/stride) + 1 values, e.g. 1 MB
+ * for the 16 Mi blocks of the benchmark slab at stride 128) and expand it again here: the segments between two
+ * kept entries are walked in parallel (milliseconds instead of the sequential walk's minutes).  Returns ZFB_ESTATE
+ * if a segment does not end where the next kept entry says (wrong parameters or corrupt stream).  Synchronises. */
+int zfb_index_expand_dev(zfb_ctx* ctx, int dtype, int dims, size_t nx, size_t ny, size_t nz, const zfb_mode* m,
+                         const void* d_stream, size_t stream_bytes, const uint64_t* d_coarse, size_t stride,
+                         uint64_t* d_index);
+
 /* Host-pointer forms (ZFPCompressor::compress / decompress bodies, zfpCompressor.hpp:96-141,186-234).
  * The uploaded field, the stream and its index stay resident, keyed by h_in / h_stream. */
 int zfb_compress_var_host(zfb_ctx* ctx, int dtype, int dims, size_t nx, size_t ny, size_t nz, const zfb_mode* m,

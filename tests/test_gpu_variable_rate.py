@@ -289,3 +289,29 @@ def test_variable_rate_host_pipeline_with_many_slabs():
     env = dict(os.environ, ZFB_SLAB_MB="1")
     r = subprocess.run([sys.executable, "-c", _SLAB_SCRIPT], cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "SLABS OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_coarse_index_expansion(codec, pkg, oracle):
+    """A stream kept for later needs only every stride-th index entry: the full index comes back by walking the
+    segments in parallel, and a coarse index that does not fit the stream is refused."""
+    torch = _torch()
+    for dtype, shape in ((np.float32, (40, 48, 64)), (np.float32, (70001,)), (np.float64, (12, 20, 28)), (np.float32, (90, 70))):
+        f = _field(shape, dtype, seed=13)
+        d_f = torch.from_numpy(f).cuda()
+        tdt = torch.float32 if dtype == np.float32 else torch.float64
+        m, p = pkg.mode_accuracy(0.02), oracle.params_accuracy(0.02)
+        ni = pkg.index_count(shape)
+        full = torch.zeros(ni + 1, dtype=torch.int64, device="cuda")
+        s, _ = codec.encode_var(d_f, m, index=full)
+        for stride in (1, 7, 128, ni + 5):
+            coarse = torch.cat([full[:-1][::stride], full[-1:]]).contiguous()
+            got = codec.index_expand(s, shape, tdt, m, coarse, stride)
+            assert torch.equal(got, full), (dtype, shape, stride)
+        out = codec.decode_var(s.clone(), shape, tdt, m, index=got)
+        g_ref, _ = oracle.decompress_ex(oracle.compress_ex(f, p), shape, dtype, p)
+        assert np.array_equal(out.cpu().numpy().view(np.uint8), g_ref.view(np.uint8)), (dtype, shape)
+        if ni > 20:
+            wrong = torch.cat([full[:-1][::7], full[-1:]]).contiguous()
+            wrong[1] += 3  # a kept entry that is not a block boundary
+            with pytest.raises(pkg.ZfbError):
+                codec.index_expand(s, shape, tdt, m, wrong, 7)

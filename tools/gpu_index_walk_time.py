@@ -19,3 +19,16 @@ for shape in ((64, 256, 256), (128, 512, 512)):
     nb = pkg.block_count(shape)
     ref = codec.decode_var(s, shape, torch.float32, m)
     print("shape", shape, "blocks", nb, "bare decode %.3f s  (%.2f us per block)" % (dt, dt / nb * 1e6), "equal", bool(torch.equal(out, ref)))
+# the same with a coarse index (every 128th entry): parallel expansion
+for shape in ((128, 512, 512), (256, 1024, 1024)):
+    f = bench.make_field(torch, shape, "float32", "lognormal", 0, torch.device("cuda", 0))
+    m = pkg.mode_accuracy(0.01)
+    full = torch.zeros(pkg.index_count(shape) + 1, dtype=torch.int64, device="cuda")
+    s, nbytes = codec.encode_var(f, m, index=full)
+    coarse = torch.cat([full[:-1][::128], full[-1:]]).contiguous()
+    torch.cuda.synchronize()
+    t = time.time()
+    got = codec.index_expand(s, shape, torch.float32, m, coarse, 128)
+    torch.cuda.synchronize()
+    dt = time.time() - t
+    print("shape", shape, "blocks", pkg.block_count(shape), "coarse entries", coarse.numel(), "expand %.1f ms" % (dt * 1e3), "equal", bool(torch.equal(got, full)))

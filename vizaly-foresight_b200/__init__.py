@@ -119,6 +119,7 @@ def lib():
         "zfb_index_unit": (sz, [i]),
         "zfb_index_count": (sz, [i, sz, sz, sz]),
         "zfb_encode_var_dev": (i, [vp, i, i, sz, sz, sz, MP, vp, vp, sz, vp, C.POINTER(sz)]),
+        "zfb_index_expand_dev": (i, [vp, i, i, sz, sz, sz, MP, vp, sz, vp, sz, vp]),
         "zfb_decode_var_dev": (i, [vp, i, i, sz, sz, sz, MP, vp, sz, vp, vp, vp]),
         "zfb_compress_var_host": (i, [vp, i, i, sz, sz, sz, MP, vp, vp, sz, C.POINTER(sz)]),
         "zfb_decompress_var_host": (i, [vp, i, i, sz, sz, sz, MP, vp, sz, vp, vp]),
@@ -380,6 +381,19 @@ class Codec:
                                              stream.numel(), index.data_ptr() if index is not None else None,
                                              out.data_ptr(), orig.data_ptr() if orig is not None else None),
                     "zfb_decode_var_dev")
+        return out
+
+    def index_expand(self, stream, shape, dtype, mode, coarse, stride, out=None):
+        """coarse: every stride-th index entry plus the total (uint64 / int64 tensor) -> the full index tensor."""
+        import torch
+
+        self.use_torch_stream()
+        d, nx, ny, nz = dims_of(shape)
+        if out is None:
+            out = torch.empty(index_count(shape) + 1, dtype=torch.int64, device=stream.device)
+        self._check(lib().zfb_index_expand_dev(self._h, _dtype_code(dtype), d, nx, ny, nz, C.byref(mode), stream.data_ptr(),
+                                               stream.numel(), coarse.data_ptr(), int(stride), out.data_ptr()),
+                    "zfb_index_expand_dev")
         return out
 
     def compress_var_host(self, a, mode):

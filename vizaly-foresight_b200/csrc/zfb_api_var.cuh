@@ -253,6 +253,45 @@ static int launch_dec_var(zfb_ctx* c, int dims, const geom& g, const stream_para
   return ZFB_OK;
 }
 
+template <typename Scalar>
+static void launch_index_expand(zfb_ctx* c, int dims, const void* d_stream, size_t stream_words, size_t nblocks,
+                                const stream_params& sp, const uint64_t* coarse, size_t stride, uint64_t* index, unsigned* bad,
+                                int grid)
+{
+  const uint64_t* st = (const uint64_t*)d_stream;
+  if (dims == 1) index_expand_kernel<Scalar, 1><<<grid, 64, 0, c->stream>>>(st, stream_words, nblocks, sp, coarse, stride, index, bad);
+  else if (dims == 2) index_expand_kernel<Scalar, 2><<<grid, 64, 0, c->stream>>>(st, stream_words, nblocks, sp, coarse, stride, index, bad);
+  else index_expand_kernel<Scalar, 3><<<grid, 64, 0, c->stream>>>(st, stream_words, nblocks, sp, coarse, stride, index, bad);
+}
+
+extern "C" int zfb_index_expand_dev(zfb_ctx* c, int dtype, int dims, size_t nx, size_t ny, size_t nz, const zfb_mode* m,
+                                    const void* d_stream, size_t stream_bytes, const uint64_t* d_coarse, size_t stride,
+                                    uint64_t* d_index)
+{
+  int rc = check_var_args(c, dtype, dims, nx, ny, nz, m);
+  if (rc) return rc;
+  if (!d_stream || !d_coarse || !d_index || !stride || !stream_bytes) { c->err = "null pointer / zero stride"; return ZFB_EINVAL; }
+  CU_TRY(c, cudaSetDevice(c->device));
+  const size_t nblocks = count_blocks(dims, nx, ny, nz);
+  const size_t units = (nblocks + index_unit(dims) - 1) / index_unit(dims);
+  const size_t nseg = (units + stride - 1) / stride;
+  if ((rc = ensure(c, c->var_chunks, 16))) return rc;
+  unsigned* bad = (unsigned*)c->var_chunks.p;
+  CU_TRY(c, cudaMemsetAsync(bad, 0, 4, c->stream));
+  const size_t want = (nseg + 63) / 64, cap = (size_t)c->sm_count * 32;
+  const int grid = (int)(want < cap ? (want ? want : 1) : cap);
+  const stream_params sp = to_params(m);
+  if (dtype == ZFB_FLOAT) launch_index_expand<float>(c, dims, d_stream, (stream_bytes + 7) / 8, nblocks, sp, d_coarse, stride, d_index, bad, grid);
+  else launch_index_expand<double>(c, dims, d_stream, (stream_bytes + 7) / 8, nblocks, sp, d_coarse, stride, d_index, bad, grid);
+  c->launches++;
+  CU_TRY(c, cudaGetLastError());
+  unsigned h_bad = 0;
+  CU_TRY(c, cudaMemcpyAsync(&h_bad, bad, 4, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  if (h_bad) { c->err = "coarse index does not match the stream (wrong mode parameters or corrupt data)"; return ZFB_ESTATE; }
+  return ZFB_OK;
+}
+
 // Decode one (sub-)field whose index entries start at `index`; metrics (d_orig != NULL) end in the context's partials.
 static int decode_var_part(zfb_ctx* c, int dtype, int dims, size_t nx, size_t ny, size_t nz, const zfb_mode* m,
                            const void* d_stream, size_t stream_words, const uint64_t* index, void* d_out, const void* d_orig)

@@ -649,4 +649,36 @@ __global__ void index_var_kernel(const uint64_t* __restrict__ stream, size_t str
   offsets[(nblocks + UNIT - 1) / UNIT] = pos;
 }
 
+// ---- index expansion: a coarse index (every `stride`-th entry) -> the full index, segments walked in parallel ----
+// Each thread walks one segment with the parse-only decoder; `bad` is raised if a walk does not end where the next
+// coarse entry says it should (wrong parameters, wrong stream, corrupt bits).
+template <typename Scalar, int DIMS>
+__global__ void __launch_bounds__(64) index_expand_kernel(const uint64_t* __restrict__ stream, size_t stream_words, size_t nblocks,
+                                                          stream_params sp, const uint64_t* __restrict__ coarse, size_t stride,
+                                                          uint64_t* __restrict__ offsets, unsigned* __restrict__ bad)
+{
+  constexpr int BS = 1 << (2 * DIMS);
+  constexpr size_t UNIT = DIMS == 1 ? VAR1_GROUP : 1;
+  const size_t units = (nblocks + UNIT - 1) / UNIT;
+  const size_t nseg = (units + stride - 1) / stride;
+  Scalar f[BS];
+  for (size_t seg = (size_t)blockIdx.x * blockDim.x + threadIdx.x; seg < nseg; seg += (size_t)gridDim.x * blockDim.x) {
+    uint64_t pos = coarse[seg];
+    const size_t u_end = (seg + 1) * stride < units ? (seg + 1) * stride : units;
+    for (size_t u = seg * stride; u < u_end; u++) {
+      offsets[u] = pos;
+      for (size_t q = 0; q < UNIT; q++) {
+        const size_t b = u * UNIT + q;
+        if (b >= nblocks) break;
+        const size_t w0 = (size_t)(pos >> 6);
+        const size_t left = stream_words > w0 ? stream_words - w0 : 0;
+        slot_reader r(stream + w0, left > 0xffffffffull ? 0xffffffffu : (unsigned)left, (unsigned)(pos & 63));
+        pos += decode_block<Scalar, DIMS, true>(f, sp, r);
+      }
+    }
+    if (pos != coarse[seg + 1]) atomicOr(bad, 1u);
+    if (seg + 1 == nseg) offsets[units] = pos;
+  }
+}
+
 }  // namespace zfb
