@@ -14,13 +14,13 @@
 using namespace zfb;
 
 static int g_use_f3 = 1;  // float/3D goes through the fast coder (zfb_codec_f3.cuh) unless switched off
-static uint16_t g_enc[256];
+static uint32_t g_enc[512];
 static uint32_t g_dec[512];
 static f3::tables host_tables()
 {
   static bool built = false;
   if (!built) {
-    for (unsigned i = 0; i < 256; i++) g_enc[i] = f3::enc_entry(i);
+    for (unsigned i = 0; i < 512; i++) g_enc[i] = f3::enc_entry(i);
     for (unsigned i = 0; i < 512; i++) g_dec[i] = f3::dec_entry(i >> 8, i & 255);
     built = true;
   }

@@ -87,12 +87,11 @@ template <class Reader, class PR>
 ZFB_HD bool decode_planes(planes64& PH, planes64& PL, int& emax, int& kend, const stream_params& sp, Reader& r,
                           const tables& tb, const PR& ps)
 {
-  const uint32_t head = r.lo;
+  const uint32_t head = f3::fetch32(r, 0);
   emax = 0;
   kend = 63;
   if (!(head & 1u)) return false;
   emax = (int)((head >> 1) & 0x7ffu) - 1023;
-  r.consume(12);
   kend = f3::parse_planes<64>(ps, sp.maxbits, 12u, 64 - block_precision<3>(emax, sp), r, tb);
   ZFB_UNROLL for (int q = 0; q < 16; q++) {
     u32x4 v = ps.ld(q);

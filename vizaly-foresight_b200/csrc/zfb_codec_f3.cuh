@@ -37,6 +37,7 @@ namespace f3 {
 struct alignas(16) u32x4 {
   uint32_t x, y, z, w;
 };
+
 // Row q lives at p[(q >> SH) * stride + (q & (2^SH - 1))]: SH = 0 for 16-byte columns (float tiles), SH = 1 for
 // the 32-byte columns of a double tile (two consecutive rows share one 32-byte row segment).
 template <int SH> struct plane_rows_t {
@@ -45,6 +46,26 @@ template <int SH> struct plane_rows_t {
   ZFB_HD unsigned at(int r) const { return SH ? ((unsigned)r >> SH) * stride + ((unsigned)r & ((1u << SH) - 1u)) : (unsigned)r * stride; }
   ZFB_HD u32x4 ld(int r) const { return p[at(r)]; }
   ZFB_HD void st(int r, const u32x4& v) const { p[at(r)] = v; }
+  // one plane: plane k is the (k & 1) half of row k >> 1
+  ZFB_HD void ld64(int k, uint32_t& lo, uint32_t& hi) const
+  {
+#if defined(__CUDA_ARCH__)
+    const uint2 v = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint32_t*>(p + at(k >> 1)) + 2 * (k & 1));
+    lo = v.x; hi = v.y;
+#else
+    const u32x4& v = p[at(k >> 1)];
+    lo = (k & 1) ? v.z : v.x; hi = (k & 1) ? v.w : v.y;
+#endif
+  }
+  ZFB_HD void st64(int k, uint32_t lo, uint32_t hi) const
+  {
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<uint2*>(reinterpret_cast<uint32_t*>(p + at(k >> 1)) + 2 * (k & 1)) = make_uint2(lo, hi);
+#else
+    u32x4& v = p[at(k >> 1)];
+    if (k & 1) { v.z = lo; v.w = hi; } else { v.x = lo; v.y = hi; }
+#endif
+  }
 };
 typedef plane_rows_t<0> plane_rows;
 
@@ -124,15 +145,27 @@ ZFB_HD uint32_t bperm(uint32_t a, uint32_t b, uint32_t sel)
 // ---------------------------------------------------------------------------------------------
 // coder tables (built once per CTA into shared memory; 512 B + 2 KiB)
 // ---------------------------------------------------------------------------------------------
-// ENC[b]: byte b (LSB = first coefficient) expanded by 0 -> "0", 1 -> "11"; 8 + popc(b) bits.
-ZFB_HD uint16_t enc_entry(unsigned b)
+// ENC[b], b in 0..255: byte b of the not yet significant part of a plane (LSB = first coefficient) expanded by
+// 0 -> "0", 1 -> "11" (a one is followed by the group test "more ones follow"); 8 + popc(b) code bits.
+// ENC[256 + b]: the same for the byte that holds the plane's LAST one: the code stops behind that one and the group
+// test that follows it is 0; msb(b) + 1 + popc(b) code bits (ENC[256] = nothing at all: a byte behind the last one).
+// Entry = code | length << 16.
+ZFB_HD uint32_t enc_entry(unsigned i)
 {
+  const unsigned b = i & 255u;
+  const bool last = i >= 256u;
   unsigned e = 0, pos = 0;
-  for (int i = 0; i < 8; i++) {
-    if ((b >> i) & 1u) { e |= 3u << pos; pos += 2; }
-    else pos += 1;
+  int top = -1;
+  for (int j = 0; j < 8; j++)
+    if ((b >> j) & 1u) top = j;
+  const int nbits = last ? top + 1 : 8;
+  for (int j = 0; j < nbits; j++) {
+    if ((b >> j) & 1u) {
+      e |= ((last && j == top) ? 1u : 3u) << pos;
+      pos += 2;
+    } else pos += 1;
   }
-  return (uint16_t)e;
+  return e | (pos << 16);
 }
 
 // DEC[state][v]: run zfp's group-test parser over the 8 stream bits v (LSB first) from `state`
@@ -170,7 +203,7 @@ ZFB_HD uint32_t dec_entry(unsigned state, unsigned v)
 }
 
 struct tables {
-  const uint16_t* enc;  // 256 entries
+  const uint32_t* enc;  // 512 entries
   const uint32_t* dec;  // 512 entries
   uint32_t enc_s, dec_s;  // device: 32-bit shared-memory addresses of the two tables
 };
@@ -181,7 +214,7 @@ ZFB_HD uint32_t enc_at(const tables& tb, uint32_t i)
 {
 #if defined(__CUDA_ARCH__)
   uint32_t v;
-  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(tb.enc_s + 2u * i));
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(tb.enc_s + 4u * i));
   return v;
 #else
   return tb.enc[i];
@@ -353,12 +386,24 @@ template <class Sink> struct writer32 {
     acc = full ? c : acc;
     cnt &= 31u;
   }
-  ZFB_HD void put64(uint32_t xl, uint32_t xh)  // a whole plane of 64 significant coefficients
+  ZFB_HD void put64(uint32_t xl, uint32_t xh)  // exactly 64 bits
   {
     const uint32_t w0 = acc | (xl << cnt);
     const uint32_t w1 = shl_pair(xl, xh, cnt);
     acc = carry_out(xh, cnt);
     sink.word2(w0, w1);
+  }
+  ZFB_HD void putv(uint32_t xl, uint32_t xh, unsigned len)  // len in [0, 64]; bits of (xh:xl) above len are zero
+  {
+    const uint32_t w0 = acc | (xl << cnt);
+    const uint32_t w1 = shl_pair(xl, xh, cnt);
+    const uint32_t w2 = carry_out(xh, cnt);
+    const unsigned t = cnt + len;  // < 96
+    const bool f1 = t >= 32u, f2 = t >= 64u;
+    sink.word_if(f1, w0);
+    sink.word_if(f2, w1);
+    acc = f2 ? w2 : (f1 ? w1 : w0);
+    cnt = t & 31u;
   }
   ZFB_HD void flush()
   {
@@ -367,6 +412,11 @@ template <class Sink> struct writer32 {
   }
 };
 
+ZFB_HD int msb64(uint32_t lo, uint32_t hi)  // (hi:lo) != 0
+{
+  return hi ? 32 + msb32(hi) : msb32(lo);
+}
+
 // ---------------------------------------------------------------------------------------------
 // encode
 // ---------------------------------------------------------------------------------------------
@@ -374,6 +424,10 @@ template <class Sink> struct writer32 {
 // NP-1 .. kmin of 64 coefficients, read from the plane rows.  On entry the top 16 planes (rows NP/2-8 ..
 // NP/2-1) are finished; every lower group of 16 planes is still in its half-transposed form and is finished
 // only when the budget reaches it.
+//
+// Per plane (n = coefficients already significant): ONE put of n + 1 bits (the verbatim bits and the first
+// group test), then -- only if the rest of the plane holds a one -- table steps of two bytes each.  No case
+// split on n: the plane is handled as a 64-bit value.
 template <int NP, class Sink, class PR>
 ZFB_HD unsigned encode_planes(const PR& ps, unsigned maxbits, uint32_t header, unsigned hbits, int kmin, Sink& sink,
                               const tables& tb)
@@ -382,51 +436,44 @@ ZFB_HD unsigned encode_planes(const PR& ps, unsigned maxbits, uint32_t header, u
   bw.put(header, hbits);
 
   unsigned n = 0;
-  u32x4 cur;
-  cur.x = cur.y = cur.z = cur.w = 0u;
   ZFB_NOUNROLL for (int k = NP - 1; k >= kmin; k--) {
     if (bw.bits() >= maxbits) break;
     if (k < NP - 16 && (k & 15) == 15) finish_rows(ps, (k - 15) >> 1);  // next 16 planes: finish their transpose now
-    if (k & 1) cur = ps.ld(k >> 1);
-    const uint32_t xl = (k & 1) ? cur.z : cur.x, xh = (k & 1) ? cur.w : cur.y;
+    uint32_t xl, xh;
+    ps.ld64(k, xl, xh);
     if (n == 64u) { bw.put64(xl, xh); continue; }  // every coefficient significant: the plane goes out verbatim
-    // y = the not yet significant coefficients; the first group test (y != 0) rides on the verbatim bits
-    uint32_t yl, yh;
-    if (n < 32) { yl = fsr(xl, xh, n); yh = xh >> n; }
-    else { yl = xh >> (n - 32); yh = 0u; }
-    const uint32_t t = (yl | yh) ? 1u : 0u;
-    if (n < 32) bw.put((xl & mask32(n)) | (t << n), n + 1u);
-    else {
-      bw.put(xl, 32);
-      bw.put((xh & mask32(n - 32)) | (t << (n - 32)), n - 31u);
+    // y = the not yet significant coefficients; t = first group test (y != 0)
+    const uint64_t x = ((uint64_t)xh << 32) | xl;
+    uint64_t y = x >> n;
+    const uint32_t t = y ? 1u : 0u;
+    {
+      // the n verbatim bits with the test bit behind them: bits >= n of x are y, so x ^ ((y ^ t) << n) clears them
+      // and leaves t at position n
+      const uint64_t v = x ^ ((y ^ (uint64_t)t) << n);
+      bw.putv((uint32_t)v, (uint32_t)(v >> 32), n + 1u);
     }
     if (t) {
-      // bytes of y up to the one holding the last one-bit, two table codes (<= 16 bits each) per put
-      const unsigned plast = yh ? 32u + (unsigned)msb32(yh) : (unsigned)msb32(yl);
-      const unsigned fpos = plast & 7u;
+      const unsigned plast = (unsigned)msb64((uint32_t)y, (uint32_t)(y >> 32));
+      // the one of coefficient 63 is implicit: neither it nor a group test behind it is coded
       const bool implicit = n + plast == 63u;
-      unsigned nb = (plast >> 3) + 1u;
-      for (;;) {
-        const uint32_t b0 = yl & 0xffu, b1 = (yl >> 8) & 0xffu;
-        uint32_t e0 = enc_at(tb, b0), e1 = enc_at(tb, b1);
-        unsigned l0 = 8u + (unsigned)popc32(b0), l1 = 8u + (unsigned)popc32(b1);
-        if (nb <= 2u) {
-          // the final byte: its code stops behind the last one; the group test that follows is 0 (no more
-          // ones in this plane), or absent together with the one itself when that is coefficient 63
-          uint32_t e = nb == 1u ? e0 : e1;
-          unsigned l = (nb == 1u ? l0 : l1) - 7u + fpos;
-          if (implicit) l -= 2u;
-          else e &= ~(1u << (l - 1u));
-          e &= mask32(l);
-          if (nb == 1u) { e0 = e; l0 = l; e1 = 0u; l1 = 0u; }
-          else { e1 = e; l1 = l; }
-        }
-        bw.put(e0 | (e1 << l0), l0 + l1);
-        if (nb <= 2u) break;
-        nb -= 2u;
-        yl = fsr(yl, yh, 16); yh >>= 16;
-      }
+      unsigned nb = (plast >> 3) + 1u;  // bytes of y up to the one holding the last one-bit
       n += plast + 1u;
+      for (;;) {
+        const uint32_t yl = (uint32_t)y;
+        const uint32_t e0 = enc_at(tb, (yl & 0xffu) + (nb == 1u ? 256u : 0u));
+        const uint32_t e1 = enc_at(tb, ((yl >> 8) & 0xffu) + (nb <= 2u ? 256u : 0u));  // nb == 1: byte 1 is 0 -> ENC[256] = nothing
+        const unsigned l0 = e0 >> 16;
+        uint32_t code = (e0 & 0xffffu) | ((e1 & 0xffffu) << l0);
+        unsigned len = l0 + (e1 >> 16);
+        if (nb <= 2u) {
+          if (implicit) { len -= 2u; code &= ~(1u << len); }
+          bw.put(code, len);
+          break;
+        }
+        bw.put(code, len);
+        nb -= 2u;
+        y >>= 16;
+      }
     }
   }
   const unsigned total = bw.bits();  // bits emitted (the fixed-rate sinks truncate / pad to the slot)
@@ -578,9 +625,50 @@ struct reader32 {
   }
 };
 
+// Bits of a slot by position (the parser keeps no streaming window: every access is a fresh, position-indexed fetch,
+// so the only loop-carried reader state is the bit position).  R needs word_at(i) and bit0.
+template <class R> ZFB_HD uint32_t fetch32(const R& r, unsigned pos)
+{
+  const unsigned p = pos + r.bit0, i = p >> 5;
+  return fsr(r.word_at(i), r.word_at(i + 1), p & 31u);
+}
+template <class R> ZFB_HD void fetch64(const R& r, unsigned pos, uint32_t& lo, uint32_t& hi)
+{
+  const unsigned p = pos + r.bit0, i = p >> 5, sh = p & 31u;
+  const uint32_t w0 = r.word_at(i), w1 = r.word_at(i + 1), w2 = r.word_at(i + 2);
+  lo = fsr(w0, w1, sh);
+  hi = fsr(w1, w2, sh);
+}
+
+// Unchecked reader over words in shared memory (tile kernels: the slot buffer is followed by other shared data, so
+// the look-ahead words of the last slot are readable; what they hold is never used).
+struct smem_words {
+  uint32_t base;  // shared-memory address of the slot's first word
+  static constexpr unsigned bit0 = 0;
+  ZFB_HD uint32_t word_at(unsigned i) const
+  {
+#if defined(__CUDA_ARCH__)
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(base + 4u * i));
+    return v;
+#else
+    (void)i;
+    return 0u;
+#endif
+  }
+};
+
 // Shared slot parser (float: NP = 32 planes, 9 header bits; double: NP = 64, 12): fills the plane rows with
 // the decoded planes (finished form) and returns the first plane index that was NOT decoded (kmin - 1 .. NP-1),
-// so the caller knows which groups of 16 planes are non-zero.  `r` is positioned behind the header.
+// so the caller knows which groups of 16 planes are non-zero.  The header has been consumed by the caller.
+//
+// Per plane (n = coefficients already significant): the min(n, budget) verbatim bits come out of one 64-bit
+// fetch; the group-test code behind them is parsed by
+//   * table steps (<= 8 stream bits each, DEC) while neither coefficient 63 nor the end of the budget can be
+//     reached within a step (n <= 54 and >= 8 bits left), and
+//   * token steps otherwise: one group test plus one zero run ending in a one, by count-trailing-zeros, with zfp's
+//     end rules done exactly (the one of coefficient 63 is implicit; a run cut off by the budget still deposits
+//     its one).
 template <int NP, class Reader, class PR>
 ZFB_HD int parse_planes(const PR& ps, unsigned maxbits, unsigned hbits, int kmin, Reader& r, const tables& tb)
 {
@@ -589,113 +677,69 @@ ZFB_HD int parse_planes(const PR& ps, unsigned maxbits, unsigned hbits, int kmin
     z.x = z.y = z.z = z.w = 0u;
     ZFB_UNROLL for (int q = 0; q < NP / 2; q++) ps.st(q, z);
   }
-  unsigned remaining = maxbits - hbits;
+  unsigned pos = hbits;  // bit position inside the slot
   unsigned n = 0;
-  u32x4 cur;
-  cur.x = cur.y = cur.z = cur.w = 0u;
   int k = NP - 1;
   ZFB_NOUNROLL for (; k >= kmin; k--) {
-    if (!remaining) break;
-    uint32_t xl = 0u, xh = 0u;
-    if (n == 64u) {
-      // every coefficient significant: the plane is the next min(64, remaining) stream bits
-      const unsigned m = remaining < 64u ? remaining : 64u;
-      r.read64_at(maxbits - remaining, xl, xh);
-      if (m < 64u) {
-        if (m < 32u) { xl &= mask32(m); xh = 0u; }
-        else xh &= mask32(m - 32u);
-      }
-      remaining -= m;
-    } else {
-      const unsigned m = n < remaining ? n : remaining;
-      remaining -= m;
-      if (m > 32) { xl = r.take(32); xh = r.take(m - 32); }
-      else if (m) xl = r.take(m);
-      unsigned state = 0;
-      // fast steps: with >= 8 bits of budget left a table step (<= 8 stream bits) cannot overrun it, and a
-      // step that stays below coefficient 63 (whose one is implicit) needs no end-of-block rule either; the
-      // first step that would touch coefficient 63 is left to the careful loop below
-      uint32_t half = tb.dec_s;  // address of the current state's half of the table
-      uint32_t last = 0u;        // last entry applied (state A before the first)
-      while (remaining >= 8u) {
-        const uint32_t e = dec_load(tb, half + 4u * byte_of(r.lo, 0));
-        const unsigned npos = dec_npos(e);
-        if (n + npos > 63u) break;
-        const uint32_t pat = dec_pat(e);
-        if (n < 32) { xl |= pat << n; xh |= carry_out(pat, n); }
-        else xh |= pat << (n - 32);
-        n += npos;
-        remaining -= dec_nbits(e);
-        r.consume_entry(e);
-        half = tb.dec_s + (e >> 20);
-        last = e;
-        if ((int32_t)e < 0) break;  // END
-      }
-      state = dec_state(last);
-      while (state != 2u && n < 64u && remaining) {
-        uint32_t wb = r.lo;
-        const bool forced = remaining < 8u;
-        // at the end of the budget a terminator is forced behind the last valid bit: in state B it becomes
-        // the one zfp's decoder deposits when the budget ends inside a zero run, in state A it deposits nothing
-        if (forced) wb = (wb & mask32(remaining)) | (1u << remaining);
-        const uint32_t e = dec_at(tb, (state << 8) | (wb & 0xffu));
-        const unsigned npos = dec_npos(e), nbits = dec_nbits(e);
-        const uint32_t pat = dec_pat(e);
-        if (n + npos <= 63u) {
-          // table step: deposit up to 8 coefficient bits at once
-          if (n < 32) { xl |= pat << n; xh |= carry_out(pat, n); }
-          else xh |= pat << (n - 32);
-          n += npos;
-          if (nbits > remaining) { remaining = 0u; state = 0u; break; }  // ran into the forced terminator
-          remaining -= nbits;
-          r.consume(nbits);
-          state = dec_state(e);
-          if (state == 2u) break;
-        } else if (!forced) {
-          // the step would read a bit for coefficient 63, whose one is implicit: keep the L = 63 - n positions
-          // before it; they used L coefficient bits, one test bit per deposited one, and the opening test bit
-          const unsigned L = 63u - n;
-          const uint32_t pt = pat & mask32(L);
-          const unsigned nb = L + (unsigned)popc32(pt) + (state == 0u ? 1u : 0u);
-          if (n < 32) { xl |= pt << n; xh |= carry_out(pt, n); }
-          else xh |= pt << (n - 32);
-          xh |= 0x80000000u;
-          n = 64u;
-          remaining -= nb;
-          r.consume(nb);
-          state = 0u;
-          break;
+    if (pos >= maxbits) break;
+    unsigned rem = maxbits - pos;
+    uint32_t rl, rh;
+    fetch64(r, pos, rl, rh);
+    const unsigned m = n < rem ? n : rem;  // verbatim bits
+    uint64_t x = ((uint64_t)rh << 32) | rl;
+    x = m >= 64u ? x : x & ~(~(uint64_t)0 << m);
+    pos += m;
+    rem -= m;
+    if (n < 64u && rem) {
+      // group tests; c = the next 32 stream bits
+      uint32_t c = m <= 32u ? fsr(rl, rh, m) : fetch32(r, pos);
+      bool inrun = false;  // inside a zero run (the group test that opened it has been consumed)
+      for (;;) {
+        if (n <= 54u && rem >= 8u) {
+          const uint32_t e = dec_at(tb, (c & 0xffu) | (inrun ? 256u : 0u));
+          x |= (uint64_t)dec_pat(e) << n;
+          n += dec_npos(e);
+          pos += dec_nbits(e);
+          rem -= dec_nbits(e);
+          inrun = (e >> 30) == 1u;
+          if ((int32_t)e < 0) break;  // a zero group test: the plane is done
         } else {
-          // budget end and block end together (rare): exact single-bit steps with zfp's loop conditions
-          if (state == 0u) {
-            remaining--;
-            if (!r.take(1)) break;
-            state = 1u;
-          } else {
-            bool one = true;
-            if (n < 63u && remaining) { remaining--; one = r.take(1) != 0u; }
-            if (one) {
-              if (n < 32) xl |= 1u << n; else xh |= 1u << (n - 32);
-              state = 0u;
-            }
-            n++;
+          const unsigned hb = inrun ? 0u : 1u;
+          if (!inrun && !(c & 1u)) { pos += 1u; break; }
+          const uint32_t z = inrun ? c : c >> 1;
+          const unsigned wb = 32u - hb;  // run bits visible in the window
+          const unsigned L = 63u - n, left = rem - hb;
+          const unsigned lb = L < left ? L : left;  // the run ends here at the latest (block end / budget end)
+          const unsigned r0 = z ? (unsigned)(msb32(z & (0u - z))) : 32u;
+          unsigned used;
+          if (r0 < (lb < wb ? lb : wb)) {  // the run's one is in the window
+            x |= (uint64_t)1 << (n + r0);
+            n += r0 + 1u;
+            used = hb + r0 + 1u;
+            inrun = false;
+          } else if (lb <= wb) {  // cut off: the one is implicit (coefficient 63) or deposited by the budget rule
+            x |= (uint64_t)1 << (n + lb);
+            n += lb + 1u;
+            used = hb + lb;
+            inrun = false;
+          } else {  // a run longer than the window
+            n += wb;
+            used = 32u;
+            inrun = true;
           }
+          pos += used;
+          rem -= used;
         }
+        if (n >= 64u || !rem) break;
+        c = fetch32(r, pos);
       }
-      if (state == 1u) {
-        // the budget ran out inside a zero run: zfp's decoder still deposits a one at the current index
-        if (n < 32) xl |= 1u << n; else xh |= 1u << (n - 32);
+      if (inrun && !rem) {  // the budget ran out inside a zero run (after a table step): the one is deposited all the same
+        x |= (uint64_t)1 << n;
         n++;
       }
     }
-    if (k & 1) { cur.z = xl; cur.w = xh; }
-    else { cur.x = xl; cur.y = xh; ps.st(k >> 1, cur); }
+    ps.st64(k, (uint32_t)x, (uint32_t)(x >> 32));
   }
-  if (k >= 0 && !(k & 1)) {  // stopped (budget, or an odd kmin) with the odd plane of a row pending; k = first plane NOT decoded
-    cur.x = 0u; cur.y = 0u;
-    ps.st(k >> 1, cur);
-  }
-
   return k;
 }
 
@@ -704,12 +748,11 @@ template <class Reader>
 ZFB_HD bool decode_planes(planes64& P, int& emax, bool& low_used_out, const stream_params& sp, Reader& r,
                           const tables& tb, const plane_rows& ps)
 {
-  const uint32_t head = r.lo;
+  const uint32_t head = fetch32(r, 0);
   emax = 0;
   low_used_out = false;
   if (!(head & 1u)) return false;
   emax = (int)((head >> 1) & 0xffu) - 127;
-  r.consume(9);
   const int prec = block_precision<3>(emax, sp);
   const int kend = parse_planes<32>(ps, sp.maxbits, 9u, prec < 32 ? 32 - prec : 0, r, tb);
   ZFB_UNROLL for (int q = 0; q < 16; q++) {

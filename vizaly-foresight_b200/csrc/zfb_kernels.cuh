@@ -109,20 +109,21 @@ struct geom {
 
 constexpr int PART_STRIDE = 8;  // doubles per CTA row in the partials scratch
 
-// float/3D coder tables in shared memory (zfb_codec_f3.cuh); every thread of the CTA must call this
-struct coder_smem {
-  uint32_t dec[512];
-  uint16_t enc[256];
+// float/3D coder tables in shared memory (zfb_codec_f3.cuh); every thread of the CTA must call build_coder_tables.
+// An encoding kernel carries only ENC (2 KiB), a decoding kernel only DEC (2 KiB).
+template <bool ENCODER> struct coder_smem_t {
+  uint32_t tab[512];
 };
-__device__ __forceinline__ f3::tables build_coder_tables(coder_smem& cs)
+typedef coder_smem_t<true> enc_coder_smem;
+typedef coder_smem_t<false> dec_coder_smem;
+template <bool ENCODER> __device__ __forceinline__ f3::tables build_coder_tables(coder_smem_t<ENCODER>& cs)
 {
-  for (unsigned i = threadIdx.x; i < 512; i += blockDim.x) cs.dec[i] = f3::dec_entry(i >> 8, i & 255u);
-  for (unsigned i = threadIdx.x; i < 256; i += blockDim.x) cs.enc[i] = f3::enc_entry(i);
+  for (unsigned i = threadIdx.x; i < 512; i += blockDim.x) cs.tab[i] = ENCODER ? f3::enc_entry(i) : f3::dec_entry(i >> 8, i & 255u);
   __syncthreads();
   f3::tables t;
-  t.enc = cs.enc; t.dec = cs.dec;
-  t.enc_s = (uint32_t)__cvta_generic_to_shared(cs.enc);
-  t.dec_s = (uint32_t)__cvta_generic_to_shared(cs.dec);
+  t.enc = cs.tab; t.dec = cs.tab;
+  t.enc_s = (uint32_t)__cvta_generic_to_shared(cs.tab);
+  t.dec_s = t.enc_s;
   // opaque to the compiler: otherwise it rebuilds the shared window address (S2UR SR_CgaCtaId, ULEA, ...) in front
   // of every table load inside the coder loops instead of keeping it in a register
   asm volatile("mov.u32 %0, %0;" : "+r"(t.enc_s));
@@ -329,7 +330,7 @@ __global__ void __launch_bounds__(128) enc_generic_kernel(const Scalar* __restri
 {
   constexpr int BS = 1 << (2 * DIMS);
   constexpr bool FAST = sizeof(Scalar) == 4 && DIMS == 3;
-  __shared__ coder_smem cs;
+  __shared__ enc_coder_smem cs;
   __shared__ fast_scratch<FAST> fsc;
   f3::tables tb;
   if (FAST) tb = build_coder_tables(cs);
@@ -394,7 +395,7 @@ __global__ void __launch_bounds__(128) dec_generic_kernel(const uint64_t* __rest
   constexpr int BS = 1 << (2 * DIMS);
   constexpr bool FAST = sizeof(Scalar) == 4 && DIMS == 3;
   __shared__ double red[7 * 4];
-  __shared__ coder_smem cs;
+  __shared__ dec_coder_smem cs;
   __shared__ fast_scratch<FAST> fsc;
   f3::tables tb;
   if (FAST) tb = build_coder_tables(cs);
@@ -517,7 +518,7 @@ enc3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t* __restr
   uint64_t* outw = reinterpret_cast<uint64_t*>(smem_raw + BOXES_PER_TILE * BOX_FLOATS * sizeof(float));
   const unsigned out_words = TILE_THREADS * tg.W;
   uint64_t* bars = outw + (size_t)out_words;
-  __shared__ coder_smem cs;
+  __shared__ enc_coder_smem cs;
 
   const unsigned tid = threadIdx.x;
   const unsigned box = tid >> 6, lb = tid & 63;
@@ -613,7 +614,7 @@ dec3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64
   const unsigned slot_words = TILE_THREADS * tg.W;
   uint64_t* bars = slots + 2 * (size_t)slot_words;  // [0,1] slot buffers full, [2,3] orig boxes full
   __shared__ double red[7 * 4];
-  __shared__ coder_smem cs;
+  __shared__ dec_coder_smem cs;
   __shared__ box_info sb[3][BOXES_PER_TILE];  // ring of box descriptors: current, next, next-next tile
 
   const unsigned tid = threadIdx.x;
@@ -675,8 +676,8 @@ dec3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64
     bool nonzero = false, low_used = false;
     if (active) {
       const unsigned p = (box ? b0.nvalid : 0u) + lb;
-      f3::reader32 r(reinterpret_cast<const uint32_t*>(slots + (size_t)buf * slot_words + (size_t)p * tg.W),
-                     2 * (nslots - p) * tg.W, 0);
+      f3::smem_words r;
+      r.base = ptx::smem_u32(slots + (size_t)buf * slot_words + (size_t)p * tg.W);
       nonzero = f3::decode_planes(P, emax, low_used, maxbits, r, tb, ps);
     }
     ptx::fence_proxy_async();  // plane-row writes (generic proxy) before the TMA load overwrites the buffer
@@ -742,7 +743,7 @@ enc3_f64_tile_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t* __restr
   double* tile = reinterpret_cast<double*>(smem_raw);
   uint64_t* outw = reinterpret_cast<uint64_t*>(smem_raw + DBOX_DOUBLES * sizeof(double));
   uint64_t* bars = outw + (size_t)DTILE_THREADS * tg.W;
-  __shared__ coder_smem cs;
+  __shared__ enc_coder_smem cs;
   __shared__ box_info sb[2];
 
   const unsigned tid = threadIdx.x;
@@ -807,7 +808,7 @@ dec3_f64_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64
   const unsigned slot_words = DTILE_THREADS * tg.W;
   uint64_t* bars = slots + 2 * (size_t)slot_words;  // [0,1] slot buffers, [2] orig box
   __shared__ double red[7 * 2];
-  __shared__ coder_smem cs;
+  __shared__ dec_coder_smem cs;
   __shared__ box_info sb[3];
 
   const unsigned tid = threadIdx.x;

@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(128) enc_var_kernel(const Scalar* __restrict__
   constexpr int BS = 1 << (2 * DIMS);
   constexpr unsigned WORDS = var_caps<Scalar, DIMS>::WORDS;
   constexpr bool FAST = sizeof(Scalar) == 4 && DIMS == 3;  // table coder with the planes parked in shared memory
-  __shared__ coder_smem cs;
+  __shared__ enc_coder_smem cs;
   __shared__ fast_scratch<FAST> fsc;
   f3::tables tb;
   if (FAST) tb = build_coder_tables(cs);
@@ -509,7 +509,7 @@ __global__ void __launch_bounds__(128, 4) dec_var_f32_kernel(const uint64_t* __r
                                                              double* __restrict__ part)
 {
   __shared__ double red[7 * 4];
-  __shared__ coder_smem cs;
+  __shared__ dec_coder_smem cs;
   __shared__ fast_scratch<true> fsc;
   __shared__ uint32_t piece[VAR_STAGE_WORDS];
   __shared__ uint64_t range[2];
@@ -585,7 +585,7 @@ __global__ void __launch_bounds__(VAR64_THREADS) enc_var_f64_kernel(const double
                                                                     uint32_t* __restrict__ lens, geom g, stream_params sp)
 {
   constexpr unsigned WORDS = var_caps<double, 3>::WORDS;
-  __shared__ coder_smem cs;
+  __shared__ enc_coder_smem cs;
   __shared__ f3::u32x4 rows[32 * VAR64_THREADS];
   const f3::tables tb = build_coder_tables(cs);
   f3::plane_rows ps;
@@ -603,7 +603,7 @@ __global__ void __launch_bounds__(VAR64_THREADS) dec_var_f64_kernel(const uint64
                                                                     const uint64_t* __restrict__ offsets, double* __restrict__ out,
                                                                     geom g, stream_params sp)
 {
-  __shared__ coder_smem cs;
+  __shared__ dec_coder_smem cs;
   __shared__ f3::u32x4 rows[32 * VAR64_THREADS];
   const f3::tables tb = build_coder_tables(cs);
   f3::plane_rows ps;
