@@ -14,14 +14,14 @@
 using namespace zfb;
 
 static int g_use_f3 = 1;  // float/3D goes through the fast coder (zfb_codec_f3.cuh) unless switched off
-static uint32_t g_enc[512];
-static uint32_t g_dec[512];
+static uint32_t g_enc[f3::ENC_WORDS];
+static uint32_t g_dec[f3::DEC_WORDS];
 static f3::tables host_tables()
 {
   static bool built = false;
   if (!built) {
-    for (unsigned i = 0; i < 512; i++) g_enc[i] = f3::enc_entry(i);
-    for (unsigned i = 0; i < 512; i++) g_dec[i] = f3::dec_entry(i >> 8, i & 255);
+    for (unsigned i = 0; i < f3::ENC_WORDS; i++) g_enc[i] = f3::enc_table_word(i);
+    for (unsigned i = 0; i < f3::DEC_WORDS; i++) g_dec[i] = f3::dec_table_word(i);
     built = true;
   }
   f3::tables t;

@@ -165,7 +165,52 @@ ZFB_HD uint32_t enc_entry(unsigned i)
       pos += 2;
     } else pos += 1;
   }
-  return e | (pos << 16);
+  return e | (pos << 16) | ((unsigned)(top + 1) << 24);  // bits 24-27: coefficients up to and including the last one
+}
+
+// Near-end tables: the last row = 64 - n <= 4 coefficients of a plane (n >= 60) are coded in at most 7 bits, so one
+// lookup does the whole group-test part of such a plane, end rules included (the one of coefficient 63 is implicit).
+// NEE[row * 16 + y] (encoder, y = the row's coefficient bits): code | length << 8 | coefficients advanced << 12.
+// NE[row * 128 + v] (decoder, v = next 7 stream bits): bits consumed | coefficients advanced << 4 | ones << 8.
+// Row 0 (n == 64) is all zero: nothing is coded.  Both follow zfp's loops literally.
+constexpr unsigned NEE_SIZE = 5 * 16, NE_SIZE = 5 * 128;
+ZFB_HD uint32_t nee_entry(unsigned i)
+{
+  const unsigned row = i >> 4;
+  unsigned x = i & 15u, code = 0, len = 0, dn = 0;
+  if (row > 4u || x >> row) return 0u;
+  while (dn < row) {
+    const unsigned t = x ? 1u : 0u;
+    code |= t << len; len++;
+    if (!t) break;
+    while (dn < row - 1u) {
+      const unsigned b = x & 1u;
+      code |= b << len; len++;
+      if (b) break;
+      x >>= 1; dn++;
+    }
+    x >>= 1; dn++;
+  }
+  return code | (len << 8) | (dn << 12);
+}
+ZFB_HD uint32_t ne_entry(unsigned i)
+{
+  const unsigned row = i >> 7, v = i & 127u;
+  unsigned nbits = 0, dn = 0, pat = 0;
+  if (row > 4u) return 0u;
+  while (dn < row) {
+    const unsigned t = (v >> nbits) & 1u;
+    nbits++;
+    if (!t) break;
+    while (dn < row - 1u) {
+      const unsigned b = (v >> nbits) & 1u;
+      nbits++;
+      if (b) break;
+      dn++;
+    }
+    pat |= 1u << dn; dn++;
+  }
+  return nbits | (dn << 4) | (pat << 8);
 }
 
 // DEC[state][v]: run zfp's group-test parser over the 8 stream bits v (LSB first) from `state`
@@ -202,9 +247,17 @@ ZFB_HD uint32_t dec_entry(unsigned state, unsigned v)
   return nbits | (pattern << 8) | (npos << 16) | (state << 30);
 }
 
+constexpr unsigned ENC_WORDS = 512 + NEE_SIZE, DEC_WORDS = 512 + NE_SIZE / 2;  // table sizes in 32-bit words (NE: 16-bit entries)
+ZFB_HD uint32_t enc_table_word(unsigned i) { return i < 512u ? enc_entry(i) : nee_entry(i - 512u); }
+ZFB_HD uint32_t dec_entry(unsigned state, unsigned v);
+ZFB_HD uint32_t dec_table_word(unsigned i)
+{
+  return i < 512u ? dec_entry(i >> 8, i & 255u) : ne_entry(2u * (i - 512u)) | (ne_entry(2u * (i - 512u) + 1u) << 16);
+}
+
 struct tables {
-  const uint32_t* enc;  // 512 entries
-  const uint32_t* dec;  // 512 entries
+  const uint32_t* enc;  // ENC_WORDS entries: ENC, then NEE
+  const uint32_t* dec;  // DEC_WORDS entries: DEC, then NE
   uint32_t enc_s, dec_s;  // device: 32-bit shared-memory addresses of the two tables
 };
 // Table lookups.  On the device the tables live in shared memory and are read with ld.shared through a 32-bit
@@ -229,6 +282,16 @@ ZFB_HD uint32_t dec_load(const tables& tb, uint32_t addr)
   return v;
 #else
   return tb.dec[(addr - tb.dec_s) >> 2];
+#endif
+}
+ZFB_HD uint32_t ne_at(const tables& tb, uint32_t i)  // NE entry i (16-bit entries behind the 512 DEC words)
+{
+#if defined(__CUDA_ARCH__)
+  uint32_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(tb.dec_s + 2048u + 2u * i));
+  return v;
+#else
+  return (tb.dec[512u + (i >> 1)] >> (16u * (i & 1u))) & 0xffffu;
 #endif
 }
 ZFB_HD uint32_t dec_at(const tables& tb, uint32_t i)
@@ -441,7 +504,26 @@ ZFB_HD unsigned encode_planes(const PR& ps, unsigned maxbits, uint32_t header, u
     if (k < NP - 16 && (k & 15) == 15) finish_rows(ps, (k - 15) >> 1);  // next 16 planes: finish their transpose now
     uint32_t xl, xh;
     ps.ld64(k, xl, xh);
-    if (n == 64u) { bw.put64(xl, xh); continue; }  // every coefficient significant: the plane goes out verbatim
+    if (n <= 15u && !xh && !(xl >> (n + 8u))) {
+      // few coefficients significant and every one-bit of the rest within its first byte (the top planes of a
+      // block): verbatim bits, group test and the byte's code are one put of at most 32 bits
+      const uint32_t b0 = xl >> n;
+      const uint32_t e = enc_at(tb, 256u + b0);  // b0 == 0: nothing behind the (zero) group test
+      bw.put((xl & mask32(n)) | ((b0 ? 1u : 0u) << n) | ((e & 0xffffu) << (n + 1u)), n + 1u + ((e >> 16) & 0x1fu));
+      n += e >> 24;
+      continue;
+    }
+    if (n >= 60u) {
+      // at most four coefficients left (or none: row 0 of the table is empty): 32 verbatim bits, then the other
+      // n - 32 with the row's whole group-test code (NEE) behind them
+      const unsigned row = 64u - n, s = n - 32u;  // s in 28..32
+      const uint32_t e = enc_at(tb, 512u + 16u * row + fsr(xh, 0u, s));
+      const uint32_t code = e & 0xffu;
+      bw.put(xl, 32u);
+      bw.putv((xh & mask32(s)) | (s < 32u ? code << s : 0u), carry_out(code, s & 31u), s + ((e >> 8) & 15u));
+      n += e >> 12;
+      continue;
+    }
     // y = the not yet significant coefficients; t = first group test (y != 0)
     const uint64_t x = ((uint64_t)xh << 32) | xl;
     uint64_t y = x >> n;
@@ -462,9 +544,9 @@ ZFB_HD unsigned encode_planes(const PR& ps, unsigned maxbits, uint32_t header, u
         const uint32_t yl = (uint32_t)y;
         const uint32_t e0 = enc_at(tb, (yl & 0xffu) + (nb == 1u ? 256u : 0u));
         const uint32_t e1 = enc_at(tb, ((yl >> 8) & 0xffu) + (nb <= 2u ? 256u : 0u));  // nb == 1: byte 1 is 0 -> ENC[256] = nothing
-        const unsigned l0 = e0 >> 16;
+        const unsigned l0 = (e0 >> 16) & 0x1fu;
         uint32_t code = (e0 & 0xffffu) | ((e1 & 0xffffu) << l0);
-        unsigned len = l0 + (e1 >> 16);
+        unsigned len = l0 + ((e1 >> 16) & 0x1fu);
         if (nb <= 2u) {
           if (implicit) { len -= 2u; code &= ~(1u << len); }
           bw.put(code, len);
@@ -682,6 +764,28 @@ ZFB_HD int parse_planes(const PR& ps, unsigned maxbits, unsigned hbits, int kmin
   int k = NP - 1;
   ZFB_NOUNROLL for (; k >= kmin; k--) {
     if (pos >= maxbits) break;
+    if (n <= 23u && pos + 31u <= maxbits) {
+      // few coefficients significant (the top planes of a block): the verbatim bits and, usually, the whole group-test
+      // code of the plane sit in one 32-bit fetch and one table step finishes the plane
+      const uint32_t c = fetch32(r, pos);
+      const uint32_t e = dec_at(tb, (c >> n) & 0xffu);
+      if ((int32_t)e < 0) {  // the step ended on a zero group test
+        ps.st64(k, (c & mask32(n)) | (dec_pat(e) << n), 0u);
+        pos += n + dec_nbits(e);
+        n += dec_npos(e);
+        continue;
+      }
+    } else if (n >= 60u && pos + 71u <= maxbits) {
+      // at most four coefficients left (none: row 0 of NE is empty): n verbatim bits and one lookup for the rest
+      uint32_t rl, rh;
+      fetch64(r, pos, rl, rh);
+      const unsigned row = 64u - n, s = n - 32u;  // s in 28..32
+      const uint32_t e = ne_at(tb, 128u * row + (fetch32(r, pos + n) & 127u));
+      ps.st64(k, rl, (rh & mask32(s)) | (s < 32u ? (e >> 8) << s : 0u));
+      pos += n + (e & 15u);
+      n += (e >> 4) & 15u;
+      continue;
+    }
     unsigned rem = maxbits - pos;
     uint32_t rl, rh;
     fetch64(r, pos, rl, rh);

@@ -110,15 +110,16 @@ struct geom {
 constexpr int PART_STRIDE = 8;  // doubles per CTA row in the partials scratch
 
 // float/3D coder tables in shared memory (zfb_codec_f3.cuh); every thread of the CTA must call build_coder_tables.
-// An encoding kernel carries only ENC (2 KiB), a decoding kernel only DEC (2 KiB).
+// An encoding kernel carries only ENC + NEE (2.3 KiB), a decoding kernel only DEC + NE (4.5 KiB).
 template <bool ENCODER> struct coder_smem_t {
-  uint32_t tab[512];
+  uint32_t tab[ENCODER ? f3::ENC_WORDS : f3::DEC_WORDS];
 };
 typedef coder_smem_t<true> enc_coder_smem;
 typedef coder_smem_t<false> dec_coder_smem;
 template <bool ENCODER> __device__ __forceinline__ f3::tables build_coder_tables(coder_smem_t<ENCODER>& cs)
 {
-  for (unsigned i = threadIdx.x; i < 512; i += blockDim.x) cs.tab[i] = ENCODER ? f3::enc_entry(i) : f3::dec_entry(i >> 8, i & 255u);
+  for (unsigned i = threadIdx.x; i < (ENCODER ? f3::ENC_WORDS : f3::DEC_WORDS); i += blockDim.x)
+    cs.tab[i] = ENCODER ? f3::enc_table_word(i) : f3::dec_table_word(i);
   __syncthreads();
   f3::tables t;
   t.enc = cs.tab; t.dec = cs.tab;
