@@ -795,19 +795,32 @@ ZFB_HD int parse_planes(const PR& ps, unsigned maxbits, unsigned hbits, int kmin
     pos += m;
     rem -= m;
     if (n < 64u && rem) {
-      // group tests; c = the next 32 stream bits
+      // group tests; c = the next cb valid stream bits (refilled when a step might need more)
       uint32_t c = m <= 32u ? fsr(rl, rh, m) : fetch32(r, pos);
+      unsigned cb = 32u;
       bool inrun = false;  // inside a zero run (the group test that opened it has been consumed)
       for (;;) {
-        if (n <= 54u && rem >= 8u) {
+        bool stepped = false;
+        if (rem >= 8u) {
+          // table step: <= 8 stream bits; taken unless it would read the bit of coefficient 63 (whose one is implicit)
           const uint32_t e = dec_at(tb, (c & 0xffu) | (inrun ? 256u : 0u));
-          x |= (uint64_t)dec_pat(e) << n;
-          n += dec_npos(e);
-          pos += dec_nbits(e);
-          rem -= dec_nbits(e);
-          inrun = (e >> 30) == 1u;
-          if ((int32_t)e < 0) break;  // a zero group test: the plane is done
-        } else {
+          const unsigned np = dec_npos(e);
+          if (n + np <= 63u) {
+            const unsigned nb = dec_nbits(e);
+            x |= (uint64_t)dec_pat(e) << n;
+            n += np;
+            pos += nb; rem -= nb;
+            c >>= nb; cb -= nb;
+            inrun = (e >> 30) == 1u;
+            if ((int32_t)e < 0) break;  // a zero group test: the plane is done
+            if (inrun && n == 63u) { x |= (uint64_t)1 << 63; n = 64u; inrun = false; }
+            stepped = true;
+          }
+        }
+        if (!stepped) {
+          // token step: one group test and one zero run, zfp's end rules done exactly
+          if (cb < 32u) c = fetch32(r, pos);
+          cb = 0u;
           const unsigned hb = inrun ? 0u : 1u;
           if (!inrun && !(c & 1u)) { pos += 1u; break; }
           const uint32_t z = inrun ? c : c >> 1;
@@ -835,7 +848,7 @@ ZFB_HD int parse_planes(const PR& ps, unsigned maxbits, unsigned hbits, int kmin
           rem -= used;
         }
         if (n >= 64u || !rem) break;
-        c = fetch32(r, pos);
+        if (cb < 8u) { c = fetch32(r, pos); cb = 32u; }
       }
       if (inrun && !rem) {  // the budget ran out inside a zero run (after a table step): the one is deposited all the same
         x |= (uint64_t)1 << n;
