@@ -498,32 +498,34 @@ ZFB_HD unsigned encode_planes(const PR& ps, unsigned maxbits, uint32_t header, u
   writer32<Sink> bw(sink);
   bw.put(header, hbits);
 
+  // Three loops, one per regime of n (the regimes follow each other, n never decreases).  Each lane walks its own
+  // planes (k is per lane), so the lanes of a warp go through a regime together even when they reach it at
+  // different planes: the expensive middle regime costs the warp the slowest lane's planes, not one pass per
+  // distinct plane index.
   unsigned n = 0;
-  ZFB_NOUNROLL for (int k = NP - 1; k >= kmin; k--) {
-    if (bw.bits() >= maxbits) break;
+  int k = NP - 1;
+  uint32_t xl = 0u, xh = 0u;
+  // next plane into (xl, xh); false when the block is finished (budget covered or no planes left)
+  auto next = [&]() -> bool {
+    if (k < kmin || bw.bits() >= maxbits) return false;
     if (k < NP - 16 && (k & 15) == 15) finish_rows(ps, (k - 15) >> 1);  // next 16 planes: finish their transpose now
-    uint32_t xl, xh;
     ps.ld64(k, xl, xh);
-    if (n <= 15u && !xh && !(xl >> (n + 8u))) {
-      // few coefficients significant and every one-bit of the rest within its first byte (the top planes of a
-      // block): verbatim bits, group test and the byte's code are one put of at most 32 bits
-      const uint32_t b0 = xl >> n;
-      const uint32_t e = enc_at(tb, 256u + b0);  // b0 == 0: nothing behind the (zero) group test
-      bw.put((xl & mask32(n)) | ((b0 ? 1u : 0u) << n) | ((e & 0xffffu) << (n + 1u)), n + 1u + ((e >> 16) & 0x1fu));
-      n += e >> 24;
-      continue;
-    }
-    if (n >= 60u) {
-      // at most four coefficients left (or none: row 0 of the table is empty): 32 verbatim bits, then the other
-      // n - 32 with the row's whole group-test code (NEE) behind them
-      const unsigned row = 64u - n, s = n - 32u;  // s in 28..32
-      const uint32_t e = enc_at(tb, 512u + 16u * row + fsr(xh, 0u, s));
-      const uint32_t code = e & 0xffu;
-      bw.put(xl, 32u);
-      bw.putv((xh & mask32(s)) | (s < 32u ? code << s : 0u), carry_out(code, s & 31u), s + ((e >> 8) & 15u));
-      n += e >> 12;
-      continue;
-    }
+    return true;
+  };
+  bool more = next();
+  // 1. few coefficients significant and every one-bit of the rest within its first byte (the top planes of a block):
+  //    verbatim bits, group test and the byte's code are one put of at most 32 bits
+  ZFB_NOUNROLL while (more && n <= 15u && !xh && !(xl >> (n + 8u))) {
+    const uint32_t b0 = xl >> n;
+    const uint32_t e = enc_at(tb, 256u + b0);  // b0 == 0: nothing behind the (zero) group test
+    bw.put((xl & mask32(n)) | ((b0 ? 1u : 0u) << n) | ((e & 0xffffu) << (n + 1u)), n + 1u + ((e >> 16) & 0x1fu));
+    n += e >> 24;
+    k--;
+    more = next();
+  }
+  // 2. the general plane: one put of n + 1 bits (the verbatim bits and the first group test), then -- only if the
+  //    rest of the plane holds a one -- table steps of two bytes each
+  ZFB_NOUNROLL while (more && n < 60u) {
     // y = the not yet significant coefficients; t = first group test (y != 0)
     const uint64_t x = ((uint64_t)xh << 32) | xl;
     uint64_t y = x >> n;
@@ -557,6 +559,20 @@ ZFB_HD unsigned encode_planes(const PR& ps, unsigned maxbits, uint32_t header, u
         y >>= 16;
       }
     }
+    k--;
+    more = next();
+  }
+  // 3. at most four coefficients left (or none: row 0 of the table is empty): 32 verbatim bits, then the other
+  //    n - 32 with the row's whole group-test code (NEE) behind them
+  ZFB_NOUNROLL while (more) {
+    const unsigned row = 64u - n, s = n - 32u;  // s in 28..32
+    const uint32_t e = enc_at(tb, 512u + 16u * row + fsr(xh, 0u, s));
+    const uint32_t code = e & 0xffu;
+    bw.put(xl, 32u);
+    bw.putv((xh & mask32(s)) | (s < 32u ? code << s : 0u), carry_out(code, s & 31u), s + ((e >> 8) & 15u));
+    n += e >> 12;
+    k--;
+    more = next();
   }
   const unsigned total = bw.bits();  // bits emitted (the fixed-rate sinks truncate / pad to the slot)
   bw.flush();
@@ -762,30 +778,22 @@ ZFB_HD int parse_planes(const PR& ps, unsigned maxbits, unsigned hbits, int kmin
   unsigned pos = hbits;  // bit position inside the slot
   unsigned n = 0;
   int k = NP - 1;
+  // One loop per regime of n, each lane walking its own planes (k is per lane): the lanes of a warp go through a
+  // regime together even when they reach it at different planes (see encode_planes).
+  // 1. few coefficients significant (the top planes of a block): the verbatim bits and the whole group-test code of
+  //    the plane sit in one 32-bit fetch, one table step finishes the plane
+  ZFB_NOUNROLL for (; k >= kmin && n <= 23u && pos + 31u <= maxbits; k--) {
+    const uint32_t c = fetch32(r, pos);
+    const uint32_t e = dec_at(tb, (c >> n) & 0xffu);
+    if ((int32_t)e >= 0) break;  // the step did not end on a zero group test: a plane for the general loop
+    ps.st64(k, (c & mask32(n)) | (dec_pat(e) << n), 0u);
+    pos += n + dec_nbits(e);
+    n += dec_npos(e);
+  }
+  for (;;) {
+  // 2. the general plane; leaves for loop 3 once at most four coefficients are left and the budget is not near its end
   ZFB_NOUNROLL for (; k >= kmin; k--) {
-    if (pos >= maxbits) break;
-    if (n <= 23u && pos + 31u <= maxbits) {
-      // few coefficients significant (the top planes of a block): the verbatim bits and, usually, the whole group-test
-      // code of the plane sit in one 32-bit fetch and one table step finishes the plane
-      const uint32_t c = fetch32(r, pos);
-      const uint32_t e = dec_at(tb, (c >> n) & 0xffu);
-      if ((int32_t)e < 0) {  // the step ended on a zero group test
-        ps.st64(k, (c & mask32(n)) | (dec_pat(e) << n), 0u);
-        pos += n + dec_nbits(e);
-        n += dec_npos(e);
-        continue;
-      }
-    } else if (n >= 60u && pos + 71u <= maxbits) {
-      // at most four coefficients left (none: row 0 of NE is empty): n verbatim bits and one lookup for the rest
-      uint32_t rl, rh;
-      fetch64(r, pos, rl, rh);
-      const unsigned row = 64u - n, s = n - 32u;  // s in 28..32
-      const uint32_t e = ne_at(tb, 128u * row + (fetch32(r, pos + n) & 127u));
-      ps.st64(k, rl, (rh & mask32(s)) | (s < 32u ? (e >> 8) << s : 0u));
-      pos += n + (e & 15u);
-      n += (e >> 4) & 15u;
-      continue;
-    }
+    if (pos >= maxbits || (n >= 60u && pos + 71u <= maxbits)) break;
     unsigned rem = maxbits - pos;
     uint32_t rl, rh;
     fetch64(r, pos, rl, rh);
@@ -857,6 +865,19 @@ ZFB_HD int parse_planes(const PR& ps, unsigned maxbits, unsigned hbits, int kmin
     }
     ps.st64(k, (uint32_t)x, (uint32_t)(x >> 32));
   }
+  if (k < kmin || pos >= maxbits) break;
+  // 3. at most four coefficients left (none: row 0 of NE is empty): n verbatim bits and one lookup for the rest
+  ZFB_NOUNROLL for (; k >= kmin && pos + 71u <= maxbits; k--) {
+    uint32_t rl, rh;
+    fetch64(r, pos, rl, rh);
+    const unsigned row = 64u - n, s = n - 32u;  // s in 28..32
+    const uint32_t e = ne_at(tb, 128u * row + (fetch32(r, pos + n) & 127u));
+    ps.st64(k, rl, (rh & mask32(s)) | (s < 32u ? (e >> 8) << s : 0u));
+    pos += n + (e & 15u);
+    n += (e >> 4) & 15u;
+  }
+  if (k < kmin || pos >= maxbits) break;
+  }  // the budget is near its end: back to the general loop for the last planes
   return k;
 }
 
