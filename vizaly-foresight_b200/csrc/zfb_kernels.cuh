@@ -196,12 +196,14 @@ struct frow {
     const float d0 = o.x - a0, d1 = o.y - a1, d2 = o.z - a2, d3 = o.w - a3;
     const float e0 = fabsf(d0), e1 = fabsf(d1), e2 = fabsf(d2), e3 = fabsf(d3);
     const float b0 = fabsf(o.x), b1 = fabsf(o.y), b2 = fabsf(o.z), b3 = fabsf(o.w);
-    float q0, q1, q2, q3;
-    asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(q0) : "f"(e0 * 0.25f), "f"(b0 * 0.25f));
-    asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(q1) : "f"(e1 * 0.25f), "f"(b1 * 0.25f));
-    asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(q2) : "f"(e2 * 0.25f), "f"(b2 * 0.25f));
-    asm("div.approx.ftz.f32 %0, %1, %2;" : "=f"(q3) : "f"(e3 * 0.25f), "f"(b3 * 0.25f));
-    const float r0 = b0 < 1.0f ? e0 : q0, r1 = b1 < 1.0f ? e1 : q1, r2 = b2 < 1.0f ? e2 : q2, r3 = b3 < 1.0f ? e3 : q3;
+    // relError(o, a, 1) = |d| / max(|o|, 1): one reciprocal estimate (MUFU.RCP, <= 2 ulp; the metric tolerance is 1e-6
+    // relative).  Divisor and dividend are scaled by 1/4 (exact) because rcp.approx.ftz returns 0 above 2^126.
+    float c0, c1, c2, c3;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(c0) : "f"(fmaxf(b0, 1.0f) * 0.25f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(c1) : "f"(fmaxf(b1, 1.0f) * 0.25f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(c2) : "f"(fmaxf(b2, 1.0f) * 0.25f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(c3) : "f"(fmaxf(b3, 1.0f) * 0.25f));
+    const float r0 = (e0 * 0.25f) * c0, r1 = (e1 * 0.25f) * c1, r2 = (e2 * 0.25f) * c2, r3 = (e3 * 0.25f) * c3;
     ssq = fmaf(d0, d0, ssq); ssq = fmaf(d1, d1, ssq); ssq = fmaf(d2, d2, ssq); ssq = fmaf(d3, d3, ssq);
     sab += (e0 + e1) + (e2 + e3);
     srl += (r0 + r1) + (r2 + r3);
