@@ -564,19 +564,13 @@ ZFB_HD unsigned encode_planes(const PR& ps, unsigned maxbits, uint32_t header, u
   }
   // 3. at most four coefficients left (or none: row 0 of the table is empty): 32 verbatim bits, then the other
   //    n - 32 with the row's whole group-test code (NEE) behind them
-  ZFB_NOUNROLL while (more && n < 64u) {
-    const unsigned row = 64u - n, s = n - 32u;  // s in 28..31
+  ZFB_NOUNROLL while (more) {
+    const unsigned row = 64u - n, s = n - 32u;  // s in 28..32
     const uint32_t e = enc_at(tb, 512u + 16u * row + fsr(xh, 0u, s));
     const uint32_t code = e & 0xffu;
     bw.put(xl, 32u);
     bw.putv((xh & mask32(s)) | (s < 32u ? code << s : 0u), carry_out(code, s & 31u), s + ((e >> 8) & 15u));
     n += e >> 12;
-    k--;
-    more = next();
-  }
-  // 4. every coefficient significant: the planes go out verbatim
-  ZFB_NOUNROLL while (more) {
-    bw.put64(xl, xh);
     k--;
     more = next();
   }
@@ -880,9 +874,10 @@ ZFB_HD int parse_planes(const PR& ps, unsigned maxbits, unsigned hbits, int kmin
     ps.st64(k, (uint32_t)x, (uint32_t)(x >> 32));
   }
   if (k < kmin || pos >= maxbits) break;
-  // 3. at most four coefficients left: n verbatim bits and one lookup for the rest; then, with every coefficient
-  //    significant, the planes are plain 64-bit pieces of the slot
-  ZFB_NOUNROLL for (; k >= kmin && n < 64u && pos + 71u <= maxbits; k--) {
+  // 3. at most four coefficients left (none: row 0 of NE is empty): n verbatim bits and one lookup for the rest.
+  //    (A separate loop for n == 64 was slower: the lanes of a warp reach 64 at different planes and the two loops
+  //    then run one after the other.)
+  ZFB_NOUNROLL for (; k >= kmin && pos + 71u <= maxbits; k--) {
     uint32_t rl, rh;
     fetch64(r, pos, rl, rh);
     const unsigned row = 64u - n, s = n - 32u;  // s in 28..32
@@ -890,14 +885,6 @@ ZFB_HD int parse_planes(const PR& ps, unsigned maxbits, unsigned hbits, int kmin
     ps.st64(k, rl, (rh & mask32(s)) | (s < 32u ? (e >> 8) << s : 0u));
     pos += n + (e & 15u);
     n += (e >> 4) & 15u;
-  }
-  if (n == 64u) {
-    ZFB_NOUNROLL for (; k >= kmin && pos + 64u <= maxbits; k--) {
-      uint32_t rl, rh;
-      fetch64(r, pos, rl, rh);
-      ps.st64(k, rl, rh);
-      pos += 64u;
-    }
   }
   if (k < kmin || pos >= maxbits) break;
   }  // the budget is near its end: back to the general loop for the last planes
