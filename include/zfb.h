@@ -138,8 +138,18 @@ int zfb_compress_host(zfb_ctx* ctx, int dtype, int dims, size_t nx, size_t ny, s
 int zfb_decompress_host(zfb_ctx* ctx, int dtype, int dims, size_t nx, size_t ny, size_t nz, unsigned maxbits,
                         const void* h_stream, void* h_out, const void* h_orig);
 
+/* The host-pointer entry points recognise "the buffers I already hold on the device" by host address and byte size
+ * only.  They cannot notice a buffer that was rewritten in place, or freed and re-allocated at the same address --
+ * CBench does the latter between scalars (main.cpp:395-398: std::free(decompdata), ioMgr->close()).  A caller whose
+ * buffers may have changed since the last call drops the residency first; zfb_host_pair_serial counts the
+ * zfb_decompress*_host calls that registered an (original, decompressed) pair, so a caller can tell whether the pair
+ * it is about to ask metrics for was produced by this library since it last looked (cbench/gpuMetrics.hpp does). */
+int zfb_host_cache_invalidate(zfb_ctx* ctx);
+unsigned long long zfb_host_pair_serial(const zfb_ctx* ctx);
+
 /* MetricInterface::execute(original, approx, n) for host arrays (main.cpp:336): reuses the fused
- * partials when (h_orig, h_approx) are the buffers of the last zfb_decompress_host, else uploads both. */
+ * partials when (h_orig, h_approx) are the buffers of the last zfb_decompress_host, else uploads both
+ * (see zfb_host_cache_invalidate for when the caller must drop the residency). */
 int zfb_metrics_host(zfb_ctx* ctx, int dtype, const void* h_orig, const void* h_approx, size_t n,
                      zfb_partials* out);
 

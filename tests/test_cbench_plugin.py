@@ -111,4 +111,45 @@ def test_mini_driver_abs_and_rel_modes_match_oracle(oracle):
         for a, b in zip(got, want):
             assert abs(a - b) <= 1.01e-5 * abs(b), (arg, got, want)
         assert abs(float(row[9]) - f.nbytes / len(s)) <= 1e-5 * f.nbytes / len(s) + 1e-3, (arg, row[9], f.nbytes / len(s))
-    # no parameters at all under the name "zfp": the CPU plugin's default abs = 1E-3 (zfpCompressor.hpp:80)
+    # no parameter at all: abs = 1E-3 under both names (zfpCompressor.hpp:80, zfpCompressorGpu.hpp:80-100)
+    p = oracle.params_accuracy(1e-3)
+    s = oracle.compress_ex(f, p)
+    for name in ("zfp", "zfp_gpu"):
+        r = subprocess.run([exe, os.path.join(GOLD, "nyx_z255_32_baryon_density.f32"), "32", "32", "32", "default",
+                            "--field", "baryon_density", "--name", name], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        row = [t.strip() for t in r.stdout.splitlines()[1].split(",")]
+        assert abs(float(row[9]) - f.nbytes / len(s)) <= 1e-5 * f.nbytes / len(s) + 1e-3, (name, row[9], f.nbytes / len(s))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,arg", [("quant", "0.05"), ("zfp_gpu", "8"), ("zfp", "abs=0.01")])
+def test_mini_driver_several_scalars_at_the_same_addresses(oracle, name, arg):
+    """main.cpp re-allocates `data` and `decompdata` for every scalar (main.cpp:395-398) and the allocator returns
+    the same addresses: every CSV row must carry ITS scalar's metrics, also when the compressor is not ours and only
+    the GPU metric classes see the arrays (the device copies are keyed by host address)."""
+    exe = build_mini()
+    path = os.path.join(GOLD, "nyx_z255_32_baryon_density.f32")
+    f = np.fromfile(path, dtype=np.float32).reshape(32, 32, 32)
+    r = subprocess.run([exe, path, "32", "32", "32", arg, "--field", "rho", "--name", name, "--scalars", "3", "--hist"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    lines = r.stdout.splitlines()
+    for sc in range(3):
+        x = (f * np.float32(sc + 1)).astype(np.float32)
+        if name == "quant":
+            step = np.float32(float(arg))
+            g = (np.rint(x / step).astype(np.int32).astype(np.float32) * step).astype(np.float32)
+        elif name == "zfp_gpu":
+            mb = oracle.maxbits(np.float32, 3, int(arg))
+            g = oracle.decompress(oracle.compress(x, mb), x.shape, np.float32, mb)
+        else:
+            p = oracle.params_accuracy(0.01)
+            g, _ = oracle.decompress_ex(oracle.compress_ex(x, p), x.shape, np.float32, p)
+        m = oracle.metrics(x, g)
+        row = [t.strip() for t in lines[1 + sc].split(",")]
+        assert row[0].startswith(name + "_rho%d__" % sc)
+        got = [float(t) for t in row[2:7]]
+        want = [m["absolute_error"], m["relative_error"], m["mse"], m["psnr"], m["minmax"]]
+        for a, b in zip(got, want):
+            assert abs(a - b) <= 1.01e-5 * abs(b), (name, sc, got, want)

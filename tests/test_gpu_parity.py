@@ -290,6 +290,96 @@ def test_host_entry_points_and_fused_metrics(codec, pkg, oracle):
     codec.release()
 
 
+def test_host_entry_points_pinned_and_pageable_buffers(codec, pkg, oracle):
+    """The same result whether the caller's buffers are pageable (CBench: new T[] / malloc, main.cpp:262-280,395; staged
+    through the pinned double buffers by the copy threads) or pinned (direct DMA); the stream zfb_compress_host left on
+    the device is reused by zfb_decompress_host only while the host buffer still holds it."""
+    torch = _torch()
+    shape = (72, 512, 512)   # 72 MiB -> two slabs, the second one shorter
+    f = smooth_field(shape, seed=21, amp=50.0)
+    mb = 512
+    s_ref = oracle.compress(f, mb)
+    g_ref = oracle.decompress(s_ref, shape, np.float32, mb)
+    # pageable
+    s = codec.compress_host(f, mb)
+    g = codec.decompress_host(s, shape, np.float32, mb, orig=f)
+    assert np.array_equal(s, s_ref)
+    assert_bits_equal(g, g_ref, "pageable")
+    check_metrics(pkg, oracle, codec.metrics_host(f, g), f, g_ref, "pageable fused")
+    # pinned
+    tf = torch.from_numpy(f).pin_memory()
+    ts = torch.empty(len(s_ref), dtype=torch.uint8).pin_memory()
+    tg = torch.empty(shape, dtype=torch.float32).pin_memory()
+    s2 = codec.compress_host(tf.numpy(), mb, out=ts.numpy())
+    g2 = codec.decompress_host(s2, shape, np.float32, mb, orig=tf.numpy(), out=tg.numpy())
+    assert np.array_equal(s2, s_ref)
+    assert_bits_equal(g2, g_ref, "pinned")
+    check_metrics(pkg, oracle, codec.metrics_host(tf.numpy(), g2), f, g_ref, "pinned fused")
+    # the caller overwrites the stream buffer between the two calls: the resident copy must not be trusted
+    f3 = smooth_field(shape, seed=22, amp=3.0)
+    s3_ref = oracle.compress(f3, mb)
+    s = codec.compress_host(f, mb)
+    s[:] = s3_ref
+    g3 = codec.decompress_host(s, shape, np.float32, mb)
+    assert_bits_equal(g3, oracle.decompress(s3_ref, shape, np.float32, mb), "rewritten stream buffer")
+    codec.release()
+
+
+def test_host_cache_invalidation_for_reused_addresses(codec, pkg, oracle):
+    """CBench frees and re-allocates `data` / `decompdata` per scalar at what are usually the same addresses
+    (main.cpp:395-398): with a compressor that is not ours the GPU metrics must not return the previous scalar's
+    numbers.  Codec.metrics_host drops the device copies unless decompress_host registered the pair."""
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal(1 << 18).astype(np.float32)
+    b = (a + 0.01 * rng.standard_normal(a.size)).astype(np.float32)
+    p1 = pkg.metric_values(codec.metrics_host(a, b))
+    r1 = oracle.metrics(a, b)
+    assert abs(p1["mse"] - r1["mse"]) <= 1e-6 * r1["mse"]
+    # "next scalar": new contents at the same addresses
+    a[:] = 100.0 * rng.standard_normal(a.size).astype(np.float32)
+    b[:] = (a + 0.5 * rng.standard_normal(a.size)).astype(np.float32)
+    p2 = pkg.metric_values(codec.metrics_host(a, b))
+    r2 = oracle.metrics(a, b)
+    for k in ("absolute_error", "relative_error", "mse", "psnr", "minmax"):
+        assert abs(p2[k] - r2[k]) <= 1e-6 * abs(r2[k]) + 1e-300, (k, p2[k], r2[k])
+    # explicit reuse keeps the device copies (the second metric of the same scalar)
+    p3 = pkg.metric_values(codec.metrics_host(a, b, reuse=True))
+    assert p3 == p2
+    codec.release()
+
+
+def test_ragged_1d_unaligned_slots_into_dirty_buffer(codec, pkg, oracle):
+    """1D line path with a trailing partial block whose 96-bit slot spans two 64-bit words: everything behind the full
+    blocks' slots is cleared before the partial block is OR-ed in (the stream buffer is reused and never zeroed)."""
+    torch = _torch()
+    for n, mb in ((11, 96), (4099, 96), (4098, 45), (10, 64)):
+        h = (256 * np.random.default_rng(n).random(n)).astype(np.float32)
+        d_h = torch.from_numpy(h).cuda()
+        nbytes = pkg.stream_bytes(h.shape, mb)
+        out = torch.full((nbytes + 16,), 0xFF, dtype=torch.uint8, device="cuda")
+        s = codec.encode(d_h, mb, out=out)
+        assert np.array_equal(s.cpu().numpy()[:nbytes], oracle.compress(h, mb)), (n, mb)
+
+
+def test_misaligned_1d_arrays_take_the_scalar_path(codec, pkg, oracle):
+    """A contiguous 1D slice such as field[1:] is only 4-byte aligned: no 16-byte accesses (a misaligned vector load is
+    a sticky fault that kills the context)."""
+    torch = _torch()
+    base = torch.from_numpy((256 * np.random.default_rng(8).random(4101)).astype(np.float32)).cuda()
+    for off in (1, 2, 3):
+        d_h = base[off:off + 4096]
+        assert d_h.data_ptr() % 16 != 0
+        h = d_h.cpu().numpy()
+        mb = 64
+        s = codec.encode(d_h, mb)
+        assert np.array_equal(s.cpu().numpy(), oracle.compress(h, mb))
+        obuf = torch.empty(4101, dtype=torch.float32, device="cuda")
+        o = codec.decode(s, h.shape, torch.float32, mb, orig=d_h, out=obuf[off:off + 4096])
+        g_ref = oracle.decompress(oracle.compress(h, mb), h.shape, np.float32, mb)
+        assert_bits_equal(o.cpu().numpy(), g_ref, off)
+        check_metrics(pkg, oracle, codec.partials(), h, g_ref, "misaligned 1D")
+
+
 def test_slab_streams_concatenate(codec, pkg):
     """slabs along the slowest axis (thickness % 4 == 0) concatenate to the whole-field stream."""
     torch = _torch()

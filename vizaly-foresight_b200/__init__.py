@@ -83,6 +83,8 @@ def lib():
     MP = C.POINTER(Mode)
     sig = {
         "zfb_maxbits": (u, [i, i, d, i]),
+        "zfb_host_cache_invalidate": (i, [vp]),
+        "zfb_host_pair_serial": (C.c_ulonglong, [vp]),
         "zfb_stream_bytes": (sz, [i, sz, sz, sz, u]),
         "zfb_stream_capacity": (sz, [i, sz, sz, sz, u]),
         "zfb_partition": (i, [i, i, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)]),
@@ -455,7 +457,17 @@ class Codec:
         self._check(lib().zfb_decompress_host(self._h, dtype_code, d, nx, ny, nz, mb, stream_ptr, out_ptr, orig_ptr),
                     "zfb_decompress_host")
 
-    def metrics_host(self, orig, approx):
+    def metrics_host(self, orig, approx, reuse=None):
+        """Metric partials of two host arrays.  The C ABI recognises buffers it already holds by address and size only,
+        and a numpy array can be rewritten in place: unless `reuse` is True, the device copies are dropped first --
+        except when decompress_host registered the pair since the previous call (then the copies are this very data
+        and the fused partials are returned without any upload)."""
+        serial = lib().zfb_host_pair_serial(self._h)
+        if reuse is None:
+            reuse = serial != getattr(self, "_pair_serial_seen", 0)
+        self._pair_serial_seen = serial
+        if not reuse:
+            self._check(lib().zfb_host_cache_invalidate(self._h), "zfb_host_cache_invalidate")
         p = Partials()
         self._check(lib().zfb_metrics_host(self._h, _dtype_code(orig.dtype), orig.ctypes.data, approx.ctypes.data,
                                            orig.size, C.byref(p)), "zfb_metrics_host")

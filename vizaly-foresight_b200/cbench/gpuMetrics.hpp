@@ -61,6 +61,7 @@ class GpuMetricBase : public MetricInterface {
       std::cout << metricName << ": no usable CUDA device (no CPU fallback)\n";
       return false;
     }
+    sh.metric_begins(metricName);  // a metric name coming round again = the next scalar: stale device copies are dropped
     // like the reference, both arrays are read as float regardless of the loader's type
     if (zfb_metrics_host(sh.ctx, ZFB_FLOAT, original, approx, n, &local) != ZFB_OK) {
       std::cout << metricName << ": " << zfb_last_error(sh.ctx) << "\n";

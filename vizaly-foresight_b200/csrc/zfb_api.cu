@@ -10,6 +10,7 @@
 
 #include "../../include/zfb.h"
 #include "zfb_kernels.cuh"
+#include "zfb_hostio.cuh"
 
 using namespace zfb;
 
@@ -43,6 +44,13 @@ struct zfb_ctx {
   const void* h_out_key = nullptr;    // host pointer the last decompressed field went to
   size_t out_bytes = 0;
   bool fused_valid = false;           // result holds metrics of (h_orig_key, h_out_key)
+  unsigned long long pair_serial = 0; // zfb_decompress*_host calls that registered an (original, decompressed) pair
+  const void* h_stream_key = nullptr; // host buffer whose fixed-rate stream is still in d_stream (zfb_compress_host)
+  size_t stream_key_bytes = 0;
+  unsigned stream_key_maxbits = 0;
+  unsigned char stream_sample[128] = {0};
+  copy_pool* pool = nullptr;          // copy threads for pageable caller buffers (zfb_hostio.cuh)
+  pinned_pair pin_in, pin_out, pin_st;  // pinned double buffers: field slabs in / out, stream pieces
   int occ_enc[80] = {0}, occ_dec[80] = {0}, occ_decm[80] = {0};  // resident CTAs per SM, by slot words
   std::vector<uint64_t> var_slab_bits;  // host copy: bit offset at which every slab of the resident stream starts (+ total)
   // variable-rate path (zfb_api_var.cuh): scratch + the block index of the last encoded stream
@@ -236,8 +244,26 @@ extern "C" int zfb_release_resident(zfb_ctx* c)
   c->h_orig_key = c->h_out_key = nullptr;
   c->orig_bytes = c->out_bytes = 0;
   c->fused_valid = false;
+  c->h_stream_key = nullptr;
+  c->pin_in.release(); c->pin_out.release(); c->pin_st.release();
   return ZFB_OK;
 }
+
+// The host-pointer entry points recognise "the same buffers as before" by address and size only: they cannot see a
+// buffer being rewritten or freed and re-allocated at the same address (CBench does exactly that between scalars,
+// main.cpp:395-398).  Callers drop the residency whenever the contents may have changed.
+extern "C" int zfb_host_cache_invalidate(zfb_ctx* c)
+{
+  if (!c) return ZFB_EINVAL;
+  c->h_orig_key = c->h_out_key = nullptr;
+  c->orig_bytes = c->out_bytes = 0;
+  c->fused_valid = false;
+  c->var_index_key = c->var_host_key = nullptr;
+  c->h_stream_key = nullptr;
+  return ZFB_OK;
+}
+
+extern "C" unsigned long long zfb_host_pair_serial(const zfb_ctx* c) { return c ? c->pair_serial : 0ull; }
 
 extern "C" int zfb_destroy(zfb_ctx* c)
 {
@@ -246,6 +272,7 @@ extern "C" int zfb_destroy(zfb_ctx* c)
   if (c->part) cudaFree(c->part);
   if (c->result) cudaFree(c->result);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c->pool;
   delete c;
   return ZFB_OK;
 }
@@ -469,11 +496,14 @@ extern "C" int zfb_encode_dev(zfb_ctx* c, int dtype, int dims, size_t nx, size_t
     return ZFB_OK;
   }
   if (line_path_ok(c, dtype, dims, g, maxbits) && ((uintptr_t)d_in & 15) == 0 && ((uintptr_t)d_stream & 15) == 0) {
-    // a trailing partial block is OR-ed into the stream by the generic kernel; when slots are not whole
-    // 64-bit words it may share the last word with the last full block, so that word is cleared FIRST
-    if ((g.nx & 3) && (maxbits & 63u)) CU_TRY(c, cudaMemsetAsync((char*)d_stream + (g.stream_words - 1) * 8, 0, 8, c->stream));
+    // a trailing partial block is OR-ed into the stream by the generic kernel: everything behind the full blocks'
+    // slots (the partial slot can span two 64-bit words, e.g. 96-bit slots) is cleared FIRST
     const size_t nfull = g.nx / 4;
     const unsigned nw = maxbits >> 5;
+    if ((g.nx & 3) && (maxbits & 63u)) {
+      const size_t written = nfull * nw * 4;
+      CU_TRY(c, cudaMemsetAsync((char*)d_stream + written, 0, g.stream_words * 8 - written, c->stream));
+    }
     size_t want = (nfull + 255) / 256;
     const int grid = (int)(want < (size_t)c->sm_count * 8 ? (want ? want : 1) : (size_t)c->sm_count * 8);
     const float* in = (const float*)d_in;
@@ -727,6 +757,47 @@ static void slab_dims(int dims, size_t nx, size_t ny, size_t nz, size_t rows, si
   else sz = rows;
 }
 
+// Streams and events of one host-pointer call (RAII: every exit path releases them).
+struct host_call {
+  cudaStream_t up = nullptr, down = nullptr;
+  cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_k[2] = {nullptr, nullptr}, ev_dn[2] = {nullptr, nullptr};
+  bool ok = false;
+  host_call()
+  {
+    ok = cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking) == cudaSuccess &&
+         cudaStreamCreateWithFlags(&down, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; i < 2 && ok; i++)
+      ok = cudaEventCreateWithFlags(&ev_up[i], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&ev_dn[i], cudaEventDisableTiming) == cudaSuccess;
+  }
+  ~host_call()
+  {
+    for (int i = 0; i < 2; i++) {
+      if (ev_up[i]) cudaEventDestroy(ev_up[i]);
+      if (ev_k[i]) cudaEventDestroy(ev_k[i]);
+      if (ev_dn[i]) cudaEventDestroy(ev_dn[i]);
+    }
+    if (up) cudaStreamDestroy(up);
+    if (down) cudaStreamDestroy(down);
+  }
+};
+
+static copy_pool& pool_of(zfb_ctx* c)
+{
+  if (!c->pool) c->pool = new copy_pool(default_copy_threads());
+  return *c->pool;
+}
+
+// 64 bytes from each end of a host buffer: enough to notice that a buffer at a known address holds something else now
+static void sample_of(const void* p, size_t bytes, unsigned char (&out)[128])
+{
+  memset(out, 0, sizeof out);
+  const size_t k = bytes < 64 ? bytes : 64;
+  memcpy(out, p, k);
+  memcpy(out + 64, (const char*)p + bytes - k, k);
+}
+
 extern "C" int zfb_compress_host(zfb_ctx* c, int dtype, int dims, size_t nx, size_t ny, size_t nz, unsigned maxbits,
                                  const void* h_in, void* h_stream, size_t* cbytes)
 {
@@ -742,49 +813,76 @@ extern "C" int zfb_compress_host(zfb_ctx* c, int dtype, int dims, size_t nx, siz
   if ((rc = ensure(c, c->d_stream, sbytes + 16))) return rc;
   c->fused_valid = false;
   c->h_orig_key = nullptr;
+  c->h_stream_key = nullptr;
 
   const slab_plan sp = plan_slabs(dims, nx, ny, nz, maxbits, esz);
-  cudaStream_t up, down;
-  cudaEvent_t ev_up[2], ev_k[2];
-  CU_TRY(c, cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking));
-  CU_TRY(c, cudaStreamCreateWithFlags(&down, cudaStreamNonBlocking));
-  for (int i = 0; i < 2; i++) { cudaEventCreateWithFlags(&ev_up[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming); }
+  // pageable buffers go through pinned double buffers filled / drained by the copy threads (zfb_hostio.cuh)
+  const bool in_direct = is_pinned(h_in), out_direct = is_pinned(h_stream);
+  size_t max_piece = 0;
+  {
+    size_t sx, sy, sz;
+    slab_dims(dims, nx, ny, nz, sp.thick, sx, sy, sz);
+    max_piece = make_geom(dims, sx, sy, sz, maxbits).stream_words * 8;
+  }
+  if (!in_direct && c->pin_in.ensure(sp.thick * sp.row_elems * esz)) { c->err = "cudaHostAlloc failed"; return ZFB_ENOMEM; }
+  if (!out_direct && c->pin_st.ensure(max_piece)) { c->err = "cudaHostAlloc failed"; return ZFB_ENOMEM; }
+  host_call hc;
+  if (!hc.ok) { c->err = "cannot create streams / events"; cudaGetLastError(); return ZFB_ECUDA; }
   int status = ZFB_OK;
   size_t row0 = 0, word0 = 0;
+  size_t prev_off = 0, prev_bytes = 0;  // the stream piece still in its pinned buffer
   for (size_t s = 0; s < sp.nslabs && status == ZFB_OK; s++) {
     const size_t rows = (row0 + sp.thick <= sp.slowest) ? sp.thick : sp.slowest - row0;
     size_t sx, sy, sz;
     slab_dims(dims, nx, ny, nz, rows, sx, sy, sz);
     const geom sg = make_geom(dims, sx, sy, sz, maxbits);
-    const size_t off_e = row0 * sp.row_elems;
+    const size_t off_e = row0 * sp.row_elems, slab_bytes = rows * sp.row_elems * esz;
     const char* hsrc = (const char*)h_in + off_e * esz;
     char* dsrc = (char*)c->d_orig.p + off_e * esz;
     char* dst = (char*)c->d_stream.p + word0 * 8;
     const int b = (int)(s & 1);
-    if (cudaMemcpyAsync(dsrc, hsrc, rows * sp.row_elems * esz, cudaMemcpyHostToDevice, up) != cudaSuccess) { status = ZFB_ECUDA; break; }
-    cudaEventRecord(ev_up[b], up);
-    cudaStreamWaitEvent(c->stream, ev_up[b], 0);
+    if (!in_direct) {
+      if (s >= 2 && cudaEventSynchronize(hc.ev_up[b]) != cudaSuccess) { status = ZFB_ECUDA; break; }  // buffer b is free again
+      pool_of(c).copy(c->pin_in.p[b], hsrc, slab_bytes);
+      hsrc = (const char*)c->pin_in.p[b];
+    }
+    if (cudaMemcpyAsync(dsrc, hsrc, slab_bytes, cudaMemcpyHostToDevice, hc.up) != cudaSuccess) { status = ZFB_ECUDA; break; }
+    cudaEventRecord(hc.ev_up[b], hc.up);
+    cudaStreamWaitEvent(c->stream, hc.ev_up[b], 0);
     status = zfb_encode_dev(c, dtype, dims, sx, sy, sz, maxbits, dsrc, dst);
     if (status) break;
-    cudaEventRecord(ev_k[b], c->stream);
-    cudaStreamWaitEvent(down, ev_k[b], 0);
-    if (cudaMemcpyAsync((char*)h_stream + word0 * 8, dst, sg.stream_words * 8, cudaMemcpyDeviceToHost, down) != cudaSuccess) { status = ZFB_ECUDA; break; }
+    cudaEventRecord(hc.ev_k[b], c->stream);
+    cudaStreamWaitEvent(hc.down, hc.ev_k[b], 0);
+    if (out_direct) {
+      if (cudaMemcpyAsync((char*)h_stream + word0 * 8, dst, sg.stream_words * 8, cudaMemcpyDeviceToHost, hc.down) != cudaSuccess) { status = ZFB_ECUDA; break; }
+    } else {
+      if (cudaMemcpyAsync(c->pin_st.p[b], dst, sg.stream_words * 8, cudaMemcpyDeviceToHost, hc.down) != cudaSuccess) { status = ZFB_ECUDA; break; }
+      cudaEventRecord(hc.ev_dn[b], hc.down);
+      if (prev_bytes) {  // the previous piece has landed by now (or will in a moment): hand it to the caller
+        if (cudaEventSynchronize(hc.ev_dn[b ^ 1]) != cudaSuccess) { status = ZFB_ECUDA; break; }
+        pool_of(c).copy((char*)h_stream + prev_off, c->pin_st.p[b ^ 1], prev_bytes);
+      }
+      prev_off = word0 * 8; prev_bytes = sg.stream_words * 8;
+    }
     row0 += rows;
     word0 += sg.stream_words;
   }
-  cudaError_t e1 = cudaStreamSynchronize(up), e2 = cudaStreamSynchronize(c->stream), e3 = cudaStreamSynchronize(down);
-  for (int i = 0; i < 2; i++) { cudaEventDestroy(ev_up[i]); cudaEventDestroy(ev_k[i]); }
-  cudaStreamDestroy(up);
-  cudaStreamDestroy(down);
+  cudaError_t e1 = cudaStreamSynchronize(hc.up), e2 = cudaStreamSynchronize(c->stream), e3 = cudaStreamSynchronize(hc.down);
   if (status == ZFB_OK && (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)) {
     c->err = std::string("compress_host: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3);
     status = ZFB_ECUDA;
   }
   if (status) return status;
+  if (!out_direct && prev_bytes) pool_of(c).copy((char*)h_stream + prev_off, c->pin_st.p[(sp.nslabs - 1) & 1], prev_bytes);
   if (word0 != g.stream_words) { c->err = "internal: slab streams do not tile the stream"; return ZFB_ESTATE; }
   if (cbytes) *cbytes = sbytes;
   c->h_orig_key = h_in;
   c->orig_bytes = n * esz;
+  // the stream stays on the device: zfb_decompress_host of this very buffer needs no upload
+  c->h_stream_key = h_stream;
+  c->stream_key_bytes = sbytes;
+  c->stream_key_maxbits = maxbits;
+  sample_of(h_stream, sbytes, c->stream_sample);
   return ZFB_OK;
 }
 
@@ -799,7 +897,18 @@ extern "C" int zfb_decompress_host(zfb_ctx* c, int dtype, int dims, size_t nx, s
   const geom g = make_geom(dims, nx, ny, nz, maxbits);
   const size_t n = g.nx * g.ny * g.nz;
   const size_t sbytes = g.stream_words * 8;
-  if ((rc = ensure(c, c->d_stream, sbytes + 16))) return rc;
+  // the stream zfb_compress_host just produced is still on the device (same buffer, same size, same ends)
+  bool stream_resident = h_stream == c->h_stream_key && c->stream_key_bytes == sbytes && c->stream_key_maxbits == maxbits &&
+                         c->d_stream.p && c->d_stream.cap >= sbytes;
+  if (stream_resident) {
+    unsigned char now[128];
+    sample_of(h_stream, sbytes, now);
+    stream_resident = memcmp(now, c->stream_sample, sizeof now) == 0;
+  }
+  if (!stream_resident) {
+    c->h_stream_key = nullptr;
+    if ((rc = ensure(c, c->d_stream, sbytes + 16))) return rc;
+  }
   if ((rc = ensure(c, c->d_out, n * esz))) return rc;
   const bool metrics = h_orig != nullptr;
   bool orig_resident = metrics && h_orig == c->h_orig_key && c->orig_bytes == n * esz && c->d_orig.p;
@@ -810,23 +919,30 @@ extern "C" int zfb_decompress_host(zfb_ctx* c, int dtype, int dims, size_t nx, s
 
   // The fused partials are per-launch, so slabs are combined on the host in slab order.
   const slab_plan sp = plan_slabs(dims, nx, ny, nz, maxbits, esz);
-  cudaStream_t up, down;
-  cudaEvent_t ev_up[2], ev_k[2];
-  CU_TRY(c, cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking));
-  CU_TRY(c, cudaStreamCreateWithFlags(&down, cudaStreamNonBlocking));
-  for (int i = 0; i < 2; i++) { cudaEventCreateWithFlags(&ev_up[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming); }
+  const bool st_direct = stream_resident || is_pinned(h_stream), out_direct = is_pinned(h_out);
+  const bool or_direct = !metrics || orig_resident || is_pinned(h_orig);
+  size_t max_piece = 0;
+  {
+    size_t sx, sy, sz;
+    slab_dims(dims, nx, ny, nz, sp.thick, sx, sy, sz);
+    max_piece = make_geom(dims, sx, sy, sz, maxbits).stream_words * 8;
+  }
+  const size_t max_slab = sp.thick * sp.row_elems * esz;
+  if (!st_direct && c->pin_st.ensure(max_piece)) { c->err = "cudaHostAlloc failed"; return ZFB_ENOMEM; }
+  if (!or_direct && c->pin_in.ensure(max_slab)) { c->err = "cudaHostAlloc failed"; return ZFB_ENOMEM; }
+  if (!out_direct && c->pin_out.ensure(max_slab)) { c->err = "cudaHostAlloc failed"; return ZFB_ENOMEM; }
+  host_call hc;
+  if (!hc.ok) { c->err = "cannot create streams / events"; cudaGetLastError(); return ZFB_ECUDA; }
   std::vector<zfb_partials> slab_parts(metrics ? sp.nslabs : 0);
   partials_dev* d_slab_parts = nullptr;
   if (metrics && cudaMalloc(&d_slab_parts, sp.nslabs * sizeof(partials_dev)) != cudaSuccess) {
     cudaGetLastError();
-    for (int i = 0; i < 2; i++) { cudaEventDestroy(ev_up[i]); cudaEventDestroy(ev_k[i]); }
-    cudaStreamDestroy(up);
-    cudaStreamDestroy(down);
     c->err = "cudaMalloc failed";
     return ZFB_ENOMEM;
   }
   int status = ZFB_OK;
   size_t row0 = 0, word0 = 0;
+  size_t prev_off = 0, prev_bytes = 0;  // the decoded slab still in its pinned buffer
   for (size_t s = 0; s < sp.nslabs && status == ZFB_OK; s++) {
     const size_t rows = (row0 + sp.thick <= sp.slowest) ? sp.thick : sp.slowest - row0;
     size_t sx, sy, sz;
@@ -838,33 +954,55 @@ extern "C" int zfb_decompress_host(zfb_ctx* c, int dtype, int dims, size_t nx, s
     char* dout = (char*)c->d_out.p + off_e * esz;
     char* dorig = metrics ? (char*)c->d_orig.p + off_e * esz : nullptr;
     const int b = (int)(s & 1);
-    if (cudaMemcpyAsync(dstream, (const char*)h_stream + word0 * 8, sg.stream_words * 8, cudaMemcpyHostToDevice, up) != cudaSuccess) { status = ZFB_ECUDA; break; }
-    if (metrics && !orig_resident &&
-        cudaMemcpyAsync(dorig, (const char*)h_orig + off_e * esz, slab_bytes, cudaMemcpyHostToDevice, up) != cudaSuccess) { status = ZFB_ECUDA; break; }
-    cudaEventRecord(ev_up[b], up);
-    cudaStreamWaitEvent(c->stream, ev_up[b], 0);
+    if ((!st_direct || !or_direct) && s >= 2 && cudaEventSynchronize(hc.ev_up[b]) != cudaSuccess) { status = ZFB_ECUDA; break; }
+    if (!stream_resident) {
+      const char* src = (const char*)h_stream + word0 * 8;
+      if (!st_direct) {
+        pool_of(c).copy(c->pin_st.p[b], src, sg.stream_words * 8);
+        src = (const char*)c->pin_st.p[b];
+      }
+      if (cudaMemcpyAsync(dstream, src, sg.stream_words * 8, cudaMemcpyHostToDevice, hc.up) != cudaSuccess) { status = ZFB_ECUDA; break; }
+    }
+    if (metrics && !orig_resident) {
+      const char* src = (const char*)h_orig + off_e * esz;
+      if (!or_direct) {
+        pool_of(c).copy(c->pin_in.p[b], src, slab_bytes);
+        src = (const char*)c->pin_in.p[b];
+      }
+      if (cudaMemcpyAsync(dorig, src, slab_bytes, cudaMemcpyHostToDevice, hc.up) != cudaSuccess) { status = ZFB_ECUDA; break; }
+    }
+    cudaEventRecord(hc.ev_up[b], hc.up);
+    cudaStreamWaitEvent(c->stream, hc.ev_up[b], 0);
     status = zfb_decode_dev(c, dtype, dims, sx, sy, sz, maxbits, dstream, dout, dorig);
     if (status) break;
     if (metrics) cudaMemcpyAsync(d_slab_parts + s, c->result, sizeof(partials_dev), cudaMemcpyDeviceToDevice, c->stream);
-    cudaEventRecord(ev_k[b], c->stream);
-    cudaStreamWaitEvent(down, ev_k[b], 0);
-    if (cudaMemcpyAsync((char*)h_out + off_e * esz, dout, slab_bytes, cudaMemcpyDeviceToHost, down) != cudaSuccess) { status = ZFB_ECUDA; break; }
+    cudaEventRecord(hc.ev_k[b], c->stream);
+    cudaStreamWaitEvent(hc.down, hc.ev_k[b], 0);
+    if (out_direct) {
+      if (cudaMemcpyAsync((char*)h_out + off_e * esz, dout, slab_bytes, cudaMemcpyDeviceToHost, hc.down) != cudaSuccess) { status = ZFB_ECUDA; break; }
+    } else {
+      if (cudaMemcpyAsync(c->pin_out.p[b], dout, slab_bytes, cudaMemcpyDeviceToHost, hc.down) != cudaSuccess) { status = ZFB_ECUDA; break; }
+      cudaEventRecord(hc.ev_dn[b], hc.down);
+      if (prev_bytes) {  // hand the previous slab to the caller while this one is in flight
+        if (cudaEventSynchronize(hc.ev_dn[b ^ 1]) != cudaSuccess) { status = ZFB_ECUDA; break; }
+        pool_of(c).copy((char*)h_out + prev_off, c->pin_out.p[b ^ 1], prev_bytes);
+      }
+      prev_off = off_e * esz; prev_bytes = slab_bytes;
+    }
     row0 += rows;
     word0 += sg.stream_words;
   }
-  cudaError_t e1 = cudaStreamSynchronize(up), e2 = cudaStreamSynchronize(c->stream), e3 = cudaStreamSynchronize(down);
+  cudaError_t e1 = cudaStreamSynchronize(hc.up), e2 = cudaStreamSynchronize(c->stream), e3 = cudaStreamSynchronize(hc.down);
   if (status == ZFB_OK && metrics) {
     if (cudaMemcpy(slab_parts.data(), d_slab_parts, sp.nslabs * sizeof(partials_dev), cudaMemcpyDeviceToHost) != cudaSuccess) status = ZFB_ECUDA;
   }
   if (d_slab_parts) cudaFree(d_slab_parts);
-  for (int i = 0; i < 2; i++) { cudaEventDestroy(ev_up[i]); cudaEventDestroy(ev_k[i]); }
-  cudaStreamDestroy(up);
-  cudaStreamDestroy(down);
   if (status == ZFB_OK && (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)) {
     c->err = std::string("decompress_host: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2 != cudaSuccess ? e2 : e3);
     status = ZFB_ECUDA;
   }
   if (status) return status;
+  if (!out_direct && prev_bytes) pool_of(c).copy((char*)h_out + prev_off, c->pin_out.p[(sp.nslabs - 1) & 1], prev_bytes);
   if (metrics) {
     zfb_partials total;
     memset(&total, 0, sizeof total);
@@ -878,6 +1016,7 @@ extern "C" int zfb_decompress_host(zfb_ctx* c, int dtype, int dims, size_t nx, s
   }
   c->h_out_key = h_out;
   c->out_bytes = n * esz;
+  c->pair_serial++;
   return ZFB_OK;
 }
 

@@ -386,6 +386,7 @@ extern "C" int zfb_compress_var_host(zfb_ctx* c, int dtype, int dims, size_t nx,
   if ((rc = ensure(c, c->d_stream, need + 16))) return rc;
   if ((rc = ensure(c, c->var_index, (units + 1) * 8))) return rc;
   c->fused_valid = false;
+  c->h_stream_key = nullptr;  // d_stream is about to hold a variable-rate stream
   c->h_orig_key = nullptr;
   c->var_host_key = nullptr;
   c->var_index_key = nullptr;
@@ -475,6 +476,7 @@ extern "C" int zfb_decompress_var_host(zfb_ctx* c, int dtype, int dims, size_t n
     if ((rc = ensure(c, c->d_orig, n * esz))) return rc;
   }
   c->fused_valid = false;
+  c->h_stream_key = nullptr;  // d_stream is about to hold a variable-rate stream
   const slab_plan sp = plan_var_slabs(dims, nx, ny, nz, esz);
   // the index kept by zfb_compress_var_host is only trusted together with the bytes it was built from, so the
   // stream is uploaded again (cheap next to the field) and the index reused when the host buffer is the same
@@ -562,5 +564,6 @@ extern "C" int zfb_decompress_var_host(zfb_ctx* c, int dtype, int dims, size_t n
   }
   c->h_out_key = h_out;
   c->out_bytes = n * esz;
+  c->pair_serial++;
   return ZFB_OK;
 }

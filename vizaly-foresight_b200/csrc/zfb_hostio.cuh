@@ -1,0 +1,152 @@
+// zfb_hostio.cuh -- host side of the host-pointer entry points: moving PAGEABLE caller buffers at PCIe speed.
+//
+// CBench hands a plugin the loader's `new T[]` array and expects malloc'd outputs (main.cpp:262-280, 395), i.e.
+// pageable memory.  cudaMemcpyAsync on pageable memory is staged by the driver through one small pinned buffer and is
+// synchronous for the host, so a slab pipeline over three streams collapses into a serial chain.  Here the staging is
+// explicit: a slab is copied by a few threads between the caller's buffer and a pinned double buffer, and the DMA of
+// slab i runs while the threads copy slab i+1 (or i-1 on the way out).  Pinned caller buffers take the direct path.
+#pragma once
+#include <condition_variable>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <vector>
+#include <cuda_runtime.h>
+#if defined(__linux__)
+#include <sched.h>
+#endif
+
+namespace zfb {
+
+// A few persistent threads that split one memcpy between them; the caller takes a share and returns when all are done.
+class copy_pool {
+ public:
+  explicit copy_pool(unsigned nthreads) : n_(nthreads < 1 ? 1 : nthreads)
+  {
+    for (unsigned i = 1; i < n_; i++) th_.emplace_back([this, i] { worker(i); });
+  }
+  ~copy_pool()
+  {
+    {
+      std::lock_guard<std::mutex> l(mu_);
+      stop_ = true;
+      gen_++;
+    }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  unsigned threads() const { return n_; }
+  void copy(void* dst, const void* src, size_t bytes)
+  {
+    if (bytes < (size_t)(4u << 20) || n_ == 1) { std::memcpy(dst, src, bytes); return; }
+    {
+      std::lock_guard<std::mutex> l(mu_);
+      dst_ = (char*)dst; src_ = (const char*)src; bytes_ = bytes;
+      pending_ = n_ - 1;
+      gen_++;
+    }
+    cv_.notify_all();
+    share(0);
+    std::unique_lock<std::mutex> l(mu_);
+    done_.wait(l, [this] { return pending_ == 0; });
+  }
+
+ private:
+  void share(unsigned i)
+  {
+    // 2 MiB granularity keeps every thread on whole (huge) pages
+    const size_t unit = (size_t)2 << 20, units = (bytes_ + unit - 1) / unit;
+    const size_t u0 = units * i / n_, u1 = units * (i + 1) / n_;
+    const size_t b0 = u0 * unit, b1 = u1 * unit < bytes_ ? u1 * unit : bytes_;
+    if (b1 > b0) std::memcpy(dst_ + b0, src_ + b0, b1 - b0);
+  }
+  void worker(unsigned i)
+  {
+    unsigned long long seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> l(mu_);
+        cv_.wait(l, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (stop_) return;
+      }
+      share(i);
+      {
+        std::lock_guard<std::mutex> l(mu_);
+        if (--pending_ == 0) done_.notify_one();
+      }
+    }
+  }
+  unsigned n_;
+  std::vector<std::thread> th_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  unsigned long long gen_ = 0;
+  unsigned pending_ = 0;
+  bool stop_ = false;
+  char* dst_ = nullptr;
+  const char* src_ = nullptr;
+  size_t bytes_ = 0;
+};
+
+inline unsigned default_copy_threads()
+{
+  if (const char* e = std::getenv("ZFB_COPY_THREADS")) {
+    const long v = std::atol(e);
+    if (v >= 1 && v <= 64) return (unsigned)v;
+  }
+  unsigned cpus = std::thread::hardware_concurrency();
+#if defined(__linux__)
+  cpu_set_t set;
+  if (sched_getaffinity(0, sizeof set, &set) == 0) cpus = (unsigned)CPU_COUNT(&set);
+#endif
+  unsigned ranks = 1;  // ranks sharing this host (one process per GPU)
+  for (const char* name : {"LOCAL_WORLD_SIZE", "OMPI_COMM_WORLD_LOCAL_SIZE"})
+    if (const char* e = std::getenv(name)) {
+      const long v = std::atol(e);
+      if (v >= 1) { ranks = (unsigned)v; break; }
+    }
+  unsigned t = cpus / ranks;
+  return t < 2 ? 2 : t > 8 ? 8 : t;
+}
+
+// pinned double buffer, grown on demand
+struct pinned_pair {
+  void* p[2] = {nullptr, nullptr};
+  size_t cap = 0;
+  int ensure(size_t bytes)
+  {
+    if (cap >= bytes) return 0;
+    release();
+    for (int i = 0; i < 2; i++)
+      if (cudaHostAlloc(&p[i], bytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        release();
+        return -1;
+      }
+    cap = bytes;
+    return 0;
+  }
+  void release()
+  {
+    for (int i = 0; i < 2; i++) {
+      if (p[i]) cudaFreeHost(p[i]);
+      p[i] = nullptr;
+    }
+    cap = 0;
+  }
+};
+
+// true if the DMA engine can read / write the buffer directly (cudaHostAlloc / cudaHostRegister memory)
+inline bool is_pinned(const void* p)
+{
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+}  // namespace zfb

@@ -339,6 +339,7 @@ __global__ void __launch_bounds__(128) enc_generic_kernel(const Scalar* __restri
   if (FAST) tb = build_coder_tables(cs);
   const f3::plane_rows ps = fsc.rows();
   const bool aligned = (maxbits & 63u) == 0;
+  const bool vec = (reinterpret_cast<size_t>(in) & 15) == 0;  // 1D: 16-byte loads only from a 16-byte aligned array
   for (size_t b = b_begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < g.nblocks; b += (size_t)gridDim.x * blockDim.x) {
     const size_t ix = b % g.bx, iy = (b / g.bx) % g.by, iz = b / (g.bx * g.by);
     const size_t x0 = 4 * ix, y0 = 4 * iy, z0 = 4 * iz;
@@ -348,7 +349,7 @@ __global__ void __launch_bounds__(128) enc_generic_kernel(const Scalar* __restri
     const bool full = mx == 4 && (DIMS < 2 || my == 4) && (DIMS < 3 || mz == 4);
     if (edge_only && full) continue;
     Scalar f[BS];
-    if (DIMS == 1 && full) {
+    if (DIMS == 1 && full && vec) {
       if constexpr (sizeof(Scalar) == 4) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(in + x0));
         f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
@@ -405,6 +406,8 @@ __global__ void __launch_bounds__(128) dec_generic_kernel(const uint64_t* __rest
   const f3::plane_rows ps = fsc.rows();
   macc_t<Scalar> m;
   m.init();
+  // 1D: 16-byte accesses only when both arrays are 16-byte aligned (a slice like field[1:] is not)
+  const bool vec = (reinterpret_cast<size_t>(out) & 15) == 0 && (!METRICS || (reinterpret_cast<size_t>(orig) & 15) == 0);
   for (size_t b = b_begin + (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < g.nblocks; b += (size_t)gridDim.x * blockDim.x) {
     const size_t ix = b % g.bx, iy = (b / g.bx) % g.by, iz = b / (g.bx * g.by);
     const size_t x0 = 4 * ix, y0 = 4 * iy, z0 = 4 * iz;
@@ -427,7 +430,7 @@ __global__ void __launch_bounds__(128) dec_generic_kernel(const uint64_t* __rest
       slot_reader r(stream + w0, left > 0xffffffffull ? 0xffffffffu : (unsigned)left, (unsigned)(startbit & 63));
       decode_block<Scalar, DIMS>(f, maxbits, r);
     }
-    if (DIMS == 1 && full && sizeof(Scalar) == 4) {
+    if (DIMS == 1 && full && sizeof(Scalar) == 4 && vec) {
       if constexpr (sizeof(Scalar) == 4) {
         float4 v;
         v.x = f[0]; v.y = f[1]; v.z = f[2]; v.w = f[3];
