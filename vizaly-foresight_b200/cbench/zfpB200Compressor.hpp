@@ -16,12 +16,17 @@
 #ifndef ZFB_ZFP_B200_COMPRESSOR_HPP
 #define ZFB_ZFP_B200_COMPRESSOR_HPP
 
+#include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
 #include <sstream>
 #include <string>
 #include <vector>
+
+#if defined(__linux__)
+#include <sys/mman.h>
+#endif
 
 #include "cbench_api.hpp"
 #include "zfb.h"
@@ -73,6 +78,20 @@ struct Shared {
     ctx = nullptr;
   }
 };
+
+// Output buffers are malloc'd per call and first touched by the copy threads: with transparent huge pages in
+// "madvise" mode this turns a million 4 KiB page faults per 4 GiB into two thousand.
+inline void advise_huge_pages(void* p, size_t bytes)
+{
+#if defined(__linux__) && defined(MADV_HUGEPAGE)
+  const uintptr_t two_mb = (uintptr_t)2 << 20;
+  if (!p || bytes < 4 * two_mb) return;
+  const uintptr_t a = ((uintptr_t)p + two_mb - 1) & ~(two_mb - 1), e = ((uintptr_t)p + bytes) & ~(two_mb - 1);
+  if (e > a) madvise((void*)a, e - a, MADV_HUGEPAGE);
+#else
+  (void)p; (void)bytes;
+#endif
+}
 
 inline double to_double(const std::string& s)
 {
@@ -171,9 +190,11 @@ class ZFPCompressorB200 : public CompressorInterface {
     if (var) {
       const size_t cap = zfb_maximum_size(dtype, s.dims, s.nx, s.ny, s.nz, &mode);
       output = std::malloc(cap);
+      zfb_cbench::advise_huge_pages(output, cap);
       rc = output ? zfb_compress_var_host(sh.ctx, dtype, s.dims, s.nx, s.ny, s.nz, &mode, input, output, cap, &got) : ZFB_ENOMEM;
     } else {
       output = std::malloc(zfb_stream_capacity(s.dims, s.nx, s.ny, s.nz, mb));
+      zfb_cbench::advise_huge_pages(output, zfb_stream_capacity(s.dims, s.nx, s.ny, s.nz, mb));
       rc = output ? zfb_compress_host(sh.ctx, dtype, s.dims, s.nx, s.ny, s.nz, mb, input, output, &got) : ZFB_ENOMEM;
     }
     if (rc != ZFB_OK || !got) {
@@ -209,6 +230,7 @@ class ZFPCompressorB200 : public CompressorInterface {
     Timer dTime;
     dTime.start();
     output = std::malloc(s.numel * dataTypeSize);
+    zfb_cbench::advise_huge_pages(output, s.numel * dataTypeSize);
     // the field uploaded by compress() is still resident: the metric partials are fused into this pass.
     // Variable rate: the stream length is the state compress() left behind (zfpCompressor.hpp:22,145,211).
     int rc = ZFB_ENOMEM;

@@ -108,7 +108,7 @@ inline unsigned default_copy_threads()
       if (v >= 1) { ranks = (unsigned)v; break; }
     }
   unsigned t = cpus / ranks;
-  return t < 2 ? 2 : t > 8 ? 8 : t;
+  return t < 2 ? 2 : t > 16 ? 16 : t;
 }
 
 // pinned double buffer, grown on demand
