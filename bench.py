@@ -30,7 +30,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    "nyx2048-slab": dict(shape=(256, 2048, 2048), dtype="float32", rate=8, kind="lognormal",
+    "nyx2048-slab": dict(shape=(256, 2048, 2048), full=(2048, 2048, 2048), dtype="float32", rate=8, kind="lognormal",
                          desc="NYX 2048^3 float32 slab-sharded along the slowest axis: one 256x2048x2048 slab per GPU "
                               "(8 slabs = the full field at N=8), zfp 3D fixed-rate + fused abs/rel/mse/psnr/minmax"),
     "nyx512": dict(shape=(512, 512, 512), dtype="float32", rate=8, kind="lognormal",
@@ -42,8 +42,9 @@ WORKLOADS = {
 }
 
 
-def make_field(torch, shape, dtype, kind, seed, device):
-    """Deterministic synthetic field generated on the device."""
+def make_field(torch, shape, dtype, kind, seed, device, zoff=None):
+    """Deterministic synthetic field generated on the device.  zoff = position of the slab's
+    first plane along z in units of 2048 planes (default: slab `seed` of 256-plane slabs)."""
     g = torch.Generator(device=device).manual_seed(20261019 + seed)
     tdt = torch.float32 if dtype == "float32" else torch.float64
     if kind == "uniform":  # HACC positions: U[0, 256)
@@ -71,7 +72,7 @@ def make_field(torch, shape, dtype, kind, seed, device):
         z1 = min(nz, z0 + chunk)
         acc = torch.zeros((z1 - z0, ny, nx), device=device, dtype=torch.float32)
         for (kz, ky, kx), ph, amp in modes:
-            arg = (6.2831853 * kz * (zs[z0:z1] * (nz / 2048.0) + seed * 0.125))[:, None, None] \
+            arg = (6.2831853 * kz * (zs[z0:z1] * (nz / 2048.0) + (seed * 0.125 if zoff is None else zoff)))[:, None, None] \
                 + (6.2831853 * ky * ys)[None, :, None] + (6.2831853 * kx * xs)[None, None, :] + ph
             acc += amp * torch.cos(arg)
         acc += 0.05 * torch.randn(acc.shape, generator=g, device=device, dtype=torch.float32)
@@ -364,6 +365,9 @@ def main():
                     help="override the workload's synthetic field kind (sweeps only)")
     ap.add_argument("--mode", default="", help="variable-rate sweep only: abs:<tolerance> (zfp fixed accuracy) or "
                                                "rel:<precision> (fixed precision); default = fixed rate")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default): every GPU owns one slab of the workload's per-GPU shape; strong: the workload's FULL "
+                         "field (nyx2048-slab: 2048^3, 32 GiB) is cut into N slabs, so N = 1 processes all of it")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
@@ -393,12 +397,19 @@ def main():
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
     shape, dtype, rate = wl["shape"], wl["dtype"], args.rate or wl["rate"]
+    zoff = None
+    if args.scaling == "strong":
+        full = wl.get("full")
+        if not full or full[0] % (4 * world):
+            raise SystemExit("--scaling strong needs a workload with a full field whose slowest extent divides by 4 N")
+        shape = (full[0] // world,) + tuple(full[1:])
+        zoff = rank * shape[0] / 2048.0
     d = len(shape)
     npdt = np.float32 if dtype == "float32" else np.float64
     tdt = torch.float32 if dtype == "float32" else torch.float64
     esz = 4 if dtype == "float32" else 8
     mb = pkg.maxbits(npdt, d, int(rate) if float(rate).is_integer() else rate, args.wra)
-    field = make_field(torch, shape, dtype, args.field or wl["kind"], rank, dev)
+    field = make_field(torch, shape, dtype, args.field or wl["kind"], rank, dev, zoff)
     n = field.numel()
     field_bytes = n * esz
     cbytes = pkg.stream_bytes(shape, mb)
@@ -414,15 +425,13 @@ def main():
     codec = pkg.Codec(local)
     codec.use_torch_stream()
     want_metrics = dtype == "float32" or True
-    import importlib.util
-    spec = importlib.util.spec_from_file_location("zfb_dist", os.path.join(ROOT, "vizaly-foresight_b200", "dist.py"))
-    zdist = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(zdist)
-    scratch = (torch.zeros(4, dtype=torch.float64, device=dev), torch.zeros(4, dtype=torch.float64, device=dev))
+    if world > 1:
+        codec.comm_init(dist, dev)  # the context's own NCCL communicator (id broadcast through the job's process group)
 
     def allreduce_partials():
-        # the only exchange step: two tiny NCCL all-reduces over NVLink (SUM f64[3]+n, MAX f64[4])
-        zdist.allreduce_partials(codec.partials_tensor(), dist, scratch)
+        # the only exchange step: ONE ncclAllGather of the 64-byte partials + a rank-ordered combine on the device,
+        # issued by the C ABI on the stream the kernels run on (zfb_allreduce_partials, csrc/zfb_comm.cuh)
+        codec.allreduce_partials()
 
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
 
@@ -478,6 +487,13 @@ def main():
 
     # ---- end to end through the host-pointer C ABI (what the CBench plugin calls) ------------------
     e2e = None
+    if not args.no_e2e and field_bytes > (8 << 30):
+        try:  # the plugin leg needs ~3 host copies of the field (input, malloc'd output, pinned arm): skip if the host is small
+            avail = [int(l.split()[1]) * 1024 for l in open("/proc/meminfo") if l.startswith("MemAvailable")][0]
+        except Exception:
+            avail = 0
+        if avail < 4 * field_bytes * (world if world > 1 else 1):
+            args.no_e2e = True
     if not args.no_e2e:
         try:
             if var_mode is not None:
@@ -560,14 +576,14 @@ def main():
     line = {
         "metric": "uncompressed_GBps_compress_decompress_metrics", "value": value, "unit": "GB/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32" if dtype == "float32" else "f64", "data": "synthetic",
-        "config": {"workload": args.workload, "description": wl["desc"], "shape_per_gpu": list(shape),
+        "config": {"workload": args.workload if args.scaling == "weak" else args.workload.replace("-slab", "") + "-strong", "description": wl["desc"], "shape_per_gpu": list(shape),
                    "rate_bpv": rate if var_mode is None else 8.0 * cbytes / n, "maxbits": mb if var_mode is None else None,
                    "mode": args.mode or "rate", "wra": args.wra, "field": args.field or wl["kind"],
                    "compressed_bytes_per_gpu": cbytes,
                    "l2": "inputs (%.1f GiB per step) are far larger than the 126 MB L2; no flush needed" % (field_bytes / 2 ** 30),
-                   "exchange": "NCCL all-reduce of metric partials (SUM f64[4], MAX f64[4])" if world > 1 else "none (1 GPU)"},
+                   "exchange": "zfb_allreduce_partials: one ncclAllGather of the 64-byte partials + rank-ordered combine" if world > 1 else "none (1 GPU)"},
         "numa_binding": numa, "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
         "enc_ms": enc_ms, "dec_ms": dec_ms,
         "metrics_check": {k: vals[k] for k in ("absolute_error", "relative_error", "mse", "psnr", "minmax")},

@@ -116,6 +116,24 @@ int zfb_partials_get(zfb_ctx* ctx, zfb_partials* out);
 /* Overwrite the device partials (used after a host-side / MPI combine so histograms see global values). */
 int zfb_partials_set(zfb_ctx* ctx, const zfb_partials* in);
 
+/* ---- multi-GPU exchange: the metric partials of all ranks over NCCL / NVLink --------------------------
+ * Replaces the three blocking MPI_Allreduce calls every metric object makes (absoluteError.hpp:80-92,
+ * relativeError.hpp:93-105, meansquareError.hpp:70-71, psnrError.hpp:75-83, minmaxMetric.hpp:77-81): one
+ * ncclAllGather of the 64-byte zfb_partials and a rank-ordered combine on the device -- the result is bitwise the same
+ * on every rank and equal to zfb_partials_combine over the ranks in order.  NCCL is loaded at run time (libnccl.so.2,
+ * or ZFB_NCCL_LIB); there is no link-time dependency.
+ *   rank 0: zfb_comm_unique_id(id) -> broadcast the 128 bytes (MPI_Bcast in CBench) -> every rank:
+ *   zfb_comm_init(ctx, nranks, rank, id).  zfb_comm_adopt takes an ncclComm_t the caller already owns (same NCCL
+ *   library).  zfb_allreduce_partials / zfb_allreduce_counts run on the context's stream and are no-ops on a
+ *   context without a communicator (single rank). */
+int zfb_comm_unique_id(void* out128);
+int zfb_comm_init(zfb_ctx* ctx, int nranks, int rank, const void* id128);
+int zfb_comm_adopt(zfb_ctx* ctx, void* nccl_comm, int nranks, int rank);
+int zfb_comm_size(const zfb_ctx* ctx);
+int zfb_comm_destroy(zfb_ctx* ctx);
+int zfb_allreduce_partials(zfb_ctx* ctx);
+int zfb_allreduce_counts(zfb_ctx* ctx, uint64_t* d_counts, size_t count);
+
 /* Second-pass histograms (absoluteError.hpp:104-139, relativeError.hpp:117-153, minmaxMetric.hpp:92-133).
  * which: 0 = abs error over [0, hi], 1 = rel error over [0, hi], 2 = approx values over [lo, hi].
  * d_counts: ZFB_NBINS uint64 device counters, zero-initialised by the call.  Values outside the range

@@ -11,7 +11,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import smooth_field
+from conftest import ROOT, smooth_field
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
@@ -416,6 +416,98 @@ def test_nyx_512_full_size_against_oracle(codec, pkg, oracle):
     assert abs(v["mse"] - float(np.mean(d * d))) <= REL * float(np.mean(d * d))
     assert v["absolute_error"] == float(np.abs(h - dec).max())
     assert v["max"] == float(h.max()) and v["min"] == float(h.min())
+
+
+def _oracle_slabs(oracle, h, mb, nslab):
+    """Oracle round trip of a field cut into nslab pieces along the slowest axis (thickness % 4 == 0, so the piece
+    streams concatenate to the whole-field stream), one host thread per piece."""
+    shape = h.shape
+    code = 1 if h.dtype == np.float32 else 2
+    d = len(shape)
+    thick = shape[0] // nslab
+    assert thick * nslab == shape[0] and thick % 4 == 0
+    nx = shape[-1] if d > 1 else thick
+    ny = shape[1] if d == 3 else (thick if d == 2 else 1)
+    nz = thick if d == 3 else 1
+    sbytes = oracle.stream_bytes((thick,) + tuple(shape[1:]), mb)
+    st = np.zeros(nslab * sbytes, dtype=np.uint8)
+    dec = np.empty_like(h)
+    oracle.lib().zfo_roundtrip_slabs(code, d, nx, ny, nz, mb, h.ctypes.data, st.ctypes.data, dec.ctypes.data, nslab, 0,
+                                     None, None)
+    return st, dec
+
+
+def _bench_field(shape, dtype, kind):
+    """The very field bench.py times (rank 0)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("zfb_bench", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    torch = _torch()
+    return b.make_field(torch, shape, dtype, kind, 0, torch.device("cuda", 0))
+
+
+def test_bench_workload_nyx_slab_against_oracle(codec, pkg, oracle):
+    """The headline workload itself (bench.py nyx2048-slab: 256 x 2048 x 2048 float32, rate 8, rank 0's field), stream
+    and decoded values bit for bit against the oracle on the host cores, fused metrics against the decoded pair."""
+    torch = _torch()
+    shape = (256, 2048, 2048)
+    f = _bench_field(shape, "float32", "lognormal")
+    mb = pkg.maxbits(np.float32, 3, 8)
+    stream = codec.encode(f, mb)
+    out = codec.decode(stream, shape, torch.float32, mb, orig=f)
+    v = pkg.metric_values(codec.partials())
+    h = f.cpu().numpy()
+    st, dec = _oracle_slabs(oracle, h, mb, 64)
+    assert np.array_equal(stream.cpu().numpy(), st)
+    del st
+    assert_bits_equal(out.cpu().numpy(), dec, "slab decode")
+    assert v["absolute_error"] == float(np.abs(h - dec).max())
+    assert v["max"] == float(h.max()) and v["min"] == float(h.min())
+    m = oracle.metrics(h[:16].ravel(), dec[:16].ravel())  # formulas on a piece; sums over the whole field below
+    assert m["absolute_error"] <= v["absolute_error"]
+    d = (h - dec).astype(np.float64)
+    mse = float(np.mean(d * d))
+    assert abs(v["mse"] - mse) <= REL * mse
+
+
+def test_bench_workload_hacc_1d_against_oracle(codec, pkg, oracle):
+    """bench.py hacc1d (BASELINE configs[1]): 268 435 456 float32, "bits" 8 and 16 (both 64-bit slots under CBench's
+    wra, zfpCompressorGpu.hpp:129) and the unaligned 32-bit slots of rate 8 without wra."""
+    torch = _torch()
+    n = 268435456
+    f = _bench_field((n,), "float32", "uniform")
+    h = f.cpu().numpy()
+    for rate, wra in ((8, 1), (16, 1), (8, 0)):
+        mb = pkg.maxbits(np.float32, 1, rate, wra)
+        stream = codec.encode(f, mb)
+        out = codec.decode(stream, (n,), torch.float32, mb, orig=f)
+        v = pkg.metric_values(codec.partials())
+        st, dec = _oracle_slabs(oracle, h, mb, 64)
+        assert np.array_equal(stream.cpu().numpy(), st), (rate, wra)
+        del st, stream
+        assert_bits_equal(out.cpu().numpy(), dec, ("hacc decode", rate, wra))
+        assert v["absolute_error"] == float(np.abs(h - dec).max())
+        del out, dec
+
+
+def test_bench_workload_f64_slab_against_oracle(codec, pkg, oracle):
+    """bench.py vpic1024-f64 (BASELINE configs[4]): 256 x 1024 x 1024 float64 at three rates of the sweep."""
+    torch = _torch()
+    shape = (256, 1024, 1024)
+    f = _bench_field(shape, "float64", "smooth")
+    h = f.cpu().numpy()
+    for rate in (1, 8, 32):
+        mb = pkg.maxbits(np.float64, 3, rate)
+        stream = codec.encode(f, mb)
+        out = codec.decode(stream, shape, torch.float64, mb, orig=f)
+        v = pkg.metric_values(codec.partials())
+        st, dec = _oracle_slabs(oracle, h, mb, 64)
+        assert np.array_equal(stream.cpu().numpy(), st), rate
+        del st, stream
+        assert_bits_equal(out.cpu().numpy(), dec, ("f64 decode", rate))
+        assert v["absolute_error"] == float(np.abs(h - dec).max()), rate
+        del out, dec
 
 
 def test_bad_arguments_return_einval(codec, pkg):

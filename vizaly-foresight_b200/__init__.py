@@ -98,6 +98,13 @@ def lib():
         "zfb_encode_dev": (i, [vp, i, i, sz, sz, sz, u, vp, vp]),
         "zfb_decode_dev": (i, [vp, i, i, sz, sz, sz, u, vp, vp, vp]),
         "zfb_metrics_dev": (i, [vp, i, vp, vp, sz]),
+        "zfb_comm_unique_id": (i, [vp]),
+        "zfb_comm_init": (i, [vp, i, i, vp]),
+        "zfb_comm_adopt": (i, [vp, vp, i, i]),
+        "zfb_comm_size": (i, [vp]),
+        "zfb_comm_destroy": (i, [vp]),
+        "zfb_allreduce_partials": (i, [vp]),
+        "zfb_allreduce_counts": (i, [vp, vp, sz]),
         "zfb_partials_dev": (vp, [vp]),
         "zfb_partials_get": (i, [vp, PP]),
         "zfb_partials_set": (i, [vp, PP]),
@@ -331,6 +338,27 @@ class Codec:
 
     def set_partials(self, p):
         self._check(lib().zfb_partials_set(self._h, C.byref(p)), "zfb_partials_set")
+
+    def comm_init(self, dist, device):
+        """The context's own NCCL communicator over the ranks of a torch.distributed job: rank 0 draws the unique id,
+        the 128 bytes travel through the job's existing broadcast (CBench would use MPI_Bcast), every rank joins."""
+        import torch
+
+        world, rank = dist.get_world_size(), dist.get_rank()
+        buf = (C.c_ubyte * 128)()
+        if rank == 0:
+            self._check(lib().zfb_comm_unique_id(buf), "zfb_comm_unique_id")
+        t = torch.tensor(list(buf), dtype=torch.uint8, device=device)
+        dist.broadcast(t, src=0)
+        raw = bytes(t.cpu().tolist())
+        self._check(lib().zfb_comm_init(self._h, world, rank, raw), "zfb_comm_init")
+
+    def allreduce_partials(self):
+        """One ncclAllGather + rank-ordered combine of the device partials, on the context's stream (no-op on one rank)."""
+        self._check(lib().zfb_allreduce_partials(self._h), "zfb_allreduce_partials")
+
+    def allreduce_counts(self, counts):
+        self._check(lib().zfb_allreduce_counts(self._h, counts.data_ptr(), counts.numel()), "zfb_allreduce_counts")
 
     def partials_tensor(self):
         """The context's device-resident zfb_partials viewed as 8 x int64 (raw bits; reinterpret with .view)."""

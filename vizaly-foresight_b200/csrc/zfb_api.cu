@@ -11,6 +11,7 @@
 #include "../../include/zfb.h"
 #include "zfb_kernels.cuh"
 #include "zfb_hostio.cuh"
+#include "zfb_comm.cuh"
 
 using namespace zfb;
 
@@ -49,6 +50,11 @@ struct zfb_ctx {
   size_t stream_key_bytes = 0;
   unsigned stream_key_maxbits = 0;
   unsigned char stream_sample[128] = {0};
+  // multi-GPU exchange (zfb_comm.cuh)
+  ncclComm_t comm = nullptr;
+  bool comm_owned = false;
+  int comm_ranks = 1, comm_rank = 0;
+  partials_dev* gathered = nullptr;   // comm_ranks entries
   copy_pool* pool = nullptr;          // copy threads for pageable caller buffers (zfb_hostio.cuh)
   pinned_pair pin_in, pin_out, pin_st;  // pinned double buffers: field slabs in / out, stream pieces
   int occ_enc[80] = {0}, occ_dec[80] = {0}, occ_decm[80] = {0};  // resident CTAs per SM, by slot words
@@ -265,9 +271,98 @@ extern "C" int zfb_host_cache_invalidate(zfb_ctx* c)
 
 extern "C" unsigned long long zfb_host_pair_serial(const zfb_ctx* c) { return c ? c->pair_serial : 0ull; }
 
+extern "C" int zfb_comm_destroy(zfb_ctx* c)
+{
+  if (!c) return ZFB_EINVAL;
+  if (c->comm && c->comm_owned && nccl().ok) {
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    nccl().CommDestroy(c->comm);
+  }
+  c->comm = nullptr;
+  c->comm_owned = false;
+  c->comm_ranks = 1; c->comm_rank = 0;
+  if (c->gathered) cudaFree(c->gathered);
+  c->gathered = nullptr;
+  return ZFB_OK;
+}
+
+extern "C" int zfb_comm_unique_id(void* out128)
+{
+  if (!out128) return ZFB_EINVAL;
+  if (!nccl().ok) return ZFB_ESTATE;
+  ncclUniqueId id;
+  if (nccl().GetUniqueId(&id) != ncclSuccess) return ZFB_ECUDA;
+  memcpy(out128, &id, sizeof id);
+  return ZFB_OK;
+}
+
+static int comm_attach(zfb_ctx* c, ncclComm_t comm, bool owned, int nranks, int rank)
+{
+  zfb_comm_destroy(c);
+  if (cudaMalloc(&c->gathered, (size_t)nranks * sizeof(partials_dev)) != cudaSuccess) {
+    cudaGetLastError();
+    if (owned) nccl().CommDestroy(comm);
+    c->err = "cudaMalloc failed";
+    return ZFB_ENOMEM;
+  }
+  c->comm = comm; c->comm_owned = owned; c->comm_ranks = nranks; c->comm_rank = rank;
+  return ZFB_OK;
+}
+
+extern "C" int zfb_comm_init(zfb_ctx* c, int nranks, int rank, const void* id128)
+{
+  if (!c || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return ZFB_EINVAL;
+  if (!nccl().ok) { c->err = "NCCL unavailable: " + nccl().why; return ZFB_ESTATE; }
+  CU_TRY(c, cudaSetDevice(c->device));
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof id);
+  ncclComm_t comm = nullptr;
+  const ncclResult_t r = nccl().CommInitRank(&comm, nranks, id, rank);
+  if (r != ncclSuccess) { c->err = std::string("ncclCommInitRank: ") + nccl().GetErrorString(r); return ZFB_ECUDA; }
+  return comm_attach(c, comm, true, nranks, rank);
+}
+
+extern "C" int zfb_comm_adopt(zfb_ctx* c, void* nccl_comm, int nranks, int rank)
+{
+  if (!c || !nccl_comm || nranks < 1 || rank < 0 || rank >= nranks) return ZFB_EINVAL;
+  if (!nccl().ok) { c->err = "NCCL unavailable: " + nccl().why; return ZFB_ESTATE; }
+  CU_TRY(c, cudaSetDevice(c->device));
+  return comm_attach(c, (ncclComm_t)nccl_comm, false, nranks, rank);
+}
+
+// In place on the context's device partials, asynchronous on the context's stream.  Without a communicator (one
+// rank) it is a no-op, so single-GPU callers need no special case.
+extern "C" int zfb_allreduce_partials(zfb_ctx* c)
+{
+  if (!c) return ZFB_EINVAL;
+  if (!c->comm || c->comm_ranks == 1) return ZFB_OK;
+  CU_TRY(c, cudaSetDevice(c->device));
+  const ncclResult_t r = nccl().AllGather(c->result, c->gathered, sizeof(partials_dev), ncclUint8, c->comm, c->stream);
+  if (r != ncclSuccess) { c->err = std::string("ncclAllGather: ") + nccl().GetErrorString(r); return ZFB_ECUDA; }
+  combine_partials_kernel<<<1, 32, 0, c->stream>>>(c->gathered, c->comm_ranks, c->result);
+  c->launches++;
+  CU_TRY(c, cudaGetLastError());
+  return ZFB_OK;
+}
+
+// SUM of histogram counters (absoluteError.hpp:129, relativeError.hpp:141, minmaxMetric.hpp:122), in place
+extern "C" int zfb_allreduce_counts(zfb_ctx* c, uint64_t* d_counts, size_t count)
+{
+  if (!c || !d_counts) return ZFB_EINVAL;
+  if (!c->comm || c->comm_ranks == 1) return ZFB_OK;
+  CU_TRY(c, cudaSetDevice(c->device));
+  const ncclResult_t r = nccl().AllReduce(d_counts, d_counts, count, ncclUint64, ncclSum, c->comm, c->stream);
+  if (r != ncclSuccess) { c->err = std::string("ncclAllReduce: ") + nccl().GetErrorString(r); return ZFB_ECUDA; }
+  return ZFB_OK;
+}
+
+extern "C" int zfb_comm_size(const zfb_ctx* c) { return c ? c->comm_ranks : 0; }
+
 extern "C" int zfb_destroy(zfb_ctx* c)
 {
   if (!c) return ZFB_EINVAL;
+  zfb_comm_destroy(c);
   zfb_release_resident(c);
   if (c->part) cudaFree(c->part);
   if (c->result) cudaFree(c->result);

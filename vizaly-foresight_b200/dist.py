@@ -1,31 +1,34 @@
 """Multi-GPU combine of the metric partials: the one exchange step of the hot path.
 
 The reference does this with blocking MPI_Allreduce calls on MPI_COMM_WORLD (absoluteError.hpp:80-92,
-relativeError.hpp:93-105, meansquareError.hpp:70-71, psnrError.hpp:75-83, minmaxMetric.hpp:77-81).  Here
-the same quantities ride two tiny all-reduces over NCCL / NVLink (SUM of f64[3] + n, MAX of f64[4]; the
-minimum is stored negated so MAX covers it).  The tensor is the context's device-resident zfb_partials
-viewed as 8 x int64 (Codec.partials_tensor()); on CPU tensors with the gloo backend the identical code
-path is what tests/test_multirank_gloo.py exercises.
+relativeError.hpp:93-105, meansquareError.hpp:70-71, psnrError.hpp:75-83, minmaxMetric.hpp:77-81).  The product path
+is the C ABI's zfb_allreduce_partials (csrc/zfb_comm.cuh): ONE ncclAllGather of the 64-byte zfb_partials and a
+rank-ordered combine on the device.  This module is the same exchange written with torch.distributed -- one
+all_gather of the 8 x int64 view (raw bits) and the same rank-ordered combine -- for back ends without NCCL:
+tests/test_multirank_gloo.py runs it on CPU tensors with gloo, world size 2.
 """
 
 
-def allreduce_partials(p_i64, dist, scratch=None):
-    """In-place all-reduce of a zfb_partials laid out as 8 x int64 (raw bits)."""
+def allreduce_partials(p_i64, dist):
+    """In-place combine of a zfb_partials laid out as 8 x int64 (raw bits): all_gather + combine in rank order, so the
+    result is bitwise the same on every rank and equal to zfb_partials_combine over the ranks."""
     import torch
 
-    pf = p_i64.view(torch.float64)
-    if scratch is None:
-        scratch = (torch.empty(4, dtype=torch.float64, device=p_i64.device),
-                   torch.empty(4, dtype=torch.float64, device=p_i64.device))
-    s, m = scratch
-    s[:3] = pf[:3]
-    s[3] = p_i64[7].to(torch.float64)  # n < 2^53: exact in float64
-    m[:] = pf[3:7]
-    dist.all_reduce(s, op=dist.ReduceOp.SUM)
-    dist.all_reduce(m, op=dist.ReduceOp.MAX)
-    pf[:3] = s[:3]
-    pf[3:7] = m
-    p_i64[7] = s[3].round().to(torch.int64)
+    world = dist.get_world_size()
+    if world == 1:
+        return p_i64
+    parts = [torch.empty_like(p_i64) for _ in range(world)]
+    dist.all_gather(parts, p_i64)
+    allp = torch.stack(parts)                      # world x 8 (int64 bits)
+    f = allp.view(torch.float64)
+    acc = f[0].clone()
+    n = allp[0, 7].clone()
+    for r in range(1, world):                      # fixed order: rank 0, 1, 2, ...
+        acc[:3] += f[r, :3]
+        acc[3:7] = torch.maximum(acc[3:7], f[r, 3:7])
+        n += allp[r, 7]
+    p_i64.view(torch.float64)[:7] = acc[:7]
+    p_i64[7] = n
     return p_i64
 
 
