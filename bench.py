@@ -368,6 +368,10 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default): every GPU owns one slab of the workload's per-GPU shape; strong: the workload's FULL "
                          "field (nyx2048-slab: 2048^3, 32 GiB) is cut into N slabs, so N = 1 processes all of it")
+    ap.add_argument("--hist", action="store_true",
+                    help="also produce the minmax metric's value-range histogram (minmaxMetric.hpp:92-133) inside the step: "
+                         "min / max harvested by the encode pass, bins filled by the decode pass, counters and range "
+                         "combined across ranks over NCCL")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
@@ -436,24 +440,35 @@ def main():
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
 
     var_bytes = [0]
+    hist_range = [0.0, 1.0]
+    hist_counts = torch.zeros(1025, dtype=torch.int64, device=dev)
 
     def step(i=None):
         if i is not None:
             ev[i][0].record()
         if var_mode is not None:
             s_var, var_bytes[0] = codec.encode_var(field, var_mode, out=stream)
+        elif args.hist:
+            codec.encode_range(field, mb, out=stream)
+            if world > 1:
+                codec.allreduce_range()
+            hist_range[:] = codec.range()   # the one host synchronisation of the step (CBench is synchronous there too)
         else:
             codec.encode(field, mb, out=stream)
         if i is not None:
             ev[i][1].record()
         if var_mode is not None:
             codec.decode_var(s_var, shape, tdt, var_mode, orig=field, out=out)
+        elif args.hist:
+            codec.decode_hist(stream, shape, tdt, mb, hist_range[0], hist_range[1], orig=field, out=out, counts=hist_counts)
         else:
             codec.decode(stream, shape, tdt, mb, orig=field if want_metrics else None, out=out)
         if i is not None:
             ev[i][2].record()
         if world > 1:
             allreduce_partials()
+            if args.hist:
+                codec.allreduce_counts(hist_counts)
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -581,6 +596,8 @@ def main():
         "config": {"workload": args.workload if args.scaling == "weak" else args.workload.replace("-slab", "") + "-strong", "description": wl["desc"], "shape_per_gpu": list(shape),
                    "rate_bpv": rate if var_mode is None else 8.0 * cbytes / n, "maxbits": mb if var_mode is None else None,
                    "mode": args.mode or "rate", "wra": args.wra, "field": args.field or wl["kind"],
+                   "histogram": ("minmax value-range histogram fused into the step: %d values binned, %d out of range"
+                                 % (int(hist_counts[:1024].sum().item()), int(hist_counts[1024].item()))) if args.hist else "none",
                    "compressed_bytes_per_gpu": cbytes,
                    "l2": "inputs (%.1f GiB per step) are far larger than the 126 MB L2; no flush needed" % (field_bytes / 2 ** 30),
                    "exchange": "zfb_allreduce_partials: one ncclAllGather of the 64-byte partials + rank-ordered combine" if world > 1 else "none (1 GPU)"},

@@ -134,6 +134,21 @@ int zfb_comm_destroy(zfb_ctx* ctx);
 int zfb_allreduce_partials(zfb_ctx* ctx);
 int zfb_allreduce_counts(zfb_ctx* ctx, uint64_t* d_counts, size_t count);
 
+/* ---- value-range (minmax) histogram without a second pass over memory ----------------------------------
+ * minmaxMetric.hpp:62-133 bins the DECOMPRESSED values over [global min, global max] of the ORIGINAL field.
+ * zfb_encode_range_dev = zfb_encode_dev that also harvests the field's min / max (fused into the float 3D tile kernel;
+ * a streaming pass for the other kernels); zfb_allreduce_range combines the ranges of all ranks (same single
+ * all-gather as the partials); zfb_range_get reads the range; zfb_decode_hist_dev = zfb_decode_dev that also bins the
+ * values it decodes into d_counts[0 .. ZFB_NBINS-1] (d_counts[ZFB_NBINS] = out-of-range values, clamped to the end
+ * bins), fused into the float 3D tile kernel -- no extra memory traffic -- and a stand-alone pass otherwise.  Counts
+ * equal the reference's loop (minmaxMetric.hpp:108-117) bin for bin. */
+int zfb_encode_range_dev(zfb_ctx* ctx, int dtype, int dims, size_t nx, size_t ny, size_t nz, unsigned maxbits,
+                         const void* d_in, void* d_stream);
+int zfb_allreduce_range(zfb_ctx* ctx);
+int zfb_range_get(zfb_ctx* ctx, double* lo, double* hi);
+int zfb_decode_hist_dev(zfb_ctx* ctx, int dtype, int dims, size_t nx, size_t ny, size_t nz, unsigned maxbits,
+                        const void* d_stream, void* d_out, const void* d_orig, double lo, double hi, uint64_t* d_counts);
+
 /* Second-pass histograms (absoluteError.hpp:104-139, relativeError.hpp:117-153, minmaxMetric.hpp:92-133).
  * which: 0 = abs error over [0, hi], 1 = rel error over [0, hi], 2 = approx values over [lo, hi].
  * d_counts: ZFB_NBINS uint64 device counters, zero-initialised by the call.  Values outside the range

@@ -105,6 +105,10 @@ def lib():
         "zfb_comm_destroy": (i, [vp]),
         "zfb_allreduce_partials": (i, [vp]),
         "zfb_allreduce_counts": (i, [vp, vp, sz]),
+        "zfb_encode_range_dev": (i, [vp, i, i, sz, sz, sz, u, vp, vp]),
+        "zfb_allreduce_range": (i, [vp]),
+        "zfb_range_get": (i, [vp, C.POINTER(d), C.POINTER(d)]),
+        "zfb_decode_hist_dev": (i, [vp, i, i, sz, sz, sz, u, vp, vp, vp, d, d, vp]),
         "zfb_partials_dev": (vp, [vp]),
         "zfb_partials_get": (i, [vp, PP]),
         "zfb_partials_set": (i, [vp, PP]),
@@ -312,6 +316,45 @@ class Codec:
         self._check(lib().zfb_encode_dev(self._h, _dtype_code(field.dtype), d, nx, ny, nz, mb, field.data_ptr(),
                                          out.data_ptr()), "zfb_encode_dev")
         return out[:nbytes]
+
+    def encode_range(self, field, mb, out=None):
+        """encode() that also harvests the field's min / max on the way (zfb_encode_range_dev); read them with
+        range() -- after allreduce_range() in a multi-GPU job."""
+        import torch
+
+        self.use_torch_stream()
+        d, nx, ny, nz = dims_of(field.shape)
+        nbytes = int(lib().zfb_stream_bytes(d, nx, ny, nz, mb))
+        if out is None:
+            out = torch.empty(nbytes + 16, dtype=torch.uint8, device=field.device)
+        assert field.is_contiguous() and out.numel() >= nbytes
+        self._check(lib().zfb_encode_range_dev(self._h, _dtype_code(field.dtype), d, nx, ny, nz, mb, field.data_ptr(),
+                                               out.data_ptr()), "zfb_encode_range_dev")
+        return out[:nbytes]
+
+    def allreduce_range(self):
+        self._check(lib().zfb_allreduce_range(self._h), "zfb_allreduce_range")
+
+    def range(self):
+        lo, hi = C.c_double(), C.c_double()
+        self._check(lib().zfb_range_get(self._h, C.byref(lo), C.byref(hi)), "zfb_range_get")
+        return lo.value, hi.value
+
+    def decode_hist(self, stream, shape, dtype, mb, lo, hi, orig=None, out=None, counts=None):
+        """decode() that also bins the decoded values over [lo, hi] (the minmax metric's histogram) in the same pass.
+        Returns (out, counts[:1024], counts[1024] = out-of-range values)."""
+        import torch
+
+        self.use_torch_stream()
+        d, nx, ny, nz = dims_of(shape)
+        if out is None:
+            out = torch.empty(tuple(shape), dtype=dtype, device=stream.device)
+        if counts is None:
+            counts = torch.empty(NBINS + 1, dtype=torch.int64, device=stream.device)
+        self._check(lib().zfb_decode_hist_dev(self._h, _dtype_code(dtype), d, nx, ny, nz, mb, stream.data_ptr(),
+                                              out.data_ptr(), orig.data_ptr() if orig is not None else None,
+                                              float(lo), float(hi), counts.data_ptr()), "zfb_decode_hist_dev")
+        return out, counts[:NBINS], counts[NBINS]
 
     def decode(self, stream, shape, dtype, mb, orig=None, out=None):
         import torch

@@ -35,6 +35,10 @@ struct zfb_ctx {
   double* part = nullptr;       // per-CTA partial rows
   int part_rows = 0;
   partials_dev* result = nullptr;
+  partials_dev* enc_result = nullptr;   // min / max of the last field encoded by zfb_encode_range_dev (other members unused)
+  uint64_t* hist_counts = nullptr;      // zfb_decode_dev bins the decoded values into these counters on the way (zfb_decode_hist_dev)
+  double hist_lo = 0, hist_hi = 0;
+  bool want_range = false;              // zfb_encode_dev harvests min / max on the way (set by zfb_encode_range_dev)
   uint64_t launches = 0;
   std::string err;
   bool force_generic = false;
@@ -201,11 +205,13 @@ extern "C" int zfb_create(zfb_ctx** out, int device)
   c->stream = c->own_stream;
   c->part_rows = c->sm_count * 32;
   if (cudaMalloc(&c->part, (size_t)c->part_rows * PART_STRIDE * sizeof(double)) != cudaSuccess ||
-      cudaMalloc(&c->result, sizeof(partials_dev)) != cudaSuccess) {
+      cudaMalloc(&c->result, sizeof(partials_dev)) != cudaSuccess ||
+      cudaMalloc(&c->enc_result, sizeof(partials_dev)) != cudaSuccess) {
     delete c;
     return ZFB_ENOMEM;
   }
   cudaMemset(c->result, 0, sizeof(partials_dev));
+  cudaMemset(c->enc_result, 0, sizeof(partials_dev));
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
@@ -216,9 +222,11 @@ extern "C" int zfb_create(zfb_ctx** out, int device)
   // opt in to large dynamic shared memory for the tile kernels
   // (the limit applies to static + dynamic, and the decode kernels keep a small static reduction buffer)
   const int max_smem = 100 * 1024 + 1024;
-  if (cudaFuncSetAttribute(enc3_f32_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) != cudaSuccess ||
-      cudaFuncSetAttribute(dec3_f32_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) != cudaSuccess ||
-      cudaFuncSetAttribute(dec3_f32_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) != cudaSuccess) {
+  if (cudaFuncSetAttribute(enc3_f32_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) != cudaSuccess ||
+      cudaFuncSetAttribute(enc3_f32_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) != cudaSuccess ||
+      cudaFuncSetAttribute(dec3_f32_tile_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) != cudaSuccess ||
+      cudaFuncSetAttribute(dec3_f32_tile_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) != cudaSuccess ||
+      cudaFuncSetAttribute(dec3_f32_tile_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) != cudaSuccess) {
     cudaGetLastError();
     c->encode_tiled = nullptr;  // tile kernels unusable: everything goes through the generic kernels
   }
@@ -366,6 +374,7 @@ extern "C" int zfb_destroy(zfb_ctx* c)
   zfb_release_resident(c);
   if (c->part) cudaFree(c->part);
   if (c->result) cudaFree(c->result);
+  if (c->enc_result) cudaFree(c->enc_result);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c->pool;
   delete c;
@@ -578,13 +587,24 @@ extern "C" int zfb_encode_dev(zfb_ctx* c, int dtype, int dims, size_t nx, size_t
     const size_t smem = enc_tile_smem(tg.W);
     int nb = c->occ_enc[tg.W];
     if (!nb) {
-      CU_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, enc3_f32_tile_kernel, TILE_THREADS, smem));
+      CU_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, enc3_f32_tile_kernel<false>, TILE_THREADS, smem));
       if (nb < 1) nb = 1;
       c->occ_enc[tg.W] = nb;
     }
     unsigned grid = (unsigned)c->sm_count * (unsigned)nb;
     if (grid > tg.ntiles) grid = tg.ntiles;
-    enc3_f32_tile_kernel<<<grid, TILE_THREADS, smem, c->stream>>>(tm, (uint64_t*)d_stream, tg, maxbits);
+    if (c->want_range && !((g.ny | g.nz) & 3) && (int)grid <= c->part_rows) {
+      // min / max of the field harvested by the same pass (zfb_encode_range_dev)
+      enc3_f32_tile_kernel<true><<<grid, TILE_THREADS, smem, c->stream>>>(tm, (uint64_t*)d_stream, tg, maxbits, c->part);
+      c->launches++;
+      CU_TRY(c, cudaGetLastError());
+      finalize_partials_kernel<<<1, 256, 0, c->stream>>>(c->part, (int)grid, c->enc_result, (unsigned long long)(g.nx * g.ny * g.nz));
+      c->launches++;
+      CU_TRY(c, cudaGetLastError());
+      c->want_range = false;  // done: the caller does not need the stand-alone pass
+      return ZFB_OK;
+    }
+    enc3_f32_tile_kernel<false><<<grid, TILE_THREADS, smem, c->stream>>>(tm, (uint64_t*)d_stream, tg, maxbits, c->part);
     c->launches++;
     CU_TRY(c, cudaGetLastError());
     if ((g.ny | g.nz) & 3) return launch_enc_generic<float>(c, dims, g, maxbits, d_in, d_stream, 1);  // partial blocks
@@ -683,8 +703,8 @@ extern "C" int zfb_decode_dev(zfb_ctx* c, int dtype, int dims, size_t nx, size_t
     const size_t smem = dec_tile_smem(tg.W, metrics);
     int nb = metrics ? c->occ_decm[tg.W] : c->occ_dec[tg.W];
     if (!nb) {
-      if (metrics) CU_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, dec3_f32_tile_kernel<true>, TILE_THREADS, smem));
-      else CU_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, dec3_f32_tile_kernel<false>, TILE_THREADS, smem));
+      if (metrics) CU_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, dec3_f32_tile_kernel<true, false>, TILE_THREADS, smem));
+      else CU_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, dec3_f32_tile_kernel<false, false>, TILE_THREADS, smem));
       if (nb < 1) nb = 1;
       (metrics ? c->occ_decm[tg.W] : c->occ_dec[tg.W]) = nb;
     }
@@ -693,15 +713,21 @@ extern "C" int zfb_decode_dev(zfb_ctx* c, int dtype, int dims, size_t nx, size_t
     if ((int)grid > c->part_rows / 2) grid = c->part_rows / 2;
     static const bool f32_unfused = [] { const char* e = std::getenv("ZFB_F32_UNFUSED"); return e && e[0] == '1'; }();
     if (metrics && f32_unfused && !((g.ny | g.nz) & 3)) {  // experiment switch (fused is faster for float)
-      dec3_f32_tile_kernel<false><<<grid, TILE_THREADS, smem, c->stream>>>(tm, (const uint64_t*)d_stream, (float*)d_out, tg, maxbits, c->part);
+      dec3_f32_tile_kernel<false, false><<<grid, TILE_THREADS, smem, c->stream>>>(tm, (const uint64_t*)d_stream, (float*)d_out, tg, maxbits, c->part, 0.0, 0.0, nullptr);
       c->launches++;
       CU_TRY(c, cudaGetLastError());
       return zfb_metrics_dev(c, dtype, d_orig, d_out, n);
     }
-    if (metrics)
-      dec3_f32_tile_kernel<true><<<grid, TILE_THREADS, smem, c->stream>>>(tm, (const uint64_t*)d_stream, (float*)d_out, tg, maxbits, c->part);
+    if (metrics && c->hist_counts && !((g.ny | g.nz) & 3)) {
+      // value-range histogram of the decoded values fused into the pass (zfb_decode_hist_dev); a CTA more of shared
+      // memory for the counters still leaves the same number of CTAs per SM
+      dec3_f32_tile_kernel<true, true><<<grid, TILE_THREADS, smem, c->stream>>>(tm, (const uint64_t*)d_stream, (float*)d_out, tg, maxbits, c->part,
+                                                                            c->hist_lo, c->hist_hi, (unsigned long long*)c->hist_counts);
+      c->hist_counts = nullptr;  // done: the caller does not need the stand-alone pass
+    } else if (metrics)
+      dec3_f32_tile_kernel<true, false><<<grid, TILE_THREADS, smem, c->stream>>>(tm, (const uint64_t*)d_stream, (float*)d_out, tg, maxbits, c->part, 0.0, 0.0, nullptr);
     else
-      dec3_f32_tile_kernel<false><<<grid, TILE_THREADS, smem, c->stream>>>(tm, (const uint64_t*)d_stream, (float*)d_out, tg, maxbits, c->part);
+      dec3_f32_tile_kernel<false, false><<<grid, TILE_THREADS, smem, c->stream>>>(tm, (const uint64_t*)d_stream, (float*)d_out, tg, maxbits, c->part, 0.0, 0.0, nullptr);
     c->launches++;
     CU_TRY(c, cudaGetLastError());
     rows = (int)grid;
@@ -771,6 +797,76 @@ extern "C" int zfb_metrics_dev(zfb_ctx* c, int dtype, const void* d_orig, const 
   c->launches++;
   CU_TRY(c, cudaGetLastError());
   return finalize(c, grid, n);
+}
+
+// ---- value-range (minmax) histogram without a second pass ------------------------------------------------
+// minmaxMetric.hpp:62-133 bins the DECOMPRESSED values over [global min, global max] of the ORIGINAL field.  The
+// range is known once the field has been read -- which the encode pass does anyway -- so the encode kernel harvests
+// it and the decode kernel bins what it has just decoded: the histogram costs no memory traffic at all.
+extern "C" int zfb_encode_range_dev(zfb_ctx* c, int dtype, int dims, size_t nx, size_t ny, size_t nz, unsigned maxbits,
+                                    const void* d_in, void* d_stream)
+{
+  if (!c) return ZFB_EINVAL;
+  c->want_range = true;
+  int rc = zfb_encode_dev(c, dtype, dims, nx, ny, nz, maxbits, d_in, d_stream);
+  const bool fused = !c->want_range;
+  c->want_range = false;
+  if (rc || fused) return rc;
+  // kernels without the fused harvest (anything but whole-block float 3D): one streaming pass over the field
+  const size_t n = nx * (dims > 1 ? ny : 1) * (dims > 2 ? nz : 1);
+  partials_dev keep;
+  CU_TRY(c, cudaMemcpyAsync(&keep, c->result, sizeof keep, cudaMemcpyDeviceToHost, c->stream));
+  if ((rc = zfb_metrics_dev(c, dtype, d_in, d_in, n))) return rc;
+  CU_TRY(c, cudaMemcpyAsync(c->enc_result, c->result, sizeof(partials_dev), cudaMemcpyDeviceToDevice, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  CU_TRY(c, cudaMemcpyAsync(c->result, &keep, sizeof keep, cudaMemcpyHostToDevice, c->stream));  // leave the metric partials as they were
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return ZFB_OK;
+}
+
+extern "C" int zfb_range_get(zfb_ctx* c, double* lo, double* hi)
+{
+  if (!c || !lo || !hi) return ZFB_EINVAL;
+  CU_TRY(c, cudaSetDevice(c->device));
+  partials_dev h;
+  CU_TRY(c, cudaMemcpyAsync(&h, c->enc_result, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  *lo = -h.neg_min_orig;
+  *hi = h.max_orig;
+  return ZFB_OK;
+}
+
+// all ranks' ranges combined (max of the maxima, min of the minima): the same single all-gather as the partials
+extern "C" int zfb_allreduce_range(zfb_ctx* c)
+{
+  if (!c) return ZFB_EINVAL;
+  if (!c->comm || c->comm_ranks == 1) return ZFB_OK;
+  CU_TRY(c, cudaSetDevice(c->device));
+  const ncclResult_t r = nccl().AllGather(c->enc_result, c->gathered, sizeof(partials_dev), ncclUint8, c->comm, c->stream);
+  if (r != ncclSuccess) { c->err = std::string("ncclAllGather: ") + nccl().GetErrorString(r); return ZFB_ECUDA; }
+  combine_partials_kernel<<<1, 32, 0, c->stream>>>(c->gathered, c->comm_ranks, c->enc_result);
+  c->launches++;
+  CU_TRY(c, cudaGetLastError());
+  return ZFB_OK;
+}
+
+// zfb_decode_dev + the value-range histogram of the decoded values over [lo, hi] in the same pass.
+// d_counts: ZFB_NBINS + 1 uint64 device counters (the last one counts out-of-range values), zeroed by the call.
+extern "C" int zfb_decode_hist_dev(zfb_ctx* c, int dtype, int dims, size_t nx, size_t ny, size_t nz, unsigned maxbits,
+                                   const void* d_stream, void* d_out, const void* d_orig, double lo, double hi,
+                                   uint64_t* d_counts)
+{
+  if (!c || !d_counts || !(hi > lo)) { if (c) c->err = "null counters or empty range"; return ZFB_EINVAL; }
+  CU_TRY(c, cudaSetDevice(c->device));
+  CU_TRY(c, cudaMemsetAsync(d_counts, 0, (ZFB_NBINS + 1) * sizeof(uint64_t), c->stream));
+  c->hist_counts = d_counts; c->hist_lo = lo; c->hist_hi = hi;
+  int rc = zfb_decode_dev(c, dtype, dims, nx, ny, nz, maxbits, d_stream, d_out, d_orig);
+  const bool fused = c->hist_counts == nullptr;
+  c->hist_counts = nullptr;
+  if (rc || fused) return rc;
+  // kernels without the fused binning: the stand-alone pass over the decoded field
+  const size_t n = nx * (dims > 1 ? ny : 1) * (dims > 2 ? nz : 1);
+  return zfb_histogram_dev(c, dtype, 2, lo, hi, nullptr, d_out, n, d_counts, d_counts + ZFB_NBINS);
 }
 
 extern "C" int zfb_histogram_dev(zfb_ctx* c, int dtype, int which, double lo, double hi, const void* d_orig,

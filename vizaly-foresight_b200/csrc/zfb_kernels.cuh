@@ -295,6 +295,38 @@ __device__ __forceinline__ void macc_block_store(const macc_t<MaxT>& mi, double*
   }
 }
 
+// Value-range (minmax) histogram of decoded float values, fused into the decode kernels: bin of v over [lo, lo + range]
+// exactly as minmaxMetric.hpp:112 computes it -- int(((range * ((v - lo) / range)) / (range / 1024)), `pos - 1` when
+// pos >= 1024 -- with out-of-range positions clamped and counted.  The quotient is first estimated in float (error
+// below 3e-4 bins: v - lo, the scale and the product each round once, q < 1025); only when the estimate lies within
+// 1e-2 of an integer, where that error could change the truncation, is the reference's double expression evaluated.
+struct value_binner {
+  double lo, range, bin;
+  float lof, scale;
+  __device__ __forceinline__ void init(double lo_, double hi_)
+  {
+    lo = lo_; range = hi_ - lo_; bin = range / 1024.0;
+    lof = (float)lo_;
+    scale = (float)(1024.0 / range);
+  }
+  __device__ __forceinline__ int bin_of(float v, unsigned int* bad) const
+  {
+    const float qf = (v - lof) * scale;
+    const float kf = rintf(qf);
+    double q = (double)qf;
+    if (!(fabsf(qf - kf) > 1e-2f) || (double)lof != lo) q = (range * (((double)v - lo) / range)) / bin;
+    int pos;
+    if (!(q >= 0.0)) { pos = 0; atomicAdd(bad, 1u); }
+    else if (q >= 1025.0) { pos = 1023; atomicAdd(bad, 1u); }
+    else {
+      pos = (int)q;
+      if (pos >= 1024) pos = pos - 1;
+      if (pos >= 1024) { pos = 1023; atomicAdd(bad, 1u); }
+    }
+    return pos;
+  }
+};
+
 struct partials_dev {  // mirrors zfb_partials (include/zfb.h)
   double sum_sq, sum_abs, sum_rel, max_abs, max_rel, max_orig, neg_min_orig;
   unsigned long long n;
@@ -515,9 +547,13 @@ __device__ __forceinline__ box_info box_of(const tile_geom& tg, unsigned q)
 // -> one __syncthreads -> thread 0 issues this tile's bulk store, waits until the store has read `out`,
 // and only then issues the next tile's TMA loads: every thread waits for those loads before it touches
 // `out` again, so one staging buffer is enough (43 KiB per CTA -> 5 CTAs per SM at 95 registers).
+// MINMAX: the minimum and maximum of the field are harvested on the way (the values are in registers anyway) into one
+// row of `part` per CTA, for the value-range histogram that the decode pass fuses (minmaxMetric.hpp:62-81 needs them
+// before any value can be binned).
+template <bool MINMAX>
 __global__ void __launch_bounds__(TILE_THREADS, 5)
 enc3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t* __restrict__ stream, tile_geom tg,
-                     unsigned maxbits)
+                     unsigned maxbits, double* __restrict__ part)
 {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   float* tile = reinterpret_cast<float*>(smem_raw);
@@ -557,6 +593,7 @@ enc3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t* __restr
   f3::plane_rows ps;
   ps.p = reinterpret_cast<f3::u32x4*>(tile + box * BOX_FLOATS) + lb;
   ps.stride = 64;
+  float vmax = -3.402823466e38f, vnmin = -3.402823466e38f;  // MINMAX: max(f), max(-f)
 
   for (unsigned it = 0; t < tg.ntiles; t += gridDim.x, it++) {
     const box_info b0 = sb[it & 1][0], b1 = sb[it & 1][1];
@@ -572,6 +609,10 @@ enc3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t* __restr
         for (int r = 0; r < 16; r++) {
           const float4 v = src[r * 64];  // row r of the box is 256 floats = 64 float4
           f[4 * r] = v.x; f[4 * r + 1] = v.y; f[4 * r + 2] = v.z; f[4 * r + 3] = v.w;
+          if (MINMAX) {
+            vmax = fmaxf(fmaxf(vmax, v.x), v.y); vmax = fmaxf(fmaxf(vmax, v.z), v.w);
+            vnmin = fmaxf(fmaxf(vnmin, -v.x), -v.y); vnmin = fmaxf(fmaxf(vnmin, -v.z), -v.w);
+          }
         }
         const unsigned p = (box ? b0.nvalid : 0u) + lb;  // slot position inside the tile's contiguous span
         f3::sink32 sink(reinterpret_cast<uint32_t*>(obuf + (size_t)p * tg.W), 2 * tg.W);
@@ -598,6 +639,13 @@ enc3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t* __restr
     }
   }
   if (tid == 0) ptx::bulk_wait0();
+  if (MINMAX) {
+    __shared__ double red[7 * 4];
+    maccf m;
+    m.init();
+    m.m_o = vmax; m.m_no = vnmin;
+    macc_block_store(m, red, part + (size_t)blockIdx.x * PART_STRIDE);
+  }
 }
 
 // dynamic shared memory layout (decode): [tile: 2 x 16 KiB plane scratch, then the original boxes]
@@ -609,10 +657,14 @@ enc3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t* __restr
 // (LDS.128) -> 16 coalesced 128-bit stores of the decoded rows -> __syncthreads.
 // 4 CTAs/SM at 128 registers: a 5-CTA / 96-register build runs at the same speed but its spills add
 // ~50 % DRAM write traffic (profiles/r01_notes.md), so the spill-free configuration is kept.
-template <bool METRICS>
+// HIST: the decoded values are also binned into the 1024-bin value-range histogram of the minmax metric
+// (minmaxMetric.hpp:92-133) over [hlo, hhi] = the field's global minimum / maximum harvested by the encode pass:
+// shared-memory counters per CTA, flushed once; no extra pass over memory.
+template <bool METRICS, bool HIST>
 __global__ void __launch_bounds__(TILE_THREADS, 4)
 dec3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64_t* __restrict__ stream,
-                     float* __restrict__ out, tile_geom tg, unsigned maxbits, double* __restrict__ part)
+                     float* __restrict__ out, tile_geom tg, unsigned maxbits, double* __restrict__ part, double hlo,
+                     double hhi, unsigned long long* __restrict__ hcounts)
 {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   float* tile = reinterpret_cast<float*>(smem_raw);
@@ -669,6 +721,15 @@ dec3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64
 
   maccf m;
   m.init();
+  __shared__ unsigned int hbins[HIST ? 1024 : 1];
+  __shared__ unsigned int hbad;
+  value_binner vb;
+  if (HIST) {
+    vb.init(hlo, hhi);
+    for (unsigned i = tid; i < 1024u; i += TILE_THREADS) hbins[i] = 0u;
+    if (tid == 0) hbad = 0u;
+    __syncthreads();
+  }
   unsigned cur = 0;  // it % 3
   for (unsigned it = 0; t < tg.ntiles; t += gridDim.x, it++, cur = cur == 2 ? 0 : cur + 1) {
     const unsigned buf = it & 1, nn = cur == 0 ? 2 : cur - 1;  // nn = (it + 2) % 3
@@ -712,6 +773,10 @@ dec3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64
           if ((r16 & 3) == 3) fr.flush(m);
         }
       }
+      if (HIST) {
+#pragma unroll 8
+        for (int i = 0; i < 64; i++) atomicAdd(&hbins[vb.bin_of(f[i], &hbad)], 1u);
+      }
       const size_t rs = tg.nx, ps2 = (size_t)tg.ny * tg.nx;
 #pragma unroll
       for (int k = 0; k < 4; k++) {
@@ -729,6 +794,12 @@ dec3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64
     if (METRICS) __syncthreads();  // the original rows are consumed before the next tile's planes land there
   }
   if (METRICS) macc_block_store(m, red, part + (size_t)blockIdx.x * PART_STRIDE);
+  if (HIST) {
+    __syncthreads();
+    for (unsigned i = tid; i < 1024u; i += TILE_THREADS)
+      if (hbins[i]) atomicAdd(&hcounts[i], (unsigned long long)hbins[i]);
+    if (tid == 0 && hbad) atomicAdd(&hcounts[1024], (unsigned long long)hbad);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
