@@ -9,3 +9,8 @@ template __global__ void dec3_f32_tile_kernel<true, false>(const __grid_constant
 template __global__ void enc3_f32_tile_kernel<false>(const __grid_constant__ CUtensorMap, uint64_t* __restrict__, tile_geom,
                                                      unsigned, double* __restrict__);
 }
+namespace zfb {
+template __global__ void dec3_f32_tile_kernel<true, true>(const __grid_constant__ CUtensorMap, const uint64_t* __restrict__,
+                                                          float* __restrict__, tile_geom, unsigned, double* __restrict__, double,
+                                                          double, unsigned long long* __restrict__);
+}

@@ -298,23 +298,25 @@ __device__ __forceinline__ void macc_block_store(const macc_t<MaxT>& mi, double*
 // Value-range (minmax) histogram of decoded float values, fused into the decode kernels: bin of v over [lo, lo + range]
 // exactly as minmaxMetric.hpp:112 computes it -- int(((range * ((v - lo) / range)) / (range / 1024)), `pos - 1` when
 // pos >= 1024 -- with out-of-range positions clamped and counted.  The quotient is first estimated in float (error
-// below 3e-4 bins: v - lo, the scale and the product each round once, q < 1025); only when the estimate lies within
-// 1e-2 of an integer, where that error could change the truncation, is the reference's double expression evaluated.
+// below 2e-4 bins: v - lo, the scale and the product each round once, 3 * 2^-24 * 1025); only when the estimate lies
+// within 1e-3 of an integer, where that error could change the truncation, is the reference's double expression
+// evaluated (0.2 % of the values: a wider margin makes nearly every warp take the slow path for some lane).
 struct value_binner {
   double lo, range, bin;
   float lof, scale;
+  bool exact_lo;  // lo is a float value (always, for float fields): the float estimate starts from the same number
   __device__ __forceinline__ void init(double lo_, double hi_)
   {
     lo = lo_; range = hi_ - lo_; bin = range / 1024.0;
     lof = (float)lo_;
     scale = (float)(1024.0 / range);
+    exact_lo = (double)lof == lo_;
   }
-  __device__ __forceinline__ int bin_of(float v, unsigned int* bad) const
+  // the reference's expression in double, range checks included; out of line: inlined 64 times (one per value of a
+  // block) its two divisions alone are 100 KB of code and the kernel stalls on instruction fetch
+  __device__ __noinline__ int bin_exact(float v, unsigned int* bad) const
   {
-    const float qf = (v - lof) * scale;
-    const float kf = rintf(qf);
-    double q = (double)qf;
-    if (!(fabsf(qf - kf) > 1e-2f) || (double)lof != lo) q = (range * (((double)v - lo) / range)) / bin;
+    const double q = (range * (((double)v - lo) / range)) / bin;
     int pos;
     if (!(q >= 0.0)) { pos = 0; atomicAdd(bad, 1u); }
     else if (q >= 1025.0) { pos = 1023; atomicAdd(bad, 1u); }
@@ -324,6 +326,13 @@ struct value_binner {
       if (pos >= 1024) { pos = 1023; atomicAdd(bad, 1u); }
     }
     return pos;
+  }
+  __device__ __forceinline__ int bin_of(float v, unsigned int* bad) const
+  {
+    const float qf = (v - lof) * scale;
+    // fast path, float only: strictly inside the range and not within 1e-3 of an integer
+    if (fabsf(qf - rintf(qf)) > 1e-3f && qf > 0.5f && qf < 1023.5f && exact_lo) return (int)qf;
+    return bin_exact(v, bad);
   }
 };
 
@@ -774,8 +783,28 @@ dec3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64
         }
       }
       if (HIST) {
-#pragma unroll 8
-        for (int i = 0; i < 64; i++) atomicAdd(&hbins[vb.bin_of(f[i], &hbad)], 1u);
+        // The 64 values of a block lie close together: they are counted in sixteen 8-bit counters (two registers)
+        // covering the 16 bins around the first value's, and only the non-empty counters go to the CTA's shared
+        // histogram -- one atomic per distinct bin instead of one per value (shared atomics at one per value cost
+        // three times the rest of the kernel).  Values outside the window take the direct atomic.
+        const int b0 = vb.bin_of(f[0], &hbad);
+        int base = b0 - 8;
+        base = base < 0 ? 0 : (base > 1008 ? 1008 : base);
+        uint64_t c_lo = 0, c_hi = 0;
+#pragma unroll
+        for (int i = 0; i < 64; i++) {  // fully unrolled: f[] must stay in registers
+          const int d = (i ? vb.bin_of(f[i], &hbad) : b0) - base;
+          const uint64_t one = (uint64_t)1 << ((d & 7) * 8);
+          if ((unsigned)d < 8u) c_lo += one;
+          else if ((unsigned)d < 16u) c_hi += one;
+          else atomicAdd(&hbins[base + d], 1u);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const unsigned n0 = (unsigned)(c_lo >> (8 * j)) & 0xffu, n1 = (unsigned)(c_hi >> (8 * j)) & 0xffu;
+          if (n0) atomicAdd(&hbins[base + j], n0);
+          if (n1) atomicAdd(&hbins[base + 8 + j], n1);
+        }
       }
       const size_t rs = tg.nx, ps2 = (size_t)tg.ny * tg.nx;
 #pragma unroll
