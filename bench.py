@@ -122,8 +122,12 @@ class ClockSampler(threading.Thread):
 
 
 def run_reference(args, wl):
-    """--impl reference: the CPU restatement of the reference path on the host cores (rank 0 only)."""
+    """--impl reference: the CPU restatement of the reference path on the host cores (rank 0 only): serial zfp per
+    "rank" + the five metric passes, one OpenMP thread per rank, on a bounded sample of the SAME workload -- the same
+    generator (make_field) with the same parameters, cut to slabs of about 32 MiB so that a step takes seconds."""
+    import ctypes as C
     import numpy as np
+    import torch
 
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -136,59 +140,74 @@ def run_reference(args, wl):
         cores = len(os.sched_getaffinity(0))
     except Exception:
         pass
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     shape, dtype, rate = wl["shape"], wl["dtype"], args.rate or wl["rate"]
-    if dtype != "float32":
-        print(json.dumps({"impl": "reference", "unavailable": "reference metrics are float-only; use a float32 workload"}))
-        return
+    if args.scaling == "strong":
+        shape = (wl["full"][0] // world,) + tuple(wl["full"][1:])
     d = len(shape)
-    mb = O.maxbits(np.float32, d, rate)
+    npdt = np.float32 if dtype == "float32" else np.float64
+    esz = 4 if dtype == "float32" else 8
+    mb = O.maxbits(npdt, d, int(rate) if float(rate).is_integer() else rate, args.wra)
     nranks = min(cores, 64)
-    # bounded sample: each "rank" gets a slab of ~32 MiB of the same synthetic distribution
+    # bounded sample: each "rank" gets a slab of ~32 MiB of the benchmark field (same generator, same parameters)
     if d == 3:
-        thick = max(4, min(shape[0], ((32 << 20) // (shape[1] * shape[2] * 4)) // 4 * 4))
+        thick = max(4, min(shape[0], ((32 << 20) // (shape[1] * shape[2] * esz)) // 4 * 4))
         sshape = (thick, shape[1], shape[2])
     else:
-        sshape = (min(shape[0], 8 << 20),)
-    rng = np.random.default_rng(20261019)
-    n1 = int(np.prod(sshape))
-    if wl["kind"] == "uniform":
-        base = (256.0 * rng.random(n1, dtype=np.float32)).reshape(sshape)
-    else:
-        zz = np.arange(sshape[0], dtype=np.float32)[:, None, None] / 2048.0
-        yy = np.arange(sshape[1], dtype=np.float32)[None, :, None] / 2048.0
-        xx = np.arange(sshape[2], dtype=np.float32)[None, None, :] / 2048.0
-        acc = np.zeros(sshape, dtype=np.float32)
-        for _ in range(6):
-            k = rng.integers(1, 9, 3)
-            acc += np.float32(rng.standard_normal() / (1 + 0.3 * k.sum())) * np.cos(
-                6.2831853 * (k[0] * zz + k[1] * yy + k[2] * xx) + np.float32(rng.uniform(0, 6.28)))
-        acc += 0.05 * rng.standard_normal(sshape).astype(np.float32)
-        base = np.exp(1.5 * acc).astype(np.float32) if wl["kind"] == "lognormal" else acc
-    field = np.broadcast_to(base, (nranks,) + sshape).copy()
+        sshape = (min(shape[0] // 4 * 4, (32 << 20) // esz),)
+    kind = args.field or wl["kind"]
+    slabs = []
     for r in range(nranks):
-        field[r] *= np.float32(1.0 + 0.01 * r)
+        zoff = (r * sshape[0] / 2048.0) if d == 3 else None
+        slabs.append(make_field(torch, sshape, dtype, kind, r if d == 1 else 0, "cpu", zoff).numpy())
+    field = np.ascontiguousarray(np.stack(slabs))
+    del slabs
     sample_bytes = field.nbytes
+
+    def one_step():
+        if dtype == "float32":
+            r = O.cbench_step(field, mb, nthreads=nranks)
+            return r["wall"], (r["t_compress"], r["t_decompress"], r["t_metrics"])
+        # float64: the reference's metric classes read the bytes as float (meaningless): codec timing only
+        dd, nx, ny, nz = O.dims_of(sshape)
+        sbytes = int(O.lib().zfo_stream_bytes(dd, nx, ny, nz, mb))
+        st = np.zeros(nranks * sbytes + 16, dtype=np.uint8)
+        out = np.empty_like(field)
+        te, td = C.c_double(), C.c_double()
+        w = O.lib().zfo_roundtrip_slabs(2, dd, nx, ny, nz, mb, field.ctypes.data, st.ctypes.data, out.ctypes.data, nranks,
+                                        nranks, C.byref(te), C.byref(td))
+        return w, (te.value, td.value, 0.0)
+
     for _ in range(max(1, min(args.warmup, 1))):
-        O.cbench_step(field, mb, nthreads=nranks)
-    t = []
-    parts = []
+        one_step()
+    t, parts = [], []
     for _ in range(args.steps):
-        r = O.cbench_step(field, mb, nthreads=nranks)
-        t.append(r["wall"])
-        parts.append((r["t_compress"], r["t_decompress"], r["t_metrics"]))
+        w, p3 = one_step()
+        t.append(w)
+        parts.append(p3)
     wall = sum(t)
     value = sample_bytes * args.steps / wall / 1e9
-    sample = "%d ranks (OpenMP threads) x %s float32 slab each = %.1f MiB per step" % (
-        nranks, "x".join(map(str, sshape)), sample_bytes / 2 ** 20)
+    n = int(np.prod(shape))
+    cbytes = int(O.stream_bytes(shape, mb))
+    sample = "%d ranks (OpenMP threads) x %s %s slab each of the benchmark field = %.1f MiB per step%s" % (
+        nranks, "x".join(map(str, sshape)), dtype, sample_bytes / 2 ** 20,
+        "" if dtype == "float32" else "; codec only (the reference's metrics are float-only)")
     line = {
         "impl": "reference", "metric": "uncompressed_GBps_compress_decompress_metrics", "value": value, "unit": "GB/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "description": wl["desc"], "rate_bpv": rate, "maxbits": mb,
-                   "note": "CPU restatement of serial zfp 0.5.5 fixed-rate + the five CBench metric passes; "
-                           "one OpenMP thread per CBench rank; libzfp / MPI are not in the image"},
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+        "dtype": "f32" if dtype == "float32" else "f64", "data": "synthetic",
+        # the same keys and values as the GPU arm's config (the workload is the same; the CPU times a bounded sample of it)
+        "config": {"workload": args.workload if args.scaling == "weak" else args.workload.replace("-slab", "") + "-strong",
+                   "description": wl["desc"], "shape_per_gpu": list(shape), "rate_bpv": rate, "maxbits": mb,
+                   "mode": args.mode or "rate", "wra": args.wra, "field": kind, "histogram": "none",
+                   "compressed_bytes_per_gpu": cbytes,
+                   "l2": "inputs (%.1f GiB per step) are far larger than the 126 MB L2; no flush needed" % (n * esz / 2 ** 30),
+                   "exchange": "zfb_allreduce_partials: one ncclAllGather of the 64-byte partials + rank-ordered combine" if world > 1 else "none (1 GPU)"},
         "cpu_baseline": {"value": value, "unit": "GB/s", "cores": nranks, "kind": "port", "sample": sample,
-                         "t_compress_s": parts[-1][0], "t_decompress_s": parts[-1][1], "t_metrics_s": parts[-1][2]},
+                         "t_compress_s": parts[-1][0], "t_decompress_s": parts[-1][1], "t_metrics_s": parts[-1][2],
+                         "note": "CPU restatement of serial zfp 0.5.5 fixed-rate + the five CBench metric passes (oracle/, "
+                                 "-O3 -march=native); one OpenMP thread per CBench rank; libzfp / MPI are not in the image"},
         "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -563,6 +582,30 @@ def main():
 
     # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) ------------------------------------
     cpu = None
+    if world == 1 and not args.no_cpu and dtype == "float64" and d == 3:
+        # float64: codec timing only (the reference's metric classes read the bytes as float)
+        import ctypes as C
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle as O
+
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except Exception:
+            cores = os.cpu_count() or 1
+        nranks = min(cores, 64)
+        thick = max(4, min(shape[0], ((32 << 20) // (shape[1] * shape[2] * 8)) // 4 * 4))
+        sample_arr = torch.stack([field[(r * thick) % (shape[0] - thick + 1):][:thick] for r in range(nranks)]).cpu().numpy()
+        sbytes = int(O.lib().zfo_stream_bytes(3, shape[2], shape[1], thick, mb))
+        st = np.zeros(nranks * sbytes + 16, dtype=np.uint8)
+        dec = np.empty_like(sample_arr)
+        te, td = C.c_double(), C.c_double()
+        args_rt = (2, 3, shape[2], shape[1], thick, mb, sample_arr.ctypes.data, st.ctypes.data, dec.ctypes.data, nranks, nranks)
+        O.lib().zfo_roundtrip_slabs(*args_rt, C.byref(te), C.byref(td))
+        w = O.lib().zfo_roundtrip_slabs(*args_rt, C.byref(te), C.byref(td))
+        cpu = {"value": sample_arr.nbytes / w / 1e9, "unit": "GB/s", "cores": nranks, "kind": "port",
+               "sample": "%d ranks x %dx%dx%d float64 slabs of the benchmark field (%.0f MiB); serial-zfp restatement, codec "
+                         "only, one OpenMP thread per rank" % (nranks, thick, shape[1], shape[2], sample_arr.nbytes / 2 ** 20),
+               "t_compress_s": te.value, "t_decompress_s": td.value, "t_metrics_s": 0.0}
     if world == 1 and not args.no_cpu and dtype == "float32":
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import oracle as O

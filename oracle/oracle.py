@@ -26,11 +26,36 @@ def build(force=False):
     so = os.path.join(HERE, "liboracle.so")
     srcs = [os.path.join(HERE, f) for f in ("zfp_ref.c", "metrics_ref.c", "cbench_step_ref.c", "Makefile")]
     stale = (not os.path.exists(so)) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs)
-    if force or stale:
-        subprocess.run(["make", "-C", HERE, "liboracle.so"], check=True, capture_output=True)
+    # built with -march=native: a library that travelled from another machine is rebuilt for this CPU
+    stamp = os.path.join(HERE, "liboracle.cpu")
+    cpu = _cpu_id()
+    if os.path.exists(stamp) and open(stamp).read() != cpu:
+        stale = True
+    if force or stale or not os.path.exists(stamp):
+        r = subprocess.run(["make", "-B", "-C", HERE, "liboracle.so"], capture_output=True, text=True)
+        if r.returncode != 0:  # e.g. a compiler that does not know this CPU: the portable baseline
+            subprocess.run(["make", "-B", "-C", HERE, "liboracle.so", "MARCH=x86-64-v2"], check=True, capture_output=True)
+        open(stamp, "w").write(cpu)
     ref_so = os.path.join(HERE, "_ref", "libcbench_ref.so")
     if os.path.isdir("/root/reference/CBench/metrics") and (force or not os.path.exists(ref_so)):
         subprocess.run(["make", "-C", HERE, "ref"], check=True, capture_output=True)
+
+
+def _cpu_id():
+    """Model name + instruction-set flags of this host (what -march=native depends on)."""
+    model, flags = "", ""
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name") and not model:
+                model = line.split(":", 1)[1].strip()
+            elif line.startswith("flags") and not flags:
+                flags = " ".join(sorted(line.split(":", 1)[1].split()))
+            if model and flags:
+                break
+    except OSError:
+        pass
+    import hashlib
+    return model + " " + hashlib.sha1(flags.encode()).hexdigest()[:12]
 
 
 class Params(C.Structure):

@@ -374,7 +374,7 @@ DEFINE_PAD(pad_d, double)
       bits += EBITS;                                                                                  \
       put_bits(s, 2 * (uint64_t)e + 1, bits);                                                         \
       for (i = 0; i < size; i++) {                                                                    \
-        volatile Scalar prod = sc * fblock[i]; /* product rounded to Scalar, then C truncation */     \
+        const Scalar prod = sc * fblock[i]; /* product rounded to Scalar (SSE: no excess precision), then C truncation */ \
         iblock[i] = (Int)prod;                                                                        \
       }                                                                                               \
       fwd_xform_##SFX(iblock, dims);                                                                  \
@@ -412,8 +412,8 @@ DEFINE_PAD(pad_d, double)
       inv_xform_##SFX(iblock, dims);                                                                  \
       sc = LDEXP((Scalar)1, emax - (8 * (int)sizeof(Scalar) - 2));                                    \
       for (i = 0; i < size; i++) {                                                                    \
-        volatile Scalar conv = (Scalar)iblock[i];                                                     \
-        volatile Scalar prod = sc * conv;                                                             \
+        const Scalar conv = (Scalar)iblock[i];                                                        \
+        const Scalar prod = sc * conv;                                                                \
         fblock[i] = prod;                                                                             \
       }                                                                                               \
     } else {                                                                                          \

@@ -721,7 +721,8 @@ extern "C" int zfb_decode_dev(zfb_ctx* c, int dtype, int dims, size_t nx, size_t
     // The in-kernel binning leaves DRAM traffic unchanged but, as measured (profiles/r02_notes.md), costs more time than
     // the stand-alone pass over the decoded field (16 ms against 4.0 + 2.9 ms on the benchmark slab: 64 shared-memory
     // updates per block next to 64 live values), so it is opt-in: ZFB_FUSED_HIST=1.
-    static const bool fused_hist = [] { const char* e = std::getenv("ZFB_FUSED_HIST"); return e && e[0] == '1'; }();
+    const char* fh = std::getenv("ZFB_FUSED_HIST");
+    const bool fused_hist = fh && fh[0] == '1';
     if (metrics && c->hist_counts && fused_hist && !((g.ny | g.nz) & 3)) {
       // value-range histogram of the decoded values fused into the pass (zfb_decode_hist_dev); a CTA more of shared
       // memory for the counters still leaves the same number of CTAs per SM
