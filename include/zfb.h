@@ -263,6 +263,40 @@ double zfb_value_minmax(const zfb_partials* p);         /* minmaxMetric.hpp:89-9
 /* Combine `count` ranks' partials the way the reference's Allreduces do (SUM / MAX / MIN). */
 void zfb_partials_combine(zfb_partials* acc, const zfb_partials* in, int count);
 
+/* ---- device-resident loaders / writers (what hands the hot path its input, and takes its output) ----------
+ * The three file kinds CBench loads from, read straight into device memory (file -> pinned double buffer -> device, no
+ * pageable host array in between) so that zfb_encode_dev can start from there, and the decompressed write-back of
+ * main.cpp:440-491.  What lands on the device is byte for byte what the reference loader hands compress().
+ *
+ * GenericIO (HACC; format GenericIO.cxx:373-441, loader HACCDataLoader.hpp:143-330): */
+typedef struct zfb_gio zfb_gio;
+int zfb_gio_open(const char* path, zfb_gio** out, char* errbuf, size_t errlen);
+int zfb_gio_close(zfb_gio* g);
+int zfb_gio_counts(const zfb_gio* g, int* nvars, int* nranks, uint64_t* nelems_total, int* header_crc_ok);
+int zfb_gio_var(const zfb_gio* g, int i, char* name256, int* elem_size, unsigned* flags);
+int zfb_gio_find(const zfb_gio* g, const char* name);                 /* index of a variable, -1 if absent */
+uint64_t zfb_gio_rank_elems(const zfb_gio* g, int rank);              /* gioReader->readNumElems(rank) */
+int zfb_gio_phys(const zfb_gio* g, double* origin3, double* scale3);
+/* the file ranks MPI rank `mpi_rank` of `mpi_size` loads (HACCDataLoader.hpp:189-194) */
+void zfb_gio_rank_range(int nfile_ranks, int mpi_rank, int mpi_size, int* r0, int* r1);
+/* variable `var` of file ranks [r0, r1), concatenated: into device memory (ctx != NULL) or host memory (ctx == NULL) */
+int zfb_gio_read(zfb_ctx* ctx, zfb_gio* g, int var, int r0, int r1, void* dst, size_t dst_bytes, uint64_t* nelems,
+                 int check_crc);
+/* one rank's file from host arrays (HACCDataLoader::writeData, HACCDataLoader.hpp:358-429), CRCs included */
+int zfb_gio_write_host(const char* path, int nvars, const char* const* names, const unsigned* flags, const int* sizes,
+                       const void* const* data, uint64_t nelems, const double* origin3, const double* scale3, char* errbuf,
+                       size_t errlen);
+/* HDF5 (NYX; NYXDataLoader.hpp:143-251): where a CONTIGUOUS dataset lives (no libhdf5 needed for that layout) */
+int zfb_h5_dataset(const char* path, const char* dataset, uint64_t* offset, uint64_t* bytes, int* ndims, uint64_t* dims8,
+                   int* elem_size, int* is_float, char* errbuf, size_t errlen);
+/* a 3D hyperslab (slowest axis first, like sizePerDim / rankOffset) of a contiguous array in a file <-> device memory:
+ * the HDF5 dataset above at its offset, or a raw .gda array at offset 0 (GDADataLoader.hpp:118-171); the write goes
+ * into an existing copy of the file (NYX write-back) or creates a raw file */
+int zfb_file_read_block_dev(zfb_ctx* ctx, const char* path, uint64_t base_offset, int elem_size, const size_t* total3,
+                            const size_t* off3, const size_t* cnt3, void* d_dst);
+int zfb_file_write_block_dev(zfb_ctx* ctx, const char* path, uint64_t base_offset, int elem_size, const size_t* total3,
+                             const size_t* off3, const size_t* cnt3, const void* d_src);
+
 #ifdef __cplusplus
 }
 #endif

@@ -139,6 +139,11 @@ def main():
         x = np.frombuffer(gio, dtype="<f4", count=int(n0), offset=int(start0))
         reps = int(np.ceil(4096 / max(1, n0)))
         np.tile(x, reps)[:4096].astype(np.float32).tofile(os.path.join(HERE, "hacc_m000_x_4096.f32"))
+        # the two toy INPUT files themselves (data, not code): the loaders of csrc/zfb_io.cuh are tested on the real
+        # GenericIO / HDF5 byte layouts, also on the GPU box where /root/reference does not exist
+        import shutil
+        shutil.copyfile(os.path.join(ref, "m000.full.mpicosmo.50"), os.path.join(HERE, "m000.full.mpicosmo.50"))
+        shutil.copyfile(os.path.join(ref, "z255_32.h5"), os.path.join(HERE, "z255_32.h5"))
 
     # metric vectors from the reference's own classes
     if O.ref_lib() is not None:

@@ -109,6 +109,21 @@ def lib():
         "zfb_allreduce_range": (i, [vp]),
         "zfb_range_get": (i, [vp, C.POINTER(d), C.POINTER(d)]),
         "zfb_decode_hist_dev": (i, [vp, i, i, sz, sz, sz, u, vp, vp, vp, d, d, vp]),
+        "zfb_gio_open": (i, [C.c_char_p, C.POINTER(vp), C.c_char_p, sz]),
+        "zfb_gio_close": (i, [vp]),
+        "zfb_gio_counts": (i, [vp, C.POINTER(i), C.POINTER(i), C.POINTER(C.c_uint64), C.POINTER(i)]),
+        "zfb_gio_var": (i, [vp, i, C.c_char_p, C.POINTER(i), C.POINTER(u)]),
+        "zfb_gio_find": (i, [vp, C.c_char_p]),
+        "zfb_gio_rank_elems": (C.c_uint64, [vp, i]),
+        "zfb_gio_phys": (i, [vp, C.POINTER(d), C.POINTER(d)]),
+        "zfb_gio_rank_range": (None, [i, i, i, C.POINTER(i), C.POINTER(i)]),
+        "zfb_gio_read": (i, [vp, vp, i, i, i, vp, sz, C.POINTER(C.c_uint64), i]),
+        "zfb_gio_write_host": (i, [C.c_char_p, i, C.POINTER(C.c_char_p), C.POINTER(u), C.POINTER(i), C.POINTER(vp), C.c_uint64,
+                                   C.POINTER(d), C.POINTER(d), C.c_char_p, sz]),
+        "zfb_h5_dataset": (i, [C.c_char_p, C.c_char_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(i),
+                               C.POINTER(C.c_uint64), C.POINTER(i), C.POINTER(i), C.c_char_p, sz]),
+        "zfb_file_read_block_dev": (i, [vp, C.c_char_p, C.c_uint64, i, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz), vp]),
+        "zfb_file_write_block_dev": (i, [vp, C.c_char_p, C.c_uint64, i, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz), vp]),
         "zfb_partials_dev": (vp, [vp]),
         "zfb_partials_get": (i, [vp, PP]),
         "zfb_partials_set": (i, [vp, PP]),
@@ -257,6 +272,109 @@ def combine_partials(parts):
     return acc
 
 
+class GenericIOFile:
+    """A GenericIO particle file (HACC): header tables parsed by the C ABI (csrc/zfb_io.cuh); columns are read into
+    host arrays (read) or straight into device memory (Codec.gio_read_dev)."""
+
+    def __init__(self, path):
+        h = C.c_void_p()
+        err = C.create_string_buffer(256)
+        rc = lib().zfb_gio_open(os.fsencode(path), C.byref(h), err, 256)
+        if rc != 0:
+            raise ZfbError("zfb_gio_open(%s): %s" % (path, err.value.decode()))
+        self._h = h
+        nv, nr, ne, ok = C.c_int(), C.c_int(), C.c_uint64(), C.c_int()
+        lib().zfb_gio_counts(h, C.byref(nv), C.byref(nr), C.byref(ne), C.byref(ok))
+        self.nvars, self.nranks, self.nelems, self.header_crc_ok = nv.value, nr.value, ne.value, bool(ok.value)
+        self.vars = []
+        for k in range(self.nvars):
+            name = C.create_string_buffer(256)
+            es, fl = C.c_int(), C.c_uint()
+            lib().zfb_gio_var(h, k, name, C.byref(es), C.byref(fl))
+            self.vars.append({"name": name.value.decode(), "size": es.value, "flags": fl.value, "is_float": bool(fl.value & 1),
+                              "is_signed": bool(fl.value & 2)})
+        self.rank_elems = [int(lib().zfb_gio_rank_elems(h, r)) for r in range(self.nranks)]
+        o, sc = (C.c_double * 3)(), (C.c_double * 3)()
+        lib().zfb_gio_phys(h, o, sc)
+        self.phys_origin, self.phys_scale = list(o), list(sc)
+
+    def find(self, name):
+        return int(lib().zfb_gio_find(self._h, name.encode()))
+
+    def rank_range(self, mpi_rank, mpi_size):
+        """File ranks CBench's MPI rank loads (HACCDataLoader.hpp:189-194)."""
+        a, b = C.c_int(), C.c_int()
+        lib().zfb_gio_rank_range(self.nranks, mpi_rank, mpi_size, C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def dtype_of(self, var):
+        import numpy as np
+
+        v = self.vars[var]
+        if v["is_float"]:
+            return np.dtype("<f%d" % v["size"])
+        return np.dtype("<%s%d" % ("i" if v["is_signed"] else "u", v["size"]))
+
+    def read(self, name, r0=0, r1=None, check_crc=True):
+        """Column `name` of file ranks [r0, r1) as a host array (what HACCDataLoader::loadData allocates)."""
+        import numpy as np
+
+        var = self.find(name)
+        if var < 0:
+            raise ZfbError("no variable %r" % name)
+        r1 = self.nranks if r1 is None else r1
+        n = sum(self.rank_elems[r0:r1])
+        out = np.empty(n, dtype=self.dtype_of(var))
+        got = C.c_uint64()
+        rc = lib().zfb_gio_read(None, self._h, var, r0, r1, out.ctypes.data, out.nbytes, C.byref(got), 1 if check_crc else 0)
+        if rc != 0 or got.value != n:
+            raise ZfbError("zfb_gio_read failed (%d)" % rc)
+        return out
+
+    def close(self):
+        if self._h:
+            lib().zfb_gio_close(self._h)
+            self._h = None
+
+
+def gio_write(path, columns, origin=None, scale=None):
+    """One rank's GenericIO file from {name: array} (HACCDataLoader::writeData for a single rank), CRCs included.
+    x / y / z get the physical-coordinate flags the HACC loader sets (HACCDataLoader.hpp:385-420)."""
+    import numpy as np
+
+    names = list(columns)
+    arrs = [np.ascontiguousarray(columns[k]) for k in names]
+    n = arrs[0].size
+    assert all(a.size == n for a in arrs)
+    cn = (C.c_char_p * len(names))(*[k.encode() for k in names])
+    fl = (C.c_uint * len(names))()
+    szs = (C.c_int * len(names))()
+    ptr = (C.c_void_p * len(names))()
+    for k, a in enumerate(arrs):
+        f = (1 if a.dtype.kind == "f" else 0) | (2 if a.dtype.kind in "fi" else 0)
+        f |= {"x": 4, "y": 8, "z": 16}.get(names[k], 0)
+        fl[k], szs[k], ptr[k] = f, a.dtype.itemsize, a.ctypes.data
+    o = (C.c_double * 3)(*(origin or [0, 0, 0]))
+    sc = (C.c_double * 3)(*(scale or [0, 0, 0]))
+    err = C.create_string_buffer(256)
+    rc = lib().zfb_gio_write_host(os.fsencode(path), len(names), cn, fl, szs, ptr, n, o, sc, err, 256)
+    if rc != 0:
+        raise ZfbError("zfb_gio_write_host: " + err.value.decode())
+
+
+def h5_dataset(path, dataset):
+    """Location and shape of a contiguous HDF5 dataset: dict(offset, bytes, shape, elem_size, is_float)."""
+    off, nb, nd, es, fl = C.c_uint64(), C.c_uint64(), C.c_int(), C.c_int(), C.c_int()
+    dims = (C.c_uint64 * 8)()
+    err = C.create_string_buffer(256)
+    rc = lib().zfb_h5_dataset(os.fsencode(path), dataset.encode(), C.byref(off), C.byref(nb), C.byref(nd), dims, C.byref(es),
+                              C.byref(fl), err, 256)
+    if rc != 0:
+        raise ZfbError("zfb_h5_dataset(%s, %s): %s" % (path, dataset, err.value.decode()))
+    return {"offset": off.value, "bytes": nb.value, "shape": tuple(int(dims[k]) for k in range(nd.value)),
+            "elem_size": es.value, "is_float": bool(fl.value)}
+
+
 class Codec:
     """One context = one GPU (zfb_create).  Device methods take torch CUDA tensors, host methods numpy arrays."""
 
@@ -402,6 +520,43 @@ class Codec:
 
     def allreduce_counts(self, counts):
         self._check(lib().zfb_allreduce_counts(self._h, counts.data_ptr(), counts.numel()), "zfb_allreduce_counts")
+
+    def gio_read_dev(self, gio, name, r0=0, r1=None, check_crc=True):
+        """Column `name` of file ranks [r0, r1) of a GenericIOFile straight into a device tensor."""
+        import torch
+
+        self.use_torch_stream()
+        var = gio.find(name)
+        if var < 0:
+            raise ZfbError("no variable %r" % name)
+        r1 = gio.nranks if r1 is None else r1
+        n = sum(gio.rank_elems[r0:r1])
+        tdt = {"f4": torch.float32, "f8": torch.float64, "i8": torch.int64, "i4": torch.int32, "u2": torch.int16,
+               "i2": torch.int16, "u1": torch.uint8}[gio.dtype_of(var).str[1:]]
+        out = torch.empty(n, dtype=tdt, device="cuda:%d" % self.device)
+        got = C.c_uint64()
+        self._check(lib().zfb_gio_read(self._h, gio._h, var, r0, r1, out.data_ptr(), out.numel() * out.element_size(),
+                                       C.byref(got), 1 if check_crc else 0), "zfb_gio_read")
+        return out
+
+    def read_block_dev(self, path, base_offset, dtype, total, off, cnt):
+        """3D hyperslab (slowest axis first) of a contiguous array in a file -> packed device tensor of shape cnt."""
+        import torch
+
+        self.use_torch_stream()
+        out = torch.empty(tuple(cnt), dtype=dtype, device="cuda:%d" % self.device)
+        t3, o3, c3 = (C.c_size_t * 3)(*total), (C.c_size_t * 3)(*off), (C.c_size_t * 3)(*cnt)
+        self._check(lib().zfb_file_read_block_dev(self._h, os.fsencode(path), base_offset, out.element_size(), t3, o3, c3,
+                                                  out.data_ptr()), "zfb_file_read_block_dev")
+        return out
+
+    def write_block_dev(self, path, base_offset, tensor, total, off):
+        """Packed device tensor -> 3D hyperslab of a contiguous array in a file (decompressed write-back)."""
+        self.use_torch_stream()
+        assert tensor.is_contiguous() and tensor.dim() == 3
+        t3, o3, c3 = (C.c_size_t * 3)(*total), (C.c_size_t * 3)(*off), (C.c_size_t * 3)(*tensor.shape)
+        self._check(lib().zfb_file_write_block_dev(self._h, os.fsencode(path), base_offset, tensor.element_size(), t3, o3, c3,
+                                                   tensor.data_ptr()), "zfb_file_write_block_dev")
 
     def partials_tensor(self):
         """The context's device-resident zfb_partials viewed as 8 x int64 (raw bits; reinterpret with .view)."""

@@ -1273,3 +1273,4 @@ extern "C" int zfb_histogram_host(zfb_ctx* c, int dtype, int which, double lo, d
 }
 
 #include "zfb_api_var.cuh"
+#include "zfb_api_io.cuh"
