@@ -197,7 +197,7 @@ static int file_block_io(zfb_ctx* c, const char* path, uint64_t base_offset, int
   const size_t stage_bytes = unit_file_bytes < chunk ? unit_file_bytes : (planes_whole || rows_whole ? chunk : unit_file_bytes);
   pinned_pair& pin = write ? c->pin_out : c->pin_in;
   if (pin.ensure(stage_bytes)) { c->err = "cudaHostAlloc failed"; return ZFB_ENOMEM; }
-  const int fd = ::open(path, write ? (O_WRONLY | O_CREAT) : O_RDONLY, 0644);
+  const int fd = ::open(path, write ? (O_RDWR | O_CREAT) : O_RDONLY, 0644);  // write: strided bricks read-modify-write their span
   if (fd < 0) { c->err = std::string("cannot open ") + path; return ZFB_EINVAL; }
   cudaEvent_t ev[2];
   for (int i = 0; i < 2; i++) cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
