@@ -260,6 +260,9 @@ double zfb_value_relative_error(const zfb_partials* p); /* relativeError.hpp:91-
 double zfb_value_mse(const zfb_partials* p);            /* meansquareError.hpp:64-72 */
 double zfb_value_psnr(const zfb_partials* p);           /* psnrError.hpp:85-88       */
 double zfb_value_minmax(const zfb_partials* p);         /* minmaxMetric.hpp:89-90    */
+/* extra metrics from the same partials: PSNR over the value range (max - min) and the normalised RMSE */
+double zfb_value_psnr_range(const zfb_partials* p);
+double zfb_value_nrmse(const zfb_partials* p);
 /* Combine `count` ranks' partials the way the reference's Allreduces do (SUM / MAX / MIN). */
 void zfb_partials_combine(zfb_partials* acc, const zfb_partials* in, int count);
 

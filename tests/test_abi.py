@@ -125,3 +125,19 @@ def test_mode_parameters_and_maximum_size_match_oracle(pkg, oracle):
     assert pkg.block_count((5, 6, 7)) == 2 * 2 * 2 and pkg.block_count((4099,)) == 1025
     with pytest.raises(pkg.ZfbError):
         pkg.mode_accuracy(-1.0)
+
+
+def test_extra_metric_values_from_partials(pkg):
+    """PSNR over the value range and NRMSE come out of the same partials as the five CBench metrics."""
+    import math
+
+    p = pkg.Partials(4.0e-3, 1.0, 1.0, 0.5, 0.5, 10.0, 2.0, 1000)      # max 10, min -2, sum of squares 4e-3 over 1000
+    v = pkg.metric_values(p)
+    mse = 4.0e-6
+    assert abs(v["mse"] - mse) < 1e-18
+    assert abs(v["psnr"] - 10 * math.log10(100.0 / mse)) < 1e-9          # CBench: max(original)^2 / mse
+    assert abs(v["psnr_range"] - 10 * math.log10(144.0 / mse)) < 1e-9    # (max - min)^2 / mse
+    assert abs(v["nrmse"] - math.sqrt(mse) / 12.0) < 1e-15
+    # the reference's running maximum starts at -999999999 (psnrError.hpp:58): an all-negative field cannot go below it
+    q = pkg.Partials(1.0, 1.0, 1.0, 0.5, 0.5, -1.7976931348623157e308, 5.0, 10)
+    assert abs(pkg.metric_values(q)["psnr"] - 10 * math.log10(999999999.0 ** 2 / 0.1)) < 1e-9

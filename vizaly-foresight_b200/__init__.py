@@ -124,6 +124,8 @@ def lib():
                                C.POINTER(C.c_uint64), C.POINTER(i), C.POINTER(i), C.c_char_p, sz]),
         "zfb_file_read_block_dev": (i, [vp, C.c_char_p, C.c_uint64, i, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz), vp]),
         "zfb_file_write_block_dev": (i, [vp, C.c_char_p, C.c_uint64, i, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz), vp]),
+        "zfb_value_psnr_range": (d, [PP]),
+        "zfb_value_nrmse": (d, [PP]),
         "zfb_partials_dev": (vp, [vp]),
         "zfb_partials_get": (i, [vp, PP]),
         "zfb_partials_set": (i, [vp, PP]),
@@ -261,7 +263,9 @@ def metric_values(p):
     return {"absolute_error": L.zfb_value_absolute_error(r), "relative_error": L.zfb_value_relative_error(r),
             "mse": L.zfb_value_mse(r), "psnr": L.zfb_value_psnr(r), "minmax": L.zfb_value_minmax(r),
             "min": -p.neg_min_orig, "max": p.max_orig, "sum_abs": p.sum_abs, "sum_rel": p.sum_rel,
-            "sum_sq": p.sum_sq, "n": p.n}
+            "sum_sq": p.sum_sq, "n": p.n,
+            # extra metrics out of the same partials: PSNR over the value range, normalised RMSE
+            "psnr_range": L.zfb_value_psnr_range(r), "nrmse": L.zfb_value_nrmse(r)}
 
 
 def combine_partials(parts):

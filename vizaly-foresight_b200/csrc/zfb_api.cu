@@ -70,6 +70,7 @@ struct zfb_ctx {
   uint64_t var_index_bits = 0;
   const void* var_host_key = nullptr;   // host stream buffer the resident d_stream + index came from
   size_t var_host_bytes = 0;
+  zfb_mode var_host_mode = {};          // parameters the resident variable-rate stream was coded with
 };
 
 #define CU_TRY(ctx, call)                                                                   \
@@ -153,9 +154,23 @@ extern "C" double zfb_value_mse(const zfb_partials* p) { return p->sum_sq / (dou
 extern "C" double zfb_value_psnr(const zfb_partials* p)
 {
   const double mse = p->sum_sq / (double)p->n;
-  return 10 * std::log10(std::pow(p->max_orig, 2.0) / mse);
+  const double mx = p->max_orig > -999999999.0 ? p->max_orig : -999999999.0;  // the reference's running maximum starts there (psnrError.hpp:58)
+  return 10 * std::log10(std::pow(mx, 2.0) / mse);
 }
 extern "C" double zfb_value_minmax(const zfb_partials* p) { return p->max_orig; }
+// Extra metrics from the same partials (no further pass): PSNR over the value RANGE (max - min), the usual definition
+// in the compression literature -- CBench's "psnr" uses max(original) alone (psnrError.hpp:85-88) -- and the
+// normalised root-mean-square error.
+extern "C" double zfb_value_psnr_range(const zfb_partials* p)
+{
+  const double mse = p->sum_sq / (double)p->n, range = p->max_orig + p->neg_min_orig;
+  return 10 * std::log10(range * range / mse);
+}
+extern "C" double zfb_value_nrmse(const zfb_partials* p)
+{
+  const double range = p->max_orig + p->neg_min_orig;
+  return std::sqrt(p->sum_sq / (double)p->n) / range;
+}
 
 extern "C" void zfb_partials_combine(zfb_partials* acc, const zfb_partials* in, int count)
 {

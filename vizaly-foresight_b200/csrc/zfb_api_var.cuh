@@ -454,8 +454,10 @@ extern "C" int zfb_compress_var_host(zfb_ctx* c, int dtype, int dims, size_t nx,
   c->var_index_key = c->d_stream.p;
   c->var_index_blocks = units;
   c->var_index_bits = total_bits;
-  c->var_host_key = h_stream;   // the resident stream + index describe this host buffer
+  c->var_host_key = h_stream;   // the resident stream + index describe this host buffer ...
   c->var_host_bytes = bytes;
+  sample_of(h_stream, bytes, c->stream_sample);  // ... as long as it still holds these bytes, coded with these parameters
+  c->var_host_mode = *m;
   return ZFB_OK;
 }
 
@@ -480,9 +482,14 @@ extern "C" int zfb_decompress_var_host(zfb_ctx* c, int dtype, int dims, size_t n
   const slab_plan sp = plan_var_slabs(dims, nx, ny, nz, esz);
   // the index kept by zfb_compress_var_host is only trusted together with the bytes it was built from, so the
   // stream is uploaded again (cheap next to the field) and the index reused when the host buffer is the same
-  const bool index_resident = c->var_host_key == h_stream && c->var_host_bytes == stream_bytes &&
-                              c->var_index_key == c->d_stream.p && c->d_stream.p && c->var_index_blocks == units &&
-                              c->var_slab_bits.size() == sp.nslabs + 1;
+  bool index_resident = c->var_host_key == h_stream && c->var_host_bytes == stream_bytes &&
+                        c->var_index_key == c->d_stream.p && c->d_stream.p && c->var_index_blocks == units &&
+                        c->var_slab_bits.size() == sp.nslabs + 1 && memcmp(&c->var_host_mode, m, sizeof *m) == 0;
+  if (index_resident) {  // same address and size is not enough: the buffer must still hold the stream the index describes
+    unsigned char now[128];
+    sample_of(h_stream, stream_bytes, now);
+    index_resident = memcmp(now, c->stream_sample, sizeof now) == 0;
+  }
   if (!index_resident) {
     // a stream from elsewhere: upload it whole, rebuild the index on the device, decode in one piece
     if ((rc = ensure(c, c->d_stream, stream_bytes + 16))) return rc;
