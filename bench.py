@@ -569,10 +569,11 @@ def main():
                            "bytes_per_value": (enc_bytes + dec_bytes) / n}}
     # DRAM traffic of one launch, from the committed ncu --set full capture of this workload (null otherwise)
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic_nyx2048slab.json")))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic_nyx2048slab.json")))
         if args.workload == "nyx2048-slab" and int(rate) == 8:
             roof["traffic"] = tr["kernels"]["decode+metrics"]["traffic"]
-            roof["traffic_source"] = "profiles/r01_traffic_nyx2048slab.json (ncu dram__bytes_read.sum + dram__bytes_write.sum)"
+            roof["traffic_source"] = ("profiles/r02_traffic_nyx2048slab.json: ncu dram__bytes_read.sum + dram__bytes_write.sum of ONE --set full "
+                                      "capture of this command with these kernels (tools/gpu_profile_final.sh); not re-measured by this run")
             roof["encode"]["traffic"] = tr["kernels"]["encode"]["traffic"]
     except Exception:
         pass

@@ -599,9 +599,9 @@ enc3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t* __restr
 
   if (tid == 0 && t < tg.ntiles) issue_loads(sb[0]);
 
-  f3::plane_rows ps;
-  ps.p = reinterpret_cast<f3::u32x4*>(tile + box * BOX_FLOATS) + lb;
-  ps.stride = 64;
+  f3::smem_rows_t<0> ps;  // the thread's 16-byte column of its box: row r at r * 1 KiB
+  ps.base = ptx::smem_u32(tile + box * BOX_FLOATS) + 16u * lb;
+  ps.stride = 1024u;
   float vmax = -3.402823466e38f, vnmin = -3.402823466e38f;  // MINMAX: max(f), max(-f)
 
   for (unsigned it = 0; t < tg.ntiles; t += gridDim.x, it++) {
@@ -624,7 +624,7 @@ enc3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t* __restr
           }
         }
         const unsigned p = (box ? b0.nvalid : 0u) + lb;  // slot position inside the tile's contiguous span
-        f3::sink32 sink(reinterpret_cast<uint32_t*>(obuf + (size_t)p * tg.W), 2 * tg.W);
+        f3::smem_sink32 sink(ptx::smem_u32(obuf + (size_t)p * tg.W), 2 * tg.W);
         f3::encode_block(f, maxbits, sink, tb, ps);
       }
     }
@@ -724,9 +724,9 @@ dec3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64
     if (t + gridDim.x < tg.ntiles) issue_slots(sb[1], 1);
   }
 
-  f3::plane_rows ps;
-  ps.p = reinterpret_cast<f3::u32x4*>(tile + box * BOX_FLOATS) + lb;
-  ps.stride = 64;
+  f3::smem_rows_t<0> ps;  // the thread's 16-byte column of its box: row r at r * 1 KiB
+  ps.base = ptx::smem_u32(tile + box * BOX_FLOATS) + 16u * lb;
+  ps.stride = 1024u;
 
   maccf m;
   m.init();
@@ -870,9 +870,9 @@ enc3_f64_tile_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t* __restr
   };
   if (tid == 0 && t < tg.nboxes) issue_load(sb[0]);
 
-  f3::plane_rows_t<1> ps;
-  ps.p = reinterpret_cast<f3::u32x4*>(tile) + 2 * tid;
-  ps.stride = 128;  // a row of the box is 256 doubles = 128 sixteen-byte units
+  f3::smem_rows_t<1> ps;  // the thread's 32-byte column: two plane rows per 2 KiB row of the box
+  ps.base = ptx::smem_u32(tile) + 32u * tid;
+  ps.stride = 2048u;
 
   for (unsigned it = 0; t < tg.nboxes; t += gridDim.x, it++) {
     const box_info b0 = sb[it & 1];
@@ -886,7 +886,7 @@ enc3_f64_tile_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t* __restr
         const double2 v0 = src[r * 128], v1 = src[r * 128 + 1];
         f[4 * r] = v0.x; f[4 * r + 1] = v0.y; f[4 * r + 2] = v1.x; f[4 * r + 3] = v1.y;
       }
-      f3::sink32 sink(reinterpret_cast<uint32_t*>(outw + (size_t)tid * tg.W), 2 * tg.W);
+      f3::smem_sink32 sink(ptx::smem_u32(outw + (size_t)tid * tg.W), 2 * tg.W);
       d3::encode_block(f, maxbits, sink, tb, ps);
     }
     ptx::fence_proxy_async();
@@ -938,9 +938,9 @@ dec3_f64_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64
     if (t + gridDim.x < tg.nboxes) issue_slots(sb[1], 1);
   }
 
-  f3::plane_rows_t<1> ps;
-  ps.p = reinterpret_cast<f3::u32x4*>(tile) + 2 * tid;
-  ps.stride = 128;
+  f3::smem_rows_t<1> ps;
+  ps.base = ptx::smem_u32(tile) + 32u * tid;
+  ps.stride = 2048u;
 
   macc m;
   m.init();
@@ -954,8 +954,8 @@ dec3_f64_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64
     int emax = 0, kend = 63;
     bool nonzero = false;
     if (active) {
-      f3::reader32 r(reinterpret_cast<const uint32_t*>(slots + (size_t)buf * slot_words + (size_t)tid * tg.W),
-                     2 * (b0.nvalid - tid) * tg.W, 0);
+      f3::smem_words r;
+      r.base = ptx::smem_u32(slots + (size_t)buf * slot_words + (size_t)tid * tg.W);
       nonzero = d3::decode_planes(PH, PL, emax, kend, maxbits, r, tb, ps);
     }
     ptx::fence_proxy_async();
