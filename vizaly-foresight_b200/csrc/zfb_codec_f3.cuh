@@ -572,11 +572,15 @@ ZFB_HD unsigned encode_planes(const PR& ps, unsigned maxbits, uint32_t header, u
   unsigned n = 0;
   int k = NP - 1;
   uint32_t xl = 0u, xh = 0u;
+  u32x4 row;  // the row (two planes) k belongs to: one conflict-free 128-bit load per two planes
+  row.x = row.y = row.z = row.w = 0u;
   // next plane into (xl, xh); false when the block is finished (budget covered or no planes left)
   auto next = [&]() -> bool {
     if (k < kmin || bw.bits() >= maxbits) return false;
     if (k < NP - 16 && (k & 15) == 15) finish_rows(ps, (k - 15) >> 1);  // next 16 planes: finish their transpose now
-    ps.ld64(k, xl, xh);
+    if (k & 1) row = ps.ld(k >> 1);  // planes come in descending order: the odd plane of a row is met first
+    xl = (k & 1) ? row.z : row.x;
+    xh = (k & 1) ? row.w : row.y;
     return true;
   };
   bool more = next();
@@ -845,6 +849,14 @@ ZFB_HD int parse_planes(const PR& ps, unsigned maxbits, unsigned hbits, int kmin
   unsigned pos = hbits;  // bit position inside the slot
   unsigned n = 0;
   int k = NP - 1;
+  // planes leave row-wise: the odd plane of a row is met first and waits in `cur` for the even one (one conflict-free
+  // 128-bit store per two planes; the rows were zeroed, so a row whose even plane is never decoded is flushed as is)
+  u32x4 cur;
+  cur.x = cur.y = cur.z = cur.w = 0u;
+  auto emit = [&](int kk, uint32_t lo, uint32_t hi) {
+    if (kk & 1) { cur.z = lo; cur.w = hi; }
+    else { cur.x = lo; cur.y = hi; ps.st(kk >> 1, cur); }
+  };
   // One loop per regime of n, each lane walking its own planes (k is per lane): the lanes of a warp go through a
   // regime together even when they reach it at different planes (see encode_planes).
   // 1. few coefficients significant (the top planes of a block): the verbatim bits and the whole group-test code of
@@ -853,7 +865,7 @@ ZFB_HD int parse_planes(const PR& ps, unsigned maxbits, unsigned hbits, int kmin
     const uint32_t c = fetch32(r, pos);
     const uint32_t e = dec_at(tb, (c >> n) & 0xffu);
     if ((int32_t)e >= 0) break;  // the step did not end on a zero group test: a plane for the general loop
-    ps.st64(k, (c & mask32(n)) | (dec_pat(e) << n), 0u);
+    emit(k, (c & mask32(n)) | (dec_pat(e) << n), 0u);
     pos += n + dec_nbits(e);
     n += dec_npos(e);
   }
@@ -938,7 +950,7 @@ ZFB_HD int parse_planes(const PR& ps, unsigned maxbits, unsigned hbits, int kmin
         n++;
       }
     }
-    ps.st64(k, (uint32_t)x, (uint32_t)(x >> 32));
+    emit(k, (uint32_t)x, (uint32_t)(x >> 32));
   }
   if (k < kmin || pos >= maxbits) break;
   // 3. at most four coefficients left (none: row 0 of NE is empty): n verbatim bits and one lookup for the rest.
@@ -949,12 +961,16 @@ ZFB_HD int parse_planes(const PR& ps, unsigned maxbits, unsigned hbits, int kmin
     fetch64(r, pos, rl, rh);
     const unsigned row = 64u - n, s = n - 32u;  // s in 28..32
     const uint32_t e = ne_at(tb, 128u * row + (fetch32(r, pos + n) & 127u));
-    ps.st64(k, rl, (rh & mask32(s)) | (s < 32u ? (e >> 8) << s : 0u));
+    emit(k, rl, (rh & mask32(s)) | (s < 32u ? (e >> 8) << s : 0u));
     pos += n + (e & 15u);
     n += (e >> 4) & 15u;
   }
   if (k < kmin || pos >= maxbits) break;
   }  // the budget is near its end: back to the general loop for the last planes
+  if (k >= 0 && !(k & 1)) {  // stopped with the odd plane of a row pending (k = first plane NOT decoded)
+    cur.x = 0u; cur.y = 0u;
+    ps.st(k >> 1, cur);
+  }
   return k;
 }
 

@@ -566,6 +566,9 @@ enc3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t* __restr
 {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   float* tile = reinterpret_cast<float*>(smem_raw);
+  // slot staging in the stream's own layout (one bulk store per tile).  The 64-byte slot stride makes the lanes of a warp
+  // hit two banks when they write word j of their slots; a padded layout with the warp copying its piece to the stream
+  // itself removes the conflicts but costs more than it saves here (2.21 against 2.16 ms, profiles/r02_notes.md).
   uint64_t* outw = reinterpret_cast<uint64_t*>(smem_raw + BOXES_PER_TILE * BOX_FLOATS * sizeof(float));
   const unsigned out_words = TILE_THREADS * tg.W;
   uint64_t* bars = outw + (size_t)out_words;
@@ -608,7 +611,6 @@ enc3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t* __restr
     const box_info b0 = sb[it & 1][0], b1 = sb[it & 1][1];
     const box_info mine = box ? b1 : b0;
     const bool active = lb < mine.nvalid;
-    uint64_t* obuf = outw;
     if (mine.nvalid) {
       ptx::mbar_wait(&bars[box], it & 1);
       if (active) {
@@ -624,7 +626,7 @@ enc3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t* __restr
           }
         }
         const unsigned p = (box ? b0.nvalid : 0u) + lb;  // slot position inside the tile's contiguous span
-        f3::smem_sink32 sink(ptx::smem_u32(obuf + (size_t)p * tg.W), 2 * tg.W);
+        f3::smem_sink32 sink(ptx::smem_u32(outw + (size_t)p * tg.W), 2 * tg.W);
         f3::encode_block(f, maxbits, sink, tb, ps);
       }
     }
@@ -637,10 +639,10 @@ enc3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t* __restr
     if (tid == 0) {
       // the two boxes' slots are adjacent in the stream except across a partial block row
       if (b1.nvalid && b1.blk0 != b0.blk0 + b0.nvalid) {
-        ptx::bulk_store(stream + b0.blk0 * tg.W, obuf, b0.nvalid * tg.W * 8u);
-        ptx::bulk_store(stream + b1.blk0 * tg.W, obuf + (size_t)b0.nvalid * tg.W, b1.nvalid * tg.W * 8u);
+        ptx::bulk_store(stream + b0.blk0 * tg.W, outw, b0.nvalid * tg.W * 8u);
+        ptx::bulk_store(stream + b1.blk0 * tg.W, outw + (size_t)b0.nvalid * tg.W, b1.nvalid * tg.W * 8u);
       } else {
-        ptx::bulk_store(stream + b0.blk0 * tg.W, obuf, (b0.nvalid + b1.nvalid) * tg.W * 8u);
+        ptx::bulk_store(stream + b0.blk0 * tg.W, outw, (b0.nvalid + b1.nvalid) * tg.W * 8u);
       }
       ptx::bulk_commit();
       ptx::bulk_wait_read0();              // `out` may be rewritten once the next tile's loads have landed
@@ -669,8 +671,15 @@ enc3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t* __restr
 // HIST: the decoded values are also binned into the 1024-bin value-range histogram of the minmax metric
 // (minmaxMetric.hpp:92-133) over [hlo, hhi] = the field's global minimum / maximum harvested by the encode pass:
 // shared-memory counters per CTA, flushed once; no extra pass over memory.
+#ifndef ZFB_DEC_SLOT_BUFS
+#define ZFB_DEC_SLOT_BUFS 1  // landing buffers for the slot span per CTA (1: the next tile's span arrives during the transform; 2: two tiles ahead)
+#endif
+#ifndef ZFB_DEC_CTAS
+#define ZFB_DEC_CTAS 4       // resident CTAs per SM the register budget is cut for
+#endif
+constexpr unsigned DEC_SLOT_BUFS = ZFB_DEC_SLOT_BUFS;
 template <bool METRICS, bool HIST>
-__global__ void __launch_bounds__(TILE_THREADS, 4)
+__global__ void __launch_bounds__(TILE_THREADS, ZFB_DEC_CTAS)
 dec3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64_t* __restrict__ stream,
                      float* __restrict__ out, tile_geom tg, unsigned maxbits, double* __restrict__ part, double hlo,
                      double hhi, unsigned long long* __restrict__ hcounts)
@@ -679,7 +688,15 @@ dec3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64
   float* tile = reinterpret_cast<float*>(smem_raw);
   uint64_t* slots = reinterpret_cast<uint64_t*>(smem_raw + BOXES_PER_TILE * BOX_FLOATS * sizeof(float));
   const unsigned slot_words = TILE_THREADS * tg.W;
-  uint64_t* bars = slots + 2 * (size_t)slot_words;  // [0,1] slot buffers full, [2,3] orig boxes full
+  // The slot span lands contiguously (bulk copy) and is re-laid by its warp into a PADDED area: slot p at 32-bit word
+  // p * (2W + 1).  With the natural 64-byte slot stride the 32 lanes of a warp hit two banks whenever they fetch the
+  // same word of their slots (ncu: 5.8 wavefronts per shared load, shared pipe 51 % busy); the odd stride is conflict
+  // free.
+  const unsigned W2 = 2u * tg.W, pstride = W2 + 1u;
+  const uint32_t land_s = ptx::smem_u32(slots);
+  const uint32_t pad_s = land_s + DEC_SLOT_BUFS * slot_words * 8u;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(slots + DEC_SLOT_BUFS * (size_t)slot_words) +
+                                               (((size_t)TILE_THREADS * pstride * 4u + 16u + 15u) & ~(size_t)15));  // [0,1] slot buffers full, [2,3] orig boxes full
   __shared__ double red[7 * 4];
   __shared__ dec_coder_smem cs;
   __shared__ box_info sb[3][BOXES_PER_TILE];  // ring of box descriptors: current, next, next-next tile
@@ -702,9 +719,11 @@ dec3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64
     uint64_t* dst = slots + (size_t)buf * slot_words;
     const unsigned bytes = (bi[0].nvalid + bi[1].nvalid) * tg.W * 8u;
     ptx::mbar_expect_tx(&bars[buf], bytes);
-    if (bi[1].nvalid && bi[1].blk0 != bi[0].blk0 + bi[0].nvalid) {
+    if (bi[1].nvalid && (bi[1].blk0 != bi[0].blk0 + bi[0].nvalid || bi[0].nvalid != (unsigned)BOX_BLOCKS)) {
+      // box 1's slots always land at slot 64 of the buffer, so that thread tid's slot is slot tid and a warp's slots
+      // are its own 32
       ptx::bulk_load(dst, stream + bi[0].blk0 * tg.W, bi[0].nvalid * tg.W * 8u, &bars[buf]);
-      ptx::bulk_load(dst + (size_t)bi[0].nvalid * tg.W, stream + bi[1].blk0 * tg.W, bi[1].nvalid * tg.W * 8u, &bars[buf]);
+      ptx::bulk_load(dst + (size_t)BOX_BLOCKS * tg.W, stream + bi[1].blk0 * tg.W, bi[1].nvalid * tg.W * 8u, &bars[buf]);
     } else {
       ptx::bulk_load(dst, stream + bi[0].blk0 * tg.W, bytes, &bars[buf]);
     }
@@ -721,7 +740,7 @@ dec3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64
 
   if (tid == 0) {
     if (t < tg.ntiles) issue_slots(sb[0], 0);
-    if (t + gridDim.x < tg.ntiles) issue_slots(sb[1], 1);
+    if (DEC_SLOT_BUFS == 2 && t + gridDim.x < tg.ntiles) issue_slots(sb[1], 1);
   }
 
   f3::smem_rows_t<0> ps;  // the thread's 16-byte column of its box: row r at r * 1 KiB
@@ -741,19 +760,49 @@ dec3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64
   }
   unsigned cur = 0;  // it % 3
   for (unsigned it = 0; t < tg.ntiles; t += gridDim.x, it++, cur = cur == 2 ? 0 : cur + 1) {
-    const unsigned buf = it & 1, nn = cur == 0 ? 2 : cur - 1;  // nn = (it + 2) % 3
+    const unsigned buf = DEC_SLOT_BUFS == 2 ? (it & 1) : 0u, nn = cur == 0 ? 2 : cur - 1;  // nn = (it + 2) % 3
     const box_info b0 = sb[cur][0], b1 = sb[cur][1];
     const box_info mine = box ? b1 : b0;
     const bool active = lb < mine.nvalid;
     const unsigned nslots = b0.nvalid + b1.nvalid;
-    ptx::mbar_wait(&bars[buf], (it >> 1) & 1);
+    ptx::mbar_wait(&bars[buf], (DEC_SLOT_BUFS == 2 ? (it >> 1) : it) & 1);
     f3::planes64 P;
     int emax = 0;
     bool nonzero = false, low_used = false;
+    {
+      // re-lay the warp's 32 slots (words [32 w W2, 32 (w + 1) W2) of the landing buffer) into the padded area
+      const uint32_t src = land_s + buf * slot_words * 8u + 4u * (tid & ~31u) * W2;
+      const uint32_t dstp = pad_s + 4u * (tid & ~31u) * pstride;
+      const unsigned lane = tid & 31u;
+      if (W2 == 16u) {  // 8 bits per value: all 16 loads in flight, then 16 stores
+        uint32_t v[16];
+#pragma unroll
+        for (int m = 0; m < 16; m++) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v[m]) : "r"(src + 4u * (lane + 32u * m)));
+#pragma unroll
+        for (int m = 0; m < 16; m++) {
+          const unsigned i = lane + 32u * m;
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(dstp + 4u * ((i >> 4) * 17u + (i & 15u))), "r"(v[m]) : "memory");
+        }
+      } else if ((W2 & (W2 - 1u)) == 0u) {
+        const unsigned sh = 31u - (unsigned)__clz((int)W2);
+#pragma unroll 4
+        for (unsigned i = lane; i < 32u * W2; i += 32u) {
+          uint32_t v;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(src + 4u * i));
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(dstp + 4u * ((i >> sh) * pstride + (i & (W2 - 1u)))), "r"(v) : "memory");
+        }
+      } else {
+        for (unsigned i = lane; i < 32u * W2; i += 32u) {
+          uint32_t v;
+          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(src + 4u * i));
+          asm volatile("st.shared.u32 [%0], %1;" ::"r"(dstp + 4u * ((i / W2) * pstride + i % W2)), "r"(v) : "memory");
+        }
+      }
+      __syncwarp();
+    }
     if (active) {
-      const unsigned p = (box ? b0.nvalid : 0u) + lb;
       f3::smem_words r;
-      r.base = ptx::smem_u32(slots + (size_t)buf * slot_words + (size_t)p * tg.W);
+      r.base = pad_s + 4u * tid * pstride;
       nonzero = f3::decode_planes(P, emax, low_used, maxbits, r, tb, ps);
     }
     ptx::fence_proxy_async();  // plane-row writes (generic proxy) before the TMA load overwrites the buffer
@@ -763,7 +812,11 @@ dec3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64
     }
     __syncthreads();           // slots[buf] parsed; planes back in registers; descriptors of tile it+2 published
     if (tid == 0) {
-      if (t + 2 * gridDim.x < tg.ntiles) issue_slots(sb[nn], buf);
+      if (DEC_SLOT_BUFS == 2) {
+        if (t + 2 * gridDim.x < tg.ntiles) issue_slots(sb[nn], buf);
+      } else if (t + gridDim.x < tg.ntiles) {
+        issue_slots(sb[cur == 2 ? 0 : cur + 1], 0);  // the one buffer has been parsed: the next tile's slots land during the transform
+      }
       if (METRICS) issue_orig(sb[cur]);
     }
     if (active) {
