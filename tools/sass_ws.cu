@@ -1,0 +1,6 @@
+// Development aid: compiles only the warp-specialised float/3D kernels (registers, spills, SASS)
+#include "../vizaly-foresight_b200/csrc/zfb_ws.cuh"
+namespace zfb { namespace ws {
+template __global__ void dec3_f32_ws_kernel<true>(const float* __restrict__, const uint64_t* __restrict__, float* __restrict__, tile_geom, unsigned, double* __restrict__);
+template __global__ void dec3_f32_ws_kernel<false>(const float* __restrict__, const uint64_t* __restrict__, float* __restrict__, tile_geom, unsigned, double* __restrict__);
+}}

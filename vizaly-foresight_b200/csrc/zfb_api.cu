@@ -10,6 +10,7 @@
 
 #include "../../include/zfb.h"
 #include "zfb_kernels.cuh"
+#include "zfb_ws.cuh"
 #include "zfb_hostio.cuh"
 #include "zfb_comm.cuh"
 
@@ -42,6 +43,7 @@ struct zfb_ctx {
   uint64_t launches = 0;
   std::string err;
   bool force_generic = false;
+  bool dec_ws = true;   // warp-specialised float decode kernel (ZFB_DEC_WS=0 switches back to the tile kernel)
   // host-pointer path: resident device copies
   devbuf d_orig, d_stream, d_out, d_hist;
   const void* h_orig_key = nullptr;   // host pointer the resident original came from
@@ -252,6 +254,17 @@ extern "C" int zfb_create(zfb_ctx** out, int device)
       cudaFuncSetAttribute(dec3_f64_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) != cudaSuccess) {
     cudaGetLastError();
     c->encode_tiled = nullptr;
+  }
+  // warp-specialised float decode (zfb_ws.cuh): one 640-thread CTA per SM with up to 227 KiB of shared memory
+  {
+    const char* e = std::getenv("ZFB_DEC_WS");
+    c->dec_ws = !(e && e[0] == '0');
+    const int ws_smem = 227 * 1024 - 8 * 1024;
+    if (cudaFuncSetAttribute(ws::dec3_f32_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws_smem) != cudaSuccess ||
+        cudaFuncSetAttribute(ws::dec3_f32_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws_smem) != cudaSuccess) {
+      cudaGetLastError();
+      c->dec_ws = false;
+    }
   }
   *out = c;
   return ZFB_OK;
@@ -717,6 +730,32 @@ extern "C" int zfb_decode_dev(zfb_ctx* c, int dtype, int dims, size_t nx, size_t
       if (rc) return rc;
     }
     const tile_geom tg = make_tile_geom(g, maxbits);
+    const char* fh0 = std::getenv("ZFB_FUSED_HIST");
+    const bool want_fused_hist = metrics && c->hist_counts && fh0 && fh0[0] == '1';
+    if (c->dec_ws && !want_fused_hist && ws::smem_bytes(tg.W) <= (size_t)(227 * 1024 - 8 * 1024) &&
+        (size_t)((tg.nbx + 31) / 32) * tg.nby * tg.nbz < (1ull << 31)) {
+      // warp-specialised kernel: parser warps and transform warps of one CTA per SM (zfb_ws.cuh)
+      const unsigned nwt = ((tg.nbx + 31) / 32) * tg.nby * tg.nbz;
+      unsigned grid = (unsigned)c->sm_count;
+      const unsigned want = (nwt + ws::P_WARPS - 1) / ws::P_WARPS;
+      if (grid > want) grid = want;
+      if ((int)grid > c->part_rows / 2) grid = c->part_rows / 2;
+      const size_t smem = ws::smem_bytes(tg.W);
+      if (metrics)
+        ws::dec3_f32_ws_kernel<true><<<grid, ws::THREADS, smem, c->stream>>>((const float*)d_orig, (const uint64_t*)d_stream, (float*)d_out, tg, maxbits, c->part);
+      else
+        ws::dec3_f32_ws_kernel<false><<<grid, ws::THREADS, smem, c->stream>>>((const float*)d_orig, (const uint64_t*)d_stream, (float*)d_out, tg, maxbits, c->part);
+      c->launches++;
+      CU_TRY(c, cudaGetLastError());
+      rows = (int)grid;
+      if ((g.ny | g.nz) & 3) {  // partial blocks
+        int erows = 0;
+        rc = metrics ? launch_dec_generic<float, true>(c, dims, g, maxbits, d_stream, d_out, d_orig, 1, &erows, 0, rows)
+                     : launch_dec_generic<float, false>(c, dims, g, maxbits, d_stream, d_out, d_orig, 1, &erows, 0, rows);
+        if (rc) return rc;
+        rows += erows;
+      }
+    } else {
     const size_t smem = dec_tile_smem(tg.W, metrics);
     int nb = metrics ? c->occ_decm[tg.W] : c->occ_dec[tg.W];
     if (!nb) {
@@ -760,6 +799,7 @@ extern "C" int zfb_decode_dev(zfb_ctx* c, int dtype, int dims, size_t nx, size_t
       if (rc) return rc;
       rows += erows;
     }
+    }  // tile kernel (not warp-specialised)
   } else if (line_path_ok(c, dtype, dims, g, maxbits) && ((uintptr_t)d_out & 15) == 0 && ((uintptr_t)d_stream & 15) == 0 &&
              (!metrics || ((uintptr_t)d_orig & 15) == 0)) {
     const size_t nfull = g.nx / 4;
