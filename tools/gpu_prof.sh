@@ -4,7 +4,7 @@ tag=${1:-dev}; wl=${2:-nyx512}; pat=${3:-"(enc3|dec3)_f32_tile"}
 mkdir -p gpurun_out
 cmd="python bench.py --workload $wl --steps 1 --warmup 3 --no-e2e --no-cpu"
 timeout 300 $cmd > gpurun_out/plain_$tag.log 2>&1 &&
-timeout 900 ncu --set full --clock-control none --import-source on --kernel-name regex:"$pat" -s 6 -c 2 -o gpurun_out/prof_$tag -f $cmd > gpurun_out/ncu_$tag.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on --kernel-name regex:"$pat" -s ${SKIP:-6} -c ${COUNT:-2} -o gpurun_out/prof_$tag -f $cmd > gpurun_out/ncu_$tag.log 2>&1
 tail -3 gpurun_out/ncu_$tag.log
 grep -h '^{' gpurun_out/plain_$tag.log | python -c "
 import sys,json

@@ -278,6 +278,34 @@ ZFB_HD uint32_t dec_entry(unsigned state, unsigned v)
   return nbits | (pattern << 8) | (npos << 16) | (state << 30);
 }
 
+// Table of the flat parser (parse_planes_flat): zfp's group-test parser run over exactly b <= 8 stream bits.
+//   FLAT[state * 512 + (1 << b) + v], state 0 (A) = expecting a test bit, 1 (B) = inside a zero run, v = the next b bits.
+//   A step parses fewer than 8 bits at the end of the budget and where more bits could carry the coefficient index past
+//   63 (whose one is implicit); b = 0 (entry 1) parses nothing.
+// Entry: bits 0-4 stream bits consumed, bit 5 END (a zero test bit was consumed: the plane is done), bit 11 next state
+// is B (= the byte offset of B's half of the table), bits 16-23 ones deposited (relative to the current coefficient),
+// bits 24-31 coefficients advanced.
+constexpr unsigned FLAT_WORDS = 1024, FLAT_B = 0x800u, FLAT_END = 0x20u;
+ZFB_HD uint32_t flat_entry(unsigned i)
+{
+  unsigned state = i >> 9;
+  const unsigned j = i & 511u;
+  if (!j) return 0u;
+  unsigned nb = 0;
+  while ((2u << nb) <= j) nb++;  // j = (1 << nb) + v
+  const unsigned v = j - (1u << nb);
+  unsigned pattern = 0, npos = 0, nbits = 0;
+  while (nbits < nb && state != 2) {
+    const unsigned bit = (v >> nbits) & 1u;
+    nbits++;
+    if (state == 0) state = bit ? 1u : 2u;
+    else {
+      if (bit) { pattern |= 1u << npos; state = 0; }
+      npos++;
+    }
+  }
+  return nbits | (state == 2 ? FLAT_END : 0u) | (state == 1 ? FLAT_B : 0u) | (pattern << 16) | (npos << 24);
+}
 constexpr unsigned ENC_WORDS = 512 + NEE_SIZE, DEC_WORDS = 512 + NE_SIZE / 2;  // table sizes in 32-bit words (NE: 16-bit entries)
 ZFB_HD uint32_t enc_table_word(unsigned i) { return i < 512u ? enc_entry(i) : nee_entry(i - 512u); }
 ZFB_HD uint32_t dec_entry(unsigned state, unsigned v);
@@ -290,7 +318,41 @@ struct tables {
   const uint32_t* enc;  // ENC_WORDS entries: ENC, then NEE
   const uint32_t* dec;  // DEC_WORDS entries: DEC, then NE
   uint32_t enc_s, dec_s;  // device: 32-bit shared-memory addresses of the two tables
+  const uint32_t* flat = nullptr;  // FLAT_WORDS entries (flat parser only)
+  uint32_t flat_s = 0;
 };
+// FLAT entry j of the state whose byte offset is st (0 or FLAT_B)
+ZFB_HD uint32_t flat_at(const tables& tb, uint32_t st, uint32_t j)
+{
+#if defined(__CUDA_ARCH__)
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(tb.flat_s + st + 4u * j));
+  return v;
+#else
+  return tb.flat[(st >> 2) + j];
+#endif
+}
+ZFB_HD uint32_t step_index(uint32_t c, unsigned b)  // (1 << b) | the b lowest bits of c, b <= 8
+{
+#if defined(__CUDA_ARCH__)
+  uint32_t lo, one;
+  asm("bmsk.clamp.b32 %0, 0, %1;" : "=r"(lo) : "r"(b));
+  asm("bmsk.clamp.b32 %0, %1, 1;" : "=r"(one) : "r"(b));
+  return (c & lo) | one;
+#else
+  return (1u << b) | (c & ((1u << b) - 1u));
+#endif
+}
+ZFB_HD uint32_t lowmask(unsigned m)  // the m lowest bits, all of them for m >= 32
+{
+#if defined(__CUDA_ARCH__)
+  uint32_t v;
+  asm("bmsk.clamp.b32 %0, 0, %1;" : "=r"(v) : "r"(m));
+  return v;
+#else
+  return m >= 32u ? 0xffffffffu : (1u << m) - 1u;
+#endif
+}
 // Table lookups.  On the device the tables live in shared memory and are read with ld.shared through a 32-bit
 // address: going through the generic pointer makes the compiler rebuild the shared window base
 // (S2UR SR_CgaCtaId -> ULEA) inside the coder loops, on their critical path.
@@ -970,6 +1032,89 @@ ZFB_HD int parse_planes(const PR& ps, unsigned maxbits, unsigned hbits, int kmin
   if (k >= 0 && !(k & 1)) {  // stopped with the odd plane of a row pending (k = first plane NOT decoded)
     cur.x = 0u; cur.y = 0u;
     ps.st(k >> 1, cur);
+  }
+  return k;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Flat slot parser: ONE loop whose iteration is "the verbatim bits of a plane start (if the lane is at one) plus one
+// table step", the same instruction sequence for every lane whatever plane it is in and however far it is.
+// parse_planes above nests a table-step loop inside the plane loop and has a loop per regime, so a warp pays for its
+// slowest lane in every plane and for every regime in turn (16 of 32 lanes active on the benchmark field); in
+// fixed-rate mode all lanes of a warp consume the same number of bits, so their TOTAL step counts are close (22.8 per
+// lane, 25.6 for the slowest lane of a warp at 8 bits per value) and the flat loop's trip count is their maximum.
+//   * a step parses b = min(8, bits of budget left, distance to coefficient 63) stream bits through the FLAT table,
+//     indexed by (state, b, the b bits): short steps at the end of the budget and near the last coefficient are the
+//     same code with another table address; b = 0 (nothing left to parse in this plane) is a lookup without effect;
+//   * zfp's two end rules are predicated instructions behind the step: in a zero run at coefficient 63 the one is
+//     implicit, and a zero run cut off by the budget still deposits its one.
+// There is no other path.  Same contract as parse_planes: fills the plane rows (zeroed here first), returns the first
+// plane NOT decoded.  Checked against parse_planes on 800 k random slots and on encoded fields (tools/flat_check.cpp).
+#ifdef ZFB_FLAT_STATS
+struct flat_stats { unsigned iters, slow; };
+#endif
+template <int NP, class Reader, class PR>
+ZFB_HD int parse_planes_flat(const PR& ps, unsigned maxbits, unsigned hbits, int kmin, Reader& r, const tables& tb
+#ifdef ZFB_FLAT_STATS
+                             , flat_stats* stt = nullptr
+#endif
+)
+{
+  {
+    u32x4 z;
+    z.x = z.y = z.z = z.w = 0u;
+    ZFB_UNROLL for (int q = 0; q < NP / 2; q++) ps.st(q, z);
+  }
+  unsigned pos = hbits, n = 0;
+  uint32_t st = 0u;  // 0: at a test bit, FLAT_B: inside a zero run
+  int k = NP - 1;
+  uint32_t xl = 0u, xh = 0u;
+  bool mid = false;  // inside a plane (its verbatim bits are done)
+  ZFB_NOUNROLL while (k >= kmin && pos < maxbits) {
+#ifdef ZFB_FLAT_STATS
+    if (stt) stt->iters++;
+#endif
+    const unsigned rem = maxbits - pos;
+    const unsigned nr = n < rem ? n : rem;
+    const unsigned m = mid ? 0u : nr;  // verbatim bits of this iteration
+    uint32_t rl, rh;
+    fetch64(r, pos, rl, rh);
+    const unsigned p2 = pos + m;
+    const uint32_t c = fetch32(r, p2);
+    const uint32_t vl = rl & lowmask(m), vh = rh & lowmask(m > 32u ? m - 32u : 0u);
+    xl = mid ? xl : vl;
+    xh = mid ? xh : vh;
+    // stream bits this step may parse: at most 8, not behind the budget, and not so many that the coefficient index
+    // could pass 63 (state A: a test bit and b - 1 run bits advance at most b - 1 coefficients; state B: b)
+    const unsigned rem2 = rem - m, lim = 64u - n - (st ? 1u : 0u);
+    unsigned b = rem2 < lim ? rem2 : lim;
+    b = b < 8u ? b : 8u;
+    const uint32_t e = flat_at(tb, st, step_index(c, b));
+    const uint64_t pat = (uint64_t)byte_of(e, 2) << n;
+    xl |= (uint32_t)pat;
+    xh |= (uint32_t)(pat >> 32);
+    n += byte_of(e, 3);
+    pos = p2 + (e & 31u);
+    st = e & FLAT_B;
+    if (st && (n == 63u || pos == maxbits)) {
+      // the one of coefficient 63 is implicit; a zero run cut off by the budget still deposits its one
+      const uint64_t o = (uint64_t)1 << n;
+      xl |= (uint32_t)o;
+      xh |= (uint32_t)(o >> 32);
+      n++;
+      st = 0u;
+    }
+    const bool done = b == 0u || (e & FLAT_END) || n >= 64u;
+    if (done) {
+      ps.st64(k, xl, xh);
+      k--;
+      st = 0u;
+    }
+    mid = !done;
+  }
+  if (mid) {  // the budget ended inside a plane
+    ps.st64(k, xl, xh);
+    k--;
   }
   return k;
 }

@@ -18,18 +18,29 @@
 // sequence, so no descriptors are passed.  A scheduler then always holds four latency-bound warps and one issue-bound
 // warp.
 #pragma once
+#include <cstdio>
 #include "zfb_kernels.cuh"
 
 namespace zfb {
 namespace ws {
 
-constexpr int T_WARPS = 4;                          // transform warps = warpgroup 0
+#ifndef ZFB_WS_T_WARPS
+#define ZFB_WS_T_WARPS 4
+#endif
+constexpr int T_WARPS = ZFB_WS_T_WARPS;             // transform warps = the first warpgroup(s)
+#ifndef ZFB_WS_OEARLY
+#define ZFB_WS_OEARLY 16                            // rows of the original requested before the inverse transform (the rest after it)
+#endif
 #ifndef ZFB_WS_P_WARPS
 #define ZFB_WS_P_WARPS 16
 #endif
 constexpr int P_WARPS = ZFB_WS_P_WARPS;             // parser warps = warpgroups 1..
 constexpr int THREADS = 32 * (T_WARPS + P_WARPS);
 constexpr int ROWS_BYTES = 32 * 256;                // plane rows of one warp-tile
+#ifndef ZFB_WS_PAD_BUFS
+#define ZFB_WS_PAD_BUFS 1                           // 2: the next tile's slots are copied while this tile is parsed
+#endif
+constexpr unsigned PAD_BUFS = ZFB_WS_PAD_BUFS;
 #ifndef ZFB_WS_REGS_T
 #define ZFB_WS_REGS_T 232
 #endif
@@ -37,13 +48,12 @@ constexpr int ROWS_BYTES = 32 * 256;                // plane rows of one warp-ti
 #define ZFB_WS_REGS_P 56
 #endif
 
-__host__ __device__ inline unsigned land_bytes(unsigned W) { return 32u * W * 8u; }
 __host__ __device__ inline unsigned pad_bytes(unsigned W) { return (32u * (2u * W + 1u) * 4u + 16u + 15u) & ~15u; }
-// dynamic shared memory: [rows: P x 8 KiB][landing buffers: P x 256 W][padded slots: P x pad_bytes][meta: P x 128 B]
+// dynamic shared memory: [rows: P x 8 KiB][padded slots: P x pad_bytes][meta: P x 128 B]
 //                        [mbarriers: 3 P]
 __host__ __device__ inline size_t smem_bytes(unsigned W)
 {
-  return (size_t)P_WARPS * (ROWS_BYTES + land_bytes(W) + pad_bytes(W) + 128u) + 3u * P_WARPS * 8u;
+  return (size_t)P_WARPS * (ROWS_BYTES + PAD_BUFS * pad_bytes(W) + 128u) + 3u * P_WARPS * 8u;
 }
 
 struct wtile {
@@ -82,23 +92,101 @@ __device__ __forceinline__ void mbar_wait_s(uint32_t bar_s, uint32_t parity)
       : "memory");
 }
 
+// The flat slot parser (f3::parse_planes_flat, checked on the CPU against parse_planes: tools/flat_check.cpp) written
+// out for this kernel: float blocks (32 planes, 9 header bits), slot words in shared memory at slot_s, plane k of this
+// lane stored as 8 bytes at planes_s + 256 k.  One loop, no divergent path; the bookkeeping is arranged so that as
+// much of it as possible runs on the FMA pipe (IMAD adds / moves) instead of the ALU pipe, which is what bounds the
+// kernel: the verbatim count of the next iteration (nv), the table half of the parser state (tab) and the store address
+// (A) are carried as loop state instead of being derived from flags every time.
+// Table entry (ws_entry): bits 0-4 stream bits consumed, bit 5 END, byte 1 next state (0 A / 1 B), byte 2 ones
+// deposited, byte 3 coefficients advanced.
+__device__ __forceinline__ uint32_t ws_entry(unsigned i)
+{
+  const uint32_t e = f3::flat_entry(i);
+  return (e & ~f3::FLAT_B) | ((e & f3::FLAT_B) ? 0x100u : 0u);
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a)
+{
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ int parse_flat_ws(uint32_t slot_s, uint32_t planes_s, uint32_t tab_s, unsigned maxbits, int kmin)
+{
+#pragma unroll
+  for (int k = 0; k < 32; k++) asm volatile("st.shared.v2.u32 [%0], {%1, %1};" ::"r"(planes_s + 256u * k), "r"(0u) : "memory");
+  unsigned pos = 9u, n = 0u, st = 0u, nv = 0u;
+  // A = where the current plane goes; the plane index is (A - planes_s) / 256, so A also is the loop counter
+  uint32_t A = planes_s + 31u * 256u, tab = tab_s;
+  const uint32_t A_min = planes_s + 256u * (unsigned)kmin;
+  uint32_t xl = 0u, xh = 0u;
+  bool mid = false;
+#pragma unroll 1
+  while (A >= A_min && pos < maxbits) {
+    const uint32_t a1 = slot_s + 4u * __umulhi(pos, 1u << 27);  // word pos / 32 (on the FMA pipe)
+    const uint32_t w0 = lds32(a1), w1 = lds32(a1 + 4u), w2 = lds32(a1 + 8u);
+    const uint32_t rl = __funnelshift_r(w0, w1, pos), rh = __funnelshift_r(w1, w2, pos);  // wrap: shifts by pos & 31
+    const unsigned rem = maxbits - pos;
+    const unsigned m = nv < rem ? nv : rem;  // verbatim bits of this iteration (nv = 0 inside a plane)
+    const unsigned p2 = pos + m;
+    const uint32_t a2 = slot_s + 4u * __umulhi(p2, 1u << 27);
+    const uint32_t u0 = lds32(a2), u1 = lds32(a2 + 4u);
+    const uint32_t c = __funnelshift_r(u0, u1, p2);
+    const int mh = (int)m - 32;
+    xl |= rl & f3::lowmask(m);
+    xh |= rh & f3::lowmask((unsigned)(mh > 0 ? mh : 0));
+    const unsigned rem2 = rem - m, lim = 64u - n - st;
+    unsigned b = rem2 < lim ? rem2 : lim;
+    b = b < 8u ? b : 8u;
+    const uint32_t e = lds32(tab + 4u * f3::step_index(c, b));
+    const unsigned np = e >> 24;
+    uint32_t pat = __byte_perm(e, 0u, 0x4442u);
+    st = __byte_perm(e, 0u, 0x4441u);
+    const unsigned n0 = n;
+    n += np;
+    pos = p2 + (e & 31u);
+    // zfp's end rules: in a zero run at coefficient 63 the one is implicit; a zero run cut off by the budget still
+    // deposits its one
+    if (st != 0u && (n == 63u || pos == maxbits)) { pat |= 1u << np; n++; st = 0u; }
+    const uint64_t dep = (uint64_t)pat << n0;
+    xl |= (uint32_t)dep;
+    xh |= (uint32_t)(dep >> 32);
+    bool done = b == 0u;
+    if (e & 0x20u) done = true;
+    if (n >= 64u) done = true;
+    if (done) {
+      asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(A), "r"(xl), "r"(xh) : "memory");
+      A -= 256u;
+      xl = 0u; xh = 0u;
+      st = 0u;
+      nv = n;
+    } else nv = 0u;
+    mid = !done;
+    tab = tab_s + 2048u * st;
+  }
+  if (mid) {  // the budget ended inside a plane
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(A), "r"(xl), "r"(xh) : "memory");
+    A -= 256u;
+  }
+  return (int)(A - planes_s) / 256;  // first plane NOT decoded (-1: all of them were); A - planes_s may be -256
+}
+
 template <bool METRICS>
 __global__ void __launch_bounds__(THREADS, 1)
 dec3_f32_ws_kernel(const float* __restrict__ orig, const uint64_t* __restrict__ stream, float* __restrict__ out,
                    tile_geom tg, unsigned maxbits, double* __restrict__ part)
 {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  __shared__ dec_coder_smem cs;
+  __shared__ uint32_t flat_tab[f3::FLAT_WORDS];
   __shared__ double red[7 * T_WARPS];
 
   const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
   const unsigned W = tg.W, W2 = 2u * W, pstride = W2 + 1u;
   const uint32_t smem_s = ptx::smem_u32(smem_raw);
   const uint32_t rows_s = smem_s;
-  const uint32_t land_s = rows_s + P_WARPS * ROWS_BYTES;
-  const uint32_t pad_s = land_s + P_WARPS * land_bytes(W);
-  const uint32_t meta_s = pad_s + P_WARPS * pad_bytes(W);
-  const uint32_t bars_s = meta_s + P_WARPS * 128u;  // [p]: slots landed, [P + p]: rows full, [2P + p]: rows empty
+  const uint32_t pad_s = rows_s + P_WARPS * ROWS_BYTES;
+  const uint32_t meta_s = pad_s + P_WARPS * PAD_BUFS * pad_bytes(W);
+  const uint32_t bars_s = meta_s + P_WARPS * 128u;  // [p]: unused, [P + p]: rows full, [2P + p]: rows empty
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (bars_s - smem_s));
 
   if (tid == 0) {
@@ -109,7 +197,13 @@ dec3_f32_ws_kernel(const float* __restrict__ orig, const uint64_t* __restrict__ 
     }
     ptx::fence_barrier_init();
   }
-  const f3::tables tb = build_coder_tables(cs);  // includes the __syncthreads that publishes the barriers
+  for (unsigned i = tid; i < f3::FLAT_WORDS; i += THREADS) flat_tab[i] = ws_entry(i);
+  __syncthreads();  // publishes the table and the barriers
+  f3::tables tb;
+  tb.enc = tb.dec = nullptr; tb.enc_s = tb.dec_s = 0u;
+  tb.flat = flat_tab;
+  tb.flat_s = ptx::smem_u32(flat_tab);
+  asm volatile("mov.u32 %0, %0;" : "+r"(tb.flat_s));  // opaque: keeps the table address in a register (see build_coder_tables)
 
   const unsigned wpr = (tg.nbx + 31u) >> 5;            // warp-tiles per block row
   const unsigned nwt = wpr * tg.nby * tg.nbz;          // warp-tiles in the field
@@ -119,66 +213,81 @@ dec3_f32_ws_kernel(const float* __restrict__ orig, const uint64_t* __restrict__ 
     // ------------------------------------------------------------------ parser warps
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ZFB_WS_REGS_P));
     const unsigned p = warp - T_WARPS;
-    const uint32_t my_land = land_s + p * land_bytes(W), my_pad = pad_s + p * pad_bytes(W);
-    const uint32_t b_slot = bars_s + 8u * p, b_full = bars_s + 8u * (P_WARPS + p), b_empty = bars_s + 8u * (2 * P_WARPS + p);
-    f3::smem_rows_t<0> ps;
-    ps.base = rows_s + p * ROWS_BYTES + 16u * lane;
-    ps.stride = 512u;
-    f3::smem_words r;
-    r.base = my_pad + 4u * lane * pstride;
-
-    auto issue_slots = [&](unsigned w) {  // lane 0
+    const uint32_t pad0 = pad_s + p * PAD_BUFS * pad_bytes(W);
+    const uint32_t b_full = bars_s + 8u * (P_WARPS + p), b_empty = bars_s + 8u * (2 * P_WARPS + p);
+    const uint32_t planes_s = rows_s + p * ROWS_BYTES + 8u * lane;  // plane k of this lane: 8 bytes at + 256 k
+    // The warp's slot span goes straight from global memory into the padded area with 4-byte asynchronous copies
+    // (LDGSTS): slot i at 32-bit word i * (2W + 1) -- the odd stride keeps the lanes' fetches of "their word j" on 32
+    // different banks.  Issued as soon as the previous tile is parsed; the copy is in flight while the transform warp
+    // takes that tile's rows (a landing buffer for a bulk copy would cost 2 KiB per warp and two parser warps per SM).
+    auto issue_slots = [&](unsigned w, uint32_t my_pad) {
       const wtile t = wtile_of(tg, wpr, w);
-      const uint32_t bytes = t.nvalid * W * 8u;
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b_slot), "r"(bytes) : "memory");
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(my_land),
-                   "l"(stream + t.blk0 * W), "r"(bytes), "r"(b_slot)
-                   : "memory");
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(stream + t.blk0 * W);
+      const unsigned nw = t.nvalid * W2;
+      if (W2 == 16u) {
+#pragma unroll
+        for (int mm = 0; mm < 16; mm++) {
+          const unsigned i = lane + 32u * mm;
+          if (i < nw)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(my_pad + 4u * ((i >> 4) * 17u + (i & 15u))), "l"(src + i) : "memory");
+        }
+      } else {
+        for (unsigned i = lane; i < nw; i += 32u)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(my_pad + 4u * ((i / W2) * pstride + i % W2)), "l"(src + i) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
     };
 
     unsigned w = blockIdx.x * P_WARPS + p;
-    if (lane == 0 && w < nwt) issue_slots(w);
+    if (w < nwt) issue_slots(w, pad0);
+#ifdef ZFB_WS_PROF
+    long long c_slots = 0, c_empty = 0, c_parse = 0, c_t0 = clock64();
+#endif
     for (unsigned it = 0; w < nwt; w += stride, it++) {
       const unsigned rem = tg.nbx - (w % wpr) * 32u;
       const unsigned nvalid = rem < 32u ? rem : 32u;
-      mbar_wait_s(b_slot, it & 1u);
-      // re-lay the 32 slots into the padded area: slot i at 32-bit word i * (2W + 1) (odd stride: conflict free)
-      if (W2 == 16u) {
-        uint32_t v[16];
-#pragma unroll
-        for (int m = 0; m < 16; m++) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v[m]) : "r"(my_land + 4u * (lane + 32u * m)));
-#pragma unroll
-        for (int m = 0; m < 16; m++) {
-          const unsigned i = lane + 32u * m;
-          asm volatile("st.shared.u32 [%0], %1;" ::"r"(my_pad + 4u * ((i >> 4) * 17u + (i & 15u))), "r"(v[m]) : "memory");
-        }
-      } else {
-        for (unsigned i = lane; i < 32u * W2; i += 32u) {
-          uint32_t v;
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(my_land + 4u * i));
-          asm volatile("st.shared.u32 [%0], %1;" ::"r"(my_pad + 4u * ((i / W2) * pstride + i % W2)), "r"(v) : "memory");
-        }
-      }
+#ifdef ZFB_WS_PROF
+      long long c0 = clock64();
+#endif
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncwarp();
-      if (lane == 0 && w + stride < nwt) {
-        ptx::fence_proxy_async();  // the landing buffer has been read (generic proxy) before the bulk copy refills it
-        issue_slots(w + stride);
-      }
+#ifdef ZFB_WS_PROF
+      long long c1 = clock64();
+      c_slots += c1 - c0;
+#endif
+      const uint32_t my_pad = pad0 + (PAD_BUFS == 2 ? (it & 1u) * pad_bytes(W) : 0u);
+      if (PAD_BUFS == 2 && w + stride < nwt) issue_slots(w + stride, pad0 + ((it & 1u) ^ 1u) * pad_bytes(W));
+      const uint32_t slot_s = my_pad + 4u * lane * pstride;
       mbar_wait_s(b_empty, (it & 1u) ^ 1u);  // the transform warp has taken the previous tile's rows
+#ifdef ZFB_WS_PROF
+      long long c2 = clock64();
+      c_empty += c2 - c1;
+#endif
       uint32_t meta = 0u;
       if (lane < nvalid) {
-        const uint32_t head = f3::fetch32(r, 0);
+        const uint32_t head = lds32(slot_s);
         if (head & 1u) {
           const int emax = (int)((head >> 1) & 0xffu) - 127;
           const stream_params sp = fixed_rate_params(maxbits);
           const int prec = block_precision<3>(emax, sp);
-          const int kend = f3::parse_planes<32>(ps, sp.maxbits, 9u, prec < 32 ? 32 - prec : 0, r, tb);
+          const int kend = parse_flat_ws(slot_s, planes_s, tb.flat_s, sp.maxbits, prec < 32 ? 32 - prec : 0);
           meta = 1u | (((head >> 1) & 0xffu) << 1) | (kend < 15 ? 512u : 0u);
         }
       }
       asm volatile("st.shared.u32 [%0], %1;" ::"r"(meta_s + 128u * p + 4u * lane), "r"(meta) : "memory");
       mbar_arrive(b_full);
+#ifdef ZFB_WS_PROF
+      c_parse += clock64() - c2;
+#endif
+      if (PAD_BUFS == 1) {
+        __syncwarp();  // every lane is done with its slot
+        if (w + stride < nwt) issue_slots(w + stride, pad0);
+      }
     }
+#ifdef ZFB_WS_PROF
+    if (blockIdx.x == 0 && lane == 0)
+      printf("P%u total %lld slots %lld empty %lld parse %lld\n", p, clock64() - c_t0, c_slots, c_empty, c_parse);
+#endif
     return;
   }
 
@@ -187,67 +296,104 @@ dec3_f32_ws_kernel(const float* __restrict__ orig, const uint64_t* __restrict__ 
   maccf m;
   m.init();
   const size_t rs = tg.nx, ps2 = (size_t)tg.ny * tg.nx;
-  for (unsigned it = 0;; it++) {
-    if (blockIdx.x * P_WARPS + warp + it * stride >= nwt) break;
+  // The warp serves its parser warps (p = warp + 4 q) in whatever order their rows become ready; itq[] are the
+  // per-parser tile counters (registers: every access is unrolled into selects).
+  constexpr unsigned NQ = P_WARPS / T_WARPS;
+  unsigned itq[NQ];
+#pragma unroll
+  for (unsigned j = 0; j < NQ; j++) itq[j] = 0u;
+  unsigned done = 0u;  // bit q: parser q has no tiles left
+#ifdef ZFB_WS_PROF
+  long long c_busy = 0, c_t0 = clock64(), c_rows = 0;
+#endif
 #pragma unroll 1
-    for (unsigned q = 0; q < (unsigned)(P_WARPS / T_WARPS); q++) {
-      const unsigned p = warp + T_WARPS * q;
-      const unsigned w = blockIdx.x * P_WARPS + p + it * stride;
-      if (w >= nwt) break;
+  for (unsigned q = 0, idle = 0; done != (1u << NQ) - 1u; q = q + 1u == NQ ? 0u : q + 1u) {
+    if (done >> q & 1u) continue;
+    unsigned it = itq[0];
+#pragma unroll
+    for (unsigned j = 1; j < NQ; j++) it = q == j ? itq[j] : it;
+    const unsigned p = warp + T_WARPS * q;
+    const unsigned w = blockIdx.x * P_WARPS + p + it * stride;
+    if (w >= nwt) { done |= 1u << q; continue; }
+    const uint32_t b_full = bars_s + 8u * (P_WARPS + p), b_empty = bars_s + 8u * (2 * P_WARPS + p);
+    {
+      uint32_t ready;
+      asm volatile(
+          "{\n.reg .pred p;\n"
+          "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+          "selp.u32 %0, 1, 0, p;\n}\n"
+          : "=r"(ready)
+          : "r"(b_full), "r"(it & 1u)
+          : "memory");
+      if (!ready) {
+        if (++idle >= NQ) { __nanosleep(100); idle = 0; }
+        continue;
+      }
+      idle = 0;
+    }
+#pragma unroll
+    for (unsigned j = 0; j < NQ; j++) itq[j] += q == j ? 1u : 0u;
+#ifdef ZFB_WS_PROF
+    long long cb0 = clock64();
+#endif
+    {
       const wtile t = wtile_of(tg, wpr, w);
       const bool active = lane < t.nvalid;
       const size_t off = ((size_t)t.z0 * tg.ny + t.y0) * tg.nx + t.x0 + 4u * lane;
       float4 o[16];
+      const float* og = orig + off;
+      auto load_orig = [&](int r16) {
+        const float* a = og + (size_t)(r16 >> 2) * ps2 + (size_t)(r16 & 3) * rs;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(o[r16].x), "=f"(o[r16].y), "=f"(o[r16].z), "=f"(o[r16].w)
+                     : "l"(a));
+      };
       if (METRICS && active) {
-        const float* og = orig + off;
 #pragma unroll
-        for (int r16 = 0; r16 < 16; r16++) {
-          const float* a = og + (size_t)(r16 >> 2) * ps2 + (size_t)(r16 & 3) * rs;
-          asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
-                       : "=f"(o[r16].x), "=f"(o[r16].y), "=f"(o[r16].z), "=f"(o[r16].w)
-                       : "l"(a));
-        }
+        for (int r16 = 0; r16 < ZFB_WS_OEARLY; r16++) load_orig(r16);
       }
-      const uint32_t b_full = bars_s + 8u * (P_WARPS + p), b_empty = bars_s + 8u * (2 * P_WARPS + p);
-      mbar_wait_s(b_full, it & 1u);
       f3::planes64 P;
-      f3::smem_rows_t<0> ps;
-      ps.base = rows_s + p * ROWS_BYTES + 16u * lane;
-      ps.stride = 512u;
+      {
+        const uint32_t planes_s = rows_s + p * ROWS_BYTES + 8u * lane;
 #pragma unroll
-      for (int k = 0; k < 16; k++) {
-        const f3::u32x4 v = ps.ld(k);
-        P.a[2 * k] = v.x; P.b[2 * k] = v.y; P.a[2 * k + 1] = v.z; P.b[2 * k + 1] = v.w;
+        for (int k = 0; k < 32; k++)
+          asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(P.a[k]), "=r"(P.b[k]) : "r"(planes_s + 256u * k));
       }
       uint32_t meta;
       asm volatile("ld.shared.u32 %0, [%1];" : "=r"(meta) : "r"(meta_s + 128u * p + 4u * lane));
       mbar_arrive(b_empty);  // release: the loads above are ordered before the parser's next writes
+#ifdef ZFB_WS_PROF
+      c_rows += clock64() - cb0;
+#endif
       if (active) {
         float f[64];
         f3::decode_finish(f, P, (int)((meta >> 1) & 0xffu) - 127, (meta & 1u) != 0u, (meta & 512u) != 0u);
         if (METRICS) {
-          frow fr;
-          fr.init();
 #pragma unroll
-          for (int r16 = 0; r16 < 16; r16++) {
+          for (int r16 = ZFB_WS_OEARLY; r16 < 16; r16++) load_orig(r16);
+        }
+        frow fr;
+        fr.init();
+        float* dst = out + off;
+#pragma unroll
+        for (int r16 = 0; r16 < 16; r16++) {
+          if (METRICS) {
             fr.add4(o[r16], f[4 * r16], f[4 * r16 + 1], f[4 * r16 + 2], f[4 * r16 + 3]);
             if ((r16 & 3) == 3) fr.flush(m);
           }
-        }
-        float* dst = out + off;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-          float* rowp = dst + (size_t)k * ps2;
-#pragma unroll
-          for (int j = 0; j < 4; j++) {
-            float4 v;
-            v.x = f[16 * k + 4 * j]; v.y = f[16 * k + 4 * j + 1]; v.z = f[16 * k + 4 * j + 2]; v.w = f[16 * k + 4 * j + 3];
-            __stcs(reinterpret_cast<float4*>(rowp + (size_t)j * rs), v);
-          }
+          float4 v;
+          v.x = f[4 * r16]; v.y = f[4 * r16 + 1]; v.z = f[4 * r16 + 2]; v.w = f[4 * r16 + 3];
+          __stcs(reinterpret_cast<float4*>(dst + (size_t)(r16 >> 2) * ps2 + (size_t)(r16 & 3) * rs), v);
         }
       }
+#ifdef ZFB_WS_PROF
+      c_busy += clock64() - cb0;
+#endif
     }
   }
+#ifdef ZFB_WS_PROF
+  if (blockIdx.x == 0 && lane == 0) printf("T%u total %lld busy %lld rows %lld\n", warp, clock64() - c_t0, c_busy, c_rows);
+#endif
   if (METRICS) {
     // reduction over the four transform warps only (the parser warps are gone): named barrier 1, 128 threads
     macc mm;
