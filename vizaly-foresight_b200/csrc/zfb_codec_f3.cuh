@@ -604,6 +604,56 @@ template <class Sink> struct writer32 {
   }
 };
 
+#if defined(__CUDACC__)
+// The bit writer of the tile kernels (slot in shared memory), arranged for the ALU pipe that bounds the encode kernel:
+// the pending bits are one 32-bit word and a put is ONE wide multiply-add on the FMA pipe -- v * 2^(pos & 31) + pending
+// as a 64-bit product: its low word is the word being filled, its high word what spills into the next -- instead of two
+// shifts, an OR and a carry extraction on the ALU pipe.  The word index comes from the bit position (carried between
+// puts), and the only ALU work left is the power of two, the new word index and the "did we cross a word" compare that
+// predicates the store.  Words at or behind the end of the slot are dropped (fixed-rate truncation).
+template <> struct writer32<smem_sink32> {
+  smem_sink32& sink;
+  uint32_t acc;   // pending bits (below bit pos & 31)
+  unsigned pos;   // bits emitted so far
+  unsigned wi;    // pos >> 5
+  __device__ __forceinline__ explicit writer32(smem_sink32& s) : sink(s), acc(0u), pos(0u), wi(0u) {}
+  __device__ __forceinline__ unsigned bits() const { return pos; }
+  __device__ __forceinline__ void put(uint32_t v, unsigned len)  // len in [0, 32]; bits of v above len are zero
+  {
+    const uint32_t p = __funnelshift_l(0u, 1u, pos);  // 1 << (pos & 31)
+    const uint64_t a = (uint64_t)v * p + acc;
+    pos += len;
+    const unsigned wn = pos >> 5;
+    // crossed a word boundary: the finished word goes to the slot (unless it lies behind the slot's end) and the spill
+    // becomes the pending word; all predicated, no branch (the lanes of a warp cross at different puts)
+    asm volatile(
+        "{\n.reg .pred q, r;\n"
+        "setp.ne.u32 q, %1, %2;\n"
+        "setp.lt.and.u32 r, %2, %3, q;\n"
+        "@r st.shared.u32 [%4], %5;\n"
+        "selp.u32 %0, %6, %5, q;\n}\n"
+        : "=r"(acc)
+        : "r"(wn), "r"(wi), "r"(sink.nwords), "r"(sink.base + 4u * wi), "r"((uint32_t)a), "r"((uint32_t)(a >> 32))
+        : "memory");
+    wi = wn;
+  }
+  __device__ __forceinline__ void put64(uint32_t xl, uint32_t xh) { put(xl, 32u); put(xh, 32u); }
+  __device__ __forceinline__ void putv(uint32_t xl, uint32_t xh, unsigned len)  // len in [0, 64]
+  {
+    const unsigned l0 = len < 32u ? len : 32u;
+    put(xl, l0);
+    put(xh, len - l0);
+  }
+  __device__ __forceinline__ void flush()
+  {
+    if ((pos & 31u) && wi < sink.nwords) asm volatile("st.shared.u32 [%0], %1;" ::"r"(sink.base + 4u * wi), "r"(acc) : "memory");
+    const unsigned w = (pos + 31u) >> 5;
+    sink.widx = w < sink.nwords ? w : sink.nwords;  // for sink.finish(): the rest of the slot is zero padding
+    acc = 0u;
+  }
+};
+#endif
+
 ZFB_HD int msb64(uint32_t lo, uint32_t hi)  // (hi:lo) != 0
 {
   return hi ? 32 + msb32(hi) : msb32(lo);
