@@ -161,6 +161,23 @@ ZFB_HD uint32_t bitsel(uint32_t a, uint32_t b, uint32_t m)  // (a & ~m) | (b & m
   return (a & ~m) | (b & m);
 #endif
 }
+// Other three-input functions of (a, b, m) as one LOP3 (device) -- used to fold the negabinary XOR into the last
+// transpose stage.  LUT = f(0xF0, 0xCC, 0xAA).
+template <int LUT> ZFB_HD uint32_t lop3(uint32_t a, uint32_t b, uint32_t m)
+{
+#if defined(__CUDA_ARCH__)
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(d) : "r"(a), "r"(b), "r"(m), "n"(LUT));
+  return d;
+#else
+  uint32_t d = 0;
+  for (int i = 0; i < 32; i++) {
+    const unsigned idx = (((a >> i) & 1u) << 2) | (((b >> i) & 1u) << 1) | ((m >> i) & 1u);
+    d |= (uint32_t)((LUT >> idx) & 1) << i;
+  }
+  return d;
+#endif
+}
 ZFB_HD uint32_t bperm(uint32_t a, uint32_t b, uint32_t sel)
 {
 #if defined(__CUDA_ARCH__)
@@ -414,8 +431,12 @@ struct planes64 {
       w[k] = lo; w[k + 16] = hi;
     }
   }
-  // stages 8, 4, 2, 1 on words [base, base+16)
-  ZFB_HD static void stages_low(uint32_t (&w)[32], int base)
+  // stages 8, 4, 2, 1 on words [base, base+16).
+  // NEG folds the negabinary XOR of float coefficients (mask 0xaaaaaaaa = the odd bits) into stage 1, whose mask it
+  // shares: flipping the odd bits of every coefficient is complementing the odd PLANES, and stage 1 is where words of
+  // odd and even index meet.  NEG = 1 (encoder: coefficients -> planes) complements the odd words it produces;
+  // NEG = 2 (decoder: planes -> coefficients) complements the odd words it consumes.  One LOP3 either way.
+  template <int NEG = 0> ZFB_HD static void stages_low(uint32_t (&w)[32], int base)
   {
     ZFB_UNROLL for (int k = 0; k < 8; k++) {
       const uint32_t p = w[base + k], q = w[base + k + 8];
@@ -435,24 +456,32 @@ struct planes64 {
       }
     ZFB_UNROLL for (int g = 0; g < 16; g += 2) {
       const uint32_t p = w[base + g], q = w[base + g + 1];
-      w[base + g] = bitsel(p, q << 1, 0xaaaaaaaau);
-      w[base + g + 1] = bitsel(q, p >> 1, 0x55555555u);
+      if (NEG == 0) {
+        w[base + g] = bitsel(p, q << 1, 0xaaaaaaaau);
+        w[base + g + 1] = bitsel(q, p >> 1, 0x55555555u);
+      } else if (NEG == 1) {
+        w[base + g] = bitsel(p, q << 1, 0xaaaaaaaau);
+        w[base + g + 1] = lop3<0x27>(q, p >> 1, 0x55555555u);  // ~((q & ~m) | ((p >> 1) & m))
+      } else {
+        w[base + g] = lop3<0x72>(p, q << 1, 0xaaaaaaaau);      // (p & ~m) | (~(q << 1) & m)
+        w[base + g + 1] = lop3<0x8D>(q, p >> 1, 0x55555555u);  // (~q & ~m) | ((p >> 1) & m)
+      }
     }
   }
   ZFB_HD void split16() { stage16(a); stage16(b); }
-  ZFB_HD void finish(int base) { stages_low(a, base); stages_low(b, base); }
+  template <int NEG = 0> ZFB_HD void finish(int base) { stages_low<NEG>(a, base); stages_low<NEG>(b, base); }
 };
 
 // Finish (or, equally, un-finish: the stages are involutions) the transpose of the 16 planes parked in rows
 // r0 .. r0+7: both 16-word groups (coefficients 0..31 and 32..63) go through stages 8, 4, 2, 1.
-template <class PR> ZFB_HD void finish_rows(const PR& ps, int r0)
+template <int NEG = 0, class PR> ZFB_HD void finish_rows(const PR& ps, int r0)
 {
   planes64 Q;
   ZFB_UNROLL for (int r = 0; r < 8; r++) {
     const u32x4 v = ps.ld(r0 + r);
     Q.a[2 * r] = v.x; Q.b[2 * r] = v.y; Q.a[2 * r + 1] = v.z; Q.b[2 * r + 1] = v.w;
   }
-  Q.finish(0);
+  Q.template finish<NEG>(0);
   ZFB_UNROLL for (int r = 0; r < 8; r++) {
     u32x4 v;
     v.x = Q.a[2 * r]; v.y = Q.b[2 * r]; v.z = Q.a[2 * r + 1]; v.w = Q.b[2 * r + 1];
@@ -689,7 +718,7 @@ ZFB_HD unsigned encode_planes(const PR& ps, unsigned maxbits, uint32_t header, u
   // next plane into (xl, xh); false when the block is finished (budget covered or no planes left)
   auto next = [&]() -> bool {
     if (k < kmin || bw.bits() >= maxbits) return false;
-    if (k < NP - 16 && (k & 15) == 15) finish_rows(ps, (k - 15) >> 1);  // next 16 planes: finish their transpose now
+    if (k < NP - 16 && (k & 15) == 15) finish_rows<NP == 32 ? 1 : 0>(ps, (k - 15) >> 1);  // next 16 planes: finish their transpose now
     if (k & 1) row = ps.ld(k >> 1);  // planes come in descending order: the odd plane of a row is met first
     xl = (k & 1) ? row.z : row.x;
     xh = (k & 1) ? row.w : row.y;
@@ -799,12 +828,13 @@ ZFB_HD unsigned encode_block(const float (&f)[64], const stream_params& sp, Sink
     if (se > 127) { ZFB_UNROLL for (int i = 0; i < 64; i++) ib[i] = T::int_min(); }  // see zfb_codec.cuh
     fwd_xform<int32_t, 3>(ib);
     ZFB_UNROLL for (int i = 0; i < 32; i++) {
-      P.a[i] = ((uint32_t)ib[order<3>::at(i)] + T::NBMASK) ^ T::NBMASK;
-      P.b[i] = ((uint32_t)ib[order<3>::at(i + 32)] + T::NBMASK) ^ T::NBMASK;
+      // negabinary (i + M) ^ M: the XOR is folded into the last transpose stage (stages_low<1>)
+      P.a[i] = (uint32_t)ib[order<3>::at(i)] + T::NBMASK;
+      P.b[i] = (uint32_t)ib[order<3>::at(i + 32)] + T::NBMASK;
     }
   }
   P.split16();
-  P.finish(16);
+  P.finish<1>(16);
   // rows 8..15: planes 16..31, finished.  rows 0..7: the lower halves, still un-transposed; they are
   // finished only if the budget reaches plane 15.
   ZFB_UNROLL for (int r = 0; r < 16; r++) {
@@ -1204,13 +1234,16 @@ ZFB_HD void decode_finish(float (&f)[64], planes64& P, int emax, bool nonzero, b
     ZFB_UNROLL for (int i = 0; i < 64; i++) f[i] = 0.f;
     return;
   }
-  P.finish(16);
-  if (low_used) P.finish(0);
+  // negabinary (u ^ M) - M: the XOR is folded into the last transpose stage (stages_low<2>); a lower half that was
+  // never decoded (all-zero planes) comes out of that stage as the constant M
+  P.finish<2>(16);
+  if (low_used) P.finish<2>(0);
+  else { ZFB_UNROLL for (int i = 0; i < 16; i++) { P.a[i] = T::NBMASK; P.b[i] = T::NBMASK; } }
   P.split16();
   int32_t ib[64];
   ZFB_UNROLL for (int i = 0; i < 32; i++) {
-    ib[order<3>::at(i)] = (int32_t)((P.a[i] ^ T::NBMASK) - T::NBMASK);
-    ib[order<3>::at(i + 32)] = (int32_t)((P.b[i] ^ T::NBMASK) - T::NBMASK);
+    ib[order<3>::at(i)] = (int32_t)(P.a[i] - T::NBMASK);
+    ib[order<3>::at(i + 32)] = (int32_t)(P.b[i] - T::NBMASK);
   }
   inv_xform<int32_t, 3>(ib);
   const float s = T::pow2(emax - 30);
