@@ -713,15 +713,11 @@ ZFB_HD unsigned encode_planes(const PR& ps, unsigned maxbits, uint32_t header, u
   unsigned n = 0;
   int k = NP - 1;
   uint32_t xl = 0u, xh = 0u;
-  u32x4 row;  // the row (two planes) k belongs to: one conflict-free 128-bit load per two planes
-  row.x = row.y = row.z = row.w = 0u;
   // next plane into (xl, xh); false when the block is finished (budget covered or no planes left)
   auto next = [&]() -> bool {
     if (k < kmin || bw.bits() >= maxbits) return false;
-    if (k < NP - 16 && (k & 15) == 15) finish_rows<NP == 32 ? 1 : 0>(ps, (k - 15) >> 1);  // next 16 planes: finish their transpose now
-    if (k & 1) row = ps.ld(k >> 1);  // planes come in descending order: the odd plane of a row is met first
-    xl = (k & 1) ? row.z : row.x;
-    xh = (k & 1) ? row.w : row.y;
+    if (NP == 32 ? k == 15 : (k < NP - 16 && (k & 15) == 15)) finish_rows<NP == 32 ? 1 : 0>(ps, (k - 15) >> 1);  // next 16 planes: finish their transpose now
+    ps.ld64(k, xl, xh);
     return true;
   };
   bool more = next();

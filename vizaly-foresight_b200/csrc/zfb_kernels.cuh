@@ -575,7 +575,8 @@ enc3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t* __restr
   __shared__ enc_coder_smem cs;
 
   const unsigned tid = threadIdx.x;
-  const unsigned box = tid >> 6, lb = tid & 63;
+  // the box index through a shuffle: warp-uniform to the compiler, so what derives from it stays in uniform registers
+  const unsigned box = __shfl_sync(0xffffffffu, tid >> 6, 0), lb = tid & 63;
 
   // box descriptors of the current / next tile, computed once by thread 0 (integer divisions) and read by all
   __shared__ box_info sb[2][BOXES_PER_TILE];

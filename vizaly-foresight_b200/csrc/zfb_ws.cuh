@@ -180,7 +180,10 @@ dec3_f32_ws_kernel(const float* __restrict__ orig, const uint64_t* __restrict__ 
   __shared__ uint32_t flat_tab[f3::FLAT_WORDS];
   __shared__ double red[7 * T_WARPS];
 
-  const unsigned tid = threadIdx.x, warp = tid >> 5, lane = tid & 31u;
+  const unsigned tid = threadIdx.x, lane = tid & 31u;
+  // the warp index through a shuffle: the compiler then knows it is warp-uniform and keeps everything derived from it
+  // (roles, tile coordinates, buffer addresses) in uniform registers, off the ALU pipe
+  const unsigned warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const unsigned W = tg.W, W2 = 2u * W, pstride = W2 + 1u;
   const uint32_t smem_s = ptx::smem_u32(smem_raw);
   const uint32_t rows_s = smem_s;
