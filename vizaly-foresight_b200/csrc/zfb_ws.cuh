@@ -103,7 +103,8 @@ __device__ __forceinline__ void mbar_wait_s(uint32_t bar_s, uint32_t parity)
 __device__ __forceinline__ uint32_t ws_entry(unsigned i)
 {
   const uint32_t e = f3::flat_entry(i);
-  return (e & ~f3::FLAT_B) | ((e & f3::FLAT_B) ? 0x100u : 0u);
+  // entry 1 of either half (a step of b = 0 bits: nothing left to parse in this plane) also carries END
+  return (e & ~f3::FLAT_B) | ((e & f3::FLAT_B) ? 0x100u : 0u) | ((i & 511u) == 1u ? 0x20u : 0u);
 }
 __device__ __forceinline__ uint32_t lds32(uint32_t a)
 {
@@ -147,13 +148,13 @@ __device__ __forceinline__ int parse_flat_ws(uint32_t slot_s, uint32_t planes_s,
     pos = p2 + (e & 31u);
     // zfp's end rules: in a zero run at coefficient 63 the one is implicit; a zero run cut off by the budget still
     // deposits its one
-    if (st != 0u && (n == 63u || pos == maxbits)) { pat |= 1u << np; n++; st = 0u; }
+    // The plane is done after a zero group test (END; the b = 0 entry carries it too) or with such a deposit: at
+    // coefficient 63 nothing is left, at the end of the budget the loop ends anyway.
+    bool done = (e & 0x20u) != 0u;
+    if (st != 0u && (n == 63u || pos == maxbits)) { pat |= 1u << np; n++; st = 0u; done = true; }
     const uint64_t dep = (uint64_t)pat << n0;
     xl |= (uint32_t)dep;
     xh |= (uint32_t)(dep >> 32);
-    bool done = b == 0u;
-    if (e & 0x20u) done = true;
-    if (n >= 64u) done = true;
     if (done) {
       asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(A), "r"(xl), "r"(xh) : "memory");
       A -= 256u;
