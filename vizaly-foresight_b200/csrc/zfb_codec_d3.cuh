@@ -53,14 +53,15 @@ ZFB_HD unsigned encode_block(const double (&f)[64], const stream_params& sp, Sin
     if (se > 1023) { ZFB_UNROLL for (int i = 0; i < 64; i++) ib[i] = T::int_min(); }  // see zfb_codec.cuh
     fwd_xform<int64_t, 3>(ib);
     ZFB_UNROLL for (int i = 0; i < 32; i++) {
-      const uint64_t ua = ((uint64_t)ib[order<3>::at(i)] + T::NBMASK) ^ T::NBMASK;
-      const uint64_t ub = ((uint64_t)ib[order<3>::at(i + 32)] + T::NBMASK) ^ T::NBMASK;
+      // negabinary (i + M) ^ M: the XOR is folded into the last transpose stage (planes64::stages_low<1>)
+      const uint64_t ua = (uint64_t)ib[order<3>::at(i)] + T::NBMASK;
+      const uint64_t ub = (uint64_t)ib[order<3>::at(i + 32)] + T::NBMASK;
       PH.a[i] = (uint32_t)(ua >> 32); PL.a[i] = (uint32_t)ua;
       PH.b[i] = (uint32_t)(ub >> 32); PL.b[i] = (uint32_t)ub;
     }
   }
   PH.split16();
-  PH.finish(16);  // planes 63..48 ready; the other three groups of 16 planes are finished on demand
+  PH.finish<1>(16);  // planes 63..48 ready; the other three groups of 16 planes are finished on demand
   PL.split16();
   ZFB_UNROLL for (int r = 0; r < 16; r++) {
     u32x4 v;
@@ -118,17 +119,20 @@ ZFB_HD void decode_finish(double (&f)[64], planes64& PH, planes64& PL, int emax,
     return;
   }
   // a group of 16 planes that was never reached is all zero: its transpose stages are skipped
-  PH.finish(16);
-  if (kend < 47) PH.finish(0);
-  if (kend < 31) PL.finish(16);
-  if (kend < 15) PL.finish(0);
+  // negabinary (u ^ M) - M: the XOR is folded into the last transpose stage (stages_low<2>); a group that was never
+  // reached comes out of that stage as the constant 0xaaaaaaaa
+  auto fill = [](planes64& P, int base) { ZFB_UNROLL for (int i = 0; i < 16; i++) { P.a[base + i] = 0xaaaaaaaau; P.b[base + i] = 0xaaaaaaaau; } };
+  PH.finish<2>(16);
+  if (kend < 47) PH.finish<2>(0); else fill(PH, 0);
+  if (kend < 31) PL.finish<2>(16); else fill(PL, 16);
+  if (kend < 15) PL.finish<2>(0); else fill(PL, 0);
   PH.split16();
   PL.split16();
   int64_t ib[64];
   ZFB_UNROLL for (int i = 0; i < 32; i++) {
     const uint64_t ua = ((uint64_t)PH.a[i] << 32) | PL.a[i], ub = ((uint64_t)PH.b[i] << 32) | PL.b[i];
-    ib[order<3>::at(i)] = (int64_t)((ua ^ T::NBMASK) - T::NBMASK);
-    ib[order<3>::at(i + 32)] = (int64_t)((ub ^ T::NBMASK) - T::NBMASK);
+    ib[order<3>::at(i)] = (int64_t)(ua - T::NBMASK);
+    ib[order<3>::at(i + 32)] = (int64_t)(ub - T::NBMASK);
   }
   inv_xform<int64_t, 3>(ib);
   const double s = T::pow2(emax - 62);

@@ -716,7 +716,7 @@ ZFB_HD unsigned encode_planes(const PR& ps, unsigned maxbits, uint32_t header, u
   // next plane into (xl, xh); false when the block is finished (budget covered or no planes left)
   auto next = [&]() -> bool {
     if (k < kmin || bw.bits() >= maxbits) return false;
-    if (NP == 32 ? k == 15 : (k < NP - 16 && (k & 15) == 15)) finish_rows<NP == 32 ? 1 : 0>(ps, (k - 15) >> 1);  // next 16 planes: finish their transpose now
+    if (NP == 32 ? k == 15 : (k < NP - 16 && (k & 15) == 15)) finish_rows<1>(ps, (k - 15) >> 1);  // next 16 planes: finish their transpose now
     ps.ld64(k, xl, xh);
     return true;
   };
