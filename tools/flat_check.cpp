@@ -42,7 +42,8 @@ int main(int argc, char** argv)
   std::mt19937_64 rng(12345);
   long bad = 0, cases = 0;
   // 1. random slots with various densities of ones, budgets and kmin
-  for (int t = 0; t < 400000 && !bad; t++) {
+  const int ncases = argc > 1 ? atoi(argv[1]) : 400000;
+  for (int t = 0; t < ncases && !bad; t++) {
     const unsigned maxbits = 16 + rng() % 2100;
     uint32_t slot[80];
     const int dens = rng() % 6;  // probability of a one: 1/2, 1/4, ... or mixed
@@ -92,6 +93,7 @@ int main(int argc, char** argv)
     }
     printf("rate %2u: warps %ld  iterations per lane %.1f  per warp (max) %.1f  slow steps per lane %.2f  (lane max per warp %.2f) mismatches %ld\n",
            rate, warps, (double)it_sum / (32.0 * warps), (double)it_max_sum / warps, (double)slow_sum / (32.0 * warps), (double)slow_any / warps, old_bad);
+    bad += old_bad;
   }
-  return 0;
+  return bad ? 1 : 0;
 }
