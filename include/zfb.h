@@ -263,6 +263,15 @@ double zfb_value_minmax(const zfb_partials* p);         /* minmaxMetric.hpp:89-9
 /* extra metrics from the same partials: PSNR over the value range (max - min) and the normalised RMSE */
 double zfb_value_psnr_range(const zfb_partials* p);
 double zfb_value_nrmse(const zfb_partials* p);
+/* Shell-binned power spectrum of a resident 3D float field, the quantity Foresight's NYX analysis compares between the
+ * original and every decompressed field: PAT plots the ratio of columns 2 and 3 (k, P(k)) of gimlet's *_ps3d.txt files
+ * (Analysis/pat/nyx/cinema.py:84-130, Analysis/pat/nyx/README.md:19-25; gimlet itself is not part of the reference, and
+ * the ratio needs no particular normalisation).  d_fhat: the real-to-complex transform of the field, nz x ny x (nx/2+1)
+ * complex float values, x fastest (the cufftExecR2C / numpy rfftn layout).  d_out receives 3 x nbins doubles:
+ * [0] number of modes in shell b = round(|k|), [1] sum of |k| over them, [2] sum of |F|^2; nbins <= 2048, extents < 4096.
+ * The mirror modes the half-spectrum leaves out are counted with weight 2. */
+int zfb_power_spectrum_bin_dev(zfb_ctx* ctx, const void* d_fhat, size_t nx, size_t ny, size_t nz, unsigned nbins,
+                               double* d_out);
 /* Combine `count` ranks' partials the way the reference's Allreduces do (SUM / MAX / MIN). */
 void zfb_partials_combine(zfb_partials* acc, const zfb_partials* in, int count);
 

@@ -337,3 +337,30 @@ def parse_hist_script(text):
         elif line.startswith("maxVal="):
             hi = float(line[7:])
     return y, lo, hi
+
+
+def power_spectrum(field, nbins=None):
+    """CPU statement of zfb_power_spectrum_bin_dev + Codec.power_spectrum (TEST INFRASTRUCTURE): the shell-binned power
+    spectrum PAT's NYX analysis compares between original and decompressed fields (Analysis/pat/nyx/cinema.py:84-130 --
+    columns 2, 3 of gimlet's *_ps3d.txt; gimlet is not in the reference tree, so the normalisation is ours and only the
+    ratio of two spectra is meaningful to PAT).  Full complex transform in float64, shells b = round(|k|), every mode
+    counted once.  Returns (k, pk, count)."""
+    f = np.asarray(field, dtype=np.float64)
+    nz, ny, nx = f.shape
+    if nbins is None:
+        nbins = min(nx, ny, nz) // 2 + 1
+    F = np.fft.fftn(f)
+    p = (F.real ** 2 + F.imag ** 2).ravel()
+    kz = np.fft.fftfreq(nz, 1.0 / nz)[:, None, None]
+    ky = np.fft.fftfreq(ny, 1.0 / ny)[None, :, None]
+    kx = np.fft.fftfreq(nx, 1.0 / nx)[None, None, :]
+    # the device folds kx onto the half-spectrum (0 .. nx/2) and kz, ky of n/2 onto +n/2: |k| is the same
+    kk = np.sqrt(kx * kx + ky * ky + kz * kz).ravel()
+    b = np.floor(kk + 0.5).astype(np.int64)
+    m = b < nbins
+    cnt = np.bincount(b[m], minlength=nbins).astype(np.float64)
+    sk = np.bincount(b[m], weights=kk[m], minlength=nbins)
+    sp = np.bincount(b[m], weights=p[m], minlength=nbins)
+    safe = np.maximum(cnt, 1.0)
+    n = float(nx) * ny * nz
+    return sk / safe, sp / safe / (n * n), cnt

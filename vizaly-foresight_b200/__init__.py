@@ -67,6 +67,15 @@ def declared_symbols():
     return sorted(set(re.findall(r"\b(zfb_[a-z0-9_]+)\s*\(", text)))
 
 
+def write_ps3d(path, k, pk, count):
+    """The spectrum as a text file PAT can plot: one row per shell, space separated, k in column 2 and P(k) in column 3
+    (Analysis/pat/nyx/cinema.py:103-105 reads exactly those two with extract_csv_col(path, ' ', 2 / 3))."""
+    with open(path, "w") as f:
+        for b in range(len(k)):
+            if float(count[b]) > 0:
+                f.write("%d %d %.17g %.17g\n" % (b, int(count[b]), float(k[b]), float(pk[b])))
+
+
 _lib = None
 
 
@@ -98,6 +107,7 @@ def lib():
         "zfb_encode_dev": (i, [vp, i, i, sz, sz, sz, u, vp, vp]),
         "zfb_decode_dev": (i, [vp, i, i, sz, sz, sz, u, vp, vp, vp]),
         "zfb_metrics_dev": (i, [vp, i, vp, vp, sz]),
+        "zfb_power_spectrum_bin_dev": (i, [vp, vp, sz, sz, sz, u, vp]),
         "zfb_comm_unique_id": (i, [vp]),
         "zfb_comm_init": (i, [vp, i, i, vp]),
         "zfb_comm_adopt": (i, [vp, vp, i, i]),
@@ -495,6 +505,26 @@ class Codec:
         self._check(lib().zfb_metrics_dev(self._h, _dtype_code(orig.dtype), orig.data_ptr(), approx.data_ptr(),
                                           orig.numel()), "zfb_metrics_dev")
         return self.partials()
+
+    def power_spectrum(self, field, nbins=None):
+        """Shell-binned power spectrum of a resident 3D float32 field (what PAT's NYX analysis compares, see
+        include/zfb.h): returns (k, pk, count) as float64 tensors; k = mean |k| of shell b = round(|k|), pk = mean
+        |F|^2 / N^2 of the shell.  The transform is torch.fft.rfftn (cuFFT), the binning is zfb_power_spectrum_bin_dev."""
+        import torch
+
+        assert field.dim() == 3 and field.dtype == torch.float32 and field.is_cuda and field.is_contiguous()
+        nz, ny, nx = field.shape
+        if nbins is None:
+            nbins = min(nx, ny, nz) // 2 + 1
+        self.use_torch_stream()
+        fhat = torch.fft.rfftn(field, dim=(0, 1, 2)).contiguous()
+        out = torch.empty(3 * nbins, dtype=torch.float64, device=field.device)
+        self._check(lib().zfb_power_spectrum_bin_dev(self._h, fhat.data_ptr(), nx, ny, nz, nbins, out.data_ptr()),
+                    "zfb_power_spectrum_bin_dev")
+        cnt, sk, sp = out[:nbins], out[nbins:2 * nbins], out[2 * nbins:]
+        n = float(nx) * float(ny) * float(nz)
+        safe = torch.clamp(cnt, min=1.0)
+        return sk / safe, sp / safe / (n * n), cnt
 
     def partials(self):
         p = Partials()

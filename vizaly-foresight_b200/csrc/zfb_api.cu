@@ -11,6 +11,7 @@
 #include "../../include/zfb.h"
 #include "zfb_kernels.cuh"
 #include "zfb_ws.cuh"
+#include "zfb_spectrum.cuh"
 #include "zfb_hostio.cuh"
 #include "zfb_comm.cuh"
 
@@ -45,7 +46,7 @@ struct zfb_ctx {
   bool force_generic = false;
   bool dec_ws = true;   // warp-specialised float decode kernel (ZFB_DEC_WS=0 switches back to the tile kernel)
   // host-pointer path: resident device copies
-  devbuf d_orig, d_stream, d_out, d_hist;
+  devbuf d_orig, d_stream, d_out, d_hist, d_pk;
   const void* h_orig_key = nullptr;   // host pointer the resident original came from
   size_t orig_bytes = 0;
   const void* h_out_key = nullptr;    // host pointer the last decompressed field went to
@@ -282,7 +283,7 @@ extern "C" int zfb_release_resident(zfb_ctx* c)
   if (!c) return ZFB_EINVAL;
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
-  free_buf(c->d_orig); free_buf(c->d_stream); free_buf(c->d_out); free_buf(c->d_hist);
+  free_buf(c->d_orig); free_buf(c->d_stream); free_buf(c->d_out); free_buf(c->d_hist); free_buf(c->d_pk);
   free_buf(c->var_stage); free_buf(c->var_lens); free_buf(c->var_chunks); free_buf(c->var_index);
   c->var_index_key = c->var_host_key = nullptr;
   c->h_orig_key = c->h_out_key = nullptr;
@@ -947,6 +948,30 @@ extern "C" int zfb_histogram_dev(zfb_ctx* c, int dtype, int which, double lo, do
   else
     hist_kernel<double><<<grid, 256, 0, c->stream>>>(which, lo, hi, (const double*)d_orig, (const double*)d_approx, n,
                                                      (unsigned long long*)d_counts, (unsigned long long*)d_oob);
+  c->launches++;
+  CU_TRY(c, cudaGetLastError());
+  return ZFB_OK;
+}
+
+static int ensure(zfb_ctx* c, devbuf& b, size_t bytes);
+
+// Shell-binned power spectrum of a resident field from its real-to-complex transform (zfb_spectrum.cuh)
+extern "C" int zfb_power_spectrum_bin_dev(zfb_ctx* c, const void* d_fhat, size_t nx, size_t ny, size_t nz, unsigned nbins,
+                                          double* d_out)
+{
+  if (!c || !d_fhat || !d_out || !nx || !ny || !nz || !nbins || nbins > (unsigned)PK_MAX_BINS) return ZFB_EINVAL;
+  if (nx >= (1ull << 12) || ny >= (1ull << 12) || nz >= (1ull << 12)) { c->err = "power spectrum: extents above 4095 are not supported"; return ZFB_EINVAL; }
+  CU_TRY(c, cudaSetDevice(c->device));
+  const size_t nlines = ny * nz;
+  unsigned grid = (unsigned)c->sm_count * 4u;
+  if ((size_t)grid > nlines) grid = (unsigned)nlines;
+  int rc = ensure(c, c->d_pk, (size_t)grid * 3u * nbins * sizeof(double));
+  if (rc) return rc;
+  pk_bin_kernel<<<grid, 256, 3u * nbins * sizeof(double), c->stream>>>((const float2*)d_fhat, (unsigned)nx, (unsigned)ny, (unsigned)nz,
+                                                                      nbins, (double*)c->d_pk.p);
+  c->launches++;
+  CU_TRY(c, cudaGetLastError());
+  pk_finalize_kernel<<<(3u * nbins + 255u) / 256u, 256, 0, c->stream>>>((const double*)c->d_pk.p, grid, nbins, d_out);
   c->launches++;
   CU_TRY(c, cudaGetLastError());
   return ZFB_OK;
