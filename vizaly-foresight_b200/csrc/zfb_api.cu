@@ -261,7 +261,8 @@ extern "C" int zfb_create(zfb_ctx** out, int device)
     const char* e = std::getenv("ZFB_DEC_WS");
     c->dec_ws = !(e && e[0] == '0');
     const int ws_smem = 227 * 1024 - 8 * 1024;
-    if (cudaFuncSetAttribute(ws::dec3_f32_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws_smem) != cudaSuccess ||
+    if (cudaFuncSetAttribute(ws::dec3_f64_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ws_smem) != cudaSuccess ||
+        cudaFuncSetAttribute(ws::dec3_f32_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws_smem) != cudaSuccess ||
         cudaFuncSetAttribute(ws::dec3_f32_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws_smem) != cudaSuccess) {
       cudaGetLastError();
       c->dec_ws = false;
@@ -697,6 +698,25 @@ extern "C" int zfb_decode_dev(zfb_ctx* c, int dtype, int dims, size_t nx, size_t
     // and instruction-fetch bound (5.4 ms vs 3.2 ms for the 1 GiB-block benchmark slab), so the default is the
     // lean decode kernel followed by the streaming metric kernel over (orig, out).  ZFB_F64_FUSED=1 fuses.
     static const bool unfused = [] { const char* e = std::getenv("ZFB_F64_FUSED"); return !(e && e[0] == '1'); }();
+    // warp-specialised decode (zfb_ws.cuh): parser warps and transform warps, no fused metrics
+    const bool ws64 = c->dec_ws && (unfused || !metrics) && ws::d::smem_bytes(tg.W) <= (size_t)(227 * 1024 - 8 * 1024) &&
+                      (size_t)((tg.nbx + 31) / 32) * tg.nby * tg.nbz < (1ull << 31);
+    if (ws64) {
+      const unsigned nwt = ((tg.nbx + 31) / 32) * tg.nby * tg.nbz;
+      unsigned wgrid = (unsigned)c->sm_count;
+      const unsigned want = (nwt + ws::d::DP_WARPS - 1) / ws::d::DP_WARPS;
+      if (wgrid > want) wgrid = want;
+      ws::dec3_f64_ws_kernel<<<wgrid, ws::d::DTHREADS, ws::d::smem_bytes(tg.W), c->stream>>>((const uint64_t*)d_stream, (double*)d_out, tg, maxbits);
+      c->launches++;
+      CU_TRY(c, cudaGetLastError());
+      if ((g.ny | g.nz) & 3) {
+        int er = 0;
+        rc = launch_dec_generic<double, false>(c, dims, g, maxbits, d_stream, d_out, d_orig, 1, &er, 0, 0);
+        if (rc) return rc;
+      }
+      if (metrics) return zfb_metrics_dev(c, dtype, d_orig, d_out, n);
+      return ZFB_OK;
+    }
     if (metrics && unfused) {
       dec3_f64_tile_kernel<false><<<grid, DTILE_THREADS, smem, c->stream>>>(tm, (const uint64_t*)d_stream, (double*)d_out, tg, maxbits, c->part);
       c->launches++;

@@ -112,13 +112,14 @@ __device__ __forceinline__ uint32_t lds32(uint32_t a)
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
   return v;
 }
+template <int NP, unsigned HBITS>  // float: 32 planes behind 9 header bits; double: 64 planes behind 12
 __device__ __forceinline__ int parse_flat_ws(uint32_t slot_s, uint32_t planes_s, uint32_t tab_s, unsigned maxbits, int kmin)
 {
 #pragma unroll
-  for (int k = 0; k < 32; k++) asm volatile("st.shared.v2.u32 [%0], {%1, %1};" ::"r"(planes_s + 256u * k), "r"(0u) : "memory");
-  unsigned pos = 9u, n = 0u, st = 0u, nv = 0u;
+  for (int k = 0; k < NP; k++) asm volatile("st.shared.v2.u32 [%0], {%1, %1};" ::"r"(planes_s + 256u * k), "r"(0u) : "memory");
+  unsigned pos = HBITS, n = 0u, st = 0u, nv = 0u;
   // A = where the current plane goes; the plane index is (A - planes_s) / 256, so A also is the loop counter
-  uint32_t A = planes_s + 31u * 256u, tab = tab_s;
+  uint32_t A = planes_s + (unsigned)(NP - 1) * 256u, tab = tab_s;
   const uint32_t A_min = planes_s + 256u * (unsigned)kmin;
   uint32_t xl = 0u, xh = 0u;
   bool mid = false;
@@ -276,7 +277,7 @@ dec3_f32_ws_kernel(const float* __restrict__ orig, const uint64_t* __restrict__ 
           const int emax = (int)((head >> 1) & 0xffu) - 127;
           const stream_params sp = fixed_rate_params(maxbits);
           const int prec = block_precision<3>(emax, sp);
-          const int kend = parse_flat_ws(slot_s, planes_s, tb.flat_s, sp.maxbits, prec < 32 ? 32 - prec : 0);
+          const int kend = parse_flat_ws<32, 9u>(slot_s, planes_s, tb.flat_s, sp.maxbits, prec < 32 ? 32 - prec : 0);
           meta = 1u | (((head >> 1) & 0xffu) << 1) | (kend < 15 ? 512u : 0u);
         }
       }
@@ -430,6 +431,163 @@ dec3_f32_ws_kernel(const float* __restrict__ orig, const uint64_t* __restrict__ 
       }
       double* pr = part + (size_t)blockIdx.x * PART_STRIDE;
       pr[0] = a0; pr[1] = a1; pr[2] = a2; pr[3] = a3; pr[4] = a4; pr[5] = a5; pr[6] = a6; pr[7] = 0.0;
+    }
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// float64: the same schedule with 8 parser warps (a warp-tile's 64 planes take 16 KiB) and 4 transform warps at 248
+// registers -- the 64 x 64-bit planes and the 64 doubles they become are what made the tile kernel a 255-register,
+// 8-warps-per-SM kernel whose parse phases nobody could hide.  No fused metrics (the double metric arithmetic unrolled
+// over 64 values is too much code): the streaming metrics_kernel follows as before.
+// ---------------------------------------------------------------------------------------------
+namespace d {
+constexpr int DT_WARPS = 4, DP_WARPS = 8;
+constexpr int DTHREADS = 32 * (DT_WARPS + DP_WARPS);
+constexpr int DROWS_BYTES = 32 * 64 * 8;
+__host__ __device__ inline size_t smem_bytes(unsigned W)
+{
+  return (size_t)DP_WARPS * (DROWS_BYTES + pad_bytes(W) + 128u) + 3u * DP_WARPS * 8u;
+}
+}  // namespace d
+
+__global__ void __launch_bounds__(d::DTHREADS, 1)
+dec3_f64_ws_kernel(const uint64_t* __restrict__ stream, double* __restrict__ out, tile_geom tg, unsigned maxbits)
+{
+  using namespace d;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  __shared__ uint32_t flat_tab[f3::FLAT_WORDS];
+
+  const unsigned tid = threadIdx.x, lane = tid & 31u;
+  const unsigned warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const unsigned W = tg.W, W2 = 2u * W, pstride = W2 + 1u;
+  const uint32_t smem_s = ptx::smem_u32(smem_raw);
+  const uint32_t rows_s = smem_s;
+  const uint32_t pad_s = rows_s + DP_WARPS * DROWS_BYTES;
+  const uint32_t meta_s = pad_s + DP_WARPS * pad_bytes(W);
+  const uint32_t bars_s = meta_s + DP_WARPS * 128u;  // [P + p]: rows full, [2P + p]: rows empty
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (bars_s - smem_s));
+  if (tid == 0) {
+    for (int p = 0; p < DP_WARPS; p++) {
+      ptx::mbar_init(&bars[p], 1);
+      ptx::mbar_init(&bars[DP_WARPS + p], 32);
+      ptx::mbar_init(&bars[2 * DP_WARPS + p], 32);
+    }
+    ptx::fence_barrier_init();
+  }
+  for (unsigned i = tid; i < f3::FLAT_WORDS; i += DTHREADS) flat_tab[i] = ws_entry(i);
+  __syncthreads();
+  uint32_t flat_s = ptx::smem_u32(flat_tab);
+  asm volatile("mov.u32 %0, %0;" : "+r"(flat_s));
+
+  const unsigned wpr = (tg.nbx + 31u) >> 5;
+  const unsigned nwt = wpr * tg.nby * tg.nbz;
+  const unsigned stride = gridDim.x * DP_WARPS;
+
+  if (warp < (unsigned)DP_WARPS) {
+    // ------------------------------------------------------------------ parser warps
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(56));
+    const unsigned p = warp;
+    const uint32_t my_pad = pad_s + p * pad_bytes(W);
+    const uint32_t b_full = bars_s + 8u * (DP_WARPS + p), b_empty = bars_s + 8u * (2 * DP_WARPS + p);
+    const uint32_t planes_s = rows_s + p * DROWS_BYTES + 8u * lane;
+    const uint32_t slot_s = my_pad + 4u * lane * pstride;
+    auto issue_slots = [&](unsigned w) {
+      const wtile t = wtile_of(tg, wpr, w);
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(stream + t.blk0 * W);
+      const unsigned nw = t.nvalid * W2;
+      for (unsigned i = lane; i < nw; i += 32u)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(my_pad + 4u * ((i / W2) * pstride + i % W2)), "l"(src + i) : "memory");
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    unsigned w = blockIdx.x * DP_WARPS + p;
+    if (w < nwt) issue_slots(w);
+    for (unsigned it = 0; w < nwt; w += stride, it++) {
+      const unsigned rem = tg.nbx - (w % wpr) * 32u;
+      const unsigned nvalid = rem < 32u ? rem : 32u;
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+      mbar_wait_s(b_empty, (it & 1u) ^ 1u);
+      uint32_t meta = 0u;
+      if (lane < nvalid) {
+        const uint32_t head = lds32(slot_s);
+        if (head & 1u) {
+          const int emax = (int)((head >> 1) & 0x7ffu) - 1023;
+          const stream_params sp = fixed_rate_params(maxbits);
+          const int kend = parse_flat_ws<64, 12u>(slot_s, planes_s, flat_s, sp.maxbits, 64 - block_precision<3>(emax, sp));
+          meta = 1u | (((head >> 1) & 0x7ffu) << 1) | ((uint32_t)(kend + 1) << 12);
+        }
+      }
+      asm volatile("st.shared.u32 [%0], %1;" ::"r"(meta_s + 128u * p + 4u * lane), "r"(meta) : "memory");
+      mbar_arrive(b_full);
+      __syncwarp();
+      if (w + stride < nwt) issue_slots(w + stride);
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- transform warps
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(248));
+  const unsigned tw = warp - DP_WARPS;
+  const size_t rs = tg.nx, ps2 = (size_t)tg.ny * tg.nx;
+  constexpr unsigned NQ = DP_WARPS / DT_WARPS;
+  unsigned itq[NQ];
+#pragma unroll
+  for (unsigned j = 0; j < NQ; j++) itq[j] = 0u;
+  unsigned done = 0u;
+#pragma unroll 1
+  for (unsigned q = 0, idle = 0; done != (1u << NQ) - 1u; q = q + 1u == NQ ? 0u : q + 1u) {
+    if (done >> q & 1u) continue;
+    unsigned it = itq[0];
+#pragma unroll
+    for (unsigned j = 1; j < NQ; j++) it = q == j ? itq[j] : it;
+    const unsigned p = tw + DT_WARPS * q;
+    const unsigned w = blockIdx.x * DP_WARPS + p + it * stride;
+    if (w >= nwt) { done |= 1u << q; continue; }
+    const uint32_t b_full = bars_s + 8u * (DP_WARPS + p), b_empty = bars_s + 8u * (2 * DP_WARPS + p);
+    {
+      uint32_t ready;
+      asm volatile(
+          "{\n.reg .pred p;\n"
+          "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+          "selp.u32 %0, 1, 0, p;\n}\n"
+          : "=r"(ready)
+          : "r"(b_full), "r"(it & 1u)
+          : "memory");
+      if (!ready) {
+        if (++idle >= NQ) { __nanosleep(100); idle = 0; }
+        continue;
+      }
+      idle = 0;
+    }
+#pragma unroll
+    for (unsigned j = 0; j < NQ; j++) itq[j] += q == j ? 1u : 0u;
+    const wtile t = wtile_of(tg, wpr, w);
+    const bool active = lane < t.nvalid;
+    const size_t off = ((size_t)t.z0 * tg.ny + t.y0) * tg.nx + t.x0 + 4u * lane;
+    f3::planes64 PH, PL;
+    {
+      const uint32_t planes_s = rows_s + p * DROWS_BYTES + 8u * lane;
+#pragma unroll
+      for (int k = 0; k < 32; k++) {
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(PL.a[k]), "=r"(PL.b[k]) : "r"(planes_s + 256u * k));
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(PH.a[k]), "=r"(PH.b[k]) : "r"(planes_s + 256u * (k + 32)));
+      }
+    }
+    uint32_t meta;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(meta) : "r"(meta_s + 128u * p + 4u * lane));
+    mbar_arrive(b_empty);
+    if (active) {
+      double f[64];
+      d3::decode_finish(f, PH, PL, (int)((meta >> 1) & 0x7ffu) - 1023, (meta & 1u) != 0u, (int)(meta >> 12) - 1);
+      double* dst = out + off;
+#pragma unroll
+      for (int r16 = 0; r16 < 16; r16++) {
+        double* rowp = dst + (size_t)(r16 >> 2) * ps2 + (size_t)(r16 & 3) * rs;
+        __stcs(reinterpret_cast<double2*>(rowp), make_double2(f[4 * r16], f[4 * r16 + 1]));
+        __stcs(reinterpret_cast<double2*>(rowp) + 1, make_double2(f[4 * r16 + 2], f[4 * r16 + 3]));
+      }
     }
   }
 }
