@@ -225,22 +225,27 @@ ZFB_HD void encode_block(const float (&f)[4], unsigned maxbits, uint32_t (&out)[
     rest &= mask32((unsigned)k + 1u);
     const int ke = rest ? 31 - clz32(rest) : -1;
     unsigned L = (unsigned)(k - ke);
+    // One iteration = a run (possibly empty) AND the event plane behind it: the lanes of a warp then walk the same code
+    // whatever mix of runs and events their blocks hold (with the run and the event as separate iterations half the
+    // lanes sat out every pass).
+    const unsigned cap = n == 0u ? 32u : (n == 1u ? 16u : 10u);  // planes whose codes fit one 32-bit put
+    const bool capped = L > cap;  // (a capped run is simply continued by the next iteration)
+    if (capped) L = cap;
     if (L) {
-      const unsigned cap = n == 0u ? 32u : (n == 1u ? 16u : 10u);  // planes whose codes fit one 32-bit put
-      if (L > cap) L = cap;
       uint32_t code = 0u;
       if (n == 1u) code = spread2(brev32(u[0] << (31 - k)) & mask32(L));
       else if (n == 2u) code = spread3(brev32(u[0] << (31 - k)) & mask32(L)) | (spread3(brev32(u[1] << (31 - k)) & mask32(L)) << 1);
       put(code, L * (n + 1u));
       k -= (int)L;
-      continue;  // (a capped run is simply continued by the next iteration)
     }
-    // event plane k
-    const unsigned x = ((u[0] >> k) & 1u) | (((u[1] >> k) & 1u) << 1) | (((u[2] >> k) & 1u) << 2) | (((u[3] >> k) & 1u) << 3);
-    const unsigned e = tb.enc[n * 16u + x];
-    put(e & 0xffu, (e >> 8) & 15u);
-    n = e >> 12;
-    k--;
+    if (!capped && k >= 0 && pos < maxbits) {
+      // event plane k
+      const unsigned x = ((u[0] >> k) & 1u) | (((u[1] >> k) & 1u) << 1) | (((u[2] >> k) & 1u) << 2) | (((u[3] >> k) & 1u) << 3);
+      const unsigned e = tb.enc[n * 16u + x];
+      put(e & 0xffu, (e >> 8) & 15u);
+      n = e >> 12;
+      k--;
+    }
   }
   if (n >= 3u && k >= 0 && pos < maxbits) {
     // planes k, k-1, ... : the raw nibble of every plane = interleave of the coefficients' bits below plane k+1
@@ -341,6 +346,10 @@ ZFB_HD void decode_block(float (&f)[4], unsigned maxbits, const uint32_t (&in)[M
     const uint32_t t = w & tests;
     unsigned L = R;
     if (t) { const unsigned z = (unsigned)ctz32(t); L = n == 0u ? z : (n == 1u ? z >> 1 : (z * 11u) >> 5); }
+    // One iteration = a run (possibly empty) AND the event plane behind it, as in the encoder.  A run that fills the
+    // whole window (L == R > 0) has not met its event yet: the next iteration continues it.
+    const bool event = L == 0u || L < R;
+    uint32_t we = w;
     if (L) {
       if (n == 1u) u[0] |= brev32(gather2(w) & mask32(L)) >> (31 - k);
       else if (n == 2u) {
@@ -348,27 +357,27 @@ ZFB_HD void decode_block(float (&f)[4], unsigned maxbits, const uint32_t (&in)[M
         u[1] |= brev32(gather3(w >> 1) & mask32(L)) >> (31 - k);
       }
       pos += L * cw; remaining -= L * cw; k -= (int)L;
-      continue;
+      we = peek(pos);
     }
-    if (R == 0u) {
-      // fewer than n + 1 bits are left: the budget ends inside this plane's code (handled exactly below)
+    if (event && k >= 0 && remaining) {
+      // (R == 0: fewer than n + 1 bits are left, the budget ends inside this plane's code -- handled exactly below)
+      const unsigned e = tb.dec[n * 128u + (we & 127u)];
+      const unsigned len = (e >> 4) & 15u;
+      if (len <= remaining) {
+        const unsigned x = e & 15u;
+        ZFB_UNROLL for (int i = 0; i < 4; i++) u[i] |= ((x >> i) & 1u) << k;
+        n = e >> 8;
+        pos += len; remaining -= len;
+      } else {
+        // the budget ends inside this plane's code (at most once per block): exact bit-serial steps, out of line
+        const unsigned xn = truncated_plane(we, remaining, n);
+        const unsigned x = xn & 15u;
+        ZFB_UNROLL for (int i = 0; i < 4; i++) u[i] |= ((x >> i) & 1u) << k;
+        remaining = 0;
+        n = xn >> 4;
+      }
+      k--;
     }
-    const unsigned e = tb.dec[n * 128u + (w & 127u)];
-    const unsigned len = (e >> 4) & 15u;
-    if (len <= remaining) {
-      const unsigned x = e & 15u;
-      ZFB_UNROLL for (int i = 0; i < 4; i++) u[i] |= ((x >> i) & 1u) << k;
-      n = e >> 8;
-      pos += len; remaining -= len;
-    } else {
-      // the budget ends inside this plane's code (at most once per block): exact bit-serial steps, out of line
-      const unsigned xn = truncated_plane(w, remaining, n);
-      const unsigned x = xn & 15u;
-      ZFB_UNROLL for (int i = 0; i < 4; i++) u[i] |= ((x >> i) & 1u) << k;
-      remaining = 0;
-      n = xn >> 4;
-    }
-    k--;
   }
   if (n >= 3u && k >= 0 && remaining) {
     const unsigned planes = (unsigned)k + 1u;
