@@ -6,17 +6,19 @@
 // dependent shared-memory fetches and table look-ups with divergent trip counts (latency bound, ~50 live registers), the
 // transform is 2 400 straight-line instructions on 64 + 64 live values (issue bound, 128+ registers).  At 128 registers
 // only 16 warps fit an SM, so the parse phases leave the schedulers idle (issue slots 53 % busy, profiles/r02_notes.md).
-// Here the two halves run in different warps of one 640-thread CTA per SM and trade registers with setmaxnreg:
-//   * 16 PARSER warps (56 registers each): a warp owns a sequence of warp-tiles (32 x-consecutive blocks); its slot
-//     span arrives by cp.async.bulk one tile ahead, is re-laid into a bank-conflict-free padded area and parsed into
-//     the warp's plane-row buffer (32 blocks x 256 B);
-//   * 4 TRANSFORM warps (232 registers, one per scheduler): take the plane rows of "their" four parser warps in turn,
-//     hand the buffer back at once, and run inverse transposes / lifting / conversion, the metric partials against the
-//     original (16 coalesced 128-bit global loads per lane, issued before the rows are awaited) and the 16 coalesced
-//     128-bit stores.
+// Here the two halves run in different warps of one 768-thread CTA per SM and trade registers with setmaxnreg (80 at
+// launch):
+//   * 16 PARSER warps (40 registers each): a warp owns a sequence of warp-tiles (32 x-consecutive blocks); its slot
+//     span goes from global memory straight into a bank-conflict-free padded area by 4-byte cp.async copies and is
+//     parsed by the flat parser into the warp's plane buffer (32 blocks x 32 planes x 8 B);
+//   * 8 TRANSFORM warps (160 registers, two per scheduler, the last warpgroups): each polls the two parser warps it is
+//     paired with, takes the planes of whichever is ready, hands the buffer back at once, and runs inverse transposes /
+//     lifting / conversion, the metric partials against the original (16 coalesced 128-bit global loads per lane, 12
+//     of them requested before the transform, 4 after) and the 16 coalesced 128-bit stores.
 // Hand-over by mbarriers (rows_full / rows_empty per parser warp); parser and transform warp walk the same static tile
-// sequence, so no descriptors are passed.  A scheduler then always holds four latency-bound warps and one issue-bound
-// warp.
+// sequence, so no descriptors are passed.  The transform warps are the critical resource (each runs ~2 100
+// straight-line instructions per tile at ~0.4 per cycle whatever the rate), which is why there are eight of them and
+// why the parsers live on 40 registers: 16 x 40 + 8 x 160 registers per lane column is the whole register file.
 #pragma once
 #include <cstdio>
 #include "zfb_kernels.cuh"
@@ -25,11 +27,11 @@ namespace zfb {
 namespace ws {
 
 #ifndef ZFB_WS_T_WARPS
-#define ZFB_WS_T_WARPS 4
+#define ZFB_WS_T_WARPS 8
 #endif
 constexpr int T_WARPS = ZFB_WS_T_WARPS;             // transform warps = the first warpgroup(s)
 #ifndef ZFB_WS_OEARLY
-#define ZFB_WS_OEARLY 16                            // rows of the original requested before the inverse transform (the rest after it)
+#define ZFB_WS_OEARLY 12                            // rows of the original requested before the inverse transform (the rest after it)
 #endif
 #ifndef ZFB_WS_P_WARPS
 #define ZFB_WS_P_WARPS 16
@@ -42,10 +44,10 @@ constexpr int ROWS_BYTES = 32 * 256;                // plane rows of one warp-ti
 #endif
 constexpr unsigned PAD_BUFS = ZFB_WS_PAD_BUFS;
 #ifndef ZFB_WS_REGS_T
-#define ZFB_WS_REGS_T 232
+#define ZFB_WS_REGS_T 160
 #endif
 #ifndef ZFB_WS_REGS_P
-#define ZFB_WS_REGS_P 56
+#define ZFB_WS_REGS_P 40
 #endif
 
 __host__ __device__ inline unsigned pad_bytes(unsigned W) { return (32u * (2u * W + 1u) * 4u + 16u + 15u) & ~15u; }
