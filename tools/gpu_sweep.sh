@@ -2,12 +2,12 @@
 mkdir -p gpurun_out; : > gpurun_out/sweep.jsonl
 for spec in "nyx512 4" "nyx512 8" "nyx512 16" "nyx2048-slab 4" "nyx2048-slab 16" "hacc1d 8" "hacc1d 16" "vpic1024-f64 1" "vpic1024-f64 4" "vpic1024-f64 8" "vpic1024-f64 16" "vpic1024-f64 32"; do
   set -- $spec
-  timeout -k 10 300 python bench.py --workload $1 --rate $2 --steps 3 --warmup 3 --no-e2e --no-cpu 2>/dev/null | grep '^{' >> gpurun_out/sweep.jsonl
+  timeout -k 10 300 python bench.py --workload $1 --rate $2 --steps 5 --warmup 3 --no-e2e --no-cpu 2>/dev/null | grep '^{' >> gpurun_out/sweep.jsonl
 done
 # coder best / worst cases, HACC velocities, unaligned (wra=0) 1D slots
 for spec in "nyx512 8 noise 1" "nyx512 8 zero 1" "hacc1d 8 velocity 1" "hacc1d 8 uniform 0" "hacc1d 16 uniform 0" "hacc1d 8 noise 1" "vpic1024-f64 8 noise 1" "vpic1024-f64 8 zero 1"; do
   set -- $spec
-  timeout -k 10 300 python bench.py --workload $1 --rate $2 --field $3 --wra $4 --steps 3 --warmup 3 --no-e2e --no-cpu 2>/dev/null | grep '^{' >> gpurun_out/sweep.jsonl
+  timeout -k 10 300 python bench.py --workload $1 --rate $2 --field $3 --wra $4 --steps 5 --warmup 3 --no-e2e --no-cpu 2>/dev/null | grep '^{' >> gpurun_out/sweep.jsonl
 done
 python - <<'PY'
 import json
