@@ -294,6 +294,42 @@ def test_generic_and_tile_paths_agree(pkg, oracle):
     c2.close()
 
 
+@pytest.mark.parametrize("dtype,shape,mb", [(np.float32, (16, 64, 516), 512), (np.float32, (12, 20, 132), 256),
+                                            (np.float32, (8, 8, 8), 1280), (np.float64, (16, 32, 260), 512),
+                                            (np.float64, (8, 12, 36), 2048)])
+def test_warp_specialised_and_tile_decode_agree(pkg, oracle, dtype, shape, mb):
+    """The warp-specialised decode kernels (default) and the tile kernels (ZFB_DEC_WS=0) decode the same stream to the
+    same bits and the same metrics, both equal to the oracle's: partial warp-tiles (nx / 4 not a multiple of 32), wide
+    slots, tiny fields with fewer warp-tiles than parser warps."""
+    torch = _torch()
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    f = smooth_field(shape, seed=21, amp=50.0, dtype=dtype)
+    s_ref = oracle.compress(f, mb)
+    g_ref = oracle.decompress(s_ref, f.shape, dtype, mb)
+    outs = []
+    for ws in ("1", "0"):
+        os.environ["ZFB_DEC_WS"] = ws
+        try:
+            c2 = pkg.Codec(0)
+        finally:
+            del os.environ["ZFB_DEC_WS"]
+        s, g, part = gpu_roundtrip(c2, f, mb)
+        assert np.array_equal(s, s_ref)
+        assert_bits_equal(g, g_ref, "decode, ZFB_DEC_WS=" + ws)
+        if dtype == np.float32:
+            check_metrics(pkg, oracle, part, f, g_ref, "ZFB_DEC_WS=" + ws)
+        else:  # metrics of doubles are computed in double (test_f64_tile_kernels_bit_exact)
+            d = f - g_ref
+            v = pkg.metric_values(part)
+            assert v["n"] == f.size and v["absolute_error"] == float(np.abs(d).max())
+            assert v["max"] == float(f.max()) and v["min"] == float(f.min())
+            assert abs(v["mse"] - float(np.mean(d * d))) <= 1e-9 * float(np.mean(d * d)) + 1e-300
+        outs.append(g)
+        c2.close()
+    assert_bits_equal(outs[0], outs[1], "warp-specialised against tile kernel")
+
+
 def test_host_entry_points_and_fused_metrics(codec, pkg, oracle):
     """zfb_compress_host / zfb_decompress_host / zfb_metrics_host, multi-slab pipeline included."""
     shape = (96, 512, 512)   # 96 MiB -> two slabs in the host pipeline
