@@ -3,7 +3,7 @@ mkdir -p gpurun_out
 cd vizaly-foresight_b200; cp libzfb.so libzfb_orig.so; cd ..
 for tag in "$@"; do
   cp vizaly-foresight_b200/libzfb_$tag.so vizaly-foresight_b200/libzfb.so
-  timeout -k 10 300 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu 2>&1 | python -c "
+  timeout -k 10 300 python bench.py ${BENCH_ARGS:-} --steps 5 --warmup 3 --no-e2e --no-cpu 2>&1 | python -c "
 import sys,json
 for l in sys.stdin:
     if l.startswith('{'):

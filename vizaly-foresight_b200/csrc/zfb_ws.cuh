@@ -439,13 +439,23 @@ dec3_f32_ws_kernel(const float* __restrict__ orig, const uint64_t* __restrict__ 
 
 
 // ---------------------------------------------------------------------------------------------
-// float64: the same schedule with 8 parser warps (a warp-tile's 64 planes take 16 KiB) and 4 transform warps at 248
-// registers -- the 64 x 64-bit planes and the 64 doubles they become are what made the tile kernel a 255-register,
-// 8-warps-per-SM kernel whose parse phases nobody could hide.  No fused metrics (the double metric arithmetic unrolled
+// float64: the same schedule with 8 parser warps at 40 registers (a warp-tile's 64 planes take 16 KiB) and 8 transform
+// warps at 208 (one per parser; a few spills are cheaper than half as many transform warps at 248: 1.88 -> 1.72 ms) --
+// the 64 x 64-bit planes and the 64 doubles they become are what made the tile kernel a 255-register, 8-warps-per-SM
+// kernel whose parse phases nobody could hide.  No fused metrics (the double metric arithmetic unrolled
 // over 64 values is too much code): the streaming metrics_kernel follows as before.
 // ---------------------------------------------------------------------------------------------
 namespace d {
-constexpr int DT_WARPS = 4, DP_WARPS = 8;
+#ifndef ZFB_WSD_T_WARPS
+#define ZFB_WSD_T_WARPS 8
+#endif
+#ifndef ZFB_WSD_REGS_T
+#define ZFB_WSD_REGS_T 208
+#endif
+#ifndef ZFB_WSD_REGS_P
+#define ZFB_WSD_REGS_P 40
+#endif
+constexpr int DT_WARPS = ZFB_WSD_T_WARPS, DP_WARPS = 8;
 constexpr int DTHREADS = 32 * (DT_WARPS + DP_WARPS);
 constexpr int DROWS_BYTES = 32 * 64 * 8;
 __host__ __device__ inline size_t smem_bytes(unsigned W)
@@ -489,7 +499,7 @@ dec3_f64_ws_kernel(const uint64_t* __restrict__ stream, double* __restrict__ out
 
   if (warp < (unsigned)DP_WARPS) {
     // ------------------------------------------------------------------ parser warps
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(56));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ZFB_WSD_REGS_P));
     const unsigned p = warp;
     const uint32_t my_pad = pad_s + p * pad_bytes(W);
     const uint32_t b_full = bars_s + 8u * (DP_WARPS + p), b_empty = bars_s + 8u * (2 * DP_WARPS + p);
@@ -530,7 +540,7 @@ dec3_f64_ws_kernel(const uint64_t* __restrict__ stream, double* __restrict__ out
   }
 
   // -------------------------------------------------------------------- transform warps
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(248));
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(ZFB_WSD_REGS_T));
   const unsigned tw = warp - DP_WARPS;
   const size_t rs = tg.nx, ps2 = (size_t)tg.ny * tg.nx;
   constexpr unsigned NQ = DP_WARPS / DT_WARPS;
