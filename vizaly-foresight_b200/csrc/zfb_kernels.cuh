@@ -560,7 +560,10 @@ __device__ __forceinline__ box_info box_of(const tile_geom& tg, unsigned q)
 // row of `part` per CTA, for the value-range histogram that the decode pass fuses (minmaxMetric.hpp:62-81 needs them
 // before any value can be binned).
 template <bool MINMAX>
-__global__ void __launch_bounds__(TILE_THREADS, 5)
+#ifndef ZFB_ENC_CTAS
+#define ZFB_ENC_CTAS 5
+#endif
+__global__ void __launch_bounds__(TILE_THREADS, ZFB_ENC_CTAS)
 enc3_f32_tile_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t* __restrict__ stream, tile_geom tg,
                      unsigned maxbits, double* __restrict__ part)
 {
