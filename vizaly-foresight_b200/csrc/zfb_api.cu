@@ -195,7 +195,7 @@ static const size_t ENC_TILE_SMEM_BASE = BOXES_PER_TILE * BOX_FLOATS * sizeof(fl
 // [tile / plane scratch 32 KiB][2 x slot staging][mbarriers]  (layouts documented at the kernels)
 // padded slot staging: (2W + 1) 32-bit words per thread, rounded to 16 bytes
 static size_t padded_slots(unsigned W) { return (((size_t)TILE_THREADS * (2 * W + 2) * 4 + 15) & ~(size_t)15); }
-static size_t enc_tile_smem(unsigned W) { return ENC_TILE_SMEM_BASE + (size_t)TILE_THREADS * W * 8 + 2 * 8; }
+static size_t enc_tile_smem(unsigned W) { return ENC_TILE_SMEM_BASE + (size_t)TILE_THREADS * W * 8 + 3 * 8; }
 static size_t dec_tile_smem(unsigned W, bool /*metrics*/)
 {
   return ENC_TILE_SMEM_BASE + DEC_SLOT_BUFS * (size_t)TILE_THREADS * W * 8 + padded_slots(W) + 16 + 4 * 8;
