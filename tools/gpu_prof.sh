@@ -1,6 +1,6 @@
 # ncu --set full capture of the float/3D tile kernels (one launch each, after warm-up) -> gpurun_out/prof_<tag>.ncu-rep
 # usage (under gpurun): bash tools/gpu_prof.sh <tag> [workload] [kernel regex]
-tag=${1:-dev}; wl=${2:-nyx512}; pat=${3:-"(enc3_f32_tile|dec3_f32_ws)"}
+tag=${1:-dev}; wl=${2:-nyx512}; pat=${3:-"(enc3_f32_warp|dec3_f32_ws)"}
 mkdir -p gpurun_out
 cmd="python bench.py --workload $wl --steps 1 --warmup 3 --no-e2e --no-cpu"
 timeout 300 $cmd > gpurun_out/plain_$tag.log 2>&1 &&

@@ -7,7 +7,7 @@ timeout 300 python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu > gpurun_out/
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --kernel-name regex:"zfb|finalize|tile_kernel|metrics_kernel|combine" -c 400 --csv \
   --log-file gpurun_out/launches_bench_final.csv python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_launches.log 2>&1
 timeout 300 python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/plain_full.log 2>&1 &&
-timeout 600 ncu --set full --clock-control none --import-source on --kernel-name regex:"(enc3_f32_tile|dec3_f32_ws)" -s 6 -c 2 -o gpurun_out/prof_final_slab -f \
+timeout 600 ncu --set full --clock-control none --import-source on --kernel-name regex:"(enc3_f32_warp|dec3_f32_ws)" -s 6 -c 2 -o gpurun_out/prof_final_slab -f \
   python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_full.log 2>&1
 tail -2 gpurun_out/ncu_full.log
 python - <<'PY'

@@ -18,7 +18,7 @@ for r in csv.DictReader(open(full)):
 def unit_bytes(v):  # ncu prints dram bytes in G (base 10) in this summary
     return float(v) * 1e9
 out = {"workload": "nyx2048-slab (256x2048x2048 f32, 8 bpv)",
-       "command": "ncu --set full --clock-control none --import-source on --kernel-name regex:\"(enc3_f32_tile|dec3_f32_ws)\" -s 6 -c 2 python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu  (tools/gpu_profile_final.sh)",
+       "command": "ncu --set full --clock-control none --import-source on --kernel-name regex:\"(enc3_f32_warp|dec3_f32_ws)\" -s 6 -c 2 python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu  (tools/gpu_profile_final.sh)",
        "algorithmic_bytes": {"encode": 5368709120, "decode+metrics": 9663676416},
        "note": "algorithmic bytes: field 4 GiB (N*s) + stream 1 GiB (8 bpv) for encode; stream + original re-read + decoded write for decode+metrics (SURVEY 8d)",
        "kernels": {}}
@@ -41,6 +41,6 @@ with open(hot, "w") as f:
             "# from the ncu --set full --import-source on capture behind %s_ncu_full_nyx2048slab.csv (tools/gpu_profile_final.sh), joined with the\n"
             "# cubin's line table (tools/ncu_lines.py).  columns: share of the kernel's warp instructions, count, average active threads per\n"
             "# instruction, stall samples, file:line, source\n\n" % tag)
-    for pat in ("enc3_f32_tile", "dec3_f32_ws"):
+    for pat in ("enc3_f32_warp", "dec3_f32_ws"):
         f.write(subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_lines.py"), rep, pat, "50"], capture_output=True, text=True).stdout + "\n")
 print(json.dumps(out["kernels"], indent=1))

@@ -45,6 +45,8 @@ struct zfb_ctx {
   std::string err;
   bool force_generic = false;
   bool dec_ws = true;   // warp-specialised float decode kernel (ZFB_DEC_WS=0 switches back to the tile kernel)
+  bool enc_warp = true; // warp-autonomous float encode kernel (ZFB_ENC_WARP=0 switches back to the tile kernel)
+  int occ_encw[64] = {0};
   // host-pointer path: resident device copies
   devbuf d_orig, d_stream, d_out, d_hist, d_pk;
   const void* h_orig_key = nullptr;   // host pointer the resident original came from
@@ -261,6 +263,15 @@ extern "C" int zfb_create(zfb_ctx** out, int device)
     const char* e = std::getenv("ZFB_DEC_WS");
     c->dec_ws = !(e && e[0] == '0');
     const int ws_smem = 227 * 1024 - 8 * 1024;
+    {
+      const char* ew = std::getenv("ZFB_ENC_WARP");
+      c->enc_warp = !(ew && ew[0] == '0');
+      if (cudaFuncSetAttribute(ws::enc3_f32_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) != cudaSuccess ||
+          cudaFuncSetAttribute(ws::enc3_f32_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem) != cudaSuccess) {
+        cudaGetLastError();
+        c->enc_warp = false;
+      }
+    }
     if (cudaFuncSetAttribute(ws::dec3_f64_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ws_smem) != cudaSuccess ||
         cudaFuncSetAttribute(ws::dec3_f32_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws_smem) != cudaSuccess ||
         cudaFuncSetAttribute(ws::dec3_f32_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ws_smem) != cudaSuccess) {
@@ -513,12 +524,12 @@ static tile_geom make_tile_geom(const geom& g, unsigned maxbits)
   return t;
 }
 
-static int make_tmap_3d(zfb_ctx* c, CUtensorMap* tm, const void* base, const geom& g, int dtype)
+static int make_tmap_3d(zfb_ctx* c, CUtensorMap* tm, const void* base, const geom& g, int dtype, unsigned box_x = 256)
 {
   const cuuint64_t es = dtype == ZFB_FLOAT ? 4 : 8;
   cuuint64_t gdim[3] = {(cuuint64_t)g.nx, (cuuint64_t)g.ny, (cuuint64_t)g.nz};
   cuuint64_t gstr[2] = {(cuuint64_t)g.nx * es, (cuuint64_t)g.nx * g.ny * es};
-  cuuint32_t box[3] = {256, 4, 4};
+  cuuint32_t box[3] = {box_x, 4, 4};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = c->encode_tiled(tm, dtype == ZFB_FLOAT ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3,
                                const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -613,6 +624,39 @@ extern "C" int zfb_encode_dev(zfb_ctx* c, int dtype, int dims, size_t nx, size_t
   }
   if (dtype == ZFB_FLOAT && tile_path_ok(c, dtype, dims, g, maxbits, false) && ((uintptr_t)d_in & 15) == 0 && ((uintptr_t)d_stream & 15) == 0) {
     CUtensorMap tm;
+    const tile_geom tg0 = make_tile_geom(g, maxbits);
+    if (c->enc_warp && tg0.W < 64 && ws::enc_warp_smem(tg0.W) <= 100 * 1024 &&
+        (size_t)((tg0.nbx + 31) / 32) * tg0.nby * tg0.nbz < (1ull << 31)) {
+      // warp-autonomous tiles (zfb_ws.cuh): a box of 128 x 4 x 4 values per warp
+      rc = make_tmap_3d(c, &tm, d_in, g, ZFB_FLOAT, 128);
+      if (rc) return rc;
+      const size_t wsmem = ws::enc_warp_smem(tg0.W);
+      int nb = c->occ_encw[tg0.W];
+      if (!nb) {
+        CU_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, ws::enc3_f32_warp_kernel<false>, 32 * ws::EW_WARPS, wsmem));
+        if (nb < 1) nb = 1;
+        c->occ_encw[tg0.W] = nb;
+      }
+      const unsigned nwt = ((tg0.nbx + 31) / 32) * tg0.nby * tg0.nbz;
+      unsigned grid = (unsigned)c->sm_count * (unsigned)nb;
+      const unsigned want = (nwt + ws::EW_WARPS - 1) / ws::EW_WARPS;
+      if (grid > want) grid = want;
+      if (c->want_range && !((g.ny | g.nz) & 3) && (int)grid <= c->part_rows) {
+        ws::enc3_f32_warp_kernel<true><<<grid, 32 * ws::EW_WARPS, wsmem, c->stream>>>(tm, (uint64_t*)d_stream, tg0, maxbits, c->part);
+        c->launches++;
+        CU_TRY(c, cudaGetLastError());
+        finalize_partials_kernel<<<1, 256, 0, c->stream>>>(c->part, (int)grid, c->enc_result, (unsigned long long)g.nx * g.ny * g.nz);
+        c->launches++;
+        CU_TRY(c, cudaGetLastError());
+        c->want_range = false;  // harvested
+        return ZFB_OK;
+      }
+      ws::enc3_f32_warp_kernel<false><<<grid, 32 * ws::EW_WARPS, wsmem, c->stream>>>(tm, (uint64_t*)d_stream, tg0, maxbits, c->part);
+      c->launches++;
+      CU_TRY(c, cudaGetLastError());
+      if ((g.ny | g.nz) & 3) return launch_enc_generic<float>(c, dims, g, maxbits, d_in, d_stream, 1);
+      return ZFB_OK;
+    }
     rc = make_tmap_3d_f32(c, &tm, d_in, g);
     if (rc) return rc;
     const tile_geom tg = make_tile_geom(g, maxbits);
