@@ -34,7 +34,7 @@ for k, ins in data.items():
         continue
     # the kernel's section in the disassembly: mangled names carry the same identifier
     ident = re.search(r"(\w+_kernel)", k).group(1)
-    sec = [m.start() for m in re.finditer(r"^\.text\._ZN3zfb\d+%s\w*:" % ident, dis, re.M)]
+    sec = [m.start() for m in re.finditer(r"^\.text\._ZN3zfb\w*?\d+%s\w*:" % ident, dis, re.M)]
     best = None
     for s in sec:
         e = dis.find("//--------------------- .text.", s)
