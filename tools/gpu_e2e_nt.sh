@@ -1,0 +1,11 @@
+# end-to-end leg with and without non-temporal staging copies (under gpurun)
+mkdir -p gpurun_out
+for nt in 1 0 1 0; do
+  ZFB_COPY_NT=$nt timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu 2>gpurun_out/e2e_nt$nt.err | python -c "
+import sys,json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); e=d['e2e']; print('nt=$nt e2e', round(e['value'],2), 'ms', round(e['ms_per_step'],1), 'c', round(e['ms_compress'],1), 'd', round(e['ms_decompress'],1), 'pinned', round(e['pinned']['value'],2))
+"
+done
+(timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_cbench_plugin.py -m gpu -q -x -k "host or plugin or cbench or mini" 2>&1 | tail -2)

@@ -17,7 +17,41 @@
 #include <sched.h>
 #endif
 
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
+
 namespace zfb {
+
+// One thread's share of a staging copy.  The destination is never read again by this CPU (it is either the pinned buffer
+// the DMA engine reads next or the caller's output array), so it is written with non-temporal stores: no read-for-
+// ownership of the destination lines, i.e. two memory transfers per byte instead of three on a host whose DRAM
+// bandwidth is what bounds the pageable path (glibc's memcpy only switches to such stores far above the 4 MiB a thread
+// gets here).  ZFB_COPY_NT=0 goes back to memcpy.
+inline void stream_copy(char* d, const char* s, size_t n)
+{
+#if defined(__x86_64__)
+  static const bool nt = [] { const char* e = std::getenv("ZFB_COPY_NT"); return !(e && e[0] == '0'); }();
+  if (nt && n >= 4096) {
+    size_t head = (size_t)((16 - ((uintptr_t)d & 15)) & 15);
+    std::memcpy(d, s, head);
+    d += head; s += head; n -= head;
+    const size_t blocks = n / 64;
+    for (size_t i = 0; i < blocks; i++) {
+      const __m128i a = _mm_loadu_si128((const __m128i*)(s + 64 * i)), b = _mm_loadu_si128((const __m128i*)(s + 64 * i + 16)),
+                    c = _mm_loadu_si128((const __m128i*)(s + 64 * i + 32)), e = _mm_loadu_si128((const __m128i*)(s + 64 * i + 48));
+      _mm_stream_si128((__m128i*)(d + 64 * i), a);
+      _mm_stream_si128((__m128i*)(d + 64 * i + 16), b);
+      _mm_stream_si128((__m128i*)(d + 64 * i + 32), c);
+      _mm_stream_si128((__m128i*)(d + 64 * i + 48), e);
+    }
+    _mm_sfence();
+    std::memcpy(d + 64 * blocks, s + 64 * blocks, n - 64 * blocks);
+    return;
+  }
+#endif
+  std::memcpy(d, s, n);
+}
 
 // A few persistent threads that split one memcpy between them; the caller takes a share and returns when all are done.
 class copy_pool {
@@ -39,7 +73,7 @@ class copy_pool {
   unsigned threads() const { return n_; }
   void copy(void* dst, const void* src, size_t bytes)
   {
-    if (bytes < (size_t)(4u << 20) || n_ == 1) { std::memcpy(dst, src, bytes); return; }
+    if (bytes < (size_t)(4u << 20) || n_ == 1) { stream_copy((char*)dst, (const char*)src, bytes); return; }
     {
       std::lock_guard<std::mutex> l(mu_);
       dst_ = (char*)dst; src_ = (const char*)src; bytes_ = bytes;
@@ -59,7 +93,7 @@ class copy_pool {
     const size_t unit = (size_t)2 << 20, units = (bytes_ + unit - 1) / unit;
     const size_t u0 = units * i / n_, u1 = units * (i + 1) / n_;
     const size_t b0 = u0 * unit, b1 = u1 * unit < bytes_ ? u1 * unit : bytes_;
-    if (b1 > b0) std::memcpy(dst_ + b0, src_ + b0, b1 - b0);
+    if (b1 > b0) stream_copy(dst_ + b0, src_ + b0, b1 - b0);
   }
   void worker(unsigned i)
   {
