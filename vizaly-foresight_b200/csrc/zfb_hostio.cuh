@@ -18,7 +18,7 @@
 #endif
 
 #if defined(__x86_64__)
-#include <emmintrin.h>
+#include <immintrin.h>
 #endif
 
 namespace zfb {
@@ -28,11 +28,39 @@ namespace zfb {
 // ownership of the destination lines, i.e. two memory transfers per byte instead of three on a host whose DRAM
 // bandwidth is what bounds the pageable path (glibc's memcpy only switches to such stores far above the 4 MiB a thread
 // gets here).  ZFB_COPY_NT=0 goes back to memcpy.
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__CUDA_ARCH__)
+__attribute__((target("avx2"))) inline void stream_copy_avx2(char* d, const char* s, size_t blocks128)
+{
+  for (size_t i = 0; i < blocks128; i++) {
+    const __m256i a = _mm256_loadu_si256((const __m256i*)(s + 128 * i)), b = _mm256_loadu_si256((const __m256i*)(s + 128 * i + 32)),
+                  c = _mm256_loadu_si256((const __m256i*)(s + 128 * i + 64)), e = _mm256_loadu_si256((const __m256i*)(s + 128 * i + 96));
+    _mm256_stream_si256((__m256i*)(d + 128 * i), a);
+    _mm256_stream_si256((__m256i*)(d + 128 * i + 32), b);
+    _mm256_stream_si256((__m256i*)(d + 128 * i + 64), c);
+    _mm256_stream_si256((__m256i*)(d + 128 * i + 96), e);
+  }
+}
+#define ZFB_HAVE_AVX2_COPY 1
+#endif
+
 inline void stream_copy(char* d, const char* s, size_t n)
 {
 #if defined(__x86_64__)
   static const bool nt = [] { const char* e = std::getenv("ZFB_COPY_NT"); return !(e && e[0] == '0'); }();
   if (nt && n >= 4096) {
+#if defined(ZFB_HAVE_AVX2_COPY)
+    static const bool avx2 = [] { const char* e = std::getenv("ZFB_COPY_NT"); return __builtin_cpu_supports("avx2") && !(e && e[0] == '1' && e[1] == '6'); }();
+    if (avx2) {  // 32-byte stores (ZFB_COPY_NT=16 keeps the 16-byte form)
+      size_t head = (size_t)((32 - ((uintptr_t)d & 31)) & 31);
+      std::memcpy(d, s, head);
+      d += head; s += head; n -= head;
+      const size_t blocks = n / 128;
+      stream_copy_avx2(d, s, blocks);
+      _mm_sfence();
+      std::memcpy(d + 128 * blocks, s + 128 * blocks, n - 128 * blocks);
+      return;
+    }
+#endif
     size_t head = (size_t)((16 - ((uintptr_t)d & 15)) & 15);
     std::memcpy(d, s, head);
     d += head; s += head; n -= head;
