@@ -951,6 +951,11 @@ enc3_f64_tile_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t* __restr
   for (unsigned it = 0; t < tg.nboxes; t += gridDim.x, it++) {
     const box_info b0 = sb[it & 1];
     const bool active = tid < b0.nvalid;
+    if (tid == 0) {
+      // the next box into L2 while this one is coded (its TMA load can only be issued when the tile buffer is free)
+      sb[(it + 1) & 1] = box_of(tg, t + gridDim.x);
+      if (sb[(it + 1) & 1].nvalid) ptx::tma_prefetch_3d(&tmap, (int)sb[(it + 1) & 1].x0, (int)sb[(it + 1) & 1].y0, (int)sb[(it + 1) & 1].z0);
+    }
     ptx::mbar_wait(&bars[0], it & 1);
     if (active) {
       double f[64];
@@ -964,7 +969,6 @@ enc3_f64_tile_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t* __restr
       d3::encode_block(f, maxbits, sink, tb, ps);
     }
     ptx::fence_proxy_async();
-    if (tid == 0) sb[(it + 1) & 1] = box_of(tg, t + gridDim.x);
     __syncthreads();
     if (tid == 0) {
       ptx::bulk_store(stream + b0.blk0 * tg.W, outw, b0.nvalid * tg.W * 8u);
