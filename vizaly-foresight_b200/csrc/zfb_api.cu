@@ -521,6 +521,8 @@ static tile_geom make_tile_geom(const geom& g, unsigned maxbits)
   t.ntiles = (t.nboxes + BOXES_PER_TILE - 1) / BOXES_PER_TILE;
   t.nx = (unsigned)g.nx; t.ny = (unsigned)g.ny; t.nz = (unsigned)g.nz;
   t.W = maxbits >> 6;
+  t.div_wpr = make_fastdiv((t.nbx + 31) / 32 ? (t.nbx + 31) / 32 : 1);
+  t.div_nby = make_fastdiv(t.nby ? t.nby : 1);
   return t;
 }
 

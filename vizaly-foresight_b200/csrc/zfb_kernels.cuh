@@ -526,7 +526,35 @@ constexpr int BOX_BLOCKS = 64;                 // blocks per TMA box (256 x-valu
 constexpr int BOX_FLOATS = 256 * 4 * 4;        // 16 KiB
 constexpr int BOXES_PER_TILE = TILE_THREADS / BOX_BLOCKS;
 
+// Division of a 32-bit index by a divisor fixed per launch: one multiply-high and two shifts (Granlund-Montgomery) in
+// place of the ~20-instruction sequence the compiler emits for `/` -- the warp-tile coordinates are derived once per tile
+// in the transform warps of the decode kernel, where every instruction is on the critical path.
+struct fastdiv {
+  unsigned d, m, s1, s2;
+  __host__ __device__ unsigned div(unsigned n) const
+  {
+#if defined(__CUDA_ARCH__)
+    const unsigned t = __umulhi(m, n);
+#else
+    const unsigned t = (unsigned)(((unsigned long long)m * n) >> 32);
+#endif
+    return (t + ((n - t) >> s1)) >> s2;
+  }
+};
+inline fastdiv make_fastdiv(unsigned d)
+{
+  fastdiv f;
+  f.d = d;
+  unsigned L = 0;
+  while ((1ull << L) < d) L++;
+  f.m = (unsigned)((((1ull << L) - d) << 32) / d + 1ull);
+  f.s1 = L < 1 ? L : 1u;
+  f.s2 = L < 1 ? 0u : L - 1u;
+  return f;
+}
+
 struct tile_geom {
+  fastdiv div_wpr, div_nby;  // warp-tiles per block row ((nbx + 31) / 32) and nby, for the warp-tile kernels
   unsigned nbx, nby, nbz;    // FULL blocks per axis handled by the tile kernels (ny/4, nz/4; nx % 4 == 0)
   unsigned nby_t;            // block rows per z-slab in the stream, partial row included ((ny+3)/4)
   unsigned bpr;              // boxes per block-row = ceil(nbx / 64)

@@ -66,8 +66,8 @@ struct wtile {
 __device__ __forceinline__ wtile wtile_of(const tile_geom& tg, unsigned wpr, unsigned w)
 {
   wtile t;
-  const unsigned row = w / wpr, xw = w - row * wpr;
-  const unsigned iz = row / tg.nby, iy = row - iz * tg.nby;
+  const unsigned row = tg.div_wpr.div(w), xw = w - row * wpr;
+  const unsigned iz = tg.div_nby.div(row), iy = row - iz * tg.nby;
   t.x0 = xw * 128u; t.y0 = iy * 4u; t.z0 = iz * 4u;
   t.blk0 = ((size_t)iz * tg.nby_t + iy) * tg.nbx + (size_t)xw * 32u;
   const unsigned rem = tg.nbx - xw * 32u;
@@ -253,7 +253,7 @@ dec3_f32_ws_kernel(const float* __restrict__ orig, const uint64_t* __restrict__ 
     long long c_slots = 0, c_empty = 0, c_parse = 0, c_t0 = clock64();
 #endif
     for (unsigned it = 0; w < nwt; w += stride, it++) {
-      const unsigned rem = tg.nbx - (w % wpr) * 32u;
+      const unsigned rem = tg.nbx - (w - tg.div_wpr.div(w) * wpr) * 32u;
       const unsigned nvalid = rem < 32u ? rem : 32u;
 #ifdef ZFB_WS_PROF
       long long c0 = clock64();
@@ -516,7 +516,7 @@ dec3_f64_ws_kernel(const uint64_t* __restrict__ stream, double* __restrict__ out
     unsigned w = blockIdx.x * DP_WARPS + p;
     if (w < nwt) issue_slots(w);
     for (unsigned it = 0; w < nwt; w += stride, it++) {
-      const unsigned rem = tg.nbx - (w % wpr) * 32u;
+      const unsigned rem = tg.nbx - (w - tg.div_wpr.div(w) * wpr) * 32u;
       const unsigned nvalid = rem < 32u ? rem : 32u;
       asm volatile("cp.async.wait_group 0;" ::: "memory");
       __syncwarp();
