@@ -651,12 +651,11 @@ enc3_f32_warp_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t* __restr
   ps.base = ptx::smem_u32(tile) + 16u * lane;
   ps.stride = 512u;
   float vmax = -3.402823466e38f, vnmin = -3.402823466e38f;
+  wtile t = wtile_of(tg, wpr, w < nwt ? w : 0u);
   for (unsigned it = 0; w < nwt; w += stride, it++) {
-    const wtile t = wtile_of(tg, wpr, w);
-    if (lane == 0 && w + stride < nwt) {
-      const wtile n = wtile_of(tg, wpr, w + stride);
-      ptx::tma_prefetch_3d(&tmap, (int)n.x0, (int)n.y0, (int)n.z0);  // the next box into L2 while this one is coded
-    }
+    const bool more = w + stride < nwt;
+    const wtile nx = wtile_of(tg, wpr, more ? w + stride : 0u);
+    if (lane == 0 && more) ptx::tma_prefetch_3d(&tmap, (int)nx.x0, (int)nx.y0, (int)nx.z0);  // the next box into L2 while this one is coded
     ptx::mbar_wait(bar, it & 1u);
     if (lane < t.nvalid) {
       float f[64];
@@ -676,12 +675,13 @@ enc3_f32_warp_kernel(const __grid_constant__ CUtensorMap tmap, uint64_t* __restr
     ptx::fence_proxy_async();  // slot words and the in-place plane rows -> async proxy
     __syncwarp();
     if (lane == 0) {
-      if (w + stride < nwt) issue_load(wtile_of(tg, wpr, w + stride));  // the box is free: the load flies during the store
+      if (more) issue_load(nx);  // the box is free: the load flies during the store
       ptx::bulk_store(stream + t.blk0 * W, outw, t.nvalid * W * 8u);
       ptx::bulk_commit();
       ptx::bulk_wait_read0();  // `out` may be rewritten
     }
     __syncwarp();
+    t = nx;
   }
   if (lane == 0) ptx::bulk_wait0();
   if (MINMAX) {
