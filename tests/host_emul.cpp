@@ -72,10 +72,15 @@ static void run(bool enc, size_t nx, size_t ny, size_t nz, unsigned maxbits, Sca
       if constexpr (std::is_same<Scalar, float>::value && DIMS == 1) {
         if (g_use_f3 && mx == 4 && (maxbits % 32) == 0 && maxbits <= 128) {
           const f1::tables tb = host_tables1();
-          uint32_t o[4];
-          f1::encode_block<4>(f, maxbits, o, tb);
           uint32_t* s32 = reinterpret_cast<uint32_t*>(stream) + startbit / 32;
-          for (unsigned i = 0; i < maxbits / 32; i++) s32[i] = o[i];
+          // the same instantiations as the kernels: <1> for 32-bit slots, <2> for 64, <4> for 96 / 128
+          if (maxbits == 32) { uint32_t o[1]; f1::encode_block<1>(f, maxbits, o, tb); s32[0] = o[0]; }
+          else if (maxbits == 64) { uint32_t o[2]; f1::encode_block<2>(f, maxbits, o, tb); s32[0] = o[0]; s32[1] = o[1]; }
+          else {
+            uint32_t o[4];
+            f1::encode_block<4>(f, maxbits, o, tb);
+            for (unsigned i = 0; i < maxbits / 32; i++) s32[i] = o[i];
+          }
           continue;
         }
       }
@@ -140,7 +145,9 @@ static void run(bool enc, size_t nx, size_t ny, size_t nz, unsigned maxbits, Sca
           uint32_t in4[4] = {0, 0, 0, 0};
           const uint32_t* s32 = reinterpret_cast<const uint32_t*>(stream) + startbit / 32;
           for (unsigned i = 0; i < maxbits / 32; i++) in4[i] = s32[i];
-          f1::decode_block<4>(f, maxbits, in4, tb);
+          if (maxbits == 32) { const uint32_t in1[1] = {in4[0]}; f1::decode_block<1>(f, maxbits, in1, tb); }
+          else if (maxbits == 64) { const uint32_t in2[2] = {in4[0], in4[1]}; f1::decode_block<2>(f, maxbits, in2, tb); }
+          else f1::decode_block<4>(f, maxbits, in4, tb);
           done = true;
         }
       }

@@ -217,36 +217,49 @@ ZFB_HD void encode_block(const float (&f)[4], unsigned maxbits, uint32_t (&out)[
   int k = 31 - clz32(any);
   pos += (unsigned)(31 - k);  // planes above k: one zero group-test bit each
   unsigned n = 0;
-  while (n < 3u && k >= 0 && pos < maxbits) {
-    // run: planes k .. ke+1 in which coefficients n..3 are all zero
+  // One head step = a run (possibly empty) of planes k .. ke+1 in which coefficients nn..3 are all zero AND the event
+  // plane behind it: the lanes of a warp then walk the same code whatever mix of runs and events their blocks hold.
+  // `nn` is the number of significant coefficients on entry (n == nn); with a literal argument the step is specialised
+  // at compile time (one spread form, fixed cap and table row).
+  auto head_step = [&](const unsigned nn) {
     uint32_t rest = u[3] | u[2];
-    if (n < 2u) rest |= u[1];
-    if (n < 1u) rest |= u[0];
+    if (nn < 2u) rest |= u[1];
+    if (nn < 1u) rest |= u[0];
     rest &= mask32((unsigned)k + 1u);
     const int ke = rest ? 31 - clz32(rest) : -1;
     unsigned L = (unsigned)(k - ke);
-    // One iteration = a run (possibly empty) AND the event plane behind it: the lanes of a warp then walk the same code
-    // whatever mix of runs and events their blocks hold (with the run and the event as separate iterations half the
-    // lanes sat out every pass).
-    const unsigned cap = n == 0u ? 32u : (n == 1u ? 16u : 10u);  // planes whose codes fit one 32-bit put
-    const bool capped = L > cap;  // (a capped run is simply continued by the next iteration)
+    const unsigned cap = nn == 0u ? 32u : (nn == 1u ? 16u : 10u);  // planes whose codes fit one 32-bit put
+    const bool capped = L > cap;  // (a capped run is simply continued by the next step)
     if (capped) L = cap;
     if (L) {
       uint32_t code = 0u;
-      if (n == 1u) code = spread2(brev32(u[0] << (31 - k)) & mask32(L));
-      else if (n == 2u) code = spread3(brev32(u[0] << (31 - k)) & mask32(L)) | (spread3(brev32(u[1] << (31 - k)) & mask32(L)) << 1);
-      put(code, L * (n + 1u));
+      if (nn == 1u) code = spread2(brev32(u[0] << (31 - k)) & mask32(L));
+      else if (nn == 2u) code = spread3(brev32(u[0] << (31 - k)) & mask32(L)) | (spread3(brev32(u[1] << (31 - k)) & mask32(L)) << 1);
+      put(code, L * (nn + 1u));
       k -= (int)L;
     }
     if (!capped && k >= 0 && pos < maxbits) {
       // event plane k
       const unsigned x = ((u[0] >> k) & 1u) | (((u[1] >> k) & 1u) << 1) | (((u[2] >> k) & 1u) << 2) | (((u[3] >> k) & 1u) << 3);
-      const unsigned e = tb.enc[n * 16u + x];
+      const unsigned e = tb.enc[nn * 16u + x];
       put(e & 0xffu, (e >> 8) & 15u);
       n = e >> 12;
       k--;
     }
+  };
+  // Every event raises n, so a block passes through each of n = 0, 1, 2 at most once: three straight-line steps, each
+  // specialised for its n, instead of a loop whose trip count is the warp's maximum and whose body serves every n.
+  // Plane k is the top set plane, so the n == 0 step is its event alone.
+  if (pos < maxbits) {
+    const unsigned x = ((u[0] >> k) & 1u) | (((u[1] >> k) & 1u) << 1) | (((u[2] >> k) & 1u) << 2) | (((u[3] >> k) & 1u) << 3);
+    const unsigned e = tb.enc[x];
+    put(e & 0xffu, (e >> 8) & 15u);
+    n = e >> 12;
+    k--;
   }
+  if (n == 1u && k >= 0 && pos < maxbits) head_step(1u);
+  if (n == 2u && k >= 0 && pos < maxbits) head_step(2u);
+  while (n < 3u && k >= 0 && pos < maxbits) head_step(n);  // only behind a capped run (> 16 / 10 planes without an event)
   if (n >= 3u && k >= 0 && pos < maxbits) {
     // planes k, k-1, ... : the raw nibble of every plane = interleave of the coefficients' bits below plane k+1
     uint32_t v[4];
@@ -334,51 +347,60 @@ ZFB_HD void decode_block(float (&f)[4], unsigned maxbits, const uint32_t (&in)[M
     pos += sk; remaining -= sk; k -= (int)sk;
   }
   unsigned n = 0;
-  while (n < 3u && k >= 0 && remaining) {
+  // the event plane k, its code in the low bits of `we`, with nn coefficients significant on entry
+  auto event_plane = [&](const uint32_t we, const unsigned nn) {
+    const unsigned e = tb.dec[nn * 128u + (we & 127u)];
+    const unsigned len = (e >> 4) & 15u;
+    if (len <= remaining) {
+      const unsigned x = e & 15u;
+      ZFB_UNROLL for (int i = 0; i < 4; i++) u[i] |= ((x >> i) & 1u) << k;
+      n = e >> 8;
+      pos += len; remaining -= len;
+    } else {
+      // the budget ends inside this plane's code (at most once per block): exact bit-serial steps, out of line
+      const unsigned xn = truncated_plane(we, remaining, nn);
+      const unsigned x = xn & 15u;
+      ZFB_UNROLL for (int i = 0; i < 4; i++) u[i] |= ((x >> i) & 1u) << k;
+      remaining = 0;
+      n = xn >> 4;
+    }
+    k--;
+  };
+  // One head step = a run (possibly empty) AND the event plane behind it, as in the encoder; nn = n on entry (a literal
+  // argument specialises the step).  A run that fills the whole window (L == R > 0) has not met its event yet: the next
+  // step continues it.
+  auto head_step = [&](const unsigned nn) {
     const uint32_t w = peek(pos);
-    const unsigned cw = n + 1u;                                   // bits per run-plane code
+    const unsigned cw = nn + 1u;                                   // bits per run-plane code
     unsigned R = (remaining < 32u ? remaining : 32u);
-    if (n == 2u && R > 30u) R = 30u;
-    R = n == 0u ? R : (n == 1u ? R >> 1 : (R * 11u) >> 5);         // whole codes in the window (n == 2: floor(R / 3) for R <= 30)
+    if (nn == 2u && R > 30u) R = 30u;
+    R = nn == 0u ? R : (nn == 1u ? R >> 1 : (R * 11u) >> 5);       // whole codes in the window (nn == 2: floor(R / 3) for R <= 30)
     if (R > (unsigned)k + 1u) R = (unsigned)k + 1u;
     // group-test bits of the run-plane codes: the last bit of every code
-    const uint32_t tests = (n == 0u ? 0xffffffffu : (n == 1u ? 0xaaaaaaaau : 0x24924924u)) & mask32(R * cw);
+    const uint32_t tests = (nn == 0u ? 0xffffffffu : (nn == 1u ? 0xaaaaaaaau : 0x24924924u)) & mask32(R * cw);
     const uint32_t t = w & tests;
     unsigned L = R;
-    if (t) { const unsigned z = (unsigned)ctz32(t); L = n == 0u ? z : (n == 1u ? z >> 1 : (z * 11u) >> 5); }
-    // One iteration = a run (possibly empty) AND the event plane behind it, as in the encoder.  A run that fills the
-    // whole window (L == R > 0) has not met its event yet: the next iteration continues it.
+    if (t) { const unsigned z = (unsigned)ctz32(t); L = nn == 0u ? z : (nn == 1u ? z >> 1 : (z * 11u) >> 5); }
     const bool event = L == 0u || L < R;
     uint32_t we = w;
     if (L) {
-      if (n == 1u) u[0] |= brev32(gather2(w) & mask32(L)) >> (31 - k);
-      else if (n == 2u) {
+      if (nn == 1u) u[0] |= brev32(gather2(w) & mask32(L)) >> (31 - k);
+      else if (nn == 2u) {
         u[0] |= brev32(gather3(w) & mask32(L)) >> (31 - k);
         u[1] |= brev32(gather3(w >> 1) & mask32(L)) >> (31 - k);
       }
       pos += L * cw; remaining -= L * cw; k -= (int)L;
       we = peek(pos);
     }
-    if (event && k >= 0 && remaining) {
-      // (R == 0: fewer than n + 1 bits are left, the budget ends inside this plane's code -- handled exactly below)
-      const unsigned e = tb.dec[n * 128u + (we & 127u)];
-      const unsigned len = (e >> 4) & 15u;
-      if (len <= remaining) {
-        const unsigned x = e & 15u;
-        ZFB_UNROLL for (int i = 0; i < 4; i++) u[i] |= ((x >> i) & 1u) << k;
-        n = e >> 8;
-        pos += len; remaining -= len;
-      } else {
-        // the budget ends inside this plane's code (at most once per block): exact bit-serial steps, out of line
-        const unsigned xn = truncated_plane(we, remaining, n);
-        const unsigned x = xn & 15u;
-        ZFB_UNROLL for (int i = 0; i < 4; i++) u[i] |= ((x >> i) & 1u) << k;
-        remaining = 0;
-        n = xn >> 4;
-      }
-      k--;
-    }
-  }
+    // (R == 0: fewer than nn + 1 bits are left, the budget ends inside this plane's code -- handled exactly in event_plane)
+    if (event && k >= 0 && remaining) event_plane(we, nn);
+  };
+  // Every event raises n: three straight-line steps, each specialised for its n (see the encoder).  Behind the skipped
+  // zero tests the next bit is a one, so the n == 0 step is its event alone.
+  if (k >= 0 && remaining) event_plane(peek(pos), 0u);
+  if (n == 1u && k >= 0 && remaining) head_step(1u);
+  if (n == 2u && k >= 0 && remaining) head_step(2u);
+  while (n < 3u && k >= 0 && remaining) head_step(n);  // only behind a run longer than one window
   if (n >= 3u && k >= 0 && remaining) {
     const unsigned planes = (unsigned)k + 1u;
     uint32_t v[4] = {0u, 0u, 0u, 0u};
