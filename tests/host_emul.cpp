@@ -30,18 +30,18 @@ static f3::tables host_tables()
 }
 
 static uint16_t g1_enc[64], g1_dec[512];
-static uint32_t g1_spread[256];
+static uint32_t g1_spread[256], g1_unspread[256];
 static f1::tables host_tables1()
 {
   static bool built = false;
   if (!built) {
     for (unsigned i = 0; i < 64; i++) g1_enc[i] = f1::enc_entry(i);
     for (unsigned i = 0; i < 512; i++) g1_dec[i] = f1::dec_entry(i);
-    for (unsigned i = 0; i < 256; i++) g1_spread[i] = f1::spread_entry(i);
+    for (unsigned i = 0; i < 256; i++) { g1_spread[i] = f1::spread_entry(i); g1_unspread[i] = f1::unspread_entry(i); }
     built = true;
   }
   f1::tables t;
-  t.enc = g1_enc; t.dec = g1_dec; t.spread = g1_spread;
+  t.enc = g1_enc; t.dec = g1_dec; t.spread = g1_spread; t.unspread = g1_unspread;
   return t;
 }
 

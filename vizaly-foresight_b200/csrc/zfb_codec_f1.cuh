@@ -108,10 +108,20 @@ ZFB_HD uint32_t spread_entry(unsigned b)
   return r;
 }
 
+// UNSPREAD[b]: the inverse for two planes at a time.  Byte b = the raw nibbles of planes j (low) and j + 1 (high);
+// coefficient i's two bits go to bits 8 i and 8 i + 1.
+ZFB_HD uint32_t unspread_entry(unsigned b)
+{
+  uint32_t r = 0;
+  for (int i = 0; i < 4; i++) r |= (((b >> i) & 1u) | (((b >> (4 + i)) & 1u) << 1)) << (8 * i);
+  return r;
+}
+
 struct tables {
-  const uint16_t* enc;     // 64
-  const uint16_t* dec;     // 512
-  const uint32_t* spread;  // 256
+  const uint16_t* enc;       // 64
+  const uint16_t* dec;       // 512
+  const uint32_t* spread;    // 256
+  const uint32_t* unspread;  // 256
 };
 
 ZFB_HD uint32_t gather4(uint32_t w)  // bits 0,4,8,...,28 of w -> bits 0..7
@@ -264,15 +274,27 @@ ZFB_HD void encode_block(const float (&f)[4], unsigned maxbits, uint32_t (&out)[
     // planes k, k-1, ... : the raw nibble of every plane = interleave of the coefficients' bits below plane k+1
     uint32_t v[4];
     ZFB_UNROLL for (int i = 0; i < 4; i++) v[i] = brev32(u[i] << (31 - k));  // bit j = bit (k - j) of u[i]
-    const unsigned planes = (unsigned)k + 1u;
-    // 32 stream bits (8 planes) per step; the writer drops what falls beyond maxbits
-    for (unsigned c = 0; c * 8u < planes && pos < maxbits; c++) {
-      const unsigned sh = 8u * c;
-      uint32_t w = tb.spread[(v[0] >> sh) & 0xffu] | (tb.spread[(v[1] >> sh) & 0xffu] << 1) |
-                   (tb.spread[(v[2] >> sh) & 0xffu] << 2) | (tb.spread[(v[3] >> sh) & 0xffu] << 3);
-      const unsigned left = planes - 8u * c;  // planes available in this chunk
-      unsigned len = left >= 8u ? 32u : 4u * left;
-      put(w & mask32(len), len);
+    if (MAXW <= 2) {
+      // at most 54 bits of the slot are left: the top 8 (16) planes, interleaved, are OR-ed in with one shift; planes
+      // that do not exist are zero bits of v[], what falls beyond the slot is dropped by the shift
+      auto chunk = [&](unsigned sh) -> uint32_t {
+        return tb.spread[(v[0] >> sh) & 0xffu] | (tb.spread[(v[1] >> sh) & 0xffu] << 1) |
+               (tb.spread[(v[2] >> sh) & 0xffu] << 2) | (tb.spread[(v[3] >> sh) & 0xffu] << 3);
+      };
+      uint64_t W = chunk(0u);
+      if (MAXW == 2) W |= (uint64_t)chunk(8u) << 32;
+      acc0 |= W << pos;
+    } else {
+      const unsigned planes = (unsigned)k + 1u;
+      // 32 stream bits (8 planes) per step; the writer drops what falls beyond maxbits
+      for (unsigned c = 0; c * 8u < planes && pos < maxbits; c++) {
+        const unsigned sh = 8u * c;
+        uint32_t w = tb.spread[(v[0] >> sh) & 0xffu] | (tb.spread[(v[1] >> sh) & 0xffu] << 1) |
+                     (tb.spread[(v[2] >> sh) & 0xffu] << 2) | (tb.spread[(v[3] >> sh) & 0xffu] << 3);
+        const unsigned left = planes - 8u * c;  // planes available in this chunk
+        unsigned len = left >= 8u ? 32u : 4u * left;
+        put(w & mask32(len), len);
+      }
     }
   }
   // bits past maxbits (a multiple of 32) live in words the caller does not store
@@ -402,18 +424,34 @@ ZFB_HD void decode_block(float (&f)[4], unsigned maxbits, const uint32_t (&in)[M
   if (n == 2u && k >= 0 && remaining) head_step(2u);
   while (n < 3u && k >= 0 && remaining) head_step(n);  // only behind a run longer than one window
   if (n >= 3u && k >= 0 && remaining) {
-    const unsigned planes = (unsigned)k + 1u;
-    uint32_t v[4] = {0u, 0u, 0u, 0u};
-    for (unsigned c = 0; c * 8u < planes && remaining; c++) {
-      uint32_t w = peek(pos);
-      const unsigned left = planes - 8u * c;
-      unsigned len = left >= 8u ? 32u : 4u * left;
-      if (len > remaining) len = remaining;
-      w &= mask32(len);
-      ZFB_UNROLL for (int i = 0; i < 4; i++) v[i] |= gather4(w >> i) << (8u * c);
-      pos += len; remaining -= len;
+    if (MAXW <= 2) {
+      // the rest of the slot (zeros shift in behind its end) is the interleave of the top planes: two planes per table
+      // lookup, coefficient i's bits collected in byte i; planes below plane 0 fall off in the final shift
+      const uint64_t r = in0 >> pos;
+      auto chunk = [&](uint32_t w) -> uint32_t {
+        return tb.unspread[w & 0xffu] | (tb.unspread[(w >> 8) & 0xffu] << 2) | (tb.unspread[(w >> 16) & 0xffu] << 4) |
+               (tb.unspread[w >> 24] << 6);
+      };
+      const uint32_t o0 = chunk((uint32_t)r);
+      const uint32_t o1 = MAXW == 2 ? chunk((uint32_t)(r >> 32)) : 0u;
+      ZFB_UNROLL for (int i = 0; i < 4; i++) {
+        const uint32_t vi = ((o0 >> (8 * i)) & 0xffu) | (((o1 >> (8 * i)) & 0xffu) << 8);
+        u[i] |= brev32(vi) >> (31 - k);
+      }
+    } else {
+      const unsigned planes = (unsigned)k + 1u;
+      uint32_t v[4] = {0u, 0u, 0u, 0u};
+      for (unsigned c = 0; c * 8u < planes && remaining; c++) {
+        uint32_t w = peek(pos);
+        const unsigned left = planes - 8u * c;
+        unsigned len = left >= 8u ? 32u : 4u * left;
+        if (len > remaining) len = remaining;
+        w &= mask32(len);
+        ZFB_UNROLL for (int i = 0; i < 4; i++) v[i] |= gather4(w >> i) << (8u * c);
+        pos += len; remaining -= len;
+      }
+      ZFB_UNROLL for (int i = 0; i < 4; i++) u[i] |= brev32(v[i]) >> (31 - k);
     }
-    ZFB_UNROLL for (int i = 0; i < 4; i++) u[i] |= brev32(v[i]) >> (31 - k);
   }
   int32_t ib[4];
   ZFB_UNROLL for (int i = 0; i < 4; i++) ib[i] = (int32_t)((u[i] ^ T::NBMASK) - T::NBMASK);

@@ -1111,17 +1111,18 @@ dec3_f64_tile_kernel(const __grid_constant__ CUtensorMap tmap_orig, const uint64
 // ---------------------------------------------------------------------------------------------
 struct coder1_smem {
   uint32_t spread[256];
+  uint32_t unspread[256];
   uint16_t dec[512];
   uint16_t enc[64];
 };
 __device__ __forceinline__ f1::tables build_coder1_tables(coder1_smem& cs)
 {
-  for (unsigned i = threadIdx.x; i < 256; i += blockDim.x) cs.spread[i] = f1::spread_entry(i);
+  for (unsigned i = threadIdx.x; i < 256; i += blockDim.x) { cs.spread[i] = f1::spread_entry(i); cs.unspread[i] = f1::unspread_entry(i); }
   for (unsigned i = threadIdx.x; i < 512; i += blockDim.x) cs.dec[i] = f1::dec_entry(i);
   for (unsigned i = threadIdx.x; i < 64; i += blockDim.x) cs.enc[i] = f1::enc_entry(i);
   __syncthreads();
   f1::tables t;
-  t.enc = cs.enc; t.dec = cs.dec; t.spread = cs.spread;
+  t.enc = cs.enc; t.dec = cs.dec; t.spread = cs.spread; t.unspread = cs.unspread;
   return t;
 }
 
