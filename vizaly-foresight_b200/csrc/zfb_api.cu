@@ -872,7 +872,10 @@ extern "C" int zfb_decode_dev(zfb_ctx* c, int dtype, int dims, size_t nx, size_t
     const size_t nfull = g.nx / 4;
     const unsigned nw = maxbits >> 5;
     size_t want = (nfull + 255) / 256;
-    int grid = (int)(want < (size_t)c->sm_count * 8 ? (want ? want : 1) : (size_t)c->sm_count * 8);
+#ifndef ZFB_DEC1_GRIDM
+#define ZFB_DEC1_GRIDM 12  // CTAs per SM of the grid-stride launch: two waves of the 6 resident CTAs (ZFB_DEC1_MINB)
+#endif
+    int grid = (int)(want < (size_t)c->sm_count * ZFB_DEC1_GRIDM ? (want ? want : 1) : (size_t)c->sm_count * ZFB_DEC1_GRIDM);
     if (grid > c->part_rows - 1) grid = c->part_rows - 1;
     const uint32_t* st = (const uint32_t*)d_stream;
     float* o = (float*)d_out;

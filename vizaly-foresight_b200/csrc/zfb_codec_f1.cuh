@@ -227,6 +227,9 @@ ZFB_HD void encode_block(const float (&f)[4], unsigned maxbits, uint32_t (&out)[
   int k = 31 - clz32(any);
   pos += (unsigned)(31 - k);  // planes above k: one zero group-test bit each
   unsigned n = 0;
+  auto nibble = [&](int kk) -> unsigned {  // plane kk as a nibble (bit i = coefficient i)
+    return ((u[0] >> kk) & 1u) | (((u[1] >> kk) & 1u) << 1) | (((u[2] >> kk) & 1u) << 2) | (((u[3] >> kk) & 1u) << 3);
+  };
   // One head step = a run (possibly empty) of planes k .. ke+1 in which coefficients nn..3 are all zero AND the event
   // plane behind it: the lanes of a warp then walk the same code whatever mix of runs and events their blocks hold.
   // `nn` is the number of significant coefficients on entry (n == nn); with a literal argument the step is specialised
@@ -250,7 +253,7 @@ ZFB_HD void encode_block(const float (&f)[4], unsigned maxbits, uint32_t (&out)[
     }
     if (!capped && k >= 0 && pos < maxbits) {
       // event plane k
-      const unsigned x = ((u[0] >> k) & 1u) | (((u[1] >> k) & 1u) << 1) | (((u[2] >> k) & 1u) << 2) | (((u[3] >> k) & 1u) << 3);
+      const unsigned x = nibble(k);
       const unsigned e = tb.enc[nn * 16u + x];
       put(e & 0xffu, (e >> 8) & 15u);
       n = e >> 12;
@@ -261,7 +264,7 @@ ZFB_HD void encode_block(const float (&f)[4], unsigned maxbits, uint32_t (&out)[
   // specialised for its n, instead of a loop whose trip count is the warp's maximum and whose body serves every n.
   // Plane k is the top set plane, so the n == 0 step is its event alone.
   if (pos < maxbits) {
-    const unsigned x = ((u[0] >> k) & 1u) | (((u[1] >> k) & 1u) << 1) | (((u[2] >> k) & 1u) << 2) | (((u[3] >> k) & 1u) << 3);
+    const unsigned x = nibble(k);
     const unsigned e = tb.enc[x];
     put(e & 0xffu, (e >> 8) & 15u);
     n = e >> 12;
@@ -355,44 +358,50 @@ ZFB_HD void decode_block(float (&f)[4], unsigned maxbits, const uint32_t (&in)[M
     if (p > 32u) v |= in1 << (64u - p);
     return (uint32_t)v;
   };
+  // 32- and 64-bit slots: the unread rest of the slot is carried in one register pair, shifted down as bits are
+  // consumed (no position arithmetic, zeros shift in behind the slot's end)
+  uint64_t cur = in0 >> 9;
+  auto window = [&]() -> uint32_t { return MAXW <= 2 ? (uint32_t)cur : peek(pos); };
   uint32_t u[4] = {0u, 0u, 0u, 0u};
   unsigned remaining = maxbits - 9u;
+  auto consume = [&](unsigned len) {  // len <= 32
+    pos += len; remaining -= len;
+    if (MAXW <= 2) cur >>= len;
+  };
   // leading all-zero planes: zero group tests while n == 0
   int k = 31;
   {
-    uint32_t w = peek(pos);
+    uint32_t w = window();
     if (remaining < 32u) w &= mask32(remaining);
     const unsigned z = w ? (unsigned)ctz32(w) : 32u;   // zero test bits before the first one
     const unsigned skip = z < remaining ? z : remaining;
     // at most 32 planes exist; a slot that is all zero after the header decodes to zero coefficients
     const unsigned sk = skip > 32u ? 32u : skip;
-    pos += sk; remaining -= sk; k -= (int)sk;
+    consume(sk); k -= (int)sk;
   }
   unsigned n = 0;
   // the event plane k, its code in the low bits of `we`, with nn coefficients significant on entry
   auto event_plane = [&](const uint32_t we, const unsigned nn) {
     const unsigned e = tb.dec[nn * 128u + (we & 127u)];
     const unsigned len = (e >> 4) & 15u;
-    if (len <= remaining) {
-      const unsigned x = e & 15u;
-      ZFB_UNROLL for (int i = 0; i < 4; i++) u[i] |= ((x >> i) & 1u) << k;
-      n = e >> 8;
-      pos += len; remaining -= len;
-    } else {
+    unsigned x = e & 15u;
+    n = e >> 8;
+    if (len <= remaining) consume(len);
+    else {
       // the budget ends inside this plane's code (at most once per block): exact bit-serial steps, out of line
       const unsigned xn = truncated_plane(we, remaining, nn);
-      const unsigned x = xn & 15u;
-      ZFB_UNROLL for (int i = 0; i < 4; i++) u[i] |= ((x >> i) & 1u) << k;
-      remaining = 0;
+      x = xn & 15u;
       n = xn >> 4;
+      remaining = 0;
     }
+    ZFB_UNROLL for (int i = 0; i < 4; i++) u[i] |= ((x >> i) & 1u) << k;
     k--;
   };
   // One head step = a run (possibly empty) AND the event plane behind it, as in the encoder; nn = n on entry (a literal
   // argument specialises the step).  A run that fills the whole window (L == R > 0) has not met its event yet: the next
   // step continues it.
   auto head_step = [&](const unsigned nn) {
-    const uint32_t w = peek(pos);
+    const uint32_t w = window();
     const unsigned cw = nn + 1u;                                   // bits per run-plane code
     unsigned R = (remaining < 32u ? remaining : 32u);
     if (nn == 2u && R > 30u) R = 30u;
@@ -411,15 +420,15 @@ ZFB_HD void decode_block(float (&f)[4], unsigned maxbits, const uint32_t (&in)[M
         u[0] |= brev32(gather3(w) & mask32(L)) >> (31 - k);
         u[1] |= brev32(gather3(w >> 1) & mask32(L)) >> (31 - k);
       }
-      pos += L * cw; remaining -= L * cw; k -= (int)L;
-      we = peek(pos);
+      consume(L * cw); k -= (int)L;
+      we = window();
     }
     // (R == 0: fewer than nn + 1 bits are left, the budget ends inside this plane's code -- handled exactly in event_plane)
     if (event && k >= 0 && remaining) event_plane(we, nn);
   };
   // Every event raises n: three straight-line steps, each specialised for its n (see the encoder).  Behind the skipped
   // zero tests the next bit is a one, so the n == 0 step is its event alone.
-  if (k >= 0 && remaining) event_plane(peek(pos), 0u);
+  if (k >= 0 && remaining) event_plane(window(), 0u);
   if (n == 1u && k >= 0 && remaining) head_step(1u);
   if (n == 2u && k >= 0 && remaining) head_step(2u);
   while (n < 3u && k >= 0 && remaining) head_step(n);  // only behind a run longer than one window
@@ -427,7 +436,7 @@ ZFB_HD void decode_block(float (&f)[4], unsigned maxbits, const uint32_t (&in)[M
     if (MAXW <= 2) {
       // the rest of the slot (zeros shift in behind its end) is the interleave of the top planes: two planes per table
       // lookup, coefficient i's bits collected in byte i; planes below plane 0 fall off in the final shift
-      const uint64_t r = in0 >> pos;
+      const uint64_t r = cur;
       auto chunk = [&](uint32_t w) -> uint32_t {
         return tb.unspread[w & 0xffu] | (tb.unspread[(w >> 8) & 0xffu] << 2) | (tb.unspread[(w >> 16) & 0xffu] << 4) |
                (tb.unspread[w >> 24] << 6);
