@@ -698,7 +698,10 @@ extern "C" int zfb_encode_dev(zfb_ctx* c, int dtype, int dims, size_t nx, size_t
       CU_TRY(c, cudaMemsetAsync((char*)d_stream + written, 0, g.stream_words * 8 - written, c->stream));
     }
     size_t want = (nfull + 255) / 256;
-    const int grid = (int)(want < (size_t)c->sm_count * 8 ? (want ? want : 1) : (size_t)c->sm_count * 8);
+#ifndef ZFB_ENC1_GRIDM
+#define ZFB_ENC1_GRIDM 16  // CTAs per SM of the grid-stride launch: two waves of the 8 resident CTAs (one wave: 0.87 ms, two or four: 0.84, sixteen: 1.02)
+#endif
+    const int grid = (int)(want < (size_t)c->sm_count * ZFB_ENC1_GRIDM ? (want ? want : 1) : (size_t)c->sm_count * ZFB_ENC1_GRIDM);
     const float* in = (const float*)d_in;
     uint32_t* st = (uint32_t*)d_stream;
     if (nw == 1) enc1_f32_kernel<1><<<grid, 256, 0, c->stream>>>(in, st, nfull, maxbits);
@@ -873,7 +876,7 @@ extern "C" int zfb_decode_dev(zfb_ctx* c, int dtype, int dims, size_t nx, size_t
     const unsigned nw = maxbits >> 5;
     size_t want = (nfull + 255) / 256;
 #ifndef ZFB_DEC1_GRIDM
-#define ZFB_DEC1_GRIDM 12  // CTAs per SM of the grid-stride launch: two waves of the 6 resident CTAs (ZFB_DEC1_MINB)
+#define ZFB_DEC1_GRIDM 24  // CTAs per SM of the grid-stride launch: four waves of the 6 resident CTAs (one wave: 1.29 ms, two: 1.19, four: 1.16)
 #endif
     int grid = (int)(want < (size_t)c->sm_count * ZFB_DEC1_GRIDM ? (want ? want : 1) : (size_t)c->sm_count * ZFB_DEC1_GRIDM);
     if (grid > c->part_rows - 1) grid = c->part_rows - 1;

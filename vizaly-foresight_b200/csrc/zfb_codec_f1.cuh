@@ -14,6 +14,7 @@
 // Works for any maxbits that is a multiple of 32 (CBench's wra rounding gives 64); other budgets take the
 // generic path.  Host-device so tests/host_emul.cpp can bit-compare it with the oracle on the CPU.
 #pragma once
+#include <math.h>
 #include "zfb_codec.cuh"
 #include "zfb_codec_f3.cuh"
 
@@ -187,10 +188,7 @@ ZFB_HD void encode_block(const float (&f)[4], unsigned maxbits, uint32_t (&out)[
   const unsigned nw = maxbits >> 5;
   ZFB_UNROLL for (int i = 0; i < MAXW; i++) out[i] = 0u;
   float mx = 0.f;
-  ZFB_UNROLL for (int i = 0; i < 4; i++) {
-    const float a = f[i] < 0 ? -f[i] : f[i];
-    mx = (mx < a) ? a : mx;
-  }
+  ZFB_UNROLL for (int i = 0; i < 4; i++) mx = fmaxf(mx, fabsf(f[i]));  // NaN operands are ignored, exactly like `if (max < f) max = f`
   if (!(mx > 0.f)) return;
   const int E = T::expfield(mx);
   const int emax = E - 126;
@@ -482,10 +480,7 @@ ZFB_HD unsigned encode_block_var(const float (&f)[4], const stream_params& sp, W
 {
   typedef traits<float> T;
   float mx = 0.f;
-  ZFB_UNROLL for (int i = 0; i < 4; i++) {
-    const float a = f[i] < 0 ? -f[i] : f[i];
-    mx = (mx < a) ? a : mx;
-  }
+  ZFB_UNROLL for (int i = 0; i < 4; i++) mx = fmaxf(mx, fabsf(f[i]));  // NaN operands are ignored, exactly like `if (max < f) max = f`
   const int E = T::expfield(mx);
   const int emax = E - 126;
   const int prec = block_precision<1>(emax, sp);

@@ -1115,11 +1115,18 @@ struct coder1_smem {
   uint16_t dec[512];
   uint16_t enc[64];
 };
+// ENC / DEC: which half of the tables the kernel needs (the decode table alone costs up to 16 plane codes per entry)
+template <bool ENC = true, bool DEC = true>
 __device__ __forceinline__ f1::tables build_coder1_tables(coder1_smem& cs)
 {
-  for (unsigned i = threadIdx.x; i < 256; i += blockDim.x) { cs.spread[i] = f1::spread_entry(i); cs.unspread[i] = f1::unspread_entry(i); }
-  for (unsigned i = threadIdx.x; i < 512; i += blockDim.x) cs.dec[i] = f1::dec_entry(i);
-  for (unsigned i = threadIdx.x; i < 64; i += blockDim.x) cs.enc[i] = f1::enc_entry(i);
+  if (ENC) {
+    for (unsigned i = threadIdx.x; i < 256; i += blockDim.x) cs.spread[i] = f1::spread_entry(i);
+    for (unsigned i = threadIdx.x; i < 64; i += blockDim.x) cs.enc[i] = f1::enc_entry(i);
+  }
+  if (DEC) {
+    for (unsigned i = threadIdx.x; i < 256; i += blockDim.x) cs.unspread[i] = f1::unspread_entry(i);
+    for (unsigned i = threadIdx.x; i < 512; i += blockDim.x) cs.dec[i] = f1::dec_entry(i);
+  }
   __syncthreads();
   f1::tables t;
   t.enc = cs.enc; t.dec = cs.dec; t.spread = cs.spread; t.unspread = cs.unspread;
@@ -1131,7 +1138,7 @@ __global__ void __launch_bounds__(256) enc1_f32_kernel(const float* __restrict__
                                                        size_t nfull, unsigned maxbits)
 {
   __shared__ coder1_smem cs;
-  const f1::tables tb = build_coder1_tables(cs);
+  const f1::tables tb = build_coder1_tables<true, false>(cs);
   const unsigned nw = maxbits >> 5;
   for (size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x; b < nfull; b += (size_t)gridDim.x * blockDim.x) {
     const float4 v = __ldcs(reinterpret_cast<const float4*>(in) + b);
@@ -1157,7 +1164,7 @@ __global__ void __launch_bounds__(256, ZFB_DEC1_MINB) dec1_f32_kernel(const uint
 {
   __shared__ coder1_smem cs;
   __shared__ double red[7 * 8];
-  const f1::tables tb = build_coder1_tables(cs);
+  const f1::tables tb = build_coder1_tables<false, true>(cs);
   const unsigned nw = maxbits >> 5;
   maccf m;
   m.init();

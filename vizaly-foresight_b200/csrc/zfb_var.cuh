@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(128) enc_var1_kernel(const Scalar* __restrict_
   constexpr bool F32 = sizeof(Scalar) == 4;
   __shared__ coder1_smem cs;
   f1::tables tb;
-  if (F32) tb = build_coder1_tables(cs);
+  if (F32) tb = build_coder1_tables<true, false>(cs);
   const bool fast = F32 && f1::var_params_ok(sp);  // per-plane table coder (accuracy / precision modes)
   const size_t ngroups = (g.nblocks + VAR1_GROUP - 1) / VAR1_GROUP;
   const bool vec = (reinterpret_cast<size_t>(in) & 15) == 0;
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(128) dec_var1_kernel(const uint64_t* __restric
   __shared__ uint32_t piece[F32 ? VAR1_STAGE_WORDS : 1];
   __shared__ uint64_t range[2];
   f1::tables tb;
-  if (F32) tb = build_coder1_tables(cs);
+  if (F32) tb = build_coder1_tables<false, true>(cs);
   const bool fast = F32 && f1::var_params_ok(sp);
   macc_t<Scalar> m;
   m.init();
