@@ -225,6 +225,10 @@ ZFB_HD void encode_block(const float (&f)[4], unsigned maxbits, uint32_t (&out)[
   int k = 31 - clz32(any);
   pos += (unsigned)(31 - k);  // planes above k: one zero group-test bit each
   unsigned n = 0;
+  // Is there budget left?  Only an early exit for 32- and 64-bit slots, where the writer drops whatever lands beyond bit
+  // 63 and the caller stores the low word(s) alone: there the head steps simply run on (a block whose budget ends inside
+  // its head is the rare case) and the test costs nothing.
+  auto room = [&]() -> bool { return MAXW <= 2 || pos < maxbits; };
   auto nibble = [&](int kk) -> unsigned {  // plane kk as a nibble (bit i = coefficient i)
     return ((u[0] >> kk) & 1u) | (((u[1] >> kk) & 1u) << 1) | (((u[2] >> kk) & 1u) << 2) | (((u[3] >> kk) & 1u) << 3);
   };
@@ -249,7 +253,7 @@ ZFB_HD void encode_block(const float (&f)[4], unsigned maxbits, uint32_t (&out)[
       put(code, L * (nn + 1u));
       k -= (int)L;
     }
-    if (!capped && k >= 0 && pos < maxbits) {
+    if (!capped && k >= 0 && room()) {
       // event plane k
       const unsigned x = nibble(k);
       const unsigned e = tb.enc[nn * 16u + x];
@@ -261,17 +265,17 @@ ZFB_HD void encode_block(const float (&f)[4], unsigned maxbits, uint32_t (&out)[
   // Every event raises n, so a block passes through each of n = 0, 1, 2 at most once: three straight-line steps, each
   // specialised for its n, instead of a loop whose trip count is the warp's maximum and whose body serves every n.
   // Plane k is the top set plane, so the n == 0 step is its event alone.
-  if (pos < maxbits) {
+  if (room()) {
     const unsigned x = nibble(k);
     const unsigned e = tb.enc[x];
     put(e & 0xffu, (e >> 8) & 15u);
     n = e >> 12;
     k--;
   }
-  if (n == 1u && k >= 0 && pos < maxbits) head_step(1u);
-  if (n == 2u && k >= 0 && pos < maxbits) head_step(2u);
-  while (n < 3u && k >= 0 && pos < maxbits) head_step(n);  // only behind a capped run (> 16 / 10 planes without an event)
-  if (n >= 3u && k >= 0 && pos < maxbits) {
+  if (n == 1u && k >= 0 && room()) head_step(1u);
+  if (n == 2u && k >= 0 && room()) head_step(2u);
+  while (n < 3u && k >= 0 && room()) head_step(n);  // only behind a capped run (> 16 / 10 planes without an event)
+  if (n >= 3u && k >= 0 && pos < (MAXW <= 2 ? 64u : maxbits)) {
     // planes k, k-1, ... : the raw nibble of every plane = interleave of the coefficients' bits below plane k+1
     uint32_t v[4];
     ZFB_UNROLL for (int i = 0; i < 4; i++) v[i] = brev32(u[i] << (31 - k));  // bit j = bit (k - j) of u[i]
