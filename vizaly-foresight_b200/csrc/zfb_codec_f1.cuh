@@ -281,7 +281,8 @@ ZFB_HD void encode_block(const float (&f)[4], unsigned maxbits, uint32_t (&out)[
     ZFB_UNROLL for (int i = 0; i < 4; i++) v[i] = brev32(u[i] << (31 - k));  // bit j = bit (k - j) of u[i]
     if (MAXW <= 2) {
       // at most 54 bits of the slot are left: the top 8 (16) planes, interleaved, are OR-ed in with one shift; planes
-      // that do not exist are zero bits of v[], what falls beyond the slot is dropped by the shift
+      // that do not exist are zero bits of v[], what falls beyond the slot is dropped by the shift.  (A table indexed by
+      // the un-reversed byte saves the four BREV and is slower: 0.78 -> 0.80 ms.)
       auto chunk = [&](unsigned sh) -> uint32_t {
         return tb.spread[(v[0] >> sh) & 0xffu] | (tb.spread[(v[1] >> sh) & 0xffu] << 1) |
                (tb.spread[(v[2] >> sh) & 0xffu] << 2) | (tb.spread[(v[3] >> sh) & 0xffu] << 3);
@@ -374,7 +375,7 @@ ZFB_HD void decode_block(float (&f)[4], unsigned maxbits, const uint32_t (&in)[M
   int k = 31;
   {
     uint32_t w = window();
-    if (remaining < 32u) w &= mask32(remaining);
+    if (MAXW > 2 && remaining < 32u) w &= mask32(remaining);  // (32/64-bit slots: zeros shift in behind the slot's end)
     const unsigned z = w ? (unsigned)ctz32(w) : 32u;   // zero test bits before the first one
     const unsigned skip = z < remaining ? z : remaining;
     // at most 32 planes exist; a slot that is all zero after the header decodes to zero coefficients
@@ -431,8 +432,8 @@ ZFB_HD void decode_block(float (&f)[4], unsigned maxbits, const uint32_t (&in)[M
   // Every event raises n: three straight-line steps, each specialised for its n (see the encoder).  Behind the skipped
   // zero tests the next bit is a one, so the n == 0 step is its event alone.
   if (k >= 0 && remaining) event_plane(window(), 0u);
-  if (n == 1u && k >= 0 && remaining) head_step(1u);
-  if (n == 2u && k >= 0 && remaining) head_step(2u);
+  if (n == 1u && k >= 0) head_step(1u);  // (with nothing left a step parses zeros and changes nothing)
+  if (n == 2u && k >= 0) head_step(2u);
   while (n < 3u && k >= 0 && remaining) head_step(n);  // only behind a run longer than one window
   if (n >= 3u && k >= 0 && remaining) {
     if (MAXW <= 2) {
@@ -445,10 +446,19 @@ ZFB_HD void decode_block(float (&f)[4], unsigned maxbits, const uint32_t (&in)[M
       };
       const uint32_t o0 = chunk((uint32_t)r);
       const uint32_t o1 = MAXW == 2 ? chunk((uint32_t)(r >> 32)) : 0u;
+#if defined(__CUDA_ARCH__)
+      // coefficient i's 16 plane bits, most significant plane first, are byte 3 - i of the two bit-reversed words: one
+      // PRMT puts them in the top half, the shift drops them at plane k
+      const uint32_t b0 = brev32(o0), b1 = brev32(o1);
+      const uint32_t keep = 0xffff0000u >> (31 - k);
+      ZFB_UNROLL for (int i = 0; i < 4; i++)
+        u[i] |= (__byte_perm(b0, b1, (unsigned)(((3 - i) << 12) | ((7 - i) << 8))) >> (31 - k)) & keep;
+#else
       ZFB_UNROLL for (int i = 0; i < 4; i++) {
         const uint32_t vi = ((o0 >> (8 * i)) & 0xffu) | (((o1 >> (8 * i)) & 0xffu) << 8);
         u[i] |= brev32(vi) >> (31 - k);
       }
+#endif
     } else {
       const unsigned planes = (unsigned)k + 1u;
       uint32_t v[4] = {0u, 0u, 0u, 0u};
