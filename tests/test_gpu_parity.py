@@ -431,6 +431,29 @@ def test_ragged_1d_unaligned_slots_into_dirty_buffer(codec, pkg, oracle):
         assert np.array_equal(s.cpu().numpy()[:nbytes], oracle.compress(h, mb)), (n, mb)
 
 
+def test_1d_line_kernels_long_runs_and_tight_budgets(codec, pkg, oracle):
+    """1D line kernels (three straight-line head steps + loop-free tails for 32/64-bit slots, zfb_codec_f1.cuh): cubic blocks
+    whose polynomial terms differ by up to 2^36 give runs of every length at n = 1 and n = 2 (longer than one window: the
+    loop behind the steps), and budgets of 32 / 64 / 96 / 128 bits end inside runs, events and the interleave tail."""
+    torch = _torch()
+    rng = np.random.default_rng(77)
+    nb = 1 << 15
+    xs = np.arange(4, dtype=np.float64) - 1.5
+    for spread in (36, 6):
+        mags = 2.0 ** -rng.integers(0, spread, (nb, 4)).astype(np.float64)
+        c = mags * rng.choice([-1.0, 1.0], mags.shape) * rng.random(mags.shape) * 1e3
+        h = (c[:, 0:1] + c[:, 1:2] * xs + c[:, 2:3] * xs ** 2 + c[:, 3:4] * xs ** 3).astype(np.float32).ravel()
+        d_h = torch.from_numpy(h).cuda()
+        for mb in (32, 64, 96, 128):
+            s_ref = oracle.compress(h, mb)
+            s = codec.encode(d_h, mb)
+            assert np.array_equal(s.cpu().numpy(), s_ref), (spread, mb)
+            o = codec.decode(s, h.shape, torch.float32, mb, orig=d_h)
+            g_ref = oracle.decompress(s_ref, h.shape, np.float32, mb)
+            assert_bits_equal(o.cpu().numpy(), g_ref, (spread, mb))
+            check_metrics(pkg, oracle, codec.partials(), h, g_ref, "1D long runs %d/%d" % (spread, mb))
+
+
 def test_misaligned_1d_arrays_take_the_scalar_path(codec, pkg, oracle):
     """A contiguous 1D slice such as field[1:] is only 4-byte aligned: no 16-byte accesses (a misaligned vector load is
     a sticky fault that kills the context)."""

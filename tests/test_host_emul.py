@@ -166,6 +166,16 @@ def test_fast_1d_coder(oracle):
                          + np.tile(np.array([0, 0, 0, 1e-3], np.float32), n // 4)),
         "pairwise": np.repeat((rng.standard_normal(n // 2) * 3).astype(np.float32), 2),
     }
+    # cubic blocks whose four polynomial terms differ by up to 2^36 in size: runs of every length at n = 1 and n = 2 (longer
+    # than one 32-bit window, i.e. the loop behind the three straight-line head steps), budgets that end inside a run, an
+    # event or the interleave tail
+    xs = np.arange(4, dtype=np.float64) - 1.5
+    for tag, spread in (("poly_wide", 36), ("poly_narrow", 6)):
+        mags = 2.0 ** -rng.integers(0, spread, (4 * n // 4, 4)).astype(np.float64)
+        sign = rng.choice([-1.0, 1.0], mags.shape)
+        c = mags * sign * rng.random(mags.shape) * 1e3
+        blocks = c[:, 0:1] + c[:, 1:2] * xs + c[:, 2:3] * xs ** 2 + c[:, 3:4] * xs ** 3
+        arrays[tag] = blocks.astype(np.float32).ravel()
     for label, f in arrays.items():
         for mb in (32, 64, 96, 128):
             s_ref = O.compress(f, mb)
