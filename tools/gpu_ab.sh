@@ -7,7 +7,7 @@ for tag in "$@"; do
 import sys,json
 for l in sys.stdin:
     if l.startswith('{'):
-        d=json.loads(l); print('$tag','value',round(d['value'],1),'enc_ms',round(d['enc_ms'],3),'dec_ms',round(d['dec_ms'],3),'rt',round(d['roofline']['round_trip']['frac'],3))
+        d=json.loads(l); print('$tag','value',round(d['value'],1),'enc_ms',round(d['enc_ms'],3),'dec_ms',round(d['dec_ms'],3),'rt',round(d['roofline']['round_trip']['frac'],3),'psnr',d['metrics_check']['psnr'],'abs',d['metrics_check']['absolute_error'],'mse',d['metrics_check']['mse'])
     else: print(l.strip()[:200])
 "
 done

@@ -229,48 +229,55 @@ ZFB_HD void encode_block(const float (&f)[4], unsigned maxbits, uint32_t (&out)[
   // 63 and the caller stores the low word(s) alone: there the head steps simply run on (a block whose budget ends inside
   // its head is the rare case) and the test costs nothing.
   auto room = [&]() -> bool { return MAXW <= 2 || pos < maxbits; };
-  auto nibble = [&](int kk) -> unsigned {  // plane kk as a nibble (bit i = coefficient i)
-    return ((u[0] >> kk) & 1u) | (((u[1] >> kk) & 1u) << 1) | (((u[2] >> kk) & 1u) << 2) | (((u[3] >> kk) & 1u) << 3);
+  // The coefficients are carried left-aligned at the current plane: bit 31 of t[i] is plane k of u[i] (no per-use shift
+  // or mask by k; planes below plane 0 are zero bits).
+  uint32_t t[4];
+  ZFB_UNROLL for (int i = 0; i < 4; i++) t[i] = u[i] << (31 - k);
+  auto nibble = [&]() -> unsigned {  // plane k as a nibble (bit i = coefficient i): four funnel shifts
+    unsigned x = t[3] >> 31;
+    x = (x << 1) | (t[2] >> 31);
+    x = (x << 1) | (t[1] >> 31);
+    return (x << 1) | (t[0] >> 31);
   };
-  // One head step = a run (possibly empty) of planes k .. ke+1 in which coefficients nn..3 are all zero AND the event
-  // plane behind it: the lanes of a warp then walk the same code whatever mix of runs and events their blocks hold.
-  // `nn` is the number of significant coefficients on entry (n == nn); with a literal argument the step is specialised
-  // at compile time (one spread form, fixed cap and table row).
+  auto advance = [&](unsigned s) {  // s < 32 planes coded
+    ZFB_UNROLL for (int i = 0; i < 4; i++) t[i] <<= s;
+    k -= (int)s;
+  };
+  // One head step = a run (possibly empty) of planes in which coefficients nn..3 are all zero AND the event plane behind
+  // it: the lanes of a warp then walk the same code whatever mix of runs and events their blocks hold.  `nn` (1 or 2) is
+  // the number of significant coefficients on entry (n == nn); with a literal argument the step is specialised at
+  // compile time (one spread form, fixed cap and table row).
   auto head_step = [&](const unsigned nn) {
-    uint32_t rest = u[3] | u[2];
-    if (nn < 2u) rest |= u[1];
-    if (nn < 1u) rest |= u[0];
-    rest &= mask32((unsigned)k + 1u);
-    const int ke = rest ? 31 - clz32(rest) : -1;
-    unsigned L = (unsigned)(k - ke);
-    const unsigned cap = nn == 0u ? 32u : (nn == 1u ? 16u : 10u);  // planes whose codes fit one 32-bit put
+    uint32_t rest = t[3] | t[2];
+    if (nn < 2u) rest |= t[1];
+    unsigned L = rest ? (unsigned)clz32(rest) : 32u;  // planes from k down without a bit of coefficients nn..3
+    if (L > (unsigned)k + 1u) L = (unsigned)k + 1u;   // (plane 0 is the last one)
+    const unsigned cap = nn == 1u ? 16u : 10u;        // planes whose codes fit one 32-bit put
     const bool capped = L > cap;  // (a capped run is simply continued by the next step)
     if (capped) L = cap;
     if (L) {
-      uint32_t code = 0u;
-      if (nn == 1u) code = spread2(brev32(u[0] << (31 - k)) & mask32(L));
-      else if (nn == 2u) code = spread3(brev32(u[0] << (31 - k)) & mask32(L)) | (spread3(brev32(u[1] << (31 - k)) & mask32(L)) << 1);
+      uint32_t code;
+      if (nn == 1u) code = spread2(brev32(t[0]) & mask32(L));
+      else code = spread3(brev32(t[0]) & mask32(L)) | (spread3(brev32(t[1]) & mask32(L)) << 1);
       put(code, L * (nn + 1u));
-      k -= (int)L;
+      advance(L);
     }
     if (!capped && k >= 0 && room()) {
       // event plane k
-      const unsigned x = nibble(k);
-      const unsigned e = tb.enc[nn * 16u + x];
+      const unsigned e = tb.enc[nn * 16u + nibble()];
       put(e & 0xffu, (e >> 8) & 15u);
       n = e >> 12;
-      k--;
+      advance(1u);
     }
   };
   // Every event raises n, so a block passes through each of n = 0, 1, 2 at most once: three straight-line steps, each
   // specialised for its n, instead of a loop whose trip count is the warp's maximum and whose body serves every n.
   // Plane k is the top set plane, so the n == 0 step is its event alone.
   if (room()) {
-    const unsigned x = nibble(k);
-    const unsigned e = tb.enc[x];
+    const unsigned e = tb.enc[nibble()];
     put(e & 0xffu, (e >> 8) & 15u);
     n = e >> 12;
-    k--;
+    advance(1u);
   }
   if (n == 1u && k >= 0 && room()) head_step(1u);
   if (n == 2u && k >= 0 && room()) head_step(2u);
@@ -278,7 +285,7 @@ ZFB_HD void encode_block(const float (&f)[4], unsigned maxbits, uint32_t (&out)[
   if (n >= 3u && k >= 0 && pos < (MAXW <= 2 ? 64u : maxbits)) {
     // planes k, k-1, ... : the raw nibble of every plane = interleave of the coefficients' bits below plane k+1
     uint32_t v[4];
-    ZFB_UNROLL for (int i = 0; i < 4; i++) v[i] = brev32(u[i] << (31 - k));  // bit j = bit (k - j) of u[i]
+    ZFB_UNROLL for (int i = 0; i < 4; i++) v[i] = brev32(t[i]);  // bit j = bit (k - j) of u[i]
     if (MAXW <= 2) {
       // at most 54 bits of the slot are left: the top 8 (16) planes, interleaved, are OR-ed in with one shift; planes
       // that do not exist are zero bits of v[], what falls beyond the slot is dropped by the shift.  (A table indexed by
