@@ -1155,10 +1155,11 @@ __global__ void __launch_bounds__(256) enc1_f32_kernel(const float* __restrict__
 }
 
 #ifndef ZFB_DEC1_MINB
-#define ZFB_DEC1_MINB 6  // resident CTAs per SM the register allocation must allow (40 registers; 4 CTAs at 50: decode 1.27 -> 1.19 ms)
+#define ZFB_DEC1_MINB 6  // resident CTAs per SM the register allocation must allow for 32/64-bit slots (40 registers; 4 CTAs at 50:
+                         // decode 1.27 -> 1.19 ms); wider slots keep 4 (at 40 registers the 128-bit instantiation spills)
 #endif
 template <int MAXW, bool METRICS>
-__global__ void __launch_bounds__(256, ZFB_DEC1_MINB) dec1_f32_kernel(const uint32_t* __restrict__ stream, float* __restrict__ out,
+__global__ void __launch_bounds__(256, MAXW <= 2 ? ZFB_DEC1_MINB : 4) dec1_f32_kernel(const uint32_t* __restrict__ stream, float* __restrict__ out,
                                                        const float* __restrict__ orig, size_t nfull, unsigned maxbits,
                                                        double* __restrict__ part)
 {
