@@ -38,6 +38,17 @@ ZFB_HD uint32_t brev32(uint32_t v)
   return (v >> 16) | (v << 16);
 #endif
 }
+ZFB_HD uint32_t byte_perm(uint32_t x, uint32_t y, unsigned sel)  // PRMT, plain byte selectors (0..7) only
+{
+#if defined(__CUDA_ARCH__)
+  return __byte_perm(x, y, sel);
+#else
+  const uint64_t xy = (uint64_t)x | ((uint64_t)y << 32);
+  uint32_t r = 0;
+  for (int j = 0; j < 4; j++) r |= (uint32_t)((xy >> (8u * ((sel >> (4 * j)) & 7u))) & 0xffu) << (8 * j);
+  return r;
+#endif
+}
 ZFB_HD int clz32(uint32_t v)  // v != 0
 {
 #if defined(__CUDA_ARCH__)
@@ -453,19 +464,12 @@ ZFB_HD void decode_block(float (&f)[4], unsigned maxbits, const uint32_t (&in)[M
       };
       const uint32_t o0 = chunk((uint32_t)r);
       const uint32_t o1 = MAXW == 2 ? chunk((uint32_t)(r >> 32)) : 0u;
-#if defined(__CUDA_ARCH__)
       // coefficient i's 16 plane bits, most significant plane first, are byte 3 - i of the two bit-reversed words: one
       // PRMT puts them in the top half, the shift drops them at plane k
       const uint32_t b0 = brev32(o0), b1 = brev32(o1);
       const uint32_t keep = 0xffff0000u >> (31 - k);
       ZFB_UNROLL for (int i = 0; i < 4; i++)
-        u[i] |= (__byte_perm(b0, b1, (unsigned)(((3 - i) << 12) | ((7 - i) << 8))) >> (31 - k)) & keep;
-#else
-      ZFB_UNROLL for (int i = 0; i < 4; i++) {
-        const uint32_t vi = ((o0 >> (8 * i)) & 0xffu) | (((o1 >> (8 * i)) & 0xffu) << 8);
-        u[i] |= brev32(vi) >> (31 - k);
-      }
-#endif
+        u[i] |= (byte_perm(b0, b1, (unsigned)(((3 - i) << 12) | ((7 - i) << 8))) >> (31 - k)) & keep;
     } else {
       const unsigned planes = (unsigned)k + 1u;
       uint32_t v[4] = {0u, 0u, 0u, 0u};
